@@ -1,0 +1,1127 @@
+/*
+ * pfe_oracle.c — CPU restatement of PaintFE's compositor / filter / adjustment / warp /
+ * brush-stamp hot path (reference: kylejckson/PaintFE v1.3.9 @ 16410bd).
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg may load it.  The product path
+ * (paintfe_b200/) never links, imports or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function below
+ * against the reference's own golden PNGs (copied as data into tests/golden/ref/).
+ * The reference itself (Rust, ~400 crates) cannot be built in this image, so there is
+ * no oracle/_ref binary; the goldens are the anchor.
+ *
+ * Rules that make this bit-exact with the Rust code:
+ *   - every arithmetic op is a separately rounded IEEE f32 op, evaluated left to right
+ *     exactly as written in the reference (compile with -ffp-contract=off, no fast-math);
+ *   - `x as u8`  == truncate toward zero, saturate to [0,255], NaN -> 0        (as_u8)
+ *   - `x.round()`== roundf (half away from zero)
+ *   - `x.clamp(a,b)`, `.min()`, `.max()` as Rust defines them for non-NaN input.
+ *
+ * All citations are file:line under /root/reference/.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PFE_CHUNK 64 /* src/canvas/defs.rs:7 */
+
+/* ------------------------------------------------------------------------- */
+/* Rust cast / math helpers                                                   */
+/* ------------------------------------------------------------------------- */
+static inline uint8_t as_u8(float v) {
+    if (!(v == v)) return 0;
+    if (v <= 0.0f) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+static inline int32_t as_i32(float v) {
+    if (!(v == v)) return 0;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    return (int32_t)v;
+}
+static inline uint32_t as_u32(float v) {
+    if (!(v == v)) return 0;
+    if (v <= 0.0f) return 0;
+    if (v >= 4294967296.0f) return UINT32_MAX;
+    return (uint32_t)v;
+}
+static inline float clampf(float v, float lo, float hi) {
+    if (v < lo) return lo;
+    if (v > hi) return hi;
+    return v;
+}
+static inline float minf(float a, float b) { return fminf(a, b); }
+static inline float maxf(float a, float b) { return fmaxf(a, b); }
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline uint8_t round_u8(float v) { return as_u8(clampf(roundf(v), 0.0f, 255.0f)); }
+
+/* ------------------------------------------------------------------------- */
+/* Blend: src/canvas/canvas_state.rs:1246-1505                                */
+/* ------------------------------------------------------------------------- */
+static inline float overlay_ch(float base, float top) { /* :1425 */
+    if (base < 0.5f) return 2.0f * base * top;
+    return 1.0f - 2.0f * (1.0f - base) * (1.0f - top);
+}
+static inline float color_burn_ch(float base, float top) { /* :1433 */
+    if (top == 0.0f) return 0.0f;
+    return maxf(1.0f - (1.0f - base) / top, 0.0f);
+}
+static inline float color_dodge_ch(float base, float top) { /* :1441 */
+    if (top >= 1.0f) return 1.0f;
+    return minf(base / (1.0f - top), 1.0f);
+}
+static inline float reflect_ch(float base, float top) { /* :1449 */
+    if (top >= 1.0f) return 1.0f;
+    return minf(base * base / (1.0f - top), 1.0f);
+}
+static inline float soft_light_ch(float base, float top) { /* :1458 */
+    if (top <= 0.5f) return base - (1.0f - 2.0f * top) * base * (1.0f - base);
+    float d;
+    if (base <= 0.25f) d = ((16.0f * base - 12.0f) * base + 4.0f) * base;
+    else d = sqrtf(base);
+    return base + (2.0f * top - 1.0f) * (d - base);
+}
+static inline float divide_ch(float base, float top) { /* :1471 */
+    if (top <= 0.0f) return 1.0f;
+    return minf(base / top, 1.0f);
+}
+static inline float vivid_light_ch(float base, float top) { /* :1479 */
+    if (top <= 0.5f) {
+        float t2 = 2.0f * top;
+        if (t2 <= 0.0f) return 0.0f;
+        return maxf(1.0f - (1.0f - base) / t2, 0.0f);
+    } else {
+        float t2 = 2.0f * (top - 0.5f);
+        if (t2 >= 1.0f) return 1.0f;
+        return minf(base / (1.0f - t2), 1.0f);
+    }
+}
+static inline float pin_light_ch(float base, float top) { /* :1499 */
+    if (top <= 0.5f) return minf(base, 2.0f * top);
+    return maxf(base, 2.0f * (top - 0.5f));
+}
+
+static inline float blend_ch(int mode, float b, float t) { /* :1304-1405 */
+    switch (mode) {
+    case 0: return t;                                          /* Normal */
+    case 1: return b * t;                                      /* Multiply */
+    case 2: return 1.0f - (1.0f - b) * (1.0f - t);             /* Screen */
+    case 3: return minf(b + t, 1.0f);                          /* Additive */
+    case 4: return reflect_ch(b, t);                           /* Reflect */
+    case 5: return reflect_ch(t, b);                           /* Glow */
+    case 6: return color_burn_ch(b, t);                        /* ColorBurn */
+    case 7: return color_dodge_ch(b, t);                       /* ColorDodge */
+    case 8: return overlay_ch(b, t);                           /* Overlay */
+    case 9: return fabsf(b - t);                               /* Difference */
+    case 10: return 1.0f - fabsf(1.0f - b - t);                /* Negation */
+    case 11: return maxf(b, t);                                /* Lighten */
+    case 12: return minf(b, t);                                /* Darken */
+    case 15: return overlay_ch(t, b);                          /* HardLight */
+    case 16: return soft_light_ch(b, t);                       /* SoftLight */
+    case 17: return b + t - 2.0f * b * t;                      /* Exclusion */
+    case 18: return maxf(b - t, 0.0f);                         /* Subtract */
+    case 19: return divide_ch(b, t);                           /* Divide */
+    case 20: return maxf(b + t - 1.0f, 0.0f);                  /* LinearBurn */
+    case 21: return vivid_light_ch(b, t);                      /* VividLight */
+    case 22: return clampf(b + 2.0f * t - 1.0f, 0.0f, 1.0f);   /* LinearLight */
+    case 23: return pin_light_ch(b, t);                        /* PinLight */
+    case 24: return (b + t >= 1.0f) ? 1.0f : 0.0f;             /* HardMix */
+    default: return t; /* BlendMode::from_u8 maps unknown ids to Normal, layers.rs:183 */
+    }
+}
+
+/* blend_pixel_static, canvas_state.rs:1246-1422.  px are RGBA8 byte quads. */
+void pfo_blend_pixel(const uint8_t base[4], const uint8_t top[4], int mode, float opacity,
+                     uint8_t out[4]) {
+    if (mode < 0 || mode > 24) mode = 0;
+    if (top[3] == 0) { memcpy(out, base, 4); return; }                         /* :1253 */
+    if (mode == 0 && opacity >= 1.0f && top[3] == 255) { memcpy(out, top, 4); return; } /* :1258 */
+    opacity = clampf(opacity, 0.0f, 1.0f);
+    float br = base[0] / 255.0f, bg = base[1] / 255.0f, bb = base[2] / 255.0f, ba = base[3] / 255.0f;
+    float tr = top[0] / 255.0f, tg = top[1] / 255.0f, tb = top[2] / 255.0f;
+    float ta = (top[3] / 255.0f) * opacity;
+    if (mode == 14) { /* Overwrite :1275 */
+        out[0] = as_u8(tr * 255.0f); out[1] = as_u8(tg * 255.0f);
+        out[2] = as_u8(tb * 255.0f); out[3] = as_u8(ta * 255.0f);
+        return;
+    }
+    if (mode == 13) { /* Xor :1283 */
+        float xa = ba * (1.0f - ta) + ta * (1.0f - ba);
+        if (xa == 0.0f) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+        float xr = (br * ba * (1.0f - ta) + tr * ta * (1.0f - ba)) / xa;
+        float xg = (bg * ba * (1.0f - ta) + tg * ta * (1.0f - ba)) / xa;
+        float xb = (bb * ba * (1.0f - ta) + tb * ta * (1.0f - ba)) / xa;
+        out[0] = as_u8(clampf(xr * 255.0f, 0.0f, 255.0f));
+        out[1] = as_u8(clampf(xg * 255.0f, 0.0f, 255.0f));
+        out[2] = as_u8(clampf(xb * 255.0f, 0.0f, 255.0f));
+        out[3] = as_u8(clampf(xa * 255.0f, 0.0f, 255.0f));
+        return;
+    }
+    float r = blend_ch(mode, br, tr), g = blend_ch(mode, bg, tg), b = blend_ch(mode, bb, tb);
+    float oa = ta + ba * (1.0f - ta);                                          /* :1407 */
+    if (oa == 0.0f) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    float orr = (r * ta + br * ba * (1.0f - ta)) / oa;
+    float og = (g * ta + bg * ba * (1.0f - ta)) / oa;
+    float ob = (b * ta + bb * ba * (1.0f - ta)) / oa;
+    out[0] = as_u8(clampf(orr * 255.0f, 0.0f, 255.0f));
+    out[1] = as_u8(clampf(og * 255.0f, 0.0f, 255.0f));
+    out[2] = as_u8(clampf(ob * 255.0f, 0.0f, 255.0f));
+    out[3] = as_u8(clampf(oa * 255.0f, 0.0f, 255.0f));
+}
+
+/* Layer descriptor shared (by layout) with include/pfe_b200.h pfe_layer_desc. */
+typedef struct pfo_layer_desc {
+    const uint8_t *rgba;  /* w*h*4 straight RGBA8; ignored for adjustment layers */
+    const uint8_t *mask;  /* w*h conceal plane (alpha of Layer::mask) or NULL, layers.rs:395-399 */
+    float opacity;
+    uint8_t blend;        /* BlendMode::to_u8, layers.rs:125-153 */
+    uint8_t visible;
+    uint8_t kind;         /* 0 raster, 1 Exposure, 2 BrightnessContrast, 3 Invert, 4 ChannelMixer */
+    uint8_t _pad;
+    float adj[16];        /* 1: [gain=2^ev]  2: [brightness, contrast]  4: red[4] green[4] blue[4] alpha[4] */
+} pfo_layer_desc;
+
+/* AdjustmentLayerData::apply_to_pixel_with_opacity, layers.rs:276-325 */
+static void adj_apply(const pfo_layer_desc *L, const uint8_t p[4], uint8_t out[4]) {
+    uint8_t a[4] = {p[0], p[1], p[2], p[3]};
+    switch (L->kind) {
+    case 1: { /* Exposure :279 — gain = 2^ev computed by the caller with powf */
+        float gain = L->adj[0];
+        for (int c = 0; c < 3; c++) a[c] = as_u8(clampf((float)p[c] * gain, 0.0f, 255.0f));
+    } break;
+    case 2: { /* BrightnessContrast :288 */
+        float brightness = L->adj[0], contrast = L->adj[1];
+        float factor = (259.0f * (contrast + 255.0f)) / (255.0f * (259.0f - contrast));
+        for (int c = 0; c < 3; c++)
+            a[c] = as_u8(clampf(factor * ((float)p[c] + brightness - 128.0f) + 128.0f, 0.0f, 255.0f));
+    } break;
+    case 3: /* Invert :298 */
+        a[0] = 255 - p[0]; a[1] = 255 - p[1]; a[2] = 255 - p[2];
+        break;
+    case 4: { /* ChannelMixer :299 */
+        float s[4] = {(float)p[0], (float)p[1], (float)p[2], (float)p[3]};
+        for (int c = 0; c < 4; c++) {
+            const float *m = &L->adj[c * 4];
+            a[c] = as_u8(clampf(s[0] * m[0] + s[1] * m[1] + s[2] * m[2] + s[3] * m[3], 0.0f, 255.0f));
+        }
+    } break;
+    default: break;
+    }
+    float t = clampf(L->opacity, 0.0f, 1.0f);                                   /* :316 */
+    float inv = 1.0f - t;
+    for (int c = 0; c < 4; c++) out[c] = as_u8(roundf((float)p[c] * inv + (float)a[c] * t));
+}
+
+/* One pixel of composite_viewport's layer loop, canvas_state.rs:575-677 (no preview layer:
+ * the CLI / export path never has one). */
+static inline void flatten_pixel(const pfo_layer_desc *layers, uint32_t n, size_t pi,
+                                 uint8_t acc[4]) {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0;                                      /* :573 */
+    for (uint32_t li = 0; li < n; li++) {
+        const pfo_layer_desc *L = &layers[li];
+        if (!L->visible) continue;                                              /* :576 */
+        if (L->kind != 0) { uint8_t o[4]; adj_apply(L, acc, o); memcpy(acc, o, 4); continue; } /* :579 */
+        uint8_t top[4];
+        memcpy(top, L->rgba + pi * 4, 4);
+        if (L->mask) {                                                          /* :660 */
+            uint32_t conceal = L->mask[pi];
+            if (conceal > 0) top[3] = (uint8_t)(((uint32_t)top[3] * (255u - conceal)) / 255u);
+        }
+        int opaque_overwrite = (L->blend == 0 && L->opacity >= 1.0f);           /* :605 */
+        if (opaque_overwrite && top[3] == 255) memcpy(acc, top, 4);             /* :667 */
+        else { uint8_t o[4]; pfo_blend_pixel(acc, top, L->blend, L->opacity, o); memcpy(acc, o, 4); }
+    }
+}
+
+/* CanvasState::composite, canvas_state.rs:482-698.  `active` is the active-chunk bitmap
+ * (ceil(w/64) x ceil(h/64) bytes, :529-550) or NULL meaning every chunk is active.
+ * Inactive chunks stay transparent zero (:506). Parallel over chunks like rayon (:565). */
+void pfo_flatten(const pfo_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
+                 const uint8_t *active, uint8_t *dst) {
+    uint32_t cxn = (w + PFE_CHUNK - 1) / PFE_CHUNK, cyn = (h + PFE_CHUNK - 1) / PFE_CHUNK;
+    long total = (long)cxn * cyn;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long ci = 0; ci < total; ci++) {
+        uint32_t cx = (uint32_t)(ci % cxn), cy = (uint32_t)(ci / cxn);
+        uint32_t x0 = cx * PFE_CHUNK, y0 = cy * PFE_CHUNK;
+        uint32_t x1 = x0 + PFE_CHUNK < w ? x0 + PFE_CHUNK : w;
+        uint32_t y1 = y0 + PFE_CHUNK < h ? y0 + PFE_CHUNK : h;
+        int on = active ? active[ci] != 0 : 1;
+        for (uint32_t y = y0; y < y1; y++)
+            for (uint32_t x = x0; x < x1; x++) {
+                size_t pi = (size_t)y * w + x;
+                if (!on) { memset(dst + pi * 4, 0, 4); continue; }
+                flatten_pixel(layers, n, pi, dst + pi * 4);
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Gaussian: src/ops/filters.rs:141-316                                       */
+/* ------------------------------------------------------------------------- */
+/* build_gaussian_kernel :214-234. Returns radius; writes 2r+1 weights (caller sizes k). */
+int pfo_gaussian_radius(float sigma) { return (int)as_u32(ceilf(sigma * 3.0f)); }
+int pfo_build_gaussian_kernel(float sigma, float *k) {
+    int radius = pfo_gaussian_radius(sigma);
+    if (radius == 0) { k[0] = 1.0f; return 0; }
+    int len = radius * 2 + 1;
+    float s2 = 2.0f * sigma * sigma;
+    float sum = 0.0f;
+    for (int i = 0; i < len; i++) {
+        float x = (float)i - (float)radius;
+        float v = expf(-x * x / s2);
+        k[i] = v;
+        sum += v;
+    }
+    float inv = 1.0f / sum;
+    for (int i = 0; i < len; i++) k[i] *= inv;
+    return radius;
+}
+
+/* parallel_gaussian_blur :242-316 */
+void pfo_gaussian_blur(const uint8_t *src, uint32_t w, uint32_t h, float sigma, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    int radius = pfo_gaussian_radius(sigma);
+    float *k = (float *)malloc(sizeof(float) * (size_t)(2 * radius + 1));
+    pfo_build_gaussian_kernel(sigma, k);
+    int len = 2 * radius + 1;
+    size_t n4 = (size_t)w * h * 4;
+    float *buf = (float *)malloc(n4 * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++) {
+        const uint8_t *row = src + (size_t)y * w * 4;
+        float *out = buf + (size_t)y * w * 4;
+        for (long x = 0; x < (long)w; x++) {
+            float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
+            for (int ki = 0; ki < len; ki++) {
+                long sx = x + ki - radius;
+                if (sx < 0) sx = 0;
+                if (sx > (long)w - 1) sx = (long)w - 1;
+                const uint8_t *p = row + sx * 4;
+                float kv = k[ki];
+                r += (float)p[0] * kv; g += (float)p[1] * kv;
+                b += (float)p[2] * kv; a += (float)p[3] * kv;
+            }
+            out[x * 4] = r; out[x * 4 + 1] = g; out[x * 4 + 2] = b; out[x * 4 + 3] = a;
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++) {
+        uint8_t *out = dst + (size_t)y * w * 4;
+        for (long x = 0; x < (long)w; x++) {
+            float r = 0.0f, g = 0.0f, b = 0.0f, a = 0.0f;
+            for (int ki = 0; ki < len; ki++) {
+                long sy = y + ki - radius;
+                if (sy < 0) sy = 0;
+                if (sy > (long)h - 1) sy = (long)h - 1;
+                const float *p = buf + ((size_t)sy * w + (size_t)x) * 4;
+                float kv = k[ki];
+                r += p[0] * kv; g += p[1] * kv; b += p[2] * kv; a += p[3] * kv;
+            }
+            out[x * 4] = round_u8(r); out[x * 4 + 1] = round_u8(g);
+            out[x * 4 + 2] = round_u8(b); out[x * 4 + 3] = round_u8(a);
+        }
+    }
+    free(buf);
+    free(k);
+}
+
+/* blur_with_selection :141-207. mask is w*h (GrayImage of canvas size) or NULL. */
+void pfo_blur_with_selection(const uint8_t *src, uint32_t w, uint32_t h, float sigma,
+                             const uint8_t *mask, uint8_t *dst) {
+    if (!mask) { pfo_gaussian_blur(src, w, h, sigma, dst); if (w == 0 || h == 0) return; return; }
+    uint32_t min_x = w, min_y = h, max_x = 0, max_y = 0;
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++)
+            if (mask[(size_t)y * w + x] > 0) {
+                if (x < min_x) min_x = x;
+                if (y < min_y) min_y = y;
+                if (x > max_x) max_x = x;
+                if (y > max_y) max_y = y;
+            }
+    memcpy(dst, src, (size_t)w * h * 4);
+    if (min_x > max_x || min_y > max_y) return;
+    uint32_t pad = as_u32(ceilf(sigma * 3.0f));
+    uint32_t cx = min_x > pad ? min_x - pad : 0, cy = min_y > pad ? min_y - pad : 0;
+    uint32_t cx2 = max_x + 1 + pad < w ? max_x + 1 + pad : w;
+    uint32_t cy2 = max_y + 1 + pad < h ? max_y + 1 + pad : h;
+    uint32_t cw = cx2 - cx, ch = cy2 - cy;
+    uint8_t *sub = (uint8_t *)malloc((size_t)cw * ch * 4), *bl = (uint8_t *)malloc((size_t)cw * ch * 4);
+    for (uint32_t y = 0; y < ch; y++)
+        memcpy(sub + (size_t)y * cw * 4, src + ((size_t)(cy + y) * w + cx) * 4, (size_t)cw * 4);
+    pfo_gaussian_blur(sub, cw, ch, sigma, bl);
+    for (uint32_t y = min_y; y <= max_y; y++)
+        for (uint32_t x = min_x; x <= max_x; x++)
+            if (mask[(size_t)y * w + x] > 0)
+                memcpy(dst + ((size_t)y * w + x) * 4, bl + ((size_t)(y - cy) * cw + (x - cx)) * 4, 4);
+    free(sub);
+    free(bl);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Box / motion / median / sharpen / vignette                                 */
+/* ------------------------------------------------------------------------- */
+static inline int masked_out(const uint8_t *mask, uint32_t w, size_t x, size_t y) {
+    return mask && mask[y * w + x] == 0;
+}
+
+/* box_blur_core, src/ops/effects/blur.rs:233-318 */
+void pfo_box_blur(const uint8_t *src, uint32_t w, uint32_t h, float radius, const uint8_t *mask,
+                  uint8_t *dst) {
+    size_t n4 = (size_t)w * h * 4;
+    if (radius < 0.5f || w == 0 || h == 0) { memcpy(dst, src, n4); return; }
+    int r = (int)as_u32(ceilf(radius));
+    int ks = r * 2 + 1;
+    uint32_t d = (uint32_t)ks;
+    uint8_t *hb = (uint8_t *)malloc(n4);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++) {
+        const uint8_t *row = src + (size_t)y * w * 4;
+        uint8_t *out = hb + (size_t)y * w * 4;
+        uint32_t s[4] = {0, 0, 0, 0};
+        for (int k = 0; k < ks; k++) {
+            int sx = clampi(k - r, 0, (int)w - 1);
+            for (int c = 0; c < 4; c++) s[c] += row[sx * 4 + c];
+        }
+        for (long x = 0; x < (long)w; x++) {
+            for (int c = 0; c < 4; c++) out[x * 4 + c] = (uint8_t)((s[c] + d / 2) / d);
+            if (x + 1 < (long)w) {
+                int rx = clampi((int)x - r, 0, (int)w - 1), ax = clampi((int)x + r + 1, 0, (int)w - 1);
+                for (int c = 0; c < 4; c++) s[c] = s[c] - row[rx * 4 + c] + row[ax * 4 + c];
+            }
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (long x = 0; x < (long)w; x++) {
+        uint32_t s[4] = {0, 0, 0, 0};
+        for (int k = 0; k < ks; k++) {
+            int sy = clampi(k - r, 0, (int)h - 1);
+            for (int c = 0; c < 4; c++) s[c] += hb[((size_t)sy * w + x) * 4 + c];
+        }
+        for (long y = 0; y < (long)h; y++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) memcpy(dst + oi, src + oi, 4);
+            else for (int c = 0; c < 4; c++) dst[oi + c] = (uint8_t)((s[c] + d / 2) / d);
+            if (y + 1 < (long)h) {
+                int ry = clampi((int)y - r, 0, (int)h - 1), ay = clampi((int)y + r + 1, 0, (int)h - 1);
+                for (int c = 0; c < 4; c++)
+                    s[c] = s[c] - hb[((size_t)ry * w + x) * 4 + c] + hb[((size_t)ay * w + x) * 4 + c];
+            }
+        }
+    }
+    free(hb);
+}
+
+/* f32::to_radians: self * (PI / 180.0) with both constants f32 */
+float pfo_to_radians(float deg) { return deg * (3.14159265358979323846f / 180.0f); }
+
+/* motion_blur_core, blur.rs:144-210 */
+void pfo_motion_blur(const uint8_t *src, uint32_t w, uint32_t h, float angle_deg, float distance,
+                     const uint8_t *mask, uint8_t *dst) {
+    size_t n4 = (size_t)w * h * 4;
+    if (distance < 1.0f || w == 0 || h == 0) { memcpy(dst, src, n4); return; }
+    float angle = pfo_to_radians(angle_deg);
+    int steps = as_i32(ceilf(distance));
+    float dx = cosf(angle), dy = sinf(angle);
+    float inv_steps = 1.0f / (float)(steps * 2 + 1);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float s[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            for (int i = -steps; i <= steps; i++) {
+                int sx = as_i32(roundf((float)x + (float)i * dx));
+                int sy = as_i32(roundf((float)y + (float)i * dy));
+                sx = clampi(sx, 0, (int)w - 1);
+                sy = clampi(sy, 0, (int)h - 1);
+                const uint8_t *p = src + ((size_t)sy * w + sx) * 4;
+                for (int c = 0; c < 4; c++) s[c] += (float)p[c];
+            }
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(s[c] * inv_steps);
+        }
+}
+
+/* median_core, src/ops/effects/noise.rs:357-410.  The reference sorts the window and takes
+ * element [len/2]; a 256-bin histogram walk gives the identical element for u8 data. */
+void pfo_median(const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius, const uint8_t *mask,
+                uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    int r = radius < 1 ? 1 : (int)radius;
+    int len = (2 * r + 1) * (2 * r + 1);
+    int target = len / 2;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            uint16_t hist[4][256];
+            memset(hist, 0, sizeof(hist));
+            for (int dy = -r; dy <= r; dy++) {
+                int sy = clampi((int)y + dy, 0, (int)h - 1);
+                for (int dxx = -r; dxx <= r; dxx++) {
+                    int sx = clampi((int)x + dxx, 0, (int)w - 1);
+                    const uint8_t *p = src + ((size_t)sy * w + sx) * 4;
+                    for (int c = 0; c < 4; c++) hist[c][p[c]]++;
+                }
+            }
+            for (int c = 0; c < 4; c++) {
+                int acc = 0, v = 0;
+                for (v = 0; v < 256; v++) { acc += hist[c][v]; if (acc > target) break; }
+                dst[oi + c] = (uint8_t)v;
+            }
+        }
+}
+
+/* sharpen_core (unsharp mask), src/ops/effects/stylize.rs:96-141 */
+void pfo_sharpen(const uint8_t *src, uint32_t w, uint32_t h, float amount, float radius,
+                 const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    size_t n = (size_t)w * h;
+    uint8_t *bl = (uint8_t *)malloc(n * 4);
+    pfo_gaussian_blur(src, w, h, radius, bl);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        size_t si = (size_t)i * 4;
+        if (mask && mask[i] == 0) { memcpy(dst + si, src + si, 4); continue; }
+        for (int c = 0; c < 3; c++) {
+            float s = (float)src[si + c], b = (float)bl[si + c];
+            dst[si + c] = round_u8(s + amount * (s - b));
+        }
+        dst[si + 3] = src[si + 3];
+    }
+    free(bl);
+}
+
+/* vignette_core, stylize.rs:170-191 via apply_per_pixel, effects.rs:53-100.
+ * powf(2.0) is folded to x*x by LLVM (and x*x is the correctly rounded square). */
+void pfo_vignette(const uint8_t *src, uint32_t w, uint32_t h, float amount, float softness,
+                  const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float fw = (float)w, fh = (float)h;
+    float cx = fw / 2.0f, cy = fh / 2.0f;
+    float max_dist = sqrtf(cx * cx + cy * cy);
+    float soft = maxf(softness, 0.01f);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float dx = (float)x - cx, dy = (float)y - cy;
+            float dist = sqrtf(dx * dx + dy * dy) / max_dist;
+            float q = minf(dist / soft, 1.0f);
+            float vf = clampf(1.0f - (amount * (q * q)), 0.0f, 1.0f);
+            dst[oi] = round_u8((float)src[oi] * vf);
+            dst[oi + 1] = round_u8((float)src[oi + 1] * vf);
+            dst[oi + 2] = round_u8((float)src[oi + 2] * vf);
+            dst[oi + 3] = round_u8((float)src[oi + 3]);
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Per-pixel adjustments: src/ops/adjustments.rs and src/ops/scripting.rs      */
+/* ------------------------------------------------------------------------- */
+/* rgb_to_hsl / hsl_to_rgb / hue_to_rgb, adjustments.rs:944-1012 */
+static void rgb_to_hsl(float r, float g, float b, float *H, float *S, float *L) {
+    float mx = maxf(maxf(r, g), b), mn = minf(minf(r, g), b);
+    float l = (mx + mn) / 2.0f;
+    if (fabsf(mx - mn) < 1e-6f) { *H = 0.0f; *S = 0.0f; *L = l; return; }
+    float d = mx - mn;
+    float s = l > 0.5f ? d / (2.0f - mx - mn) : d / (mx + mn);
+    float hh;
+    if (fabsf(mx - r) < 1e-6f) { hh = (g - b) / d; if (hh < 0.0f) hh += 6.0f; hh = hh / 6.0f; }
+    else if (fabsf(mx - g) < 1e-6f) hh = ((b - r) / d + 2.0f) / 6.0f;
+    else hh = ((r - g) / d + 4.0f) / 6.0f;
+    *H = hh; *S = s; *L = l;
+}
+static float hue_to_rgb(float p, float q, float t) {
+    if (t < 0.0f) t += 1.0f;
+    if (t > 1.0f) t -= 1.0f;
+    if (t < 1.0f / 6.0f) return p + (q - p) * 6.0f * t;
+    if (t < 1.0f / 2.0f) return q;
+    if (t < 2.0f / 3.0f) return p + (q - p) * (2.0f / 3.0f - t) * 6.0f;
+    return p;
+}
+static void hsl_to_rgb(float h, float s, float l, float *r, float *g, float *b) {
+    if (fabsf(s) < 1e-6f) { *r = *g = *b = l; return; }
+    float q = l < 0.5f ? l * (1.0f + s) : l + s - l * s;
+    float p = 2.0f * l - q;
+    *r = hue_to_rgb(p, q, h + 1.0f / 3.0f);
+    *g = hue_to_rgb(p, q, h);
+    *b = hue_to_rgb(p, q, h - 1.0f / 3.0f);
+}
+
+/* build_levels_lut, adjustments.rs:424-446 */
+void pfo_build_levels_lut(float in_black, float in_white, float gamma, float out_black,
+                          float out_white, uint8_t lut[256]) {
+    float in_range = maxf(in_white - in_black, 1.0f);
+    float out_range = out_white - out_black;
+    float inv_gamma = 1.0f / maxf(gamma, 0.01f);
+    for (int i = 0; i < 256; i++) {
+        float v = (float)i;
+        float normalized = clampf((v - in_black) / in_range, 0.0f, 1.0f);
+        float gc = powf(normalized, inv_gamma);
+        float output = out_black + gc * out_range;
+        lut[i] = round_u8(output);
+    }
+}
+/* scripting apply_levels LUT, scripting.rs:1054-1066 (truncating, output range fixed 0..255) */
+void pfo_build_levels_lut_script(float in_black, float in_white, float gamma, uint8_t lut[256]) {
+    float in_range = maxf(in_white - in_black, 1.0f);
+    float inv_gamma = 1.0f / maxf(gamma, 0.01f);
+    for (int i = 0; i < 256; i++) {
+        float normalized = clampf(((float)i - in_black) / in_range, 0.0f, 1.0f);
+        float gc = powf(normalized, inv_gamma);
+        lut[i] = as_u8(clampf(gc * 255.0f, 0.0f, 255.0f));
+    }
+}
+/* build_stretch_lut, adjustments.rs:232-253 */
+void pfo_build_stretch_lut(uint8_t mn, uint8_t mx, uint8_t lut[256]) {
+    if (mx <= mn) { for (int i = 0; i < 256; i++) lut[i] = (uint8_t)i; return; }
+    float range = (float)(mx - mn);
+    for (int i = 0; i < 256; i++) {
+        float v;
+        if ((uint8_t)i <= mn) v = 0.0f;
+        else if ((uint8_t)i >= mx) v = 255.0f;
+        else v = ((float)i - (float)mn) / range * 255.0f;
+        lut[i] = round_u8(v);
+    }
+}
+/* build_curves_lut (Fritsch-Carlson), adjustments.rs:634-729. pts = n (x,y) pairs. */
+void pfo_build_curves_lut(const float *pts, int n, uint8_t lut[256]) {
+    if (n < 2) { for (int i = 0; i < 256; i++) lut[i] = (uint8_t)i; return; }
+    float *delta = (float *)malloc(sizeof(float) * (size_t)(n - 1));
+    float *m = (float *)calloc((size_t)n, sizeof(float));
+#define PX(i) pts[(i) * 2]
+#define PY(i) pts[(i) * 2 + 1]
+    for (int i = 0; i < n - 1; i++) {
+        float dx = PX(i + 1) - PX(i), dy = PY(i + 1) - PY(i);
+        delta[i] = fabsf(dx) < 1e-6f ? 0.0f : dy / dx;
+    }
+    m[0] = delta[0];
+    m[n - 1] = delta[n - 2];
+    for (int i = 1; i < n - 1; i++) {
+        if (delta[i - 1] * delta[i] <= 0.0f) m[i] = 0.0f;
+        else m[i] = (delta[i - 1] + delta[i]) / 2.0f;
+    }
+    for (int i = 0; i < n - 1; i++) {
+        if (fabsf(delta[i]) < 1e-6f) { m[i] = 0.0f; m[i + 1] = 0.0f; }
+        else {
+            float alpha = m[i] / delta[i], beta = m[i + 1] / delta[i];
+            float s = alpha * alpha + beta * beta;
+            if (s > 9.0f) {
+                float tau = 3.0f / sqrtf(s);
+                m[i] = tau * alpha * delta[i];
+                m[i + 1] = tau * beta * delta[i];
+            }
+        }
+    }
+    for (int i = 0; i < 256; i++) {
+        float x = (float)i;
+        int seg = 0;
+        for (int j = 0; j < n - 1; j++) if (x >= PX(j)) seg = j;
+        if (x <= PX(0)) lut[i] = round_u8(PY(0));
+        else if (x >= PX(n - 1)) lut[i] = round_u8(PY(n - 1));
+        else {
+            float x0 = PX(seg), x1 = PX(seg + 1), y0 = PY(seg), y1 = PY(seg + 1);
+            float hh = x1 - x0;
+            if (fabsf(hh) < 1e-6f) lut[i] = round_u8(y0);
+            else {
+                float t = (x - x0) / hh, t2 = t * t, t3 = t2 * t;
+                float h00 = 2.0f * t3 - 3.0f * t2 + 1.0f;
+                float h10 = t3 - 2.0f * t2 + t;
+                float h01 = -2.0f * t3 + 3.0f * t2;
+                float h11 = t3 - t2;
+                float val = h00 * y0 + h10 * hh * m[seg] + h01 * y1 + h11 * hh * m[seg + 1];
+                lut[i] = round_u8(val);
+            }
+        }
+    }
+#undef PX
+#undef PY
+    free(delta);
+    free(m);
+}
+/* build_multi_channel_luts, adjustments.rs:576-626. in: 5 LUTs [RGB,R,G,B,A] (identity when
+ * the channel is disabled); out: 4 composed LUTs [R,G,B,A]. */
+void pfo_compose_curve_luts(const uint8_t in[5][256], uint8_t out[4][256]) {
+    for (int i = 0; i < 256; i++) {
+        out[0][i] = in[1][in[0][i]];
+        out[1][i] = in[2][in[0][i]];
+        out[2][i] = in[3][in[0][i]];
+        out[3][i] = in[4][i];
+    }
+}
+
+/* Op ids shared with include/pfe_b200.h (PFE_ADJ_*). */
+enum {
+    PFO_INVERT = 0,         /* adjustments.rs:115  (255-r, 255-g, 255-b, a) */
+    PFO_INVERT_ALPHA = 1,   /* :122 */
+    PFO_SEPIA = 2,          /* :133 */
+    PFO_DESATURATE = 3,     /* filters.rs:320 (BT.709, rounds) */
+    PFO_BRIGHTNESS_CONTRAST = 4, /* adjustments.rs:265  p=[brightness, contrast] */
+    PFO_HSL = 5,            /* :300  p=[hue, sat, light] */
+    PFO_EXPOSURE = 6,       /* :352  p=[gain=2^ev] */
+    PFO_LUT_RGB = 7,        /* levels :424 — one LUT on r,g,b; alpha kept */
+    PFO_LUT_RGBA = 8,       /* curves :549 — four LUTs; per-channel levels :490 */
+    PFO_TEMPERATURE_TINT = 9,   /* :518  p=[temperature, tint] */
+    PFO_HIGHLIGHTS_SHADOWS = 10,/* :371  p=[shadows, highlights] */
+    /* scripting.rs inline variants: truncating casts, no mask, alpha untouched */
+    PFO_S_INVERT = 32,      /* scripting.rs:869 */
+    PFO_S_DESATURATE = 33,  /* :883 integer 299/587/114 */
+    PFO_S_SEPIA = 34,       /* :900 */
+    PFO_S_SEPIA_STRENGTH = 35,  /* :921 p=[strength] */
+    PFO_S_BRIGHTNESS_CONTRAST = 36, /* :944 */
+    PFO_S_HSL = 37,         /* :964 */
+    PFO_S_EXPOSURE = 38,    /* :1040 p=[gain] */
+    PFO_S_LUT_RGB = 39      /* :1054 apply_levels */
+};
+
+static inline void adjust_pixel(int op, const float *p, const uint8_t *luts, const uint8_t in[4],
+                                uint8_t out[4]) {
+    float r = (float)in[0], g = (float)in[1], b = (float)in[2], a = (float)in[3];
+    float nr = r, ng = g, nb = b, na = a;
+    switch (op) {
+    case PFO_INVERT: nr = 255.0f - r; ng = 255.0f - g; nb = 255.0f - b; break;
+    case PFO_INVERT_ALPHA: na = 255.0f - a; break;
+    case PFO_SEPIA:
+        nr = minf(0.393f * r + 0.769f * g + 0.189f * b, 255.0f);
+        ng = minf(0.349f * r + 0.686f * g + 0.168f * b, 255.0f);
+        nb = minf(0.272f * r + 0.534f * g + 0.131f * b, 255.0f);
+        break;
+    case PFO_DESATURATE: {
+        uint8_t lum = round_u8(0.2126f * r + 0.7152f * g + 0.0722f * b);
+        out[0] = out[1] = out[2] = lum; out[3] = in[3];
+        return;
+    }
+    case PFO_BRIGHTNESS_CONTRAST: {
+        float brightness = p[0], contrast = p[1];
+        float factor = (259.0f * (contrast + 255.0f)) / (255.0f * (259.0f - contrast));
+        nr = factor * (r + brightness - 128.0f) + 128.0f;
+        ng = factor * (g + brightness - 128.0f) + 128.0f;
+        nb = factor * (b + brightness - 128.0f) + 128.0f;
+    } break;
+    case PFO_HSL: {
+        float sat_factor = 1.0f + p[1] / 100.0f;
+        float light_offset = p[2] * 255.0f / 100.0f;
+        float hh, s, l;
+        rgb_to_hsl(r / 255.0f, g / 255.0f, b / 255.0f, &hh, &s, &l);
+        float t = hh + p[0] / 360.0f;
+        float nh = t - truncf(t); /* f32::fract */
+        if (nh < 0.0f) nh = nh + 1.0f;
+        float ns = clampf(s * sat_factor, 0.0f, 1.0f);
+        float rr, gg, bb;
+        hsl_to_rgb(nh, ns, l, &rr, &gg, &bb);
+        nr = rr * 255.0f + light_offset; ng = gg * 255.0f + light_offset; nb = bb * 255.0f + light_offset;
+    } break;
+    case PFO_EXPOSURE: nr = r * p[0]; ng = g * p[0]; nb = b * p[0]; break;
+    case PFO_LUT_RGB:
+        nr = (float)luts[in[0]]; ng = (float)luts[in[1]]; nb = (float)luts[in[2]];
+        break;
+    case PFO_LUT_RGBA:
+        nr = (float)luts[in[0]]; ng = (float)luts[256 + in[1]];
+        nb = (float)luts[512 + in[2]]; na = (float)luts[768 + in[3]];
+        break;
+    case PFO_TEMPERATURE_TINT: {
+        float temp_shift = p[0] * 1.5f, tint_shift = p[1] * 1.0f;
+        nr = r + temp_shift; ng = g - tint_shift * 0.5f; nb = b - temp_shift;
+    } break;
+    case PFO_HIGHLIGHTS_SHADOWS: {
+        float shadow_amt = p[0] / 100.0f, highlight_amt = p[1] / 100.0f;
+        float lum = (0.2126f * r + 0.7152f * g + 0.0722f * b) / 255.0f;
+        float sw = (1.0f - lum) * (1.0f - lum);
+        float hw = lum * lum;
+        float adj = sw * shadow_amt * 128.0f + hw * highlight_amt * 128.0f;
+        nr = r + adj; ng = g + adj; nb = b + adj;
+    } break;
+    /* ---- scripting variants: write u8 directly ---- */
+    case PFO_S_INVERT: out[0] = 255 - in[0]; out[1] = 255 - in[1]; out[2] = 255 - in[2]; out[3] = in[3]; return;
+    case PFO_S_DESATURATE: {
+        uint32_t gray = ((uint32_t)in[0] * 299u + (uint32_t)in[1] * 587u + (uint32_t)in[2] * 114u) / 1000u;
+        out[0] = out[1] = out[2] = (uint8_t)gray; out[3] = in[3];
+        return;
+    }
+    case PFO_S_SEPIA:
+        out[0] = as_u8(minf(r * 0.393f + g * 0.769f + b * 0.189f, 255.0f));
+        out[1] = as_u8(minf(r * 0.349f + g * 0.686f + b * 0.168f, 255.0f));
+        out[2] = as_u8(minf(r * 0.272f + g * 0.534f + b * 0.131f, 255.0f));
+        out[3] = in[3];
+        return;
+    case PFO_S_SEPIA_STRENGTH: {
+        float strength = p[0], inv = 1.0f - strength;
+        float sr = minf(r * 0.393f + g * 0.769f + b * 0.189f, 255.0f);
+        float sg = minf(r * 0.349f + g * 0.686f + b * 0.168f, 255.0f);
+        float sb = minf(r * 0.272f + g * 0.534f + b * 0.131f, 255.0f);
+        out[0] = as_u8(r * inv + sr * strength);
+        out[1] = as_u8(g * inv + sg * strength);
+        out[2] = as_u8(b * inv + sb * strength);
+        out[3] = in[3];
+        return;
+    }
+    case PFO_S_BRIGHTNESS_CONTRAST: {
+        float bright = p[0], contrast = p[1];
+        float factor = (259.0f * (contrast + 255.0f)) / (255.0f * (259.0f - contrast));
+        out[0] = as_u8(clampf(factor * (r + bright - 128.0f) + 128.0f, 0.0f, 255.0f));
+        out[1] = as_u8(clampf(factor * (g + bright - 128.0f) + 128.0f, 0.0f, 255.0f));
+        out[2] = as_u8(clampf(factor * (b + bright - 128.0f) + 128.0f, 0.0f, 255.0f));
+        out[3] = in[3];
+        return;
+    }
+    case PFO_S_HSL: {
+        float hue_shift = p[0];
+        float sat_factor = 1.0f + p[1] / 100.0f;
+        float light_offset = p[2] * 255.0f / 100.0f;
+        float fr = r / 255.0f, fg = g / 255.0f, fb = b / 255.0f;
+        float cmax = maxf(maxf(fr, fg), fb), cmin = minf(minf(fr, fg), fb);
+        float l = (cmax + cmin) / 2.0f;
+        float hh = 0.0f, s = 0.0f;
+        if (!(fabsf(cmax - cmin) < 1e-10f)) {
+            float d = cmax - cmin;
+            s = l > 0.5f ? d / (2.0f - cmax - cmin) : d / (cmax + cmin);
+            float h6;
+            if (fabsf(cmax - fr) < 1e-10f) h6 = (fg - fb) / d + (fg < fb ? 6.0f : 0.0f);
+            else if (fabsf(cmax - fg) < 1e-10f) h6 = (fb - fr) / d + 2.0f;
+            else h6 = (fr - fg) / d + 4.0f;
+            hh = h6 / 6.0f;
+        }
+        float t = hh + hue_shift / 360.0f;
+        float nh = fmodf(t, 1.0f); /* rem_euclid(1.0) */
+        if (nh < 0.0f) nh = nh + 1.0f;
+        float ns = clampf(s * sat_factor, 0.0f, 1.0f);
+        float rr, gg, bb;
+        if (fabsf(ns) < 1e-10f) { rr = gg = bb = l; }
+        else {
+            float q = l < 0.5f ? l * (1.0f + ns) : l + ns - l * ns;
+            float pp = 2.0f * l - q;
+            rr = hue_to_rgb(pp, q, nh + 1.0f / 3.0f);
+            gg = hue_to_rgb(pp, q, nh);
+            bb = hue_to_rgb(pp, q, nh - 1.0f / 3.0f);
+        }
+        out[0] = as_u8(clampf(rr * 255.0f + light_offset, 0.0f, 255.0f));
+        out[1] = as_u8(clampf(gg * 255.0f + light_offset, 0.0f, 255.0f));
+        out[2] = as_u8(clampf(bb * 255.0f + light_offset, 0.0f, 255.0f));
+        out[3] = in[3];
+        return;
+    }
+    case PFO_S_EXPOSURE:
+        out[0] = as_u8(clampf(r * p[0], 0.0f, 255.0f));
+        out[1] = as_u8(clampf(g * p[0], 0.0f, 255.0f));
+        out[2] = as_u8(clampf(b * p[0], 0.0f, 255.0f));
+        out[3] = in[3];
+        return;
+    case PFO_S_LUT_RGB:
+        out[0] = luts[in[0]]; out[1] = luts[in[1]]; out[2] = luts[in[2]]; out[3] = in[3];
+        return;
+    default: break;
+    }
+    /* apply_pixel_transform rounding, adjustments.rs:33-39 */
+    out[0] = round_u8(nr); out[1] = round_u8(ng); out[2] = round_u8(nb); out[3] = round_u8(na);
+}
+
+/* apply_pixel_transform_from_flat (adjustments.rs:46-108) when `occupancy` is NULL;
+ * apply_pixel_transform / par_map_populated (adjustments.rs:21-42, tiled_image.rs:905-933)
+ * when `occupancy` (chunk bitmap) is given: pixels in unpopulated chunks are left untouched. */
+void pfo_adjust(const uint8_t *src, uint32_t w, uint32_t h, int op, const float *params,
+                const uint8_t *luts, const uint8_t *mask, const uint8_t *occupancy, uint8_t *dst) {
+    uint32_t cxn = (w + PFE_CHUNK - 1) / PFE_CHUNK;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if ((occupancy && !occupancy[(size_t)(y / PFE_CHUNK) * cxn + (size_t)(x / PFE_CHUNK)]) ||
+                (op < 32 && masked_out(mask, w, (size_t)x, (size_t)y))) {
+                memcpy(dst + oi, src + oi, 4);
+                continue;
+            }
+            adjust_pixel(op, params, luts, src + oi, dst + oi);
+        }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Warps: src/ops/transform.rs:1015-1345, 1558-1761                           */
+/* ------------------------------------------------------------------------- */
+static inline void cr_weights(float t, float w[4]) { /* :1558 */
+    float t2 = t * t, t3 = t2 * t;
+    w[0] = -0.5f * t3 + t2 - 0.5f * t;
+    w[1] = 1.5f * t3 - 2.5f * t2 + 1.0f;
+    w[2] = -1.5f * t3 + 2.0f * t2 + 0.5f * t;
+    w[3] = 0.5f * t3 - 0.5f * t2;
+}
+void pfo_catmull_rom_weights(float t, float w[4]) { cr_weights(t, w); }
+
+/* catmull_rom_surface :1589-1646. points row-major (rows+1)x(cols+1) of [x,y]. */
+void pfo_catmull_rom_surface(const float *pts, int cols, int rows, float ug, float vg, float out[2]) {
+    int ppr = cols + 1, nrows = rows + 1;
+    float col_f = clampf(ug, 0.0f, (float)cols - 0.0001f);
+    float row_f = clampf(vg, 0.0f, (float)rows - 0.0001f);
+    int ci = (int)as_u32(col_f); if (ci > cols - 1) ci = cols - 1;
+    int ri = (int)as_u32(row_f); if (ri > rows - 1) ri = rows - 1;
+    float ul = col_f - (float)ci, vl = row_f - (float)ri;
+    float wv[4], wu[4];
+    cr_weights(vl, wv);
+    int rv[4] = {ri == 0 ? 0 : ri - 1, ri, ri + 1 < nrows - 1 ? ri + 1 : nrows - 1,
+                 ri + 2 < nrows - 1 ? ri + 2 : nrows - 1};
+    cr_weights(ul, wu);
+    int cu[4] = {ci == 0 ? 0 : ci - 1, ci, ci + 1 < ppr - 1 ? ci + 1 : ppr - 1,
+                 ci + 2 < ppr - 1 ? ci + 2 : ppr - 1};
+    float rvx[4], rvy[4];
+    for (int j = 0; j < 4; j++) {
+        const float *b = pts + (size_t)rv[j] * ppr * 2;
+        const float *p0 = b + cu[0] * 2, *p1 = b + cu[1] * 2, *p2 = b + cu[2] * 2, *p3 = b + cu[3] * 2;
+        rvx[j] = wu[0] * p0[0] + wu[1] * p1[0] + wu[2] * p2[0] + wu[3] * p3[0];
+        rvy[j] = wu[0] * p0[1] + wu[1] * p1[1] + wu[2] * p2[1] + wu[3] * p3[1];
+    }
+    out[0] = wv[0] * rvx[0] + wv[1] * rvx[1] + wv[2] * rvx[2] + wv[3] * rvx[3];
+    out[1] = wv[0] * rvy[0] + wv[1] * rvy[1] + wv[2] * rvy[2] + wv[3] * rvy[3];
+}
+
+/* generate_displacement_from_mesh :1670-1706 (orig != NULL) and _fast :1712-1739 (orig NULL) */
+void pfo_mesh_displacement(const float *orig, const float *def, int cols, int rows, uint32_t w,
+                           uint32_t h, float *out) {
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            float ug = ((float)x + 0.5f) / (float)w * (float)cols;
+            float vg = ((float)y + 0.5f) / (float)h * (float)rows;
+            float d[2];
+            pfo_catmull_rom_surface(def, cols, rows, ug, vg, d);
+            float *o = out + ((size_t)y * w + x) * 2;
+            if (orig) {
+                float og[2];
+                pfo_catmull_rom_surface(orig, cols, rows, ug, vg, og);
+                o[0] = d[0] - og[0]; o[1] = d[1] - og[1];
+            } else {
+                o[0] = d[0] - ((float)x + 0.5f); o[1] = d[1] - ((float)y + 0.5f);
+            }
+        }
+}
+
+/* warp_displacement_full :1288-1345. src is sw x sh; disp / dst are w x h. */
+void pfo_warp_displacement(const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp,
+                           uint32_t w, uint32_t h, uint8_t *dst) {
+    int src_w = (int)sw, src_h = (int)sh;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t i = (size_t)y * w + x;
+            uint8_t *o = dst + i * 4;
+            float sx = (float)x - disp[i * 2], sy = (float)y - disp[i * 2 + 1];
+            int x0 = as_i32(floorf(sx)), y0 = as_i32(floorf(sy));
+            if (x0 < -1 || y0 < -1 || x0 >= src_w || y0 >= src_h) { o[0] = o[1] = o[2] = o[3] = 0; continue; }
+            float fx = sx - (float)x0, fy = sy - (float)y0;
+            float tl[4], tr[4], bl[4], br[4];
+            int xs[2] = {x0, x0 + 1}, ys[2] = {y0, y0 + 1};
+            float *q[4] = {tl, tr, bl, br};
+            for (int k = 0; k < 4; k++) {
+                int px = xs[k & 1], py = ys[k >> 1];
+                if (px < 0 || py < 0 || px >= src_w || py >= src_h) { q[k][0] = q[k][1] = q[k][2] = q[k][3] = 0.0f; }
+                else { const uint8_t *s = src + ((size_t)py * sw + px) * 4; for (int c = 0; c < 4; c++) q[k][c] = (float)s[c]; }
+            }
+            for (int c = 0; c < 4; c++) {
+                float top = tl[c] + (tr[c] - tl[c]) * fx;
+                float bot = bl[c] + (br[c] - bl[c]) * fx;
+                o[c] = round_u8(top + (bot - top) * fy);
+            }
+        }
+}
+
+/* warp_mesh_catmull_rom :1743-1761 */
+void pfo_mesh_warp(const uint8_t *src, uint32_t sw, uint32_t sh, const float *orig, const float *def,
+                   int cols, int rows, uint32_t w, uint32_t h, uint8_t *dst) {
+    float *d = (float *)malloc((size_t)w * h * 2 * sizeof(float));
+    pfo_mesh_displacement(orig, def, cols, rows, w, h, d);
+    pfo_warp_displacement(src, sw, sh, d, w, h, dst);
+    free(d);
+}
+
+/* DisplacementField::apply_push/expand/contract/twirl :1051-1200.
+ * kind: 0 push (a0=delta_x, a1=delta_y), 1 expand, 2 contract, 3 twirl (a0 = clockwise?1:0). */
+void pfo_liquify(float *field, uint32_t w, uint32_t h, int kind, float cx, float cy, float radius,
+                 float strength, float a0, float a1, int bbox[4]) {
+    float r = maxf(radius, 1.0f);
+    float sigma = r / 3.0f;
+    float s2 = 2.0f * sigma * sigma;
+    int x0 = as_i32(floorf(cx - r)); if (x0 < 0) x0 = 0;
+    int y0 = as_i32(floorf(cy - r)); if (y0 < 0) y0 = 0;
+    int x1 = as_i32(ceilf(cx + r)); if (x1 > (int)w) x1 = (int)w;
+    int y1 = as_i32(ceilf(cy + r)); if (y1 > (int)h) y1 = (int)h;
+    float dir = a0 != 0.0f ? 1.0f : -1.0f;
+    for (int py = y0; py < y1; py++)
+        for (int px = x0; px < x1; px++) {
+            float dx = (float)px - cx, dy = (float)py - cy;
+            float dsq = dx * dx + dy * dy;
+            if (dsq > r * r) continue;
+            float *f = field + ((size_t)py * w + px) * 2;
+            if (kind == 0) {
+                float wgt = expf(-dsq / s2) * strength;
+                f[0] += a0 * wgt; f[1] += a1 * wgt;
+            } else if (kind == 1) {
+                float dist = maxf(sqrtf(dsq), 0.001f);
+                float t = dist / r;
+                float wgt = (1.0f - t) * (1.0f - t) * strength * 3.0f;
+                f[0] += dx / dist * wgt; f[1] += dy / dist * wgt;
+            } else if (kind == 2) {
+                float dist = maxf(sqrtf(dsq), 0.001f);
+                float wgt = expf(-dsq / s2) * strength;
+                f[0] += -dx / dist * wgt * 2.0f; f[1] += -dy / dist * wgt * 2.0f;
+            } else {
+                float wgt = expf(-dsq / s2) * strength * dir;
+                f[0] += -dy * wgt * 0.1f; f[1] += dx * wgt * 0.1f;
+            }
+        }
+    if (bbox) { bbox[0] = x0; bbox[1] = y0; bbox[2] = x1; bbox[3] = y1; }
+}
+
+/* ------------------------------------------------------------------------- */
+/* Brush stamp: src/ui/panels/tools/behavior/raster/brush_render.rs           */
+/* ------------------------------------------------------------------------- */
+typedef struct pfo_brush {
+    float size, hardness, flow;   /* ToolProperties: state.rs:136-150 (pressure off) */
+    int anti_aliased;
+    float color[4];               /* brush colour, straight RGBA in 0..1 */
+    int is_eraser;
+} pfo_brush;
+
+/* compute_brush_alpha :54-82 */
+float pfo_brush_alpha(const pfo_brush *b, float dist, float radius) {
+    if (radius <= 0.0f) return 0.0f;
+    float sh = clampf(b->hardness, 0.0f, 1.0f);
+    float t = clampf(dist / radius, 0.0f, 1.0f);
+    float falloff = t * t * (3.0f - 2.0f * t);
+    float material = 1.0f + (sh - 1.0f) * falloff;
+    float coverage;
+    if (b->anti_aliased) {
+        float e0 = radius + 0.5f, e1 = radius - 0.5f;
+        if (dist <= e1) coverage = 1.0f;
+        else if (dist >= e0) coverage = 0.0f;
+        else { float x = clampf((dist - e0) / (e1 - e0), 0.0f, 1.0f); coverage = x * x * (3.0f - 2.0f * x); }
+    } else coverage = dist <= radius ? 1.0f : 0.0f;
+    return material * coverage;
+}
+/* rebuild_brush_lut :27-50 */
+void pfo_brush_lut(const pfo_brush *b, uint8_t lut[256]) {
+    float radius = b->size / 2.0f;
+    if (radius < 0.001f) { memset(lut, 0, 256); return; }
+    for (int i = 0; i < 256; i++) {
+        float t_sq = (float)i / 255.0f;
+        float dist = sqrtf(t_sq) * radius;
+        float alpha = pfo_brush_alpha(b, dist, radius);
+        lut[i] = as_u8(minf(roundf(alpha * 255.0f), 255.0f));
+    }
+}
+/* draw_circle_no_dirty :135-400, circle tip, BrushMode::Normal or eraser, no scatter/jitter,
+ * on a flat w*h RGBA8 target (the chunk walk only decides which tiles get allocated). */
+void pfo_brush_stamp(uint8_t *img, uint32_t w, uint32_t h, const pfo_brush *b, float cx, float cy,
+                     const uint8_t *sel_mask) {
+    uint8_t lut[256];
+    pfo_brush_lut(b, lut);
+    float radius = b->size / 2.0f, radius_sq = radius * radius;
+    if (radius_sq < 0.001f) return;
+    float draw_radius = b->anti_aliased ? radius + 0.5f : radius;
+    float draw_radius_sq = draw_radius * draw_radius;
+    int direct = draw_radius > radius;
+    float inv_radius_sq = 1.0f / radius_sq;
+    uint32_t min_x = as_u32(maxf(floorf(cx - draw_radius), 0.0f));
+    uint32_t max_x = as_u32(ceilf(cx + draw_radius)); if (max_x > (w ? w - 1 : 0)) max_x = w ? w - 1 : 0;
+    uint32_t min_y = as_u32(maxf(floorf(cy - draw_radius), 0.0f));
+    uint32_t max_y = as_u32(ceilf(cy + draw_radius)); if (max_y > (h ? h - 1 : 0)) max_y = h ? h - 1 : 0;
+    if (min_x > max_x || min_y > max_y) return;
+    uint8_t r8 = as_u8(b->color[0] * 255.0f), g8 = as_u8(b->color[1] * 255.0f), b8 = as_u8(b->color[2] * 255.0f);
+    float src_a = b->color[3];
+    for (uint32_t gy = min_y; gy <= max_y; gy++) {
+        float dy = (float)gy - cy, dy_sq = dy * dy;
+        for (uint32_t gx = min_x; gx <= max_x; gx++) {
+            if (sel_mask && sel_mask[(size_t)gy * w + gx] == 0) continue;
+            float dx = (float)gx - cx;
+            float dist_sq = dx * dx + dy_sq;
+            if (dist_sq > draw_radius_sq) continue;
+            uint8_t ga8;
+            if (direct) ga8 = as_u8(minf(roundf(pfo_brush_alpha(b, sqrtf(dist_sq), radius) * 255.0f), 255.0f));
+            else ga8 = lut[as_u32(minf(dist_sq * inv_radius_sq * 255.0f, 255.0f))];
+            if (ga8 == 0) continue;
+            float ga = (float)ga8 / 255.0f;
+            uint8_t *p = img + ((size_t)gy * w + gx) * 4;
+            float strength = ga * src_a * b->flow;
+            if (strength < 0.01f) continue;
+            if (b->is_eraser) {
+                float old_mask = (float)p[3] / 255.0f;
+                if (strength > old_mask) { p[0] = p[1] = p[2] = 0; p[3] = as_u8(strength * 255.0f); }
+            } else {
+                uint8_t a8 = as_u8(strength * 255.0f);
+                if (a8 >= p[3]) { p[0] = r8; p[1] = g8; p[2] = b8; p[3] = a8; }
+            }
+        }
+    }
+}
+/* draw_line_no_dirty :762-838 (circle tip: 1-px stepping). Writes stamp centres into
+ * `centres` (x,y pairs; capacity cap) and returns their count, so the same list can be fed to
+ * the device kernel. */
+int pfo_brush_line_centres(uint32_t w, uint32_t h, float x0, float y0, float x1, float y1,
+                           float *centres, int cap) {
+    float dx = x1 - x0, dy = y1 - y0;
+    float distance = sqrtf(dx * dx + dy * dy);
+    int n = 0;
+    if (distance < 0.1f) {
+        if (x0 >= 0.0f && as_u32(x0) < w && y0 >= 0.0f && as_u32(y0) < h && n < cap) {
+            centres[0] = x0; centres[1] = y0; n = 1;
+        }
+        return n;
+    }
+    float step = 1.0f;
+    uint32_t steps = as_u32(ceilf(distance / step));
+    for (uint32_t i = 0; i <= steps; i++) {
+        float t = (float)i / (float)steps;
+        float x = x0 + dx * t, y = y0 + dy * t;
+        if (x >= 0.0f && as_u32(x) < w && y >= 0.0f && as_u32(y) < h && n < cap) {
+            centres[n * 2] = x; centres[n * 2 + 1] = y; n++;
+        }
+    }
+    return n;
+}
+void pfo_brush_line(uint8_t *img, uint32_t w, uint32_t h, const pfo_brush *b, float x0, float y0,
+                    float x1, float y1, const uint8_t *sel_mask) {
+    float dx = x1 - x0, dy = y1 - y0;
+    int cap = (int)ceilf(sqrtf(dx * dx + dy * dy)) + 4;
+    float *c = (float *)malloc(sizeof(float) * 2 * (size_t)cap);
+    int n = pfo_brush_line_centres(w, h, x0, y0, x1, y1, c, cap);
+    for (int i = 0; i < n; i++) pfo_brush_stamp(img, w, h, b, c[i * 2], c[i * 2 + 1], sel_mask);
+    free(c);
+}
+
+/* ------------------------------------------------------------------------- */
+/* TiledImage chunk semantics: src/canvas/tiled_image.rs:50-104, 271-293       */
+/* ------------------------------------------------------------------------- */
+/* from_rgba_image keeps a chunk only if some pixel in it has alpha != 0; to_rgba_image of
+ * the result therefore zeroes RGB in chunks that were fully transparent. occupancy is
+ * ceil(w/64)*ceil(h/64) bytes; dst may be NULL to compute occupancy only. */
+void pfo_tiled_roundtrip(const uint8_t *src, uint32_t w, uint32_t h, uint8_t *occupancy, uint8_t *dst) {
+    uint32_t cxn = (w + PFE_CHUNK - 1) / PFE_CHUNK, cyn = (h + PFE_CHUNK - 1) / PFE_CHUNK;
+    for (uint32_t cy = 0; cy < cyn; cy++)
+        for (uint32_t cx = 0; cx < cxn; cx++) {
+            uint32_t x0 = cx * PFE_CHUNK, y0 = cy * PFE_CHUNK;
+            uint32_t x1 = x0 + PFE_CHUNK < w ? x0 + PFE_CHUNK : w, y1 = y0 + PFE_CHUNK < h ? y0 + PFE_CHUNK : h;
+            int has = 0;
+            for (uint32_t y = y0; y < y1 && !has; y++)
+                for (uint32_t x = x0; x < x1; x++)
+                    if (src[((size_t)y * w + x) * 4 + 3] != 0) { has = 1; break; }
+            if (occupancy) occupancy[(size_t)cy * cxn + cx] = (uint8_t)has;
+            if (dst)
+                for (uint32_t y = y0; y < y1; y++) {
+                    size_t o = ((size_t)y * w + x0) * 4;
+                    if (has) memcpy(dst + o, src + o, (size_t)(x1 - x0) * 4);
+                    else memset(dst + o, 0, (size_t)(x1 - x0) * 4);
+                }
+        }
+}
+
+int pfo_num_threads(void) {
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,321 @@
+"""ctypes binding for the CPU oracle (oracle/pfe_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference leg.  Nothing under paintfe_b200/ may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpfe_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "pfe_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("rgba", C.c_void_p),
+        ("mask", C.c_void_p),
+        ("opacity", C.c_float),
+        ("blend", C.c_uint8),
+        ("visible", C.c_uint8),
+        ("kind", C.c_uint8),
+        ("_pad", C.c_uint8),
+        ("adj", C.c_float * 16),
+    ]
+
+
+class Brush(C.Structure):
+    _fields_ = [
+        ("size", C.c_float),
+        ("hardness", C.c_float),
+        ("flow", C.c_float),
+        ("anti_aliased", C.c_int),
+        ("color", C.c_float * 4),
+        ("is_eraser", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.pfo_brush_alpha.restype = C.c_float
+        _lib.pfo_to_radians.restype = C.c_float
+        _lib.pfo_build_gaussian_kernel.restype = C.c_int
+        _lib.pfo_gaussian_radius.restype = C.c_int
+        _lib.pfo_brush_line_centres.restype = C.c_int
+        _lib.pfo_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def num_threads() -> int:
+    return int(lib().pfo_num_threads())
+
+
+# -- flatten ----------------------------------------------------------------------------
+def make_layer(rgba=None, opacity=1.0, blend=0, visible=True, mask=None, kind=0, adj=()):
+    return dict(rgba=_u8(rgba), opacity=float(opacity), blend=int(blend), visible=bool(visible),
+                mask=_u8(mask), kind=int(kind), adj=tuple(float(v) for v in adj))
+
+
+def flatten(layers, w, h, active=None):
+    arr = (LayerDesc * len(layers))()
+    keep = []
+    for i, L in enumerate(layers):
+        if L["rgba"] is not None:
+            assert L["rgba"].shape == (h, w, 4)
+            keep.append(L["rgba"])
+            arr[i].rgba = L["rgba"].ctypes.data
+        if L["mask"] is not None:
+            assert L["mask"].shape == (h, w)
+            keep.append(L["mask"])
+            arr[i].mask = L["mask"].ctypes.data
+        arr[i].opacity = L["opacity"]
+        arr[i].blend = L["blend"]
+        arr[i].visible = 1 if L["visible"] else 0
+        arr[i].kind = L["kind"]
+        for j, v in enumerate(L["adj"]):
+            arr[i].adj[j] = v
+    dst = np.empty((h, w, 4), np.uint8)
+    active = _u8(active)
+    lib().pfo_flatten(arr, C.c_uint32(len(layers)), C.c_uint32(w), C.c_uint32(h), _p(active), _p(dst))
+    return dst
+
+
+def blend_pixel(base, top, mode, opacity):
+    b = (C.c_uint8 * 4)(*base)
+    t = (C.c_uint8 * 4)(*top)
+    o = (C.c_uint8 * 4)()
+    lib().pfo_blend_pixel(b, t, C.c_int(mode), C.c_float(opacity), o)
+    return tuple(o)
+
+
+# -- filters ----------------------------------------------------------------------------
+def _img_call(fn, src, *args, mask=None):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty_like(src)
+    mask = _u8(mask)
+    fn(_p(src), C.c_uint32(w), C.c_uint32(h), *args, _p(mask), _p(dst))
+    return dst
+
+
+def gaussian_kernel(sigma):
+    r = lib().pfo_gaussian_radius(C.c_float(sigma))
+    k = np.empty(2 * r + 1, np.float32)
+    lib().pfo_build_gaussian_kernel(C.c_float(sigma), _p(k))
+    return k
+
+
+def gaussian_blur(src, sigma, mask=None):
+    return _img_call(lib().pfo_blur_with_selection, src, C.c_float(sigma), mask=mask)
+
+
+def box_blur(src, radius, mask=None):
+    return _img_call(lib().pfo_box_blur, src, C.c_float(radius), mask=mask)
+
+
+def motion_blur(src, angle_deg, distance, mask=None):
+    return _img_call(lib().pfo_motion_blur, src, C.c_float(angle_deg), C.c_float(distance), mask=mask)
+
+
+def median(src, radius, mask=None):
+    return _img_call(lib().pfo_median, src, C.c_uint32(radius), mask=mask)
+
+
+def sharpen(src, amount, radius, mask=None):
+    return _img_call(lib().pfo_sharpen, src, C.c_float(amount), C.c_float(radius), mask=mask)
+
+
+def vignette(src, amount, softness, mask=None):
+    return _img_call(lib().pfo_vignette, src, C.c_float(amount), C.c_float(softness), mask=mask)
+
+
+# -- adjustments ------------------------------------------------------------------------
+INVERT, INVERT_ALPHA, SEPIA, DESATURATE, BRIGHTNESS_CONTRAST, HSL, EXPOSURE, LUT_RGB, LUT_RGBA, \
+    TEMPERATURE_TINT, HIGHLIGHTS_SHADOWS = range(11)
+S_INVERT, S_DESATURATE, S_SEPIA, S_SEPIA_STRENGTH, S_BRIGHTNESS_CONTRAST, S_HSL, S_EXPOSURE, \
+    S_LUT_RGB = range(32, 40)
+
+
+def adjust(src, op, params=(), luts=None, mask=None, occupancy=None):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty_like(src)
+    p = np.zeros(8, np.float32)
+    p[: len(params)] = params
+    luts = _u8(luts)
+    mask = _u8(mask)
+    occupancy = _u8(occupancy)
+    lib().pfo_adjust(_p(src), C.c_uint32(w), C.c_uint32(h), C.c_int(op), _p(p), _p(luts), _p(mask),
+                     _p(occupancy), _p(dst))
+    return dst
+
+
+def levels_lut(in_black, in_white, gamma, out_black=0.0, out_white=255.0):
+    lut = np.empty(256, np.uint8)
+    lib().pfo_build_levels_lut(C.c_float(in_black), C.c_float(in_white), C.c_float(gamma),
+                               C.c_float(out_black), C.c_float(out_white), _p(lut))
+    return lut
+
+
+def levels_lut_script(in_black, in_white, gamma):
+    lut = np.empty(256, np.uint8)
+    lib().pfo_build_levels_lut_script(C.c_float(in_black), C.c_float(in_white), C.c_float(gamma), _p(lut))
+    return lut
+
+
+def stretch_lut(mn, mx):
+    lut = np.empty(256, np.uint8)
+    lib().pfo_build_stretch_lut(C.c_uint8(mn), C.c_uint8(mx), _p(lut))
+    return lut
+
+
+def curves_lut(points):
+    pts = _f32(np.asarray(points, np.float32).reshape(-1, 2))
+    lut = np.empty(256, np.uint8)
+    lib().pfo_build_curves_lut(_p(pts), C.c_int(len(pts)), _p(lut))
+    return lut
+
+
+def compose_curve_luts(five):
+    five = _u8(np.asarray(five, np.uint8).reshape(5, 256))
+    out = np.empty((4, 256), np.uint8)
+    lib().pfo_compose_curve_luts(_p(five), _p(out))
+    return out
+
+
+# -- warps ------------------------------------------------------------------------------
+def catmull_rom_weights(t):
+    w = np.empty(4, np.float32)
+    lib().pfo_catmull_rom_weights(C.c_float(t), _p(w))
+    return w
+
+
+def catmull_rom_surface(points, cols, rows, u, v):
+    pts = _f32(points)
+    out = np.empty(2, np.float32)
+    lib().pfo_catmull_rom_surface(_p(pts), C.c_int(cols), C.c_int(rows), C.c_float(u), C.c_float(v), _p(out))
+    return out
+
+
+def mesh_displacement(orig, deformed, cols, rows, w, h):
+    orig = _f32(orig)
+    deformed = _f32(deformed)
+    out = np.empty((h, w, 2), np.float32)
+    lib().pfo_mesh_displacement(_p(orig), _p(deformed), C.c_int(cols), C.c_int(rows), C.c_uint32(w),
+                                C.c_uint32(h), _p(out))
+    return out
+
+
+def warp_displacement(src, disp):
+    src = _u8(src)
+    disp = _f32(disp)
+    sh, sw = src.shape[:2]
+    h, w = disp.shape[:2]
+    dst = np.empty((h, w, 4), np.uint8)
+    lib().pfo_warp_displacement(_p(src), C.c_uint32(sw), C.c_uint32(sh), _p(disp), C.c_uint32(w),
+                                C.c_uint32(h), _p(dst))
+    return dst
+
+
+def mesh_warp(src, orig, deformed, cols, rows, w, h):
+    src = _u8(src)
+    sh, sw = src.shape[:2]
+    orig = _f32(orig)
+    deformed = _f32(deformed)
+    dst = np.empty((h, w, 4), np.uint8)
+    lib().pfo_mesh_warp(_p(src), C.c_uint32(sw), C.c_uint32(sh), _p(orig), _p(deformed), C.c_int(cols),
+                        C.c_int(rows), C.c_uint32(w), C.c_uint32(h), _p(dst))
+    return dst
+
+
+PUSH, EXPAND, CONTRACT, TWIRL = range(4)
+
+
+def liquify(field, kind, cx, cy, radius, strength, a0=0.0, a1=0.0):
+    """In place on `field` (h, w, 2) float32; returns the (x0, y0, x1, y1) bbox."""
+    assert field.dtype == np.float32 and field.flags.c_contiguous
+    h, w = field.shape[:2]
+    bbox = (C.c_int * 4)()
+    lib().pfo_liquify(_p(field), C.c_uint32(w), C.c_uint32(h), C.c_int(kind), C.c_float(cx), C.c_float(cy),
+                      C.c_float(radius), C.c_float(strength), C.c_float(a0), C.c_float(a1), bbox)
+    return tuple(bbox)
+
+
+# -- brush ------------------------------------------------------------------------------
+def make_brush(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False):
+    b = Brush()
+    b.size, b.hardness, b.flow = size, hardness, flow
+    b.anti_aliased = 1 if anti_aliased else 0
+    for i in range(4):
+        b.color[i] = color[i]
+    b.is_eraser = 1 if is_eraser else 0
+    return b
+
+
+def brush_lut(brush):
+    lut = np.empty(256, np.uint8)
+    lib().pfo_brush_lut(C.byref(brush), _p(lut))
+    return lut
+
+
+def brush_stamp(img, brush, cx, cy, sel_mask=None):
+    assert img.dtype == np.uint8 and img.flags.c_contiguous
+    h, w = img.shape[:2]
+    sel_mask = _u8(sel_mask)
+    lib().pfo_brush_stamp(_p(img), C.c_uint32(w), C.c_uint32(h), C.byref(brush), C.c_float(cx), C.c_float(cy),
+                          _p(sel_mask))
+
+
+def brush_line_centres(w, h, x0, y0, x1, y1):
+    cap = int(np.ceil(np.hypot(x1 - x0, y1 - y0))) + 4
+    c = np.empty((cap, 2), np.float32)
+    n = lib().pfo_brush_line_centres(C.c_uint32(w), C.c_uint32(h), C.c_float(x0), C.c_float(y0),
+                                     C.c_float(x1), C.c_float(y1), _p(c), C.c_int(cap))
+    return c[:n].copy()
+
+
+def brush_line(img, brush, x0, y0, x1, y1, sel_mask=None):
+    assert img.dtype == np.uint8 and img.flags.c_contiguous
+    h, w = img.shape[:2]
+    sel_mask = _u8(sel_mask)
+    lib().pfo_brush_line(_p(img), C.c_uint32(w), C.c_uint32(h), C.byref(brush), C.c_float(x0), C.c_float(y0),
+                         C.c_float(x1), C.c_float(y1), _p(sel_mask))
+
+
+# -- tiles ------------------------------------------------------------------------------
+def tiled_roundtrip(src):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    occ = np.empty(((h + 63) // 64, (w + 63) // 64), np.uint8)
+    dst = np.empty_like(src)
+    lib().pfo_tiled_roundtrip(_p(src), C.c_uint32(w), C.c_uint32(h), _p(occ), _p(dst))
+    return dst, occ

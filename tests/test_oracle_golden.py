@@ -1,0 +1,211 @@
+"""Pins the CPU oracle against the reference's own golden PNGs (tolerance 0).
+
+Each case restates one reference test: inputs from tests/fixtures.py (closed-form, same as
+tests/common/mod.rs), expected output = the reference's committed golden, copied as data into
+tests/golden/ref/.  Reference tests: tests/visual_blend.rs, visual_filters.rs,
+visual_adjustments.rs, scripting.rs, transform_ops.rs, tool_strokes.rs.
+"""
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+BLEND_IDS = {  # src/canvas/layers.rs:125-153
+    "normal": 0, "multiply": 1, "screen": 2, "additive": 3, "reflect": 4, "glow": 5, "color_burn": 6,
+    "color_dodge": 7, "overlay": 8, "difference": 9, "negation": 10, "lighten": 11, "darken": 12, "xor": 13,
+    "overwrite": 14, "hard_light": 15, "soft_light": 16, "exclusion": 17, "subtract": 18, "divide": 19,
+    "linear_burn": 20, "vivid_light": 21, "linear_light": 22, "pin_light": 23, "hard_mix": 24,
+}
+
+
+def assert_exact(actual, category, name):
+    exp = fx.golden(category, name)
+    assert actual.shape == exp.shape, (actual.shape, exp.shape)
+    bad, mx = fx.diff_stats(actual, exp)
+    assert bad == 0, f"{category}/{name}: {bad} mismatched pixels, max channel diff {mx}"
+
+
+# ---- blend (tests/visual_blend.rs:19-106) ---------------------------------------------
+@pytest.mark.parametrize("name", sorted(BLEND_IDS))
+def test_blend_golden(oracle, name):
+    layers = [oracle.make_layer(fx.checkerboard(64, 64)),
+              oracle.make_layer(fx.blend_foreground(), blend=BLEND_IDS[name])]
+    assert_exact(oracle.flatten(layers, 64, 64), "blend", name)
+
+
+def test_blend_half_opacity(oracle):
+    layers = [oracle.make_layer(fx.checkerboard(64, 64)), oracle.make_layer(fx.gradient(64, 64), opacity=0.5)]
+    assert_exact(oracle.flatten(layers, 64, 64), "blend", "normal_half_opacity")
+
+
+# ---- filters (tests/visual_filters.rs:30-176) -----------------------------------------
+FILTERS = {
+    "gaussian_blur_s2": lambda o, im: o.gaussian_blur(im, 2.0),
+    "gaussian_blur_s5": lambda o, im: o.gaussian_blur(im, 5.0),
+    "box_blur_r3": lambda o, im: o.box_blur(im, 3.0),
+    "motion_blur_45_10": lambda o, im: o.motion_blur(im, 45.0, 10.0),
+    "median_r2": lambda o, im: o.median(im, 2),
+    "sharpen_a1_r1": lambda o, im: o.sharpen(im, 1.0, 1.0),
+    "vignette_08_05": lambda o, im: o.vignette(im, 0.8, 0.5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FILTERS))
+def test_filter_golden(oracle, name):
+    assert_exact(FILTERS[name](oracle, fx.gradient(64, 64)), "filters", name)
+
+
+# ---- adjustments (tests/visual_adjustments.rs:50-216) ---------------------------------
+def _auto_levels(o, im):
+    sel = im[..., 3] != 0
+    luts = np.empty((4, 256), np.uint8)
+    for c in range(3):
+        luts[c] = o.stretch_lut(int(im[..., c][sel].min()), int(im[..., c][sel].max()))
+    luts[3] = np.arange(256, dtype=np.uint8)
+    return o.adjust(im, o.LUT_RGBA, luts=luts)
+
+
+ADJUST = {
+    "invert_colors": lambda o, im: o.adjust(im, o.INVERT),
+    "invert_alpha": lambda o, im: o.adjust(im, o.INVERT_ALPHA),
+    "invert_alpha_double": lambda o, im: o.adjust(im, o.INVERT_ALPHA),
+    "sepia": lambda o, im: o.adjust(im, o.SEPIA),
+    "auto_levels": _auto_levels,
+    "desaturate": lambda o, im: o.adjust(im, o.DESATURATE),
+    "brightness_30_contrast_20": lambda o, im: o.adjust(im, o.BRIGHTNESS_CONTRAST, (30.0, 20.0)),
+    "hsl_h30_s-20_l10": lambda o, im: o.adjust(im, o.HSL, (30.0, -20.0, 10.0)),
+    "exposure_1ev": lambda o, im: o.adjust(im, o.EXPOSURE, (2.0,)),
+    "highlights_shadows": lambda o, im: o.adjust(im, o.HIGHLIGHTS_SHADOWS, (30.0, -20.0)),
+    "levels": lambda o, im: o.adjust(im, o.LUT_RGB, luts=o.levels_lut(20.0, 235.0, 1.2, 0.0, 255.0)),
+    "temperature_tint": lambda o, im: o.adjust(im, o.TEMPERATURE_TINT, (30.0, 10.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ADJUST))
+def test_adjust_golden(oracle, name):
+    out = ADJUST[name](oracle, fx.gradient(64, 64))
+    # results go back through TiledImage::from_rgba_image + to_rgba_image (extract_layer)
+    out, _ = oracle.tiled_roundtrip(out)
+    assert_exact(out, "adjustments", name)
+
+
+# ---- scripting inline variants (tests/scripting.rs:118-146) ---------------------------
+SCRIPT = {
+    "apply_blur": lambda o, im: o.gaussian_blur(im, 2.0),
+    "apply_invert": lambda o, im: o.adjust(im, o.S_INVERT),
+    "apply_sepia": lambda o, im: o.adjust(im, o.S_SEPIA),
+    "apply_desaturate": lambda o, im: o.adjust(im, o.S_DESATURATE),
+    "apply_brightness_contrast": lambda o, im: o.adjust(im, o.S_BRIGHTNESS_CONTRAST, (20.0, 10.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCRIPT))
+def test_scripting_golden(oracle, name):
+    assert_exact(SCRIPT[name](oracle, fx.gradient(64, 64)), "scripting", name)
+
+
+def test_scripting_bc_is_truncating(oracle):
+    """the rounding variant must NOT match the scripting golden."""
+    out = oracle.adjust(fx.gradient(64, 64), oracle.BRIGHTNESS_CONTRAST, (20.0, 10.0))
+    bad, _ = fx.diff_stats(out, fx.golden("scripting", "apply_brightness_contrast"))
+    assert bad > 0
+
+
+# ---- warps (tests/transform_ops.rs:162-208, 345-359) ----------------------------------
+def test_displacement_radial_push(oracle):
+    field = np.zeros((32, 32, 2), np.float32)
+    bbox = oracle.liquify(field, oracle.PUSH, 16.0, 16.0, 10.0, 0.8, 3.0, 0.0)
+    assert bbox == (6, 6, 26, 26)
+    assert_exact(oracle.warp_displacement(fx.gradient_32(), field), "transform", "displacement_radial_push")
+
+
+def test_displacement_swirl(oracle):
+    assert_exact(oracle.warp_displacement(fx.gradient_32(), fx.swirl_field()), "transform", "displacement_swirl")
+
+
+def test_mesh_warp_deformed(oracle):
+    orig = fx.uniform_grid(2, 2, 32.0, 32.0)
+    deformed = orig.copy()
+    deformed[4] = (20.0, 20.0)
+    assert_exact(oracle.mesh_warp(fx.gradient_32(), orig, deformed, 2, 2, 32, 32), "transform", "mesh_warp_deformed")
+
+
+def test_catmull_rom_known_answers(oracle):
+    """tests/transform_ops.rs:51-118"""
+    w0 = oracle.catmull_rom_weights(0.0)
+    assert np.allclose(w0, [0, 1, 0, 0], atol=1e-6)
+    w1 = oracle.catmull_rom_weights(1.0)
+    assert np.allclose(w1, [0, 0, 1, 0], atol=1e-6)
+    for i in range(11):
+        assert abs(float(oracle.catmull_rom_weights(i / 10.0).sum()) - 1.0) < 1e-5
+    grid = fx.uniform_grid(2, 2, 32.0, 32.0)
+    p = oracle.catmull_rom_surface(grid, 2, 2, 1.0, 1.0)
+    assert abs(p[0] - 16.0) < 0.5 and abs(p[1] - 16.0) < 0.5
+    p0 = oracle.catmull_rom_surface(grid, 2, 2, 0.0, 0.0)
+    assert abs(p0[0]) < 0.5 and abs(p0[1]) < 0.5
+
+
+def test_warp_identity_and_translate(oracle):
+    """tests/transform_ops.rs:125-160"""
+    src = fx.gradient_32()
+    zero = np.zeros((32, 32, 2), np.float32)
+    assert np.array_equal(oracle.warp_displacement(src, zero), src)
+    shift = zero.copy()
+    shift[..., 0] = 5.0
+    out = oracle.warp_displacement(src, shift)
+    assert tuple(out[16, 10]) == tuple(src[16, 5])
+
+
+def test_mesh_warp_identity(oracle):
+    """tests/transform_ops.rs:170-195: identity mesh within 2 levels."""
+    src = fx.gradient_32()
+    grid = fx.uniform_grid(2, 2, 32.0, 32.0)
+    out = oracle.mesh_warp(src, grid, grid, 2, 2, 32, 32)
+    assert np.abs(out.astype(int) - src.astype(int)).max() <= 2
+
+
+# ---- brush stamps (tests/tool_strokes.rs) ---------------------------------------------
+BLACK, WHITE, RED, BLUE_SEMI = (0, 0, 0, 1), (1, 1, 1, 1), (1, 0, 0, 1), (0, 0, 1, 0.5)
+# name -> (size, hardness, aa, colour, eraser, background, kind, args)
+STROKES = {
+    "brush_circle_center": (20.0, 1.0, True, BLACK, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_circle_soft": (30.0, 0.0, True, BLACK, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_circle_hard": (20.0, 1.0, False, BLACK, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_circle_tiny": (3.0, 1.0, True, RED, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_circle_large": (60.0, 0.5, True, BLACK, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_semi_transparent": (20.0, 1.0, True, BLUE_SEMI, False, "blank", "stamp", [(32.0, 32.0)]),
+    "brush_secondary_color": (20.0, 1.0, True, RED, False, "blank", "stamp", [(32.0, 32.0)]),
+    "eraser_circle": (20.0, 1.0, True, BLACK, True, "white", "stamp", [(32.0, 32.0)]),
+    "eraser_soft": (30.0, 0.0, True, BLACK, True, "white", "stamp", [(32.0, 32.0)]),
+    "line_horizontal": (8.0, 1.0, True, BLACK, False, "blank", "line", (4.0, 32.0, 60.0, 32.0)),
+    "line_vertical": (8.0, 1.0, True, BLACK, False, "blank", "line", (32.0, 4.0, 32.0, 60.0)),
+    "line_diagonal": (6.0, 0.8, True, BLACK, False, "blank", "line", (4.0, 4.0, 60.0, 60.0)),
+    "line_soft_thick": (16.0, 0.3, True, RED, False, "blank", "line", (10.0, 50.0, 54.0, 10.0)),
+    "line_eraser": (10.0, 1.0, True, BLACK, True, "white", "line", (4.0, 32.0, 60.0, 32.0)),
+    "stroke_multiple_stamps": (10.0, 0.8, True, BLACK, False, "blank", "stamp",
+                               [(8.0 + i * 7.0, 32.0) for i in range(8)]),
+    "brush_at_origin": (10.0, 1.0, True, BLACK, False, "blank", "stamp", [(0.0, 0.0)]),
+    "brush_at_corner": (20.0, 1.0, True, BLACK, False, "blank", "stamp", [(63.0, 63.0)]),
+    "line_zero_length": (12.0, 1.0, True, BLACK, False, "blank", "line", (32.0, 32.0, 32.0, 32.0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(STROKES))
+def test_stroke_golden(oracle, name):
+    size, hard, aa, color, eraser, bg, kind, args = STROKES[name]
+    img = fx.solid(64, 64, (255, 255, 255, 255) if bg == "white" else (0, 0, 0, 0))
+    b = oracle.make_brush(size, hard, aa, color, is_eraser=eraser)
+    if kind == "stamp":
+        for (x, y) in args:
+            oracle.brush_stamp(img, b, x, y)
+    else:
+        oracle.brush_line(img, b, *args)
+    assert_exact(img, "tools", name)
+
+
+def test_stroke_selection_mask(oracle):
+    img = fx.solid(64, 64, (0, 0, 0, 0))
+    mask = np.zeros((64, 64), np.uint8)
+    mask[:, :32] = 255
+    oracle.brush_stamp(img, oracle.make_brush(40.0, 1.0, True, BLACK), 32.0, 32.0, sel_mask=mask)
+    assert_exact(img, "tools", "brush_with_selection_mask")
