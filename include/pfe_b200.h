@@ -1,0 +1,280 @@
+/*
+ * pfe_b200.h — C ABI of libpfe_b200.so, the B200 (sm_100a) pixel engine that replaces
+ * PaintFE's layer compositor and filter / adjustment / warp / brush-stamp kernels.
+ *
+ * Every entry point names the reference interface it stands in for (file:line under the
+ * PaintFE tree, v1.3.9 @ 16410bd).  Shapes follow the reference's own conventions:
+ *   - images are dense, row-major, straight-alpha RGBA8, exactly w*h*4 bytes
+ *     (what `RgbaImage::as_raw()` / `RgbaImage::from_raw()` hold);
+ *   - selection masks are `GrayImage` planes of the image's size, w*h bytes, 0 = unselected;
+ *   - displacement fields are w*h*2 f32, (dx,dy) interleaved (`DisplacementField::data`);
+ *   - the caller owns every buffer; nothing is allocated across the ABI; outputs are written
+ *     into caller-provided buffers and may not alias inputs unless stated.
+ *
+ * Two tiers, same semantics:
+ *   pfe_<op>      host pointers; copies in, runs the CUDA kernels, copies out, returns when the
+ *                 result is in `dst` (what a `*_core(&RgbaImage, …) -> RgbaImage` call needs).
+ *   pfe_dev_<op>  device pointers on the context's device; asynchronous on the context's
+ *                 stream; for chaining ops without PCIe round trips.
+ *
+ * There is no CPU fallback.  Every function returns PFE_OK or a negative status; on error the
+ * output buffer content is unspecified and pfe_last_error() describes the failure.
+ * A pfe_ctx may be used from one thread at a time; distinct contexts are independent.
+ */
+#ifndef PFE_B200_H
+#define PFE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFE_ABI_VERSION 1
+#define PFE_CHUNK_SIZE 64u /* src/canvas/defs.rs:7 */
+
+typedef enum pfe_status {
+    PFE_OK = 0,
+    PFE_ERR_INVALID_ARG = -1, /* null pointer, zero size, bad enum */
+    PFE_ERR_UNSUPPORTED = -2, /* the `Option::None` of GpuRenderer::median_rgba etc. */
+    PFE_ERR_CUDA = -3,        /* a CUDA runtime call failed; see pfe_last_error */
+    PFE_ERR_NO_DEVICE = -4,   /* no CUDA device: the library never computes on the CPU */
+    PFE_ERR_OOM = -5
+} pfe_status;
+
+typedef struct pfe_ctx pfe_ctx;
+
+/* -- context ---------------------------------------------------------------------------
+ * Replaces GpuRenderer::try_new / GpuContext (src/gpu/renderer.rs:245, src/gpu/context.rs:9).
+ * One context = one device + one stream + scratch buffers. */
+int pfe_ctx_create(int device, pfe_ctx **out);
+int pfe_ctx_destroy(pfe_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. a framework's current stream); NULL = own stream. */
+int pfe_ctx_set_stream(pfe_ctx *ctx, void *cuda_stream);
+int pfe_ctx_sync(pfe_ctx *ctx);
+const char *pfe_last_error(const pfe_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t pfe_ctx_launch_count(const pfe_ctx *ctx);
+int pfe_abi_version(void);
+/* Per-kernel device timing: when enabled every kernel launch is bracketed by CUDA events on the
+ * launching stream. pfe_ctx_profile_read synchronises, writes a JSON object
+ * {"<kernel>": {"launches": n, "ms": total}, ...} into buf and clears the record. */
+int pfe_ctx_profile(pfe_ctx *ctx, int enable);
+int pfe_ctx_profile_read(pfe_ctx *ctx, char *buf, size_t cap);
+/* Pinned host memory for callers that want full-rate PCIe copies. */
+int pfe_host_alloc(size_t bytes, void **out);
+int pfe_host_free(void *p);
+/* Plain device memory helpers so non-CUDA hosts (Rust, Python) can use the pfe_dev_ tier. */
+int pfe_dev_alloc(pfe_ctx *ctx, size_t bytes, void **out);
+int pfe_dev_free(pfe_ctx *ctx, void *p);
+int pfe_dev_upload(pfe_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int pfe_dev_download(pfe_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* -- flatten ---------------------------------------------------------------------------
+ * Replaces CanvasState::composite (src/canvas/canvas_state.rs:482-698), blend_pixel_static
+ * (:1246-1505) and GpuRenderer::composite (src/gpu/renderer.rs:533-583). Bit-exact with the
+ * CPU compositor (not with the premultiplied wgpu shader). */
+typedef enum pfe_layer_kind {
+    PFE_LAYER_RASTER = 0,
+    PFE_LAYER_ADJ_EXPOSURE = 1,            /* adj[0] = gain = 2^ev (host powf), layers.rs:279 */
+    PFE_LAYER_ADJ_BRIGHTNESS_CONTRAST = 2, /* adj[0] = brightness, adj[1] = contrast, :288 */
+    PFE_LAYER_ADJ_INVERT = 3,              /* :298 */
+    PFE_LAYER_ADJ_CHANNEL_MIXER = 4        /* adj[0..16] = red[4] green[4] blue[4] alpha[4], :299 */
+} pfe_layer_kind;
+
+typedef struct pfe_layer_desc {
+    const uint8_t *rgba; /* w*h*4; NULL for adjustment layers. Layer::pixels flattened */
+    const uint8_t *mask; /* w*h conceal plane = alpha of Layer::mask, or NULL (layers.rs:395-399) */
+    float opacity;       /* Layer::opacity */
+    uint8_t blend;       /* BlendMode::to_u8, layers.rs:125-153 (unknown ids = Normal, :183) */
+    uint8_t visible;     /* layer_effectively_visible */
+    uint8_t kind;        /* pfe_layer_kind */
+    uint8_t _pad;
+    float adj[16];
+} pfe_layer_desc;
+
+/* `active_chunks`: ceil(w/64)*ceil(h/64) bytes, row-major, non-zero where any visible layer
+ * has a populated tile (canvas_state.rs:529-550); pixels of inactive chunks stay (0,0,0,0).
+ * NULL = all chunks active (dense canvas). Only matters when adjustment layers are present. */
+int pfe_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n_layers, uint32_t w,
+                uint32_t h, const uint8_t *active_chunks, uint8_t *dst);
+int pfe_dev_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers_with_dev_ptrs, uint32_t n_layers,
+                    uint32_t w, uint32_t h, const uint8_t *active_chunks_dev, uint8_t *dst_dev);
+
+/* -- blurs -----------------------------------------------------------------------------
+ * flags for the Gaussian family: */
+#define PFE_GAUSS_EXACT 1u /* reference tap order with separate mul/add: bit-exact with the CPU
+                              path. Default (0) uses FMA accumulation: within +-1 level. */
+
+/* blur_with_selection_pub (src/ops/filters.rs:130-207) / parallel_gaussian_blur (:242-316) /
+ * GpuRenderer::blur_rgba (src/gpu/renderer.rs:915). mask NULL = whole image. */
+int pfe_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float sigma,
+                      const uint8_t *mask, uint8_t *dst, uint32_t flags);
+int pfe_dev_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float sigma,
+                          const uint8_t *mask, uint8_t *dst, uint32_t flags);
+/* box_blur_core (src/ops/effects/blur.rs:233-318): integer, bit-exact. */
+int pfe_box_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                 const uint8_t *mask, uint8_t *dst);
+int pfe_dev_box_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                     const uint8_t *mask, uint8_t *dst);
+/* motion_blur_core (blur.rs:144-210). */
+int pfe_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg,
+                    float distance, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg,
+                        float distance, const uint8_t *mask, uint8_t *dst);
+/* median_core (src/ops/effects/noise.rs:357-410) / GpuRenderer::median_rgba (renderer.rs:945).
+ * Any radius >= 1 (radius 0 is treated as 1, noise.rs:364); integer, bit-exact. */
+int pfe_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+               const uint8_t *mask, uint8_t *dst);
+int pfe_dev_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+                   const uint8_t *mask, uint8_t *dst);
+/* sharpen_core / unsharp mask (src/ops/effects/stylize.rs:96-141). */
+int pfe_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
+                float radius, const uint8_t *mask, uint8_t *dst, uint32_t flags);
+int pfe_dev_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
+                    float radius, const uint8_t *mask, uint8_t *dst, uint32_t flags);
+/* vignette_core (stylize.rs:170-191). */
+int pfe_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
+                 float softness, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
+                     float softness, const uint8_t *mask, uint8_t *dst);
+
+/* -- per-pixel adjustments ---------------------------------------------------------------
+ * Ops 0..31 follow src/ops/adjustments.rs (round-to-nearest, selection mask honoured,
+ * apply_pixel_transform[_from_flat] :21-108). Ops 32.. follow the inline Rhai bindings in
+ * src/ops/scripting.rs:869-1075 (truncating casts, alpha untouched, no mask). Both exist in
+ * the reference and are pinned by different goldens. */
+typedef enum pfe_adjust_op {
+    PFE_ADJ_INVERT = 0,              /* invert_colors, adjustments.rs:115; invert_rgba */
+    PFE_ADJ_INVERT_ALPHA = 1,        /* :122 */
+    PFE_ADJ_SEPIA = 2,               /* :133 */
+    PFE_ADJ_DESATURATE = 3,          /* desaturate_layer, filters.rs:320 */
+    PFE_ADJ_BRIGHTNESS_CONTRAST = 4, /* :265; params = {brightness, contrast} */
+    PFE_ADJ_HSL = 5,                 /* :300; params = {hue_deg, saturation, lightness} */
+    PFE_ADJ_EXPOSURE = 6,            /* :352; params = {gain = 2^ev} */
+    PFE_ADJ_LUT_RGB = 7,             /* levels :398-446; luts = 256 bytes applied to r,g,b */
+    PFE_ADJ_LUT_RGBA = 8,            /* curves :549-626, per-channel levels :490; luts = 4*256 */
+    PFE_ADJ_TEMPERATURE_TINT = 9,    /* :518; params = {temperature, tint} */
+    PFE_ADJ_HIGHLIGHTS_SHADOWS = 10, /* :371; params = {shadows, highlights} */
+    PFE_ADJ_S_INVERT = 32,              /* apply_invert, scripting.rs:869 */
+    PFE_ADJ_S_DESATURATE = 33,          /* apply_desaturate :883 */
+    PFE_ADJ_S_SEPIA = 34,               /* apply_sepia() :900 */
+    PFE_ADJ_S_SEPIA_STRENGTH = 35,      /* apply_sepia(strength) :921; params = {strength in [0,1]} */
+    PFE_ADJ_S_BRIGHTNESS_CONTRAST = 36, /* :944 */
+    PFE_ADJ_S_HSL = 37,                 /* :964 */
+    PFE_ADJ_S_EXPOSURE = 38,            /* :1040; params = {gain} */
+    PFE_ADJ_S_LUT_RGB = 39              /* apply_levels :1054 */
+} pfe_adjust_op;
+
+typedef struct pfe_adjust_desc {
+    int32_t op;          /* pfe_adjust_op */
+    float params[8];
+    const uint8_t *luts; /* HOST pointer in both tiers (<= 1 KiB, copied with the launch) */
+} pfe_adjust_desc;
+
+/* `occupancy` (chunk bitmap like active_chunks) selects apply_pixel_transform's in-place tile
+ * walk: pixels of unpopulated chunks are copied through untouched (tiled_image.rs:905-933).
+ * NULL = the _from_flat form: every pixel is transformed. src may equal dst. */
+int pfe_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const pfe_adjust_desc *d,
+               const uint8_t *mask, const uint8_t *occupancy, uint8_t *dst);
+int pfe_dev_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h,
+                   const pfe_adjust_desc *d, const uint8_t *mask, const uint8_t *occupancy_dev,
+                   uint8_t *dst);
+/* LUT builders (host arithmetic, identical to the reference's): build_levels_lut
+ * adjustments.rs:424, scripting apply_levels LUT scripting.rs:1054, build_stretch_lut :232,
+ * build_curves_lut :634 (n_points (x,y) pairs), build_multi_channel_luts :576. */
+void pfe_build_levels_lut(float in_black, float in_white, float gamma, float out_black,
+                          float out_white, uint8_t lut[256]);
+void pfe_build_levels_lut_script(float in_black, float in_white, float gamma, uint8_t lut[256]);
+void pfe_build_stretch_lut(uint8_t min, uint8_t max, uint8_t lut[256]);
+void pfe_build_curves_lut(const float *points_xy, int n_points, uint8_t lut[256]);
+void pfe_compose_curve_luts(const uint8_t in_rgb_r_g_b_a[5 * 256], uint8_t out_r_g_b_a[4 * 256]);
+/* Per-channel min/max over pixels with alpha != 0 that are selected (auto_levels,
+ * adjustments.rs:144-196). out = {min_r,max_r,min_g,max_g,min_b,max_b}. */
+int pfe_channel_minmax(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h,
+                       const uint8_t *mask, uint8_t out[6]);
+int pfe_dev_channel_minmax(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h,
+                           const uint8_t *mask, uint8_t out_host[6]);
+
+/* -- warps -----------------------------------------------------------------------------
+ * warp_displacement_full (src/ops/transform.rs:1288-1345) / GpuLiquifyPipeline::warp_into
+ * (src/gpu/compute/liquify.rs:176): dst(x,y) = bilinear src(x-dx, y-dy), zero outside. */
+int pfe_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h,
+                          const float *disp, uint32_t w, uint32_t h, uint8_t *dst);
+int pfe_dev_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h,
+                              const float *disp, uint32_t w, uint32_t h, uint8_t *dst);
+/* generate_displacement_from_mesh (:1670-1706; original_points != NULL) and _fast (:1712-1739;
+ * original_points == NULL) / GpuMeshWarpDisplacementPipeline::generate_displacement
+ * (src/gpu/compute/mesh_warp.rs:131). points: (rows+1)*(cols+1) [x,y] pairs, HOST pointers in
+ * both tiers (<= PFE_MESH_MAX_POINTS). */
+#define PFE_MESH_MAX_POINTS 256
+int pfe_mesh_displacement(pfe_ctx *ctx, const float *original_points, const float *deformed_points,
+                          uint32_t cols, uint32_t rows, uint32_t w, uint32_t h, float *out_disp);
+int pfe_dev_mesh_displacement(pfe_ctx *ctx, const float *original_points,
+                              const float *deformed_points, uint32_t cols, uint32_t rows, uint32_t w,
+                              uint32_t h, float *out_disp_dev);
+/* warp_mesh_catmull_rom (:1743-1761), fused: the w*h*2 field is never materialised.
+ * Band form: produce only output rows [y0, y0+rows_out) of the full w x h result, reading the
+ * full source (used by the multi-GPU row-band split); y0=0, rows_out=h for the whole image. */
+int pfe_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h,
+                  const float *original_points, const float *deformed_points, uint32_t cols,
+                  uint32_t rows, uint32_t w, uint32_t h, uint8_t *dst);
+int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h,
+                      const float *original_points, const float *deformed_points, uint32_t cols,
+                      uint32_t rows, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out,
+                      uint8_t *dst_band);
+/* DisplacementField::apply_push / expand / contract / twirl (:1051-1200), in place on a
+ * w*h*2 field. a0,a1: push = (delta_x, delta_y); twirl = (clockwise ? 1 : 0, -).
+ * bbox_out (may be NULL) = (x0, y0, x1, y1) like the reference's return value. */
+typedef enum pfe_liquify_kind { PFE_LIQ_PUSH = 0, PFE_LIQ_EXPAND = 1, PFE_LIQ_CONTRACT = 2, PFE_LIQ_TWIRL = 3 } pfe_liquify_kind;
+int pfe_liquify(pfe_ctx *ctx, float *field, uint32_t w, uint32_t h, int kind, float center_x,
+                float center_y, float radius, float strength, float a0, float a1, int32_t bbox_out[4]);
+int pfe_dev_liquify(pfe_ctx *ctx, float *field_dev, uint32_t w, uint32_t h, int kind, float center_x,
+                    float center_y, float radius, float strength, float a0, float a1,
+                    int32_t bbox_out[4]);
+
+/* -- brush stamps ------------------------------------------------------------------------
+ * ToolsPanel::draw_circle_no_dirty (src/ui/panels/tools/behavior/raster/brush_render.rs:135-400)
+ * for the circle tip in BrushMode::Normal and the eraser, plus rebuild_brush_lut (:27-50) and
+ * draw_line_no_dirty's stamp placement (:762-838). One launch applies a whole list of stamps
+ * in order, in place. */
+typedef struct pfe_brush_desc {
+    float size;          /* ToolProperties::size (diameter) */
+    float hardness;
+    float flow;
+    int32_t anti_aliased;
+    float color[4];      /* straight RGBA, 0..1 (primary or secondary, chosen by the caller) */
+    int32_t is_eraser;
+} pfe_brush_desc;
+int pfe_brush_stamps(pfe_ctx *ctx, uint8_t *image, uint32_t w, uint32_t h, const pfe_brush_desc *brush,
+                     const float *centres_xy, uint32_t n_stamps, const uint8_t *selection_mask);
+int pfe_dev_brush_stamps(pfe_ctx *ctx, uint8_t *image_dev, uint32_t w, uint32_t h,
+                         const pfe_brush_desc *brush, const float *centres_xy_host, uint32_t n_stamps,
+                         const uint8_t *selection_mask_dev);
+/* Stamp centres of draw_line_no_dirty (circle tip: 1 px stepping). Returns the count written
+ * (<= cap). Host-only helper. */
+int pfe_brush_line_centres(uint32_t w, uint32_t h, float x0, float y0, float x1, float y1,
+                           float *centres_xy, int cap);
+void pfe_brush_lut(const pfe_brush_desc *brush, uint8_t lut[256]);
+
+/* -- tiles -----------------------------------------------------------------------------
+ * TiledImage marshalling (src/canvas/tiled_image.rs). chunk_table[cy*chunks_per_row+cx] points
+ * to a 64*64*4-byte tile or is NULL for an unpopulated chunk (`Vec<Option<Arc<RgbaImage>>>`,
+ * :2-7). Host-side, multithreaded memcpy; no device work. */
+int pfe_tiles_to_flat(const uint8_t *const *chunk_table, uint32_t w, uint32_t h, uint8_t *flat); /* to_rgba_image :271 */
+/* from_rgba_image :50-104: writes occupancy (1 where the chunk has any alpha != 0) and, when
+ * tiles_out != NULL, copies populated chunks into tiles_out + idx*16384 (zero-padded edges). */
+int pfe_flat_to_tiles(const uint8_t *flat, uint32_t w, uint32_t h, uint8_t *occupancy, uint8_t *tiles_out);
+
+/* -- fused headline pipeline -------------------------------------------------------------
+ * composite() followed by parallel_gaussian_blur on the result, without leaving the device
+ * (cli.rs:282-285 + scripting apply_blur). Equivalent to pfe_flatten then pfe_gaussian_blur. */
+int pfe_flatten_gaussian(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n_layers, uint32_t w,
+                         uint32_t h, const uint8_t *active_chunks, float sigma, uint8_t *dst,
+                         uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFE_B200_H */

@@ -1,0 +1,185 @@
+// Brush-stamp inner loop: a whole stroke's stamps in one launch.
+// Reference: ToolsPanel::draw_circle_no_dirty (src/ui/panels/tools/behavior/raster/brush_render.rs:
+// 135-400) for the circle tip in BrushMode::Normal and the eraser; rebuild_brush_lut (:27-50);
+// compute_brush_alpha (:54-82); draw_line_no_dirty's stamp placement (:762-838).
+//
+// The reference stamps sequentially, one circle per pixel of stroke length, each a read-modify-
+// write of the target tiles. Here one thread owns one pixel of the stroke's bounding box and walks
+// the stamp list in order, so the per-pixel sequence of compares and writes is the reference's,
+// the pixel is read once and written once, and overdraw costs registers instead of memory traffic.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct BrushParams {
+    float radius, radius_sq, draw_radius_sq, inv_radius_sq;
+    float hardness;  // clamped to [0,1]
+    float src_a, flow;
+    int anti_aliased, direct, is_eraser;
+    uint32_t rgb;  // packed r8 | g8<<8 | b8<<16
+    uint8_t lut[256];
+};
+
+// compute_brush_alpha, brush_render.rs:54-82
+__host__ __device__ inline float brush_alpha(float dist, float radius, float hardness, int aa) {
+    if (radius <= 0.0f) return 0.0f;
+    float t = dist / radius;
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    float falloff = t * t * (3.0f - 2.0f * t);
+    float material = 1.0f + (hardness - 1.0f) * falloff;
+    float coverage;
+    if (aa) {
+        float e0 = radius + 0.5f, e1 = radius - 0.5f;
+        if (dist <= e1) coverage = 1.0f;
+        else if (dist >= e0) coverage = 0.0f;
+        else {
+            float x = (dist - e0) / (e1 - e0);
+            x = x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x);
+            coverage = x * x * (3.0f - 2.0f * x);
+        }
+    } else {
+        coverage = dist <= radius ? 1.0f : 0.0f;
+    }
+    return material * coverage;
+}
+
+__global__ void __launch_bounds__(256) brush_kernel(const __grid_constant__ BrushParams B, uint32_t *img, uint32_t w,
+                                                    const float2 *centres, uint32_t n, const uint8_t *sel, int bx0,
+                                                    int by0, int bw, int bh, float draw_radius) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = B.lut[threadIdx.x];
+    __syncthreads();
+    const int lx = blockIdx.x * 32 + (threadIdx.x & 31), ly = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (lx >= bw || ly >= bh) return;
+    const int gx = bx0 + lx, gy = by0 + ly;
+    const size_t o = (size_t)gy * w + gx;
+    if (sel && sel[o] == 0) return;                                           // :309-317
+    uint32_t px = img[o];
+    const uint32_t before = px;
+    const float fgx = (float)gx, fgy = (float)gy;
+    for (uint32_t s = 0; s < n; s++) {
+        const float2 c = __ldg(centres + s);
+        // the stamp's own bounding box (:205-211); pixels outside it are never visited
+        if (fgx < fmaxf(floorf(c.x - draw_radius), 0.0f) || fgx > ceilf(c.x + draw_radius) ||
+            fgy < fmaxf(floorf(c.y - draw_radius), 0.0f) || fgy > ceilf(c.y + draw_radius))
+            continue;
+        float dy = fgy - c.y, dx = fgx - c.x;
+        float dist_sq = dx * dx + dy * dy;
+        if (dist_sq > B.draw_radius_sq) continue;                             // :321
+        uint32_t ga8;
+        if (B.direct) {                                                       // :325-332
+            float a = brush_alpha(sqrtf(dist_sq), B.radius, B.hardness, B.anti_aliased);
+            ga8 = (uint32_t)__float2int_rz(fminf(fmaxf(fminf(roundf(a * 255.0f), 255.0f), 0.0f), 255.0f));
+        } else {                                                              // :334-336
+            float fi = fminf(dist_sq * B.inv_radius_sq * 255.0f, 255.0f);
+            ga8 = lut[(uint32_t)__float2int_rz(fmaxf(fi, 0.0f))];
+        }
+        if (ga8 == 0) continue;
+        float strength = (float)ga8 / 255.0f * B.src_a * B.flow;              // :340, :347, :361
+        if (strength < 0.01f) continue;
+        if (B.is_eraser) {
+            float old_mask = (float)(px >> 24) / 255.0f;
+            if (strength > old_mask) px = pfe_as_u8(strength * 255.0f) << 24; // :352-357
+        } else {
+            uint32_t a8 = pfe_as_u8(strength * 255.0f);
+            if (a8 >= (px >> 24)) px = B.rgb | (a8 << 24);                    // :366-372
+        }
+    }
+    if (px != before) img[o] = px;
+}
+
+void fill_params(const pfe_brush_desc *b, BrushParams *P) {
+    memset(P, 0, sizeof(*P));
+    const float radius = b->size / 2.0f;
+    P->radius = radius;
+    P->radius_sq = radius * radius;
+    const float draw_radius = b->anti_aliased ? radius + 0.5f : radius;
+    P->draw_radius_sq = draw_radius * draw_radius;
+    P->direct = draw_radius > radius;
+    P->inv_radius_sq = 1.0f / P->radius_sq;
+    P->hardness = std::min(std::max(b->hardness, 0.0f), 1.0f);
+    P->src_a = b->color[3];
+    P->flow = b->flow;
+    P->anti_aliased = b->anti_aliased ? 1 : 0;
+    P->is_eraser = b->is_eraser ? 1 : 0;
+    auto as_u8 = [](float v) -> uint32_t { return v != v || v <= 0.0f ? 0u : (v >= 255.0f ? 255u : (uint32_t)v); };
+    P->rgb = as_u8(b->color[0] * 255.0f) | (as_u8(b->color[1] * 255.0f) << 8) | (as_u8(b->color[2] * 255.0f) << 16);
+    pfe_brush_lut(b, P->lut);
+}
+
+}  // namespace
+
+// rebuild_brush_lut, brush_render.rs:27-50 (host arithmetic)
+extern "C" void pfe_brush_lut(const pfe_brush_desc *b, uint8_t lut[256]) {
+    const float radius = b->size / 2.0f;
+    if (radius < 0.001f) { memset(lut, 0, 256); return; }
+    const float hardness = std::min(std::max(b->hardness, 0.0f), 1.0f);
+    for (int i = 0; i < 256; i++) {
+        float t_sq = (float)i / 255.0f;
+        float dist = sqrtf(t_sq) * radius;
+        float alpha = brush_alpha(dist, radius, hardness, b->anti_aliased ? 1 : 0);
+        float v = fminf(roundf(alpha * 255.0f), 255.0f);
+        lut[i] = (uint8_t)(v != v || v <= 0.0f ? 0 : (int)v);
+    }
+}
+
+// draw_line_no_dirty, brush_render.rs:762-838 (circle tip: step = 1 px)
+extern "C" int pfe_brush_line_centres(uint32_t w, uint32_t h, float x0, float y0, float x1, float y1, float *c, int cap) {
+    if (!c || cap <= 0) return 0;
+    auto as_u32 = [](float v) -> uint32_t { return v != v || v <= 0.0f ? 0u : (v >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)v); };
+    const float dx = x1 - x0, dy = y1 - y0;
+    const float distance = sqrtf(dx * dx + dy * dy);
+    int n = 0;
+    if (distance < 0.1f) {
+        if (x0 >= 0.0f && as_u32(x0) < w && y0 >= 0.0f && as_u32(y0) < h) { c[0] = x0; c[1] = y0; n = 1; }
+        return n;
+    }
+    const uint32_t steps = as_u32(ceilf(distance / 1.0f));
+    for (uint32_t i = 0; i <= steps && n < cap; i++) {
+        float t = (float)i / (float)steps;
+        float x = x0 + dx * t, y = y0 + dy * t;
+        if (x >= 0.0f && as_u32(x) < w && y >= 0.0f && as_u32(y) < h) { c[n * 2] = x; c[n * 2 + 1] = y; n++; }
+    }
+    return n;
+}
+
+extern "C" int pfe_dev_brush_stamps(pfe_ctx *ctx, uint8_t *image, uint32_t w, uint32_t h, const pfe_brush_desc *brush,
+                                    const float *centres, uint32_t n, const uint8_t *sel) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!image || !brush || (n && !centres) || !w || !h) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "brush: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return PFE_OK;
+    BrushParams P;
+    fill_params(brush, &P);
+    if (P.radius_sq < 0.001f) return PFE_OK;                                  // :196-198
+    const float draw_radius = brush->anti_aliased ? P.radius + 0.5f : P.radius;
+    // union of the stamps' bounding boxes (:205-211)
+    float fx0 = 3.0e38f, fy0 = 3.0e38f, fx1 = -3.0e38f, fy1 = -3.0e38f;
+    for (uint32_t i = 0; i < n; i++) {
+        fx0 = std::min(fx0, centres[i * 2]); fx1 = std::max(fx1, centres[i * 2]);
+        fy0 = std::min(fy0, centres[i * 2 + 1]); fy1 = std::max(fy1, centres[i * 2 + 1]);
+    }
+    auto clampi = [](double v, double lo, double hi) { return (int)std::min(std::max(v, lo), hi); };
+    const int bx0 = clampi(floor((double)fx0 - draw_radius), 0, (double)w - 1), by0 = clampi(floor((double)fy0 - draw_radius), 0, (double)h - 1);
+    const int bx1 = clampi(ceil((double)fx1 + draw_radius), 0, (double)w - 1), by1 = clampi(ceil((double)fy1 + draw_radius), 0, (double)h - 1);
+    if (bx1 < bx0 || by1 < by0) return PFE_OK;
+    const size_t cbytes = (size_t)n * 8;
+    void *cdev;
+    if (cbytes <= PFE_SMALL_BYTES / 2) {
+        PFE_TRY(pfe_small_upload(ctx, centres, cbytes, &cdev));
+    } else {
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, cbytes, &cdev));
+        PFE_CUDA(ctx, cudaMemcpyAsync(cdev, centres, cbytes, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // centres is caller memory
+    }
+    const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+    PFE_KERNEL(ctx, "brush", brush_kernel<<<dim3(pfe_div_up(bw, 32), pfe_div_up(bh, 8)), 256, 0, ctx->stream>>>(
+        P, (uint32_t *)image, w, (const float2 *)cdev, n, sel, bx0, by0, bw, bh, draw_radius));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}

@@ -1,0 +1,455 @@
+// Context, memory helpers and the host-pointer tier of the C ABI.
+// The host tier is plumbing only: copy in, call the pfe_dev_* entry point, copy out.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+int pfe_fail(pfe_ctx *ctx, int code, const char *what, cudaError_t e) {
+    if (ctx) {
+        ctx->err = what ? what : "";
+        if (e != cudaSuccess) {
+            ctx->err += ": ";
+            ctx->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+int pfe_scratch(pfe_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes[slot]) {
+        if (ctx->scratch[slot]) {
+            PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            PFE_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pfe_fail(ctx, PFE_ERR_OOM, "scratch cudaMalloc", e);
+        }
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return PFE_OK;
+}
+
+int pfe_small_upload(pfe_ctx *ctx, const void *host, size_t bytes, void **dev_out) {
+    size_t need = (bytes + 255) & ~size_t(255);
+    if (need > PFE_SMALL_BYTES) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "parameter table too large");
+    if (ctx->small_cursor + need > PFE_SMALL_BYTES) {
+        // the pinned staging ring is about to be reused: make sure earlier copies have drained
+        PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->small_cursor = 0;
+    }
+    char *stage = (char *)ctx->pinned + ctx->small_cursor;
+    char *dev = (char *)ctx->dev_small + ctx->small_cursor;
+    memcpy(stage, host, bytes);
+    PFE_CUDA(ctx, cudaMemcpyAsync(dev, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->small_cursor += need;
+    *dev_out = dev;
+    return PFE_OK;
+}
+
+static cudaEvent_t take_event(pfe_ctx *c) {
+    cudaEvent_t e = nullptr;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
+pfe_span::pfe_span(pfe_ctx *ctx, const char *n) : c(ctx), name(n) {
+    if (!c->profiling || c->spans.size() >= (1u << 16)) { c = nullptr; return; }
+    a = take_event(c);
+    b = take_event(c);
+    if (!a || !b) { c = nullptr; return; }
+    cudaEventRecord(a, c->stream);
+}
+pfe_span::~pfe_span() {
+    if (!c) return;
+    cudaEventRecord(b, c->stream);
+    c->spans.push_back({name, a, b});
+}
+
+extern "C" {
+
+int pfe_abi_version(void) { return PFE_ABI_VERSION; }
+
+int pfe_ctx_profile(pfe_ctx *c, int enable) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    c->profiling = enable != 0;
+    return PFE_OK;
+}
+
+int pfe_ctx_profile_read(pfe_ctx *c, char *buf, size_t cap) {
+    if (!c || !buf || cap < 4) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    struct Agg { const char *name; uint64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (auto &s : c->spans) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        c->event_pool.push_back(s.a);
+        c->event_pool.push_back(s.b);
+        size_t k = 0;
+        for (; k < agg.size(); k++) if (strcmp(agg[k].name, s.name) == 0) break;
+        if (k == agg.size()) agg.push_back({s.name, 0, 0.0});
+        agg[k].n++;
+        agg[k].ms += ms;
+    }
+    c->spans.clear();
+    std::string out = "{";
+    for (size_t k = 0; k < agg.size(); k++) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", k ? ", " : "", agg[k].name,
+                 (unsigned long long)agg[k].n, agg[k].ms);
+        out += tmp;
+    }
+    out += "}";
+    if (out.size() + 1 > cap) return pfe_fail(c, PFE_ERR_INVALID_ARG, "profile buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return PFE_OK;
+}
+
+int pfe_ctx_create(int device, pfe_ctx **out) {
+    if (!out) return PFE_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return PFE_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return PFE_ERR_INVALID_ARG;
+    pfe_ctx *c = new (std::nothrow) pfe_ctx();
+    if (!c) return PFE_ERR_OOM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return PFE_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMallocHost(&c->pinned, PFE_SMALL_BYTES) == cudaSuccess &&
+              cudaMalloc(&c->dev_small, PFE_SMALL_BYTES) == cudaSuccess;
+    if (!ok) { pfe_ctx_destroy(c); return PFE_ERR_CUDA; }
+    c->pinned_bytes = PFE_SMALL_BYTES;
+    c->stream = c->own_stream;
+    *out = c;
+    return PFE_OK;
+}
+
+int pfe_ctx_destroy(pfe_ctx *c) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &s : c->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    if (c->dev_small) cudaFree(c->dev_small);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return PFE_OK;
+}
+
+int pfe_ctx_set_stream(pfe_ctx *c, void *s) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return PFE_OK;
+}
+
+int pfe_ctx_sync(pfe_ctx *c) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PFE_OK;
+}
+
+const char *pfe_last_error(const pfe_ctx *c) { return c ? c->err.c_str() : "null context"; }
+uint64_t pfe_ctx_launch_count(const pfe_ctx *c) { return c ? c->launches : 0; }
+
+int pfe_host_alloc(size_t bytes, void **out) {
+    if (!out) return PFE_ERR_INVALID_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return PFE_ERR_OOM; }
+    return PFE_OK;
+}
+int pfe_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? PFE_OK : PFE_ERR_CUDA; }
+
+int pfe_dev_alloc(pfe_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return pfe_fail(c, PFE_ERR_OOM, "cudaMalloc", e); }
+    return PFE_OK;
+}
+int pfe_dev_free(pfe_ctx *c, void *p) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    PFE_CUDA(c, cudaFree(p));
+    return PFE_OK;
+}
+int pfe_dev_upload(pfe_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (bytes && (!dst || !src))) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return PFE_OK;
+}
+int pfe_dev_download(pfe_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (!c || (bytes && (!dst || !src))) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PFE_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Host tier.  One image in, one image out, optional selection mask.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct Staged {
+    uint8_t *src = nullptr, *dst = nullptr, *mask = nullptr;
+};
+
+int stage_in(pfe_ctx *c, const uint8_t *src, uint32_t w, uint32_t h, const uint8_t *mask, Staged *s) {
+    if (!c || !src || w == 0 || h == 0) return c ? pfe_fail(c, PFE_ERR_INVALID_ARG, "null image or zero size") : PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    size_t n4 = (size_t)w * h * 4;
+    void *a, *b, *m = nullptr;
+    // one arena for src | dst | mask so a single grow covers the call
+    size_t total = 2 * ((n4 + 255) & ~size_t(255)) + (mask ? (size_t)w * h : 0);
+    PFE_TRY(pfe_scratch(c, PFE_SCRATCH_A, total, &a));
+    b = (char *)a + ((n4 + 255) & ~size_t(255));
+    if (mask) m = (char *)b + ((n4 + 255) & ~size_t(255));
+    PFE_CUDA(c, cudaMemcpyAsync(a, src, n4, cudaMemcpyHostToDevice, c->stream));
+    if (mask) PFE_CUDA(c, cudaMemcpyAsync(m, mask, (size_t)w * h, cudaMemcpyHostToDevice, c->stream));
+    s->src = (uint8_t *)a;
+    s->dst = (uint8_t *)b;
+    s->mask = (uint8_t *)m;
+    return PFE_OK;
+}
+
+int stage_out(pfe_ctx *c, const Staged &s, uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!dst) return pfe_fail(c, PFE_ERR_INVALID_ARG, "null dst");
+    PFE_CUDA(c, cudaMemcpyAsync(dst, s.dst, (size_t)w * h * 4, cudaMemcpyDeviceToHost, c->stream));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PFE_OK;
+}
+
+}  // namespace
+
+#define HOST_TIER(call_dev)                       \
+    Staged s;                                     \
+    PFE_TRY(stage_in(ctx, src, w, h, mask, &s));  \
+    PFE_TRY(call_dev);                            \
+    return stage_out(ctx, s, w, h, dst);
+
+extern "C" {
+
+int pfe_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float sigma,
+                      const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    HOST_TIER(pfe_dev_gaussian_blur(ctx, s.src, w, h, sigma, s.mask, s.dst, flags));
+}
+int pfe_box_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                 const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_box_blur(ctx, s.src, w, h, radius, s.mask, s.dst));
+}
+int pfe_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg,
+                    float distance, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_motion_blur(ctx, s.src, w, h, angle_deg, distance, s.mask, s.dst));
+}
+int pfe_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+               const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_median(ctx, s.src, w, h, radius, s.mask, s.dst));
+}
+int pfe_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float radius,
+                const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    HOST_TIER(pfe_dev_sharpen(ctx, s.src, w, h, amount, radius, s.mask, s.dst, flags));
+}
+int pfe_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
+                 float softness, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_vignette(ctx, s.src, w, h, amount, softness, s.mask, s.dst));
+}
+
+int pfe_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const pfe_adjust_desc *d,
+               const uint8_t *mask, const uint8_t *occupancy, uint8_t *dst) {
+    if (!ctx || !d) return PFE_ERR_INVALID_ARG;
+    Staged s;
+    PFE_TRY(stage_in(ctx, src, w, h, mask, &s));
+    void *occ = nullptr;
+    if (occupancy) {
+        size_t nb = (size_t)pfe_div_up(w, PFE_CHUNK_SIZE) * pfe_div_up(h, PFE_CHUNK_SIZE);
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, nb, &occ));
+        PFE_CUDA(ctx, cudaMemcpyAsync(occ, occupancy, nb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PFE_TRY(pfe_dev_adjust(ctx, s.src, w, h, d, s.mask, (const uint8_t *)occ, s.dst));
+    return stage_out(ctx, s, w, h, dst);
+}
+
+int pfe_channel_minmax(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const uint8_t *mask,
+                       uint8_t out[6]) {
+    Staged s;
+    PFE_TRY(stage_in(ctx, src, w, h, mask, &s));
+    return pfe_dev_channel_minmax(ctx, s.src, w, h, s.mask, out);
+}
+
+int pfe_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp,
+                          uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!ctx || !src || !disp || !dst || !sw || !sh || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t sb = (size_t)sw * sh * 4, db = (size_t)w * h * 4, fb = (size_t)w * h * 8;
+    void *a, *b, *f;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, sb, &a));
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, db, &b));
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, fb, &f));
+    PFE_CUDA(ctx, cudaMemcpyAsync(a, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_CUDA(ctx, cudaMemcpyAsync(f, disp, fb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_TRY(pfe_dev_warp_displacement(ctx, (uint8_t *)a, sw, sh, (float *)f, w, h, (uint8_t *)b));
+    PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, db, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_mesh_displacement(pfe_ctx *ctx, const float *orig, const float *def, uint32_t cols, uint32_t rows,
+                          uint32_t w, uint32_t h, float *out) {
+    if (!ctx || !def || !out || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t fb = (size_t)w * h * 8;
+    void *f;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, fb, &f));
+    PFE_TRY(pfe_dev_mesh_displacement(ctx, orig, def, cols, rows, w, h, (float *)f));
+    PFE_CUDA(ctx, cudaMemcpyAsync(out, f, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *orig,
+                  const float *def, uint32_t cols, uint32_t rows, uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!ctx || !src || !dst || !def || !sw || !sh || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t sb = (size_t)sw * sh * 4, db = (size_t)w * h * 4;
+    void *a, *b;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, sb, &a));
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, db, &b));
+    PFE_CUDA(ctx, cudaMemcpyAsync(a, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_TRY(pfe_dev_mesh_warp(ctx, (uint8_t *)a, sw, sh, orig, def, cols, rows, w, h, 0, h, (uint8_t *)b));
+    PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, db, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_liquify(pfe_ctx *ctx, float *field, uint32_t w, uint32_t h, int kind, float cx, float cy,
+                float radius, float strength, float a0, float a1, int32_t bbox[4]) {
+    if (!ctx || !field || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t fb = (size_t)w * h * 8;
+    void *f;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, fb, &f));
+    PFE_CUDA(ctx, cudaMemcpyAsync(f, field, fb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_TRY(pfe_dev_liquify(ctx, (float *)f, w, h, kind, cx, cy, radius, strength, a0, a1, bbox));
+    PFE_CUDA(ctx, cudaMemcpyAsync(field, f, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_brush_stamps(pfe_ctx *ctx, uint8_t *image, uint32_t w, uint32_t h, const pfe_brush_desc *brush,
+                     const float *centres, uint32_t n, const uint8_t *sel) {
+    if (!ctx || !image || !brush || (n && !centres) || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t db = (size_t)w * h * 4;
+    void *a, *m = nullptr;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, db, &a));
+    PFE_CUDA(ctx, cudaMemcpyAsync(a, image, db, cudaMemcpyHostToDevice, ctx->stream));
+    if (sel) {
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, (size_t)w * h, &m));
+        PFE_CUDA(ctx, cudaMemcpyAsync(m, sel, (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PFE_TRY(pfe_dev_brush_stamps(ctx, (uint8_t *)a, w, h, brush, centres, n, (uint8_t *)m));
+    PFE_CUDA(ctx, cudaMemcpyAsync(image, a, db, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+// ---- flatten host tier: upload every raster layer (and mask), run, download ----------------
+static int flatten_upload(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
+                          const uint8_t *active, std::vector<pfe_layer_desc> *dev_layers,
+                          uint8_t **active_dev, uint8_t **dst_dev) {
+    if (!ctx || (!layers && n) || !w || !h) return ctx ? pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: bad args") : PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n4 = (size_t)w * h * 4, n1 = (size_t)w * h;
+    size_t a4 = (n4 + 255) & ~size_t(255), a1 = (n1 + 255) & ~size_t(255);
+    size_t total = a4;  // dst
+    for (uint32_t i = 0; i < n; i++) {
+        if (!layers[i].visible) continue;
+        if (layers[i].kind == PFE_LAYER_RASTER) {
+            if (!layers[i].rgba) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: raster layer without pixels");
+            total += a4;
+            if (layers[i].mask) total += a1;
+        }
+    }
+    size_t nb = (size_t)pfe_div_up(w, PFE_CHUNK_SIZE) * pfe_div_up(h, PFE_CHUNK_SIZE);
+    if (active) total += (nb + 255) & ~size_t(255);
+    void *base;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, total, &base));
+    char *cur = (char *)base;
+    *dst_dev = (uint8_t *)cur;
+    cur += a4;
+    dev_layers->assign(layers, layers + n);
+    for (uint32_t i = 0; i < n; i++) {
+        pfe_layer_desc &L = (*dev_layers)[i];
+        if (!L.visible || L.kind != PFE_LAYER_RASTER) { L.rgba = nullptr; L.mask = nullptr; continue; }
+        PFE_CUDA(ctx, cudaMemcpyAsync(cur, layers[i].rgba, n4, cudaMemcpyHostToDevice, ctx->stream));
+        L.rgba = (uint8_t *)cur;
+        cur += a4;
+        if (layers[i].mask) {
+            PFE_CUDA(ctx, cudaMemcpyAsync(cur, layers[i].mask, n1, cudaMemcpyHostToDevice, ctx->stream));
+            L.mask = (uint8_t *)cur;
+            cur += a1;
+        }
+    }
+    *active_dev = nullptr;
+    if (active) {
+        PFE_CUDA(ctx, cudaMemcpyAsync(cur, active, nb, cudaMemcpyHostToDevice, ctx->stream));
+        *active_dev = (uint8_t *)cur;
+    }
+    return PFE_OK;
+}
+
+int pfe_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
+                const uint8_t *active, uint8_t *dst) {
+    if (!dst) return PFE_ERR_INVALID_ARG;
+    std::vector<pfe_layer_desc> dl;
+    uint8_t *act, *d;
+    PFE_TRY(flatten_upload(ctx, layers, n, w, h, active, &dl, &act, &d));
+    PFE_TRY(pfe_dev_flatten(ctx, dl.data(), n, w, h, act, d));
+    PFE_CUDA(ctx, cudaMemcpyAsync(dst, d, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_flatten_gaussian(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
+                         const uint8_t *active, float sigma, uint8_t *dst, uint32_t flags) {
+    if (!dst) return PFE_ERR_INVALID_ARG;
+    std::vector<pfe_layer_desc> dl;
+    uint8_t *act, *d;
+    PFE_TRY(flatten_upload(ctx, layers, n, w, h, active, &dl, &act, &d));
+    PFE_TRY(pfe_dev_flatten(ctx, dl.data(), n, w, h, act, d));
+    void *b;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, (size_t)w * h * 4, &b));
+    PFE_TRY(pfe_dev_gaussian_blur(ctx, d, w, h, sigma, nullptr, (uint8_t *)b, flags));
+    PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,359 @@
+// Separable Gaussian blur (and the unsharp-mask epilogue that rides on its V pass).
+//
+// Replaces build_gaussian_kernel / parallel_gaussian_blur / blur_with_selection
+// (src/ops/filters.rs:141-316), sharpen_core (src/ops/effects/stylize.rs:96-141) and
+// GpuRenderer::blur_rgba (src/gpu/renderer.rs:915).  Same structure as the reference: H pass
+// u8 -> f32 intermediate, V pass f32 -> u8 with round-half-away + clamp, straight alpha,
+// clamp-to-edge, taps accumulated in ascending index order.
+//
+// Both passes are FP32-pipe bound (16*(2r+1) FLOP per pixel against 8 compulsory bytes), so the
+// design goal is "every issue slot is an FFMA":
+//   * register blocking along the filter axis: a thread owns N consecutive outputs (4N
+//     accumulators) and streams N+2r inputs past them, so one input load feeds 4N FMAs;
+//   * the N live weights sit in a rotating register window (one uniform smem read per step);
+//   * H pass: a warp owns one row segment of 32*N pixels; the u8 pixels are converted to f32 once
+//     while being staged into a skewed shared-memory tile (conflict-free LDS.128), and results go
+//     back through the same tile so global stores are fully coalesced;
+//   * V pass: lanes run along x (512 B coalesced f32x4 rows); re-reads of neighbouring row blocks
+//     are served by L2.
+// EXACT=true keeps the reference's separate multiply and add (bit-exact, 2x the FP32 work);
+// EXACT=false uses FMA (one rounding per tap instead of two; results within +-1 level).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct GaussParams {
+    const uint8_t *src;   // H: region origin inside the source image
+    float *mid;           // rw*rh*4 f32 intermediate
+    uint8_t *dst;         // V: region origin inside the destination image
+    const float *wp;      // padded weights, device
+    const uint8_t *orig;  // sharpen: original pixels (same geometry as dst), else null
+    const uint8_t *mask;  // sharpen: selection mask plane (w*h) at region origin, or null
+    float amount;         // sharpen amount
+    uint32_t src_pitch;   // pixels per source row
+    uint32_t dst_pitch;   // pixels per destination row
+    uint32_t mask_pitch;
+    uint32_t rw, rh;      // region size
+    int radius;
+    int steps;            // T: padded step count, multiple of N
+    int wp_len;           // steps + N - 1
+};
+
+// wp[m] = w[m-(N-1)] inside the kernel support, 0 outside: lets every output use the same
+// unrolled N-step body.  Zero-weight taps are exact no-ops in both modes (x*0 + acc == acc).
+template <int N, bool EXACT>
+__device__ __forceinline__ void tap(float4 &acc, const float4 &in, float w) {
+    if (EXACT) {
+        acc.x = __fadd_rn(acc.x, __fmul_rn(in.x, w));
+        acc.y = __fadd_rn(acc.y, __fmul_rn(in.y, w));
+        acc.z = __fadd_rn(acc.z, __fmul_rn(in.z, w));
+        acc.w = __fadd_rn(acc.w, __fmul_rn(in.w, w));
+    } else {
+        acc.x = __fmaf_rn(in.x, w, acc.x);
+        acc.y = __fmaf_rn(in.y, w, acc.y);
+        acc.z = __fmaf_rn(in.z, w, acc.z);
+        acc.w = __fmaf_rn(in.w, w, acc.w);
+    }
+}
+
+// One group of N steps with a static rotation phase. LOAD(i) yields the input for step i.
+#define PFE_GAUSS_GROUP(LOAD)                                                         \
+    _Pragma("unroll") for (int s = 0; s < N; s++) {                                   \
+        const int i = g + s;                                                          \
+        R[(s + N - 1) % N] = wsm[i + N - 1];                                          \
+        const float4 in = LOAD(i);                                                    \
+        _Pragma("unroll") for (int j = 0; j < N; j++) tap<N, EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N]); \
+    }
+
+__device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
+
+// ---- H pass: u8 -> f32 ----------------------------------------------------------------------
+template <int N, bool EXACT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *wsm = reinterpret_cast<float *>(smem_raw);
+    const int wp_pad = (P.wp_len + 3) & ~3;
+    const int tile_px = 31 * N + P.steps;
+    const int tile_len = skew(tile_px, N) + 1;
+    float4 *tiles = reinterpret_cast<float4 *>(wsm + wp_pad);
+    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *tile = tiles + (size_t)warp * tile_len;
+    constexpr int SEG = 32 * N;
+    const uint32_t nseg = (P.rw + SEG - 1) / SEG;
+    const uint64_t ntask = (uint64_t)nseg * P.rh;
+    const int rw = (int)P.rw;
+
+    for (uint64_t task = (uint64_t)blockIdx.x * WARPS + warp; task < ntask; task += (uint64_t)gridDim.x * WARPS) {
+        const uint32_t y = (uint32_t)(task / nseg);
+        const int x0 = (int)(task % nseg) * SEG;
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
+        // stage + convert: tile[p] = pixel clamp(x0 - r + p)
+        for (int p = lane; p < tile_px; p += 32) {
+            int sx = min(max(x0 - P.radius + p, 0), rw - 1);
+            uint32_t v = __ldg(row + sx);
+            tile[skew(p, N)] = make_float4((float)(v & 255u), (float)((v >> 8) & 255u),
+                                           (float)((v >> 16) & 255u), (float)(v >> 24));
+        }
+        __syncwarp();
+        float4 acc[N];
+        float R[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+        const int base = lane * N;
+#define H_LOAD(i) tile[skew(base + (i), N)]
+        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(H_LOAD) }
+#undef H_LOAD
+        __syncwarp();
+        // results through the tile -> coalesced 512 B stores
+#pragma unroll
+        for (int j = 0; j < N; j++) tile[skew(base + j, N)] = acc[j];
+        __syncwarp();
+        float4 *out = reinterpret_cast<float4 *>(P.mid) + (size_t)y * P.rw;
+#pragma unroll 4
+        for (int p = lane; p < SEG; p += 32)
+            if (x0 + p < rw) out[x0 + p] = tile[skew(p, N)];
+        __syncwarp();
+    }
+}
+
+// ---- V pass: f32 -> u8 ----------------------------------------------------------------------
+template <int N, bool EXACT>
+__global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ GaussParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *wsm = reinterpret_cast<float *>(smem_raw);
+    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    __syncthreads();
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= (int)P.rw) return;
+    const int rh = (int)P.rh;
+    const float4 *mid = reinterpret_cast<const float4 *>(P.mid) + x;
+    for (int y0 = blockIdx.y * N; y0 < rh; y0 += gridDim.y * N) {
+        float4 acc[N];
+        float R[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+        const int ybase = y0 - P.radius;
+#define V_LOAD(i) __ldg(mid + (size_t)min(max(ybase + (i), 0), rh - 1) * P.rw)
+        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(V_LOAD) }
+#undef V_LOAD
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const int y = y0 + j;
+            if (y >= rh) break;
+            uint32_t r8 = pfe_round_u8(acc[j].x), g8 = pfe_round_u8(acc[j].y), b8 = pfe_round_u8(acc[j].z),
+                     a8 = pfe_round_u8(acc[j].w);
+            uint32_t outv;
+            if (P.orig) {  // sharpen_core, stylize.rs:116-134
+                uint32_t s = reinterpret_cast<const uint32_t *>(P.orig)[(size_t)y * P.dst_pitch + x];
+                if (P.mask && P.mask[(size_t)y * P.mask_pitch + x] == 0) {
+                    outv = s;
+                } else {
+                    float sr = (float)(s & 255u), sg = (float)((s >> 8) & 255u), sb = (float)((s >> 16) & 255u);
+                    outv = pfe_pack(pfe_round_u8(sr + P.amount * (sr - (float)r8)),
+                                    pfe_round_u8(sg + P.amount * (sg - (float)g8)),
+                                    pfe_round_u8(sb + P.amount * (sb - (float)b8)), s >> 24);
+                }
+            } else {
+                outv = pfe_pack(r8, g8, b8, a8);
+            }
+            reinterpret_cast<uint32_t *>(P.dst)[(size_t)y * P.dst_pitch + x] = outv;
+        }
+    }
+}
+
+// blur_with_selection's copy-back (filters.rs:183-200): dst = mask > 0 ? blurred : src
+__global__ void select_kernel(const uint32_t *src, const uint32_t *blur, const uint8_t *mask, uint32_t *dst,
+                              size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = mask[i] > 0 ? blur[i] : src[i];
+}
+
+// Selection bounding box (filters.rs:146-162): bb = {min_x, min_y, max_x, max_y}
+__global__ void bbox_kernel(const uint8_t *mask, uint32_t w, uint32_t h, uint32_t *bb) {
+    uint32_t mnx = 0xFFFFFFFFu, mny = 0xFFFFFFFFu, mxx = 0, mxy = 0;
+    bool any = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)w * h; i += (size_t)gridDim.x * blockDim.x) {
+        if (mask[i] > 0) {
+            uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (size_t)y * w);
+            mnx = min(mnx, x); mny = min(mny, y); mxx = max(mxx, x); mxy = max(mxy, y);
+            any = true;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    any = __any_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && any) {
+        atomicMin(&bb[0], mnx); atomicMin(&bb[1], mny); atomicMax(&bb[2], mxx); atomicMax(&bb[3], mxy);
+    }
+}
+
+// build_gaussian_kernel, filters.rs:214-234 — host arithmetic with libm expf, like the reference.
+std::vector<float> build_kernel(float sigma, int *radius_out) {
+    float c = ceilf(sigma * 3.0f);
+    int radius = (c != c || c <= 0.0f) ? 0 : (c >= 1.0e9f ? 1000000000 : (int)c);
+    *radius_out = radius;
+    if (radius == 0) return std::vector<float>(1, 1.0f);
+    std::vector<float> k((size_t)radius * 2 + 1);
+    volatile float s2 = 2.0f * sigma * sigma;
+    float sum = 0.0f;
+    for (size_t i = 0; i < k.size(); i++) {
+        float x = (float)i - (float)radius;
+        volatile float q = -x * x;   // keep each op separately rounded
+        volatile float e = q / s2;
+        float v = expf(e);
+        k[i] = v;
+        volatile float t = sum + v;
+        sum = t;
+    }
+    volatile float inv = 1.0f / sum;
+    for (float &v : k) { volatile float t = v * inv; v = t; }
+    return k;
+}
+
+template <int N, bool EXACT>
+int run_passes(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+    const int taps = (int)k.size();
+    P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
+    P.wp_len = P.steps + N - 1;
+    std::vector<float> wp((size_t)P.wp_len, 0.0f);
+    for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = k[(size_t)t];
+    void *wdev;
+    PFE_TRY(pfe_small_upload(ctx, wp.data(), wp.size() * sizeof(float), &wdev));
+    P.wp = (const float *)wdev;
+    const int wp_pad = (P.wp_len + 3) & ~3;
+
+    // H pass
+    {
+        const int tile_len = skew(31 * N + P.steps, N) + 1;
+        int warps = 4;
+        size_t smem = (size_t)wp_pad * 4 + (size_t)warps * tile_len * 16;
+        if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 4 + (size_t)tile_len * 16; }
+        if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
+        const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
+        unsigned blocks = (unsigned)std::min<uint64_t>((ntask + warps - 1) / warps, (uint64_t)ctx->sm_count * 8);
+        if (warps == 4) {
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4><<<blocks, 128, smem, ctx->stream>>>(P));
+        } else {
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1><<<blocks, 32, smem, ctx->stream>>>(P));
+        }
+        PFE_LAUNCHED(ctx);
+    }
+    // V pass
+    {
+        size_t smem = (size_t)wp_pad * 4;
+        if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+        if (smem > 48 * 1024)
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
+        PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
+        PFE_LAUNCHED(ctx);
+    }
+    return PFE_OK;
+}
+
+template <bool EXACT>
+int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    const int taps = (int)k.size();
+    // pick the register-block size that wastes the fewest padded steps per output
+    auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + 6.0) / n; };
+    int best = 1;
+    if (taps >= 3) {
+        best = 4;
+        if (taps >= 9 && cost(8) < cost(best)) best = 8;
+        if (taps >= 17 && cost(16) < cost(best)) best = 16;
+    }
+    switch (best) {
+        case 16: return run_passes<16, EXACT>(ctx, P, k);
+        case 8: return run_passes<8, EXACT>(ctx, P, k);
+        case 4: return run_passes<4, EXACT>(ctx, P, k);
+        default: return run_passes<1, EXACT>(ctx, P, k);
+    }
+}
+
+int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pitch, uint32_t dst_pitch,
+                 uint32_t rw, uint32_t rh, float sigma, uint32_t flags, const uint8_t *orig, float amount,
+                 const uint8_t *mask, uint32_t mask_pitch) {
+    int radius;
+    std::vector<float> k = build_kernel(sigma, &radius);
+    if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+    void *mid;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)rw * rh * 16, &mid));
+    GaussParams P;
+    memset(&P, 0, sizeof(P));
+    P.src = src; P.mid = (float *)mid; P.dst = dst;
+    P.orig = orig; P.mask = mask; P.amount = amount;
+    P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
+    P.rw = rw; P.rh = rh; P.radius = radius;
+    return (flags & PFE_GAUSS_EXACT) ? dispatch_n<true>(ctx, P, k) : dispatch_n<false>(ctx, P, k);
+}
+
+}  // namespace
+
+int pfe_gauss_region(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t pitch_px, uint32_t x0, uint32_t y0,
+                     uint32_t rw, uint32_t rh, float sigma, uint32_t flags) {
+    const uint8_t *s = src + ((size_t)y0 * pitch_px + x0) * 4;
+    uint8_t *d = dst + ((size_t)y0 * pitch_px + x0) * 4;
+    return gauss_common(ctx, s, d, pitch_px, pitch_px, rw, rh, sigma, flags, nullptr, 0.0f, nullptr, 0);
+}
+
+extern "C" int pfe_dev_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float sigma,
+                                     const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !dst || !w || !h) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "gaussian: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!mask) return gauss_common(ctx, src, dst, w, w, w, h, sigma, flags, nullptr, 0.0f, nullptr, 0);
+    // blur_with_selection, filters.rs:141-207
+    void *bbd;
+    uint32_t init[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u};
+    PFE_TRY(pfe_small_upload(ctx, init, sizeof(init), &bbd));
+    PFE_KERNEL(ctx, "mask_bbox", bbox_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mask, w, h, (uint32_t *)bbd));
+    PFE_LAUNCHED(ctx);
+    uint32_t bb[4];
+    PFE_CUDA(ctx, cudaMemcpyAsync(bb, bbd, sizeof(bb), cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = (size_t)w * h;
+    if (bb[0] > bb[2] || bb[1] > bb[3]) {  // nothing selected: clone
+        if (dst != src) PFE_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        return PFE_OK;
+    }
+    float padf = ceilf(sigma * 3.0f);
+    uint32_t pad = padf > 0.0f ? (padf > 4.0e9f ? 0xFFFFFFFFu : (uint32_t)padf) : 0u;
+    uint32_t cx = bb[0] > pad ? bb[0] - pad : 0, cy = bb[1] > pad ? bb[1] - pad : 0;
+    uint64_t cx2 = std::min<uint64_t>((uint64_t)bb[2] + 1 + pad, w), cy2 = std::min<uint64_t>((uint64_t)bb[3] + 1 + pad, h);
+    void *tmp;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, n * 4, &tmp));
+    PFE_TRY(pfe_gauss_region(ctx, src, (uint8_t *)tmp, w, cx, cy, (uint32_t)(cx2 - cx), (uint32_t)(cy2 - cy), sigma, flags));
+    // pixels outside the crop are never selected (the crop contains the bbox), so reading the
+    // uninitialised part of tmp is masked out by mask == 0.
+    PFE_KERNEL(ctx, "select", select_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint32_t *)src, (const uint32_t *)tmp, mask,
+                                                              (uint32_t *)dst, n));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float radius,
+                               const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !dst || !w || !h || src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "sharpen: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // blur(sigma = radius) with the unsharp epilogue fused into the V pass: the blurred image is
+    // quantised to u8 in registers exactly as the reference stores it, never written to memory.
+    return gauss_common(ctx, src, dst, w, w, w, h, radius, flags, src, amount, mask, w);
+}

@@ -1,0 +1,245 @@
+// Displacement warp, Catmull-Rom mesh displacement, the fused mesh warp, and the Liquify brushes.
+// Reference: src/ops/transform.rs:1015-1345 and :1558-1761; wgpu twins
+// src/gpu/compute/liquify.rs:176 and src/gpu/compute/mesh_warp.rs:131.
+// The "Catmull-Rom" part is the control-point surface; the pixel resample is bilinear with a
+// transparent border (transform.rs:1317-1341) and that is what is built here.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+struct MeshParams {
+    float orig[PFE_MESH_MAX_POINTS * 2];
+    float def[PFE_MESH_MAX_POINTS * 2];
+    int cols, rows;
+    int has_orig;
+};
+
+__device__ __forceinline__ void cr_weights(float t, float w[4]) {  // transform.rs:1558
+    float t2 = t * t, t3 = t2 * t;
+    w[0] = -0.5f * t3 + t2 - 0.5f * t;
+    w[1] = 1.5f * t3 - 2.5f * t2 + 1.0f;
+    w[2] = -1.5f * t3 + 2.0f * t2 + 0.5f * t;
+    w[3] = 0.5f * t3 - 0.5f * t2;
+}
+
+// catmull_rom_surface, transform.rs:1589-1646
+__device__ __forceinline__ void cr_surface(const float *pts, int cols, int rows, float ug, float vg, float &ox, float &oy) {
+    const int ppr = cols + 1, nrows = rows + 1;
+    float col_f = pfe_clampf(ug, 0.0f, (float)cols - 0.0001f);
+    float row_f = pfe_clampf(vg, 0.0f, (float)rows - 0.0001f);
+    int ci = min(__float2int_rz(col_f), cols - 1), ri = min(__float2int_rz(row_f), rows - 1);
+    ci = max(ci, 0); ri = max(ri, 0);
+    float wu[4], wv[4];
+    cr_weights(row_f - (float)ri, wv);
+    cr_weights(col_f - (float)ci, wu);
+    const int rv[4] = {ri == 0 ? 0 : ri - 1, ri, min(ri + 1, nrows - 1), min(ri + 2, nrows - 1)};
+    const int cu[4] = {ci == 0 ? 0 : ci - 1, ci, min(ci + 1, ppr - 1), min(ci + 2, ppr - 1)};
+    float rx[4], ry[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float *b = pts + (size_t)rv[j] * ppr * 2;
+        const float *p0 = b + cu[0] * 2, *p1 = b + cu[1] * 2, *p2 = b + cu[2] * 2, *p3 = b + cu[3] * 2;
+        rx[j] = wu[0] * p0[0] + wu[1] * p1[0] + wu[2] * p2[0] + wu[3] * p3[0];
+        ry[j] = wu[0] * p0[1] + wu[1] * p1[1] + wu[2] * p2[1] + wu[3] * p3[1];
+    }
+    ox = wv[0] * rx[0] + wv[1] * rx[1] + wv[2] * rx[2] + wv[3] * rx[3];
+    oy = wv[0] * ry[0] + wv[1] * ry[1] + wv[2] * ry[2] + wv[3] * ry[3];
+}
+
+// generate_displacement_from_mesh[_fast], transform.rs:1670-1739, for one pixel
+__device__ __forceinline__ void mesh_disp(const MeshParams &M, const float *sdef, const float *sorig, int x, int y,
+                                          uint32_t w, uint32_t h, float &dx, float &dy) {
+    float ug = ((float)x + 0.5f) / (float)w * (float)M.cols;
+    float vg = ((float)y + 0.5f) / (float)h * (float)M.rows;
+    float ax, ay;
+    cr_surface(sdef, M.cols, M.rows, ug, vg, ax, ay);
+    if (M.has_orig) {
+        float bx, by;
+        cr_surface(sorig, M.cols, M.rows, ug, vg, bx, by);
+        dx = ax - bx; dy = ay - by;
+    } else {
+        dx = ax - ((float)x + 0.5f); dy = ay - ((float)y + 0.5f);
+    }
+}
+
+// warp_displacement_full inner body, transform.rs:1303-1342
+__device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int sh, int x, int y, float ddx, float ddy) {
+    float sx = (float)x - ddx, sy = (float)y - ddy;
+    float flx = floorf(sx), fly = floorf(sy);
+    // `as i32` saturates; anything outside [-1, size) leaves the pixel transparent
+    if (!(flx >= -1.0f) || !(fly >= -1.0f) || !(flx < (float)sw) || !(fly < (float)sh)) return 0u;
+    int x0 = (int)flx, y0 = (int)fly;
+    float fx = sx - flx, fy = sy - fly;
+    uint32_t q[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int px = x0 + (k & 1), py = y0 + (k >> 1);
+        q[k] = (px < 0 || py < 0 || px >= sw || py >= sh) ? 0u : __ldg(src + (size_t)py * sw + px);
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        float tl = (float)((q[0] >> (8 * c)) & 255u), tr = (float)((q[1] >> (8 * c)) & 255u);
+        float bl = (float)((q[2] >> (8 * c)) & 255u), br = (float)((q[3] >> (8 * c)) & 255u);
+        float top = tl + (tr - tl) * fx;
+        float bot = bl + (br - bl) * fx;
+        o[c] = pfe_round_u8(top + (bot - top) * fy);
+    }
+    return pfe_pack(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(256) warp_kernel(const uint32_t *src, int sw, int sh, const float2 *disp,
+                                                   uint32_t *dst, int w, int h) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const size_t o = (size_t)y * w + x;
+    const float2 d = __ldg(disp + o);
+    dst[o] = warp_sample(src, sw, sh, x, y, d.x, d.y);
+}
+
+__global__ void __launch_bounds__(256) mesh_disp_kernel(const __grid_constant__ MeshParams M, float2 *out, uint32_t w,
+                                                        uint32_t h) {
+    __shared__ float sdef[PFE_MESH_MAX_POINTS * 2], sorig[PFE_MESH_MAX_POINTS * 2];
+    const int np = (M.cols + 1) * (M.rows + 1) * 2;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= (int)w || y >= (int)h) return;
+    float dx, dy;
+    mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
+    out[(size_t)y * w + x] = make_float2(dx, dy);
+}
+
+// warp_mesh_catmull_rom fused: displacement stays in registers. Rows [y0, y0+rows_out).
+__global__ void __launch_bounds__(256) mesh_warp_kernel(const __grid_constant__ MeshParams M, const uint32_t *src,
+                                                        int sw, int sh, uint32_t *dst, uint32_t w, uint32_t h,
+                                                        uint32_t y0, uint32_t rows_out) {
+    __shared__ float sdef[PFE_MESH_MAX_POINTS * 2], sorig[PFE_MESH_MAX_POINTS * 2];
+    const int np = (M.cols + 1) * (M.rows + 1) * 2;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t ry = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= (int)w || ry >= rows_out) return;
+    const int y = (int)(y0 + ry);
+    float dx, dy;
+    mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
+    dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy);
+}
+
+// exp() as the reference's libm expf sees it: correctly rounded f32. Evaluated in f64 and rounded
+// once, which agrees with a <1-ulp libm except when the f64 result sits within ~1e-16 of a
+// rounding boundary.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+
+// DisplacementField::apply_*, transform.rs:1051-1200, one thread per bbox pixel
+__global__ void __launch_bounds__(256) liquify_kernel(float2 *field, uint32_t w, int kind, float cx, float cy, float r,
+                                                      float s2, float strength, float a0, float a1, int x0, int y0,
+                                                      int bw, int bh) {
+    const int lx = blockIdx.x * 32 + (threadIdx.x & 31), ly = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (lx >= bw || ly >= bh) return;
+    const int px = x0 + lx, py = y0 + ly;
+    float dx = (float)px - cx, dy = (float)py - cy;
+    float dsq = dx * dx + dy * dy;
+    if (dsq > r * r) return;
+    float2 *f = field + (size_t)py * w + px;
+    float2 v = *f;
+    if (kind == PFE_LIQ_PUSH) {
+        float wgt = exp_cr(-dsq / s2) * strength;
+        v.x += a0 * wgt; v.y += a1 * wgt;
+    } else if (kind == PFE_LIQ_EXPAND) {
+        float dist = fmaxf(sqrtf(dsq), 0.001f);
+        float t = dist / r;
+        float wgt = (1.0f - t) * (1.0f - t) * strength * 3.0f;
+        v.x += dx / dist * wgt; v.y += dy / dist * wgt;
+    } else if (kind == PFE_LIQ_CONTRACT) {
+        float dist = fmaxf(sqrtf(dsq), 0.001f);
+        float wgt = exp_cr(-dsq / s2) * strength;
+        v.x += -dx / dist * wgt * 2.0f; v.y += -dy / dist * wgt * 2.0f;
+    } else {
+        float dir = a0 != 0.0f ? 1.0f : -1.0f;
+        float wgt = exp_cr(-dsq / s2) * strength * dir;
+        v.x += -dy * wgt * 0.1f; v.y += dx * wgt * 0.1f;
+    }
+    *f = v;
+}
+
+int fill_mesh(pfe_ctx *ctx, MeshParams *M, const float *orig, const float *def, uint32_t cols, uint32_t rows) {
+    if (!def || cols == 0 || rows == 0) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "mesh: bad grid");
+    const size_t np = (size_t)(cols + 1) * (rows + 1);
+    if (np > PFE_MESH_MAX_POINTS) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "mesh: more than PFE_MESH_MAX_POINTS control points");
+    memset(M, 0, sizeof(*M));
+    memcpy(M->def, def, np * 2 * sizeof(float));
+    if (orig) memcpy(M->orig, orig, np * 2 * sizeof(float));
+    M->cols = (int)cols; M->rows = (int)rows; M->has_orig = orig ? 1 : 0;
+    return PFE_OK;
+}
+
+int f2i_sat(float v) {  // Rust `as i32`
+    if (v != v) return 0;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    return (int)v;
+}
+
+}  // namespace
+
+extern "C" int pfe_dev_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp,
+                                         uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !disp || !dst || !sw || !sh || !w || !h || src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFE_KERNEL(ctx, "warp", warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
+        (const uint32_t *)src, (int)sw, (int)sh, (const float2 *)disp, (uint32_t *)dst, (int)w, (int)h));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_mesh_displacement(pfe_ctx *ctx, const float *orig, const float *def, uint32_t cols, uint32_t rows,
+                                         uint32_t w, uint32_t h, float *out) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!out || !w || !h) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "mesh_displacement: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    MeshParams M;
+    PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
+    PFE_KERNEL(ctx, "mesh_disp", mesh_disp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(M, (float2 *)out, w, h));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *orig,
+                                 const float *def, uint32_t cols, uint32_t rows, uint32_t w, uint32_t h, uint32_t y0,
+                                 uint32_t rows_out, uint8_t *dst) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !dst || !sw || !sh || !w || !h || !rows_out || (uint64_t)y0 + rows_out > h)
+        return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "mesh_warp: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    MeshParams M;
+    PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
+    PFE_KERNEL(ctx, "mesh_warp", mesh_warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8)), 256, 0, ctx->stream>>>(
+        M, (const uint32_t *)src, (int)sw, (int)sh, (uint32_t *)dst, w, h, y0, rows_out));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_liquify(pfe_ctx *ctx, float *field, uint32_t w, uint32_t h, int kind, float cx, float cy,
+                               float radius, float strength, float a0, float a1, int32_t bbox[4]) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!field || !w || !h || kind < 0 || kind > 3) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "liquify: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const float r = fmaxf(radius, 1.0f);
+    const float sigma = r / 3.0f;
+    const float s2 = 2.0f * sigma * sigma;
+    int x0 = std::max(f2i_sat(floorf(cx - r)), 0), y0 = std::max(f2i_sat(floorf(cy - r)), 0);
+    int x1 = std::min(f2i_sat(ceilf(cx + r)), (int)w), y1 = std::min(f2i_sat(ceilf(cy + r)), (int)h);
+    if (bbox) { bbox[0] = x0; bbox[1] = y0; bbox[2] = x1; bbox[3] = y1; }
+    if (x1 <= x0 || y1 <= y0) return PFE_OK;
+    PFE_KERNEL(ctx, "liquify", liquify_kernel<<<dim3(pfe_div_up(x1 - x0, 32), pfe_div_up(y1 - y0, 8)), 256, 0, ctx->stream>>>(
+        (float2 *)field, w, kind, cx, cy, r, s2, strength, a0, a1, x0, y0, x1 - x0, y1 - y0));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}

@@ -1,0 +1,410 @@
+"""Thin Python handle on a pfe_ctx: numpy arrays go through the host tier (pfe_*), torch CUDA
+tensors through the device tier (pfe_dev_*) on torch's current stream.  No compute happens in
+Python and nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is plumbing only (device memory + streams for the device tier)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _np_u8(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_tensor(a):
+        if not a.is_contiguous():
+            raise ValueError("device tensors must be contiguous")
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Layer(dict):
+    """Marshalled form of one `Layer` for flatten(): keys rgba, mask, opacity, blend, visible, kind, adj."""
+
+
+def make_layer(rgba=None, opacity=1.0, blend=0, visible=True, mask=None, kind=0, adj=()):
+    return Layer(rgba=rgba, mask=mask, opacity=float(opacity), blend=int(blend), visible=bool(visible),
+                 kind=int(kind), adj=tuple(float(v) for v in adj))
+
+
+class Engine:
+    """One CUDA device, one stream, scratch buffers (`pfe_ctx`)."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = L.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.pfe_ctx_create(device, C.byref(h))
+        if rc != L.PFE_OK:
+            raise L.PfeError(rc, "pfe_ctx_create (the pixel engine needs a CUDA device; there is no CPU path)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pfe_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != L.PFE_OK:
+            raise L.PfeError(rc, (self.lib.pfe_last_error(self.h) or b"").decode())
+
+    def sync(self):
+        self._ck(self.lib.pfe_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.pfe_ctx_launch_count(self.h))
+
+    def profile(self, enable: bool):
+        """Bracket every kernel launch with CUDA events (see pfe_ctx_profile)."""
+        self._ck(self.lib.pfe_ctx_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.pfe_ctx_profile_read(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
+    def use_torch_stream(self):
+        """Enqueue device-tier work on torch's current stream for this device."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self._ck(self.lib.pfe_ctx_set_stream(self.h, C.c_void_p(s)))
+
+    def _dev(self, *xs) -> bool:
+        """True when the call should use the device tier (any torch tensor among the images)."""
+        d = any(_is_tensor(x) for x in xs if x is not None)
+        if d:
+            for x in xs:
+                if x is not None and not (_is_tensor(x) and x.is_cuda):
+                    raise ValueError("device-tier call: every image must be a CUDA tensor")
+            self.use_torch_stream()
+        return d
+
+    def _out_like(self, src, shape=None, dtype=None):
+        if _is_tensor(src):
+            return torch.empty(shape or tuple(src.shape), dtype=dtype or src.dtype, device=src.device)
+        return np.empty(shape or src.shape, dtype or src.dtype)
+
+    @staticmethod
+    def _hw(img):
+        if img.ndim != 3 or img.shape[2] != 4:
+            raise ValueError("images are (h, w, 4) uint8")
+        return int(img.shape[0]), int(img.shape[1])
+
+    def _prep(self, img):
+        return img if _is_tensor(img) else _np_u8(img)
+
+    def _prep_mask(self, mask, h, w):
+        if mask is None:
+            return None
+        if _is_tensor(mask):
+            if tuple(mask.shape) != (h, w):
+                raise ValueError("mask must be (h, w)")
+            return mask
+        return _np_u8(mask, (h, w))
+
+    # -- flatten ------------------------------------------------------------------------------
+    def _layer_array(self, layers: Sequence[Layer], h, w):
+        arr = (L.LayerDesc * max(len(layers), 1))()
+        keep = []
+        dev = None
+        for i, Ly in enumerate(layers):
+            rgba, mask = Ly.get("rgba"), Ly.get("mask")
+            if rgba is not None:
+                rgba = self._prep(rgba)
+                if tuple(rgba.shape) != (h, w, 4):
+                    raise ValueError(f"layer {i}: expected {(h, w, 4)}, got {tuple(rgba.shape)}")
+                dev = _is_tensor(rgba) if dev is None else dev
+                if _is_tensor(rgba) != dev:
+                    raise ValueError("all layers must be on the same side (numpy or CUDA tensors)")
+                arr[i].rgba = _ptr(rgba).value
+                keep.append(rgba)
+            if mask is not None:
+                mask = self._prep_mask(mask, h, w)
+                arr[i].mask = _ptr(mask).value
+                keep.append(mask)
+            arr[i].opacity = Ly.get("opacity", 1.0)
+            arr[i].blend = Ly.get("blend", 0) & 0xFF
+            arr[i].visible = 1 if Ly.get("visible", True) else 0
+            arr[i].kind = Ly.get("kind", 0)
+            for j, v in enumerate(Ly.get("adj", ())):
+                arr[i].adj[j] = v
+        return arr, keep, bool(dev)
+
+    def flatten(self, layers: Sequence[Layer], w: int, h: int, active=None, out=None):
+        """CanvasState::composite over marshalled layers (canvas_state.rs:482)."""
+        arr, keep, dev = self._layer_array(layers, h, w)
+        if dev:
+            self.use_torch_stream()
+            dst = out if out is not None else torch.empty((h, w, 4), dtype=torch.uint8, device=keep[0].device)
+            self._ck(self.lib.pfe_dev_flatten(self.h, arr, len(layers), w, h, _ptr(active), _ptr(dst)))
+        else:
+            dst = out if out is not None else np.empty((h, w, 4), np.uint8)
+            active = None if active is None else _np_u8(active)
+            self._ck(self.lib.pfe_flatten(self.h, arr, len(layers), w, h, _ptr(active), _ptr(dst)))
+        return dst
+
+    def flatten_gaussian(self, layers, w, h, sigma, active=None, exact=False, out=None):
+        """Host tier only: composite() then parallel_gaussian_blur without leaving the device."""
+        arr, keep, dev = self._layer_array(layers, h, w)
+        if dev:
+            raise ValueError("flatten_gaussian is the host-tier fused call; chain flatten + gaussian_blur on device")
+        dst = out if out is not None else np.empty((h, w, 4), np.uint8)
+        active = None if active is None else _np_u8(active)
+        self._ck(self.lib.pfe_flatten_gaussian(self.h, arr, len(layers), w, h, _ptr(active), C.c_float(sigma),
+                                               _ptr(dst), L.GAUSS_EXACT if exact else 0))
+        return dst
+
+    # -- single-image ops -----------------------------------------------------------------------
+    def _img_op(self, host_fn, dev_fn, src, mask, out, *mid, tail=()):
+        src = self._prep(src)
+        h, w = self._hw(src)
+        mask = self._prep_mask(mask, h, w)
+        dst = out if out is not None else self._out_like(src)
+        fn = dev_fn if self._dev(src, mask, dst) else host_fn
+        self._ck(fn(self.h, _ptr(src), w, h, *mid, _ptr(mask), _ptr(dst), *tail))
+        return dst
+
+    def gaussian_blur(self, src, sigma, mask=None, exact=False, out=None):
+        return self._img_op(self.lib.pfe_gaussian_blur, self.lib.pfe_dev_gaussian_blur, src, mask, out,
+                            C.c_float(sigma), tail=(L.GAUSS_EXACT if exact else 0,))
+
+    def box_blur(self, src, radius, mask=None, out=None):
+        return self._img_op(self.lib.pfe_box_blur, self.lib.pfe_dev_box_blur, src, mask, out, C.c_float(radius))
+
+    def motion_blur(self, src, angle_deg, distance, mask=None, out=None):
+        return self._img_op(self.lib.pfe_motion_blur, self.lib.pfe_dev_motion_blur, src, mask, out,
+                            C.c_float(angle_deg), C.c_float(distance))
+
+    def median(self, src, radius, mask=None, out=None):
+        return self._img_op(self.lib.pfe_median, self.lib.pfe_dev_median, src, mask, out, C.c_uint32(radius))
+
+    def sharpen(self, src, amount, radius, mask=None, exact=False, out=None):
+        return self._img_op(self.lib.pfe_sharpen, self.lib.pfe_dev_sharpen, src, mask, out, C.c_float(amount),
+                            C.c_float(radius), tail=(L.GAUSS_EXACT if exact else 0,))
+
+    def vignette(self, src, amount, softness, mask=None, out=None):
+        return self._img_op(self.lib.pfe_vignette, self.lib.pfe_dev_vignette, src, mask, out, C.c_float(amount),
+                            C.c_float(softness))
+
+    def adjust(self, src, op, params=(), luts=None, mask=None, occupancy=None, out=None):
+        src = self._prep(src)
+        h, w = self._hw(src)
+        mask = self._prep_mask(mask, h, w)
+        d = L.AdjustDesc()
+        d.op = int(op)
+        for i, v in enumerate(params):
+            d.params[i] = float(v)
+        luts_np = None
+        if luts is not None:
+            luts_np = _np_u8(np.asarray(luts).reshape(-1))
+            d.luts = luts_np.ctypes.data
+        dst = out if out is not None else self._out_like(src)
+        if self._dev(src, mask, dst):
+            if occupancy is not None and not _is_tensor(occupancy):
+                occupancy = torch.as_tensor(np.ascontiguousarray(occupancy, dtype=np.uint8), device=src.device)
+            self._ck(self.lib.pfe_dev_adjust(self.h, _ptr(src), w, h, C.byref(d), _ptr(mask), _ptr(occupancy), _ptr(dst)))
+        else:
+            occupancy = None if occupancy is None else _np_u8(occupancy)
+            self._ck(self.lib.pfe_adjust(self.h, _ptr(src), w, h, C.byref(d), _ptr(mask), _ptr(occupancy), _ptr(dst)))
+        return dst
+
+    def channel_minmax(self, src, mask=None):
+        src = self._prep(src)
+        h, w = self._hw(src)
+        mask = self._prep_mask(mask, h, w)
+        out = np.zeros(6, np.uint8)
+        fn = self.lib.pfe_dev_channel_minmax if self._dev(src, mask) else self.lib.pfe_channel_minmax
+        self._ck(fn(self.h, _ptr(src), w, h, _ptr(mask), _ptr(out)))
+        return out
+
+    # -- LUT builders (host arithmetic inside the library) -----------------------------------
+    def levels_lut(self, in_black, in_white, gamma, out_black=0.0, out_white=255.0):
+        lut = np.empty(256, np.uint8)
+        self.lib.pfe_build_levels_lut(in_black, in_white, gamma, out_black, out_white, _ptr(lut))
+        return lut
+
+    def levels_lut_script(self, in_black, in_white, gamma):
+        lut = np.empty(256, np.uint8)
+        self.lib.pfe_build_levels_lut_script(in_black, in_white, gamma, _ptr(lut))
+        return lut
+
+    def stretch_lut(self, mn, mx):
+        lut = np.empty(256, np.uint8)
+        self.lib.pfe_build_stretch_lut(int(mn), int(mx), _ptr(lut))
+        return lut
+
+    def curves_lut(self, points):
+        pts = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1, 2))
+        lut = np.empty(256, np.uint8)
+        self.lib.pfe_build_curves_lut(_ptr(pts), len(pts), _ptr(lut))
+        return lut
+
+    def compose_curve_luts(self, five):
+        five = _np_u8(np.asarray(five).reshape(5 * 256))
+        out = np.empty(4 * 256, np.uint8)
+        self.lib.pfe_compose_curve_luts(_ptr(five), _ptr(out))
+        return out.reshape(4, 256)
+
+    # -- warps --------------------------------------------------------------------------------
+    def warp_displacement(self, src, disp, out=None):
+        src = self._prep(src)
+        sh, sw = self._hw(src)
+        if not _is_tensor(disp):
+            disp = np.ascontiguousarray(disp, dtype=np.float32)
+        h, w = int(disp.shape[0]), int(disp.shape[1])
+        dst = out if out is not None else self._out_like(src, (h, w, 4))
+        fn = self.lib.pfe_dev_warp_displacement if self._dev(src, disp, dst) else self.lib.pfe_warp_displacement
+        self._ck(fn(self.h, _ptr(src), sw, sh, _ptr(disp), w, h, _ptr(dst)))
+        return dst
+
+    @staticmethod
+    def _pts(p):
+        return None if p is None else np.ascontiguousarray(np.asarray(p, np.float32).reshape(-1, 2))
+
+    def mesh_displacement(self, original, deformed, cols, rows, w, h, device_out=False):
+        original, deformed = self._pts(original), self._pts(deformed)
+        if device_out:
+            self.use_torch_stream()
+            out = torch.empty((h, w, 2), dtype=torch.float32, device=f"cuda:{self.device}")
+            self._ck(self.lib.pfe_dev_mesh_displacement(self.h, _ptr(original), _ptr(deformed), cols, rows, w, h, _ptr(out)))
+        else:
+            out = np.empty((h, w, 2), np.float32)
+            self._ck(self.lib.pfe_mesh_displacement(self.h, _ptr(original), _ptr(deformed), cols, rows, w, h, _ptr(out)))
+        return out
+
+    def mesh_warp(self, src, original, deformed, cols, rows, w, h, y0=0, rows_out=None, out=None):
+        src = self._prep(src)
+        sh, sw = self._hw(src)
+        original, deformed = self._pts(original), self._pts(deformed)
+        rows_out = h if rows_out is None else rows_out
+        dst = out if out is not None else self._out_like(src, (rows_out, w, 4))
+        if self._dev(src, dst):
+            self._ck(self.lib.pfe_dev_mesh_warp(self.h, _ptr(src), sw, sh, _ptr(original), _ptr(deformed), cols, rows,
+                                                w, h, y0, rows_out, _ptr(dst)))
+        else:
+            if y0 != 0 or rows_out != h:
+                raise ValueError("band form is device-tier only")
+            self._ck(self.lib.pfe_mesh_warp(self.h, _ptr(src), sw, sh, _ptr(original), _ptr(deformed), cols, rows, w, h,
+                                            _ptr(dst)))
+        return dst
+
+    def liquify(self, field, kind, cx, cy, radius, strength, a0=0.0, a1=0.0):
+        """In place on `field` ((h, w, 2) float32, numpy or CUDA tensor). Returns the bbox."""
+        h, w = int(field.shape[0]), int(field.shape[1])
+        bbox = (C.c_int32 * 4)()
+        if _is_tensor(field):
+            self._dev(field)
+            fn = self.lib.pfe_dev_liquify
+        else:
+            if field.dtype != np.float32 or not field.flags.c_contiguous:
+                raise ValueError("field must be contiguous float32")
+            fn = self.lib.pfe_liquify
+        self._ck(fn(self.h, _ptr(field), w, h, int(kind), cx, cy, radius, strength, a0, a1, bbox))
+        return tuple(bbox)
+
+    # -- brush --------------------------------------------------------------------------------
+    @staticmethod
+    def brush_desc(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False):
+        b = L.BrushDesc()
+        b.size, b.hardness, b.flow = size, hardness, flow
+        b.anti_aliased = 1 if anti_aliased else 0
+        for i in range(4):
+            b.color[i] = color[i]
+        b.is_eraser = 1 if is_eraser else 0
+        return b
+
+    def brush_lut(self, brush):
+        lut = np.empty(256, np.uint8)
+        self.lib.pfe_brush_lut(C.byref(brush), _ptr(lut))
+        return lut
+
+    def brush_line_centres(self, w, h, x0, y0, x1, y1):
+        cap = int(np.ceil(np.hypot(x1 - x0, y1 - y0))) + 4
+        c = np.empty((cap, 2), np.float32)
+        n = self.lib.pfe_brush_line_centres(w, h, x0, y0, x1, y1, _ptr(c), cap)
+        return c[:n].copy()
+
+    def brush_stamps(self, image, brush, centres, selection_mask=None):
+        """In place on `image`; centres is (n, 2) float32 host data."""
+        h, w = self._hw(image)
+        centres = np.ascontiguousarray(np.asarray(centres, np.float32).reshape(-1, 2))
+        selection_mask = self._prep_mask(selection_mask, h, w)
+        if _is_tensor(image):
+            self._dev(image, selection_mask)
+            fn = self.lib.pfe_dev_brush_stamps
+        else:
+            if image.dtype != np.uint8 or not image.flags.c_contiguous:
+                raise ValueError("image must be contiguous uint8")
+            fn = self.lib.pfe_brush_stamps
+        self._ck(fn(self.h, _ptr(image), w, h, C.byref(brush), _ptr(centres), len(centres), _ptr(selection_mask)))
+        return image
+
+    # -- tiles (host only) --------------------------------------------------------------------
+    def flat_to_tiles(self, flat, want_tiles=True):
+        flat = _np_u8(flat)
+        h, w = self._hw(flat)
+        cyn, cxn = (h + 63) // 64, (w + 63) // 64
+        occ = np.empty((cyn, cxn), np.uint8)
+        tiles = np.zeros((cyn * cxn, 64, 64, 4), np.uint8) if want_tiles else None
+        rc = self.lib.pfe_flat_to_tiles(_ptr(flat), w, h, _ptr(occ), _ptr(tiles))
+        if rc != L.PFE_OK:
+            raise L.PfeError(rc, "pfe_flat_to_tiles")
+        return occ, tiles
+
+    def tiles_to_flat(self, table, w, h):
+        """table: list (row-major chunk grid) of (64,64,4) uint8 arrays or None."""
+        n = len(table)
+        arr = (C.c_void_p * n)()
+        keep = []
+        for i, t in enumerate(table):
+            if t is not None:
+                t = _np_u8(t, (64, 64, 4))
+                keep.append(t)
+                arr[i] = t.ctypes.data
+        flat = np.empty((h, w, 4), np.uint8)
+        rc = self.lib.pfe_tiles_to_flat(arr, w, h, _ptr(flat))
+        if rc != L.PFE_OK:
+            raise L.PfeError(rc, "pfe_tiles_to_flat")
+        return flat
+
+
+_default = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on cuda:LOCAL_RANK (one process per GPU)."""
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default

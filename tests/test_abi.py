@@ -1,0 +1,151 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds for sm_100a, loads, exports
+every symbol include/pfe_b200.h declares, and refuses to compute without a GPU (no CPU fallback).
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pfe_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from paintfe_b200 import build, _lib
+
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pfe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    from paintfe_b200 import _lib
+
+    names = declared_symbols()
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in pfe_b200.h but not exported by libpfe_b200.so"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_library_is_sm100a_only(lib):
+    from paintfe_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_library_does_not_link_oracle_or_torch(lib):
+    from paintfe_b200 import _lib
+
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "torch" not in out and "libpython" not in out
+
+
+def test_struct_layouts_match_oracle_and_header():
+    from oracle import pfo
+    from paintfe_b200 import _lib
+
+    assert C.sizeof(_lib.LayerDesc) == C.sizeof(pfo.LayerDesc) == 88
+    assert C.sizeof(_lib.BrushDesc) == C.sizeof(pfo.Brush) == 36
+    assert C.sizeof(_lib.AdjustDesc) == 48
+
+
+def test_host_lut_builders_match_oracle(lib, oracle):
+    """LUT construction is host arithmetic inside the library; it must equal the oracle's."""
+    from paintfe_b200 import _lib
+
+    def lut(fn, *a):
+        out = np.empty(256, np.uint8)
+        fn(*a, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    for args in [(20.0, 235.0, 1.2, 0.0, 255.0), (0.0, 255.0, 1.0, 0.0, 255.0), (50.0, 60.0, 0.3, 10.0, 200.0),
+                 (0.0, 255.0, 2.2, 255.0, 0.0)]:
+        assert np.array_equal(lut(lib.pfe_build_levels_lut, *args), oracle.levels_lut(*args))
+    for args in [(10.0, 240.0, 0.8), (0.0, 255.0, 1.0), (100.0, 90.0, 5.0)]:
+        assert np.array_equal(lut(lib.pfe_build_levels_lut_script, *args), oracle.levels_lut_script(*args))
+    for mn, mx in [(0, 255), (10, 200), (50, 50), (200, 10), (3, 4)]:
+        assert np.array_equal(lut(lib.pfe_build_stretch_lut, mn, mx), oracle.stretch_lut(mn, mx))
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 2, 3, 5, 9):
+        xs = np.sort(rng.uniform(0, 255, n)).astype(np.float32)
+        ys = rng.uniform(-20, 275, n).astype(np.float32)
+        pts = np.ascontiguousarray(np.stack([xs, ys], 1)) if n else np.zeros((0, 2), np.float32)
+        out = np.empty(256, np.uint8)
+        lib.pfe_build_curves_lut(pts.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out, oracle.curves_lut(pts)), n
+    # identity when all channels disabled (tests/visual_adjustments.rs:228-246)
+    ident = np.tile(np.arange(256, dtype=np.uint8), (5, 1))
+    out = np.empty(1024, np.uint8)
+    lib.pfe_compose_curve_luts(ident.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out.reshape(4, 256), oracle.compose_curve_luts(ident))
+    five = rng.integers(0, 256, (5, 256), dtype=np.uint8)
+    lib.pfe_compose_curve_luts(five.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out.reshape(4, 256), oracle.compose_curve_luts(five))
+
+
+def test_brush_host_helpers_match_oracle(lib, oracle):
+    from paintfe_b200 import _lib
+
+    for size, hard, aa in [(20.0, 1.0, True), (30.0, 0.0, True), (20.0, 1.0, False), (3.0, 1.0, True),
+                           (60.0, 0.5, True), (0.001, 0.5, True), (10.0, 2.0, False)]:
+        b = _lib.BrushDesc()
+        b.size, b.hardness, b.flow, b.anti_aliased = size, hard, 1.0, int(aa)
+        out = np.empty(256, np.uint8)
+        lib.pfe_brush_lut(C.byref(b), out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(out, oracle.brush_lut(oracle.make_brush(size, hard, aa, (0, 0, 0, 1))))
+    for seg in [(4.0, 32.0, 60.0, 32.0), (4.0, 4.0, 60.0, 60.0), (32.0, 32.0, 32.0, 32.0), (-5.0, 10.0, 70.0, 80.0),
+                (10.0, 50.0, 54.0, 10.0)]:
+        cap = 256
+        c = np.empty((cap, 2), np.float32)
+        n = lib.pfe_brush_line_centres(64, 64, *seg, c.ctypes.data_as(C.c_void_p), cap)
+        assert np.array_equal(c[:n], oracle.brush_line_centres(64, 64, *seg))
+
+
+def test_tile_marshalling_matches_oracle(lib, oracle):
+    """TiledImage::from_rgba_image / to_rgba_image semantics, incl. ragged edges and empty chunks."""
+    from paintfe_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    for (w, h) in [(64, 64), (65, 63), (200, 130), (1, 1), (129, 64)]:
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[: h // 2, : w // 2, 3] = 0  # a fully transparent region with non-zero RGB
+        cyn, cxn = (h + 63) // 64, (w + 63) // 64
+        occ = np.empty((cyn, cxn), np.uint8)
+        tiles = np.zeros((cyn * cxn, 64, 64, 4), np.uint8)
+        assert lib.pfe_flat_to_tiles(img.ctypes.data_as(C.c_void_p), w, h, occ.ctypes.data_as(C.c_void_p),
+                                     tiles.ctypes.data_as(C.c_void_p)) == 0
+        table = (C.c_void_p * (cyn * cxn))()
+        for i in range(cyn * cxn):
+            if occ.reshape(-1)[i]:
+                table[i] = tiles[i].ctypes.data
+        flat = np.empty_like(img)
+        assert lib.pfe_tiles_to_flat(table, w, h, flat.ctypes.data_as(C.c_void_p)) == 0
+        exp, exp_occ = oracle.tiled_roundtrip(img)
+        assert np.array_equal(occ, exp_occ)
+        assert np.array_equal(flat, exp)
+
+
+def test_no_cpu_fallback_without_gpu(lib):
+    """On a box without a CUDA device the engine must fail loudly, never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from paintfe_b200 import _lib, engine
+
+    h = C.c_void_p()
+    assert lib.pfe_ctx_create(0, C.byref(h)) == -4  # PFE_ERR_NO_DEVICE
+    with pytest.raises(_lib.PfeError):
+        engine.Engine(0)

@@ -1,0 +1,453 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+
+Bar: bit-exact for flatten, adjustments, box, motion, median, vignette, sharpen/gaussian in EXACT
+mode, warps and brush stamps; <= 1 level per channel for the default (FMA) Gaussian family and for
+liquify-derived warps (device exp vs libm expf).
+"""
+import numpy as np
+import pytest
+
+import fixtures as fx
+from test_oracle_golden import ADJUST, BLEND_IDS, FILTERS, SCRIPT, STROKES, BLACK
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from paintfe_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def exact(a, b, what=""):
+    bad, mx = fx.diff_stats(np.asarray(a), np.asarray(b))
+    assert bad == 0, f"{what}: {bad} mismatched pixels, max diff {mx}"
+
+
+def within1(a, b, what=""):
+    d = np.abs(np.asarray(a).astype(np.int16) - np.asarray(b).astype(np.int16))
+    assert d.max() <= 1, f"{what}: max diff {d.max()}"
+    return float((d > 0).mean())
+
+
+# ---------------------------------------------------------------------------------------------
+# goldens, straight through the engine
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(BLEND_IDS))
+def test_blend_golden(eng, name):
+    from paintfe_b200.engine import make_layer
+
+    out = eng.flatten([make_layer(fx.checkerboard(64, 64)), make_layer(fx.blend_foreground(), blend=BLEND_IDS[name])], 64, 64)
+    exact(out, fx.golden("blend", name), name)
+
+
+def test_blend_half_opacity_golden(eng):
+    from paintfe_b200.engine import make_layer
+
+    out = eng.flatten([make_layer(fx.checkerboard(64, 64)), make_layer(fx.gradient(64, 64), opacity=0.5)], 64, 64)
+    exact(out, fx.golden("blend", "normal_half_opacity"))
+
+
+class _EngAsOracle:
+    """Adapter so the golden tables written for the oracle drive the engine unchanged."""
+
+    def __init__(self, eng, exact_gauss=True):
+        self.e, self.x = eng, exact_gauss
+        from oracle import pfo
+        for k in dir(pfo):
+            if k.isupper():
+                setattr(self, k, getattr(pfo, k))
+
+    def gaussian_blur(self, im, s, mask=None): return self.e.gaussian_blur(im, s, mask=mask, exact=self.x)
+    def box_blur(self, im, r, mask=None): return self.e.box_blur(im, r, mask=mask)
+    def motion_blur(self, im, a, d, mask=None): return self.e.motion_blur(im, a, d, mask=mask)
+    def median(self, im, r, mask=None): return self.e.median(im, r, mask=mask)
+    def sharpen(self, im, a, r, mask=None): return self.e.sharpen(im, a, r, mask=mask, exact=self.x)
+    def vignette(self, im, a, s, mask=None): return self.e.vignette(im, a, s, mask=mask)
+    def adjust(self, im, op, params=(), luts=None, mask=None, occupancy=None):
+        return self.e.adjust(im, op, params, luts=luts, mask=mask, occupancy=occupancy)
+    def levels_lut(self, *a): return self.e.levels_lut(*a)
+    def levels_lut_script(self, *a): return self.e.levels_lut_script(*a)
+    def stretch_lut(self, mn, mx): return self.e.stretch_lut(mn, mx)
+
+
+@pytest.mark.parametrize("name", sorted(FILTERS))
+def test_filter_golden_exact(eng, name):
+    exact(FILTERS[name](_EngAsOracle(eng, True), fx.gradient(64, 64)), fx.golden("filters", name), name)
+
+
+@pytest.mark.parametrize("name", sorted(FILTERS))
+def test_filter_golden_fast(eng, name):
+    within1(FILTERS[name](_EngAsOracle(eng, False), fx.gradient(64, 64)), fx.golden("filters", name), name)
+
+
+@pytest.mark.parametrize("name", sorted(ADJUST))
+def test_adjust_golden(eng, oracle, name):
+    if name == "auto_levels":
+        im = fx.gradient(64, 64)
+        mm = eng.channel_minmax(im)
+        luts = np.stack([eng.stretch_lut(mm[0], mm[1]), eng.stretch_lut(mm[2], mm[3]), eng.stretch_lut(mm[4], mm[5]),
+                         np.arange(256, dtype=np.uint8)])
+        out = eng.adjust(im, oracle.LUT_RGBA, luts=luts)
+    else:
+        out = ADJUST[name](_EngAsOracle(eng), fx.gradient(64, 64))
+    occ, tiles = eng.flat_to_tiles(out)
+    table = [tiles[i] if occ.reshape(-1)[i] else None for i in range(occ.size)]
+    exact(eng.tiles_to_flat(table, 64, 64), fx.golden("adjustments", name), name)
+
+
+@pytest.mark.parametrize("name", sorted(SCRIPT))
+def test_scripting_golden(eng, name):
+    exact(SCRIPT[name](_EngAsOracle(eng), fx.gradient(64, 64)), fx.golden("scripting", name), name)
+
+
+def test_warp_goldens(eng, oracle):
+    exact(eng.warp_displacement(fx.gradient_32(), fx.swirl_field()), fx.golden("transform", "displacement_swirl"))
+    orig = fx.uniform_grid(2, 2, 32.0, 32.0)
+    deformed = orig.copy()
+    deformed[4] = (20.0, 20.0)
+    exact(eng.mesh_warp(fx.gradient_32(), orig, deformed, 2, 2, 32, 32), fx.golden("transform", "mesh_warp_deformed"))
+    d = eng.mesh_displacement(orig, deformed, 2, 2, 32, 32)
+    assert np.array_equal(d, oracle.mesh_displacement(orig, deformed, 2, 2, 32, 32))
+    exact(eng.warp_displacement(fx.gradient_32(), d), fx.golden("transform", "mesh_warp_deformed"))
+    field = np.zeros((32, 32, 2), np.float32)
+    assert eng.liquify(field, 0, 16.0, 16.0, 10.0, 0.8, 3.0, 0.0) == (6, 6, 26, 26)
+    within1(eng.warp_displacement(fx.gradient_32(), field), fx.golden("transform", "displacement_radial_push"))
+
+
+@pytest.mark.parametrize("name", sorted(STROKES))
+def test_stroke_golden(eng, name):
+    size, hard, aa, color, eraser, bg, kind, args = STROKES[name]
+    img = fx.solid(64, 64, (255, 255, 255, 255) if bg == "white" else (0, 0, 0, 0))
+    b = eng.brush_desc(size, hard, aa, color, is_eraser=eraser)
+    centres = np.asarray(args, np.float32) if kind == "stamp" else eng.brush_line_centres(64, 64, *args)
+    eng.brush_stamps(img, b, centres)
+    exact(img, fx.golden("tools", name), name)
+
+
+def test_stroke_selection_mask_golden(eng):
+    img = fx.solid(64, 64, (0, 0, 0, 0))
+    mask = np.zeros((64, 64), np.uint8)
+    mask[:, :32] = 255
+    eng.brush_stamps(img, eng.brush_desc(40.0, 1.0, True, BLACK), [(32.0, 32.0)], selection_mask=mask)
+    exact(img, fx.golden("tools", "brush_with_selection_mask"))
+
+
+# ---------------------------------------------------------------------------------------------
+# randomised parity against the oracle
+# ---------------------------------------------------------------------------------------------
+SIZES = [(64, 64), (67, 45), (1, 1), (3, 130), (256, 192), (129, 1)]
+
+
+def _stack(rng, oracle, w, h, n, alpha="uniform", masks=True, adj=True):
+    from paintfe_b200.engine import make_layer
+
+    o_layers, e_layers = [], []
+    for i in range(n):
+        kind = 0
+        if adj and rng.random() < 0.15:
+            kind = int(rng.integers(1, 5))
+        if kind:
+            params = {1: (float(2.0 ** rng.uniform(-2, 2)),), 2: (float(rng.uniform(-100, 100)), float(rng.uniform(-100, 100))),
+                      3: (), 4: tuple(float(v) for v in rng.uniform(-0.5, 1.2, 16))}[kind]
+            kw = dict(opacity=float(rng.choice([1.0, 0.0, rng.uniform(0, 1)])), kind=kind, adj=params,
+                      visible=bool(rng.random() > 0.1))
+            o_layers.append(oracle.make_layer(**kw))
+            e_layers.append(make_layer(**kw))
+            continue
+        img = fx.random_rgba(rng, w, h, alpha)
+        mask = None
+        if masks and rng.random() < 0.3:
+            mask = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            mask[rng.random((h, w)) < 0.5] = 0
+        kw = dict(opacity=float(rng.choice([1.0, 0.0, 0.5, 1.5, -0.2, rng.uniform(0, 1)])),
+                  blend=int(rng.integers(0, 25)) if rng.random() > 0.05 else 77, visible=bool(rng.random() > 0.1), mask=mask)
+        o_layers.append(oracle.make_layer(img, **kw))
+        e_layers.append(make_layer(img, **kw))
+    return o_layers, e_layers
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("alpha", ["uniform", "binary"])
+def test_flatten_random_stacks(eng, oracle, w, h, alpha):
+    rng = np.random.default_rng(w * 1000 + h + (7 if alpha == "binary" else 0))
+    for n in (0, 1, 2, 7, 16, 40):
+        ol, el = _stack(rng, oracle, w, h, n, alpha)
+        exact(eng.flatten(el, w, h), oracle.flatten(ol, w, h), f"{w}x{h} n={n}")
+
+
+def test_flatten_every_mode_every_byte_pair(eng, oracle):
+    """All 25 modes over a dense sweep of (base, top) channel/alpha values, several opacities."""
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(11)
+    v = np.arange(256, dtype=np.uint8)
+    base = np.empty((256, 256, 4), np.uint8)
+    top = np.empty((256, 256, 4), np.uint8)
+    base[..., 0] = v[:, None]; top[..., 0] = v[None, :]
+    for op in (1.0, 0.5, 0.25, 0.999):
+        base[..., 1] = rng.integers(0, 256, (256, 256)); top[..., 1] = rng.integers(0, 256, (256, 256))
+        base[..., 2] = v[None, ::-1]; top[..., 2] = v[:, None]
+        base[..., 3] = rng.choice([0, 1, 127, 128, 254, 255], (256, 256)); top[..., 3] = rng.choice([0, 1, 64, 200, 254, 255], (256, 256))
+        for mode in range(25):
+            got = eng.flatten([make_layer(base, blend=14), make_layer(top, blend=mode, opacity=op)], 256, 256)
+            exp = oracle.flatten([oracle.make_layer(base, blend=14), oracle.make_layer(top, blend=mode, opacity=op)], 256, 256)
+            exact(got, exp, f"mode {mode} opacity {op}")
+
+
+def test_flatten_active_chunks_with_adjustment(eng, oracle):
+    """Adjustment layers only touch active chunks (canvas_state.rs:579-584)."""
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(5)
+    w, h = 200, 130
+    img = fx.random_rgba(rng, w, h)
+    img[:64, 64:128] = 0
+    _, occ = oracle.tiled_roundtrip(img)
+    assert occ[0, 1] == 0
+    kw = [dict(rgba=img), dict(kind=3, opacity=1.0)]
+    got = eng.flatten([make_layer(**k) for k in kw], w, h, active=occ)
+    exp = oracle.flatten([oracle.make_layer(**k) for k in kw], w, h, active=occ)
+    exact(got, exp)
+    assert tuple(got[10, 70]) == (0, 0, 0, 0)
+    dense = eng.flatten([make_layer(**k) for k in kw], w, h)
+    assert tuple(dense[10, 70]) == (255, 255, 255, 0)
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(700, 300)])
+@pytest.mark.parametrize("sigma", [0.0, 0.3, 0.7, 2.0, 5.0, 9.5, 20.0])
+def test_gaussian_random(eng, oracle, w, h, sigma):
+    rng = np.random.default_rng(int(sigma * 10) + w)
+    img = fx.random_rgba(rng, w, h)
+    exp = oracle.gaussian_blur(img, sigma)
+    exact(eng.gaussian_blur(img, sigma, exact=True), exp, f"exact {w}x{h} s={sigma}")
+    within1(eng.gaussian_blur(img, sigma), exp, f"fast {w}x{h} s={sigma}")
+
+
+def test_gaussian_selection_mask(eng, oracle):
+    rng = np.random.default_rng(2)
+    w, h = 300, 200
+    img = fx.random_rgba(rng, w, h)
+    for mask in (np.zeros((h, w), np.uint8), np.full((h, w), 255, np.uint8), None):
+        if mask is None:
+            mask = np.zeros((h, w), np.uint8)
+            mask[40:90, 100:260] = rng.integers(0, 2, (50, 160), dtype=np.uint8) * 200
+            mask[199, 0] = 1
+        exact(eng.gaussian_blur(img, 4.0, mask=mask, exact=True), oracle.gaussian_blur(img, 4.0, mask=mask))
+    small = np.zeros((h, w), np.uint8)
+    small[100:110, 150:160] = 255
+    exact(eng.gaussian_blur(img, 6.0, mask=small, exact=True), oracle.gaussian_blur(img, 6.0, mask=small))
+
+
+@pytest.mark.parametrize("w,h", SIZES + [(700, 300)])
+def test_box_motion_median_vignette_sharpen_random(eng, oracle, w, h):
+    rng = np.random.default_rng(w * 7 + h)
+    img = fx.random_rgba(rng, w, h)
+    mask = (rng.random((h, w)) < 0.7).astype(np.uint8) * 255
+    for r in (0.4, 0.5, 1.0, 3.0, 10.5, 40.0):
+        exact(eng.box_blur(img, r), oracle.box_blur(img, r), f"box r={r}")
+    exact(eng.box_blur(img, 3.0, mask=mask), oracle.box_blur(img, 3.0, mask=mask), "box mask")
+    for ang, dist in ((45.0, 10.0), (0.0, 0.5), (90.0, 1.0), (-30.0, 25.5), (200.0, 3.0)):
+        exact(eng.motion_blur(img, ang, dist), oracle.motion_blur(img, ang, dist), f"motion {ang},{dist}")
+    exact(eng.motion_blur(img, 30.0, 7.0, mask=mask), oracle.motion_blur(img, 30.0, 7.0, mask=mask), "motion mask")
+    for r in (0, 1, 2, 3, 7):
+        exact(eng.median(img, r), oracle.median(img, r), f"median r={r}")
+    exact(eng.median(img, 2, mask=mask), oracle.median(img, 2, mask=mask), "median mask")
+    for a, s in ((0.8, 0.5), (0.0, 0.3), (1.5, 0.0), (0.5, 2.0)):
+        exact(eng.vignette(img, a, s), oracle.vignette(img, a, s), f"vignette {a},{s}")
+    exact(eng.vignette(img, 0.5, 0.3, mask=mask), oracle.vignette(img, 0.5, 0.3, mask=mask), "vignette mask")
+    for a, r in ((1.0, 1.0), (0.0, 2.0), (2.5, 3.0), (1.0, 0.0)):
+        exp = oracle.sharpen(img, a, r)
+        exact(eng.sharpen(img, a, r, exact=True), exp, f"sharpen {a},{r}")
+        d = np.abs(eng.sharpen(img, a, r).astype(int) - exp.astype(int)).max()
+        assert d <= int(np.ceil(abs(a))) + 1  # a +-1 blur level moves the result by <= amount (+ rounding)
+    exact(eng.sharpen(img, 1.0, 2.0, mask=mask, exact=True), oracle.sharpen(img, 1.0, 2.0, mask=mask), "sharpen mask")
+
+
+def test_median_large_radius(eng, oracle):
+    rng = np.random.default_rng(9)
+    img = fx.random_rgba(rng, 90, 70)
+    for r in (12, 40):
+        exact(eng.median(img, r), oracle.median(img, r), f"median r={r}")
+
+
+def test_adjust_all_ops_random(eng, oracle):
+    rng = np.random.default_rng(21)
+    for (w, h) in [(67, 45), (256, 192), (1, 1)]:
+        img = fx.random_rgba(rng, w, h)
+        img[0, 0] = (10, 10, 10, 255)  # grey pixel: HSL's achromatic branch
+        mask = (rng.random((h, w)) < 0.6).astype(np.uint8) * 255
+        lut1 = rng.integers(0, 256, 256, dtype=np.uint8)
+        lut4 = rng.integers(0, 256, (4, 256), dtype=np.uint8)
+        cases = [(oracle.INVERT, (), None), (oracle.INVERT_ALPHA, (), None), (oracle.SEPIA, (), None),
+                 (oracle.DESATURATE, (), None), (oracle.BRIGHTNESS_CONTRAST, (30.0, 20.0), None),
+                 (oracle.BRIGHTNESS_CONTRAST, (-100.0, 100.0), None), (oracle.HSL, (30.0, -20.0, 10.0), None),
+                 (oracle.HSL, (-170.0, 80.0, -30.0), None), (oracle.HSL, (0.0, 0.0, 0.0), None),
+                 (oracle.EXPOSURE, (2.0,), None), (oracle.EXPOSURE, (0.3,), None), (oracle.LUT_RGB, (), lut1),
+                 (oracle.LUT_RGBA, (), lut4), (oracle.TEMPERATURE_TINT, (30.0, 10.0), None),
+                 (oracle.HIGHLIGHTS_SHADOWS, (30.0, -20.0), None), (oracle.S_INVERT, (), None),
+                 (oracle.S_DESATURATE, (), None), (oracle.S_SEPIA, (), None), (oracle.S_SEPIA_STRENGTH, (0.4,), None),
+                 (oracle.S_BRIGHTNESS_CONTRAST, (20.0, 10.0), None), (oracle.S_HSL, (10.0, 15.0, 0.0), None),
+                 (oracle.S_HSL, (-200.0, -50.0, 20.0), None), (oracle.S_EXPOSURE, (1.7,), None),
+                 (oracle.S_LUT_RGB, (), lut1)]
+        for op, params, luts in cases:
+            exact(eng.adjust(img, op, params, luts=luts), oracle.adjust(img, op, params, luts=luts), f"op {op} {params}")
+            exact(eng.adjust(img, op, params, luts=luts, mask=mask), oracle.adjust(img, op, params, luts=luts, mask=mask),
+                  f"op {op} masked")
+        _, occ = oracle.tiled_roundtrip(img)
+        occ[0, 0] = 0
+        exact(eng.adjust(img, oracle.INVERT, occupancy=occ), oracle.adjust(img, oracle.INVERT, occupancy=occ), "occupancy")
+    mm = eng.channel_minmax(img, mask=mask)
+    sel = (mask > 0) & (img[..., 3] != 0)
+    exp = [f(img[..., c][sel]) for c in range(3) for f in (np.min, np.max)] if sel.any() else [255, 0] * 3
+    assert list(mm) == [int(v) for v in exp]
+
+
+def test_adjust_exhaustive_hsl_inputs(eng, oracle):
+    """Every (r,g,b) on a 64-step lattice plus random triples, both HSL variants."""
+    g = np.arange(0, 256, 5, dtype=np.uint8)
+    r_, g_, b_ = np.meshgrid(g, g, g, indexing="ij")
+    n = r_.size
+    w = 512
+    h = (n + w - 1) // w
+    img = np.zeros((h * w, 4), np.uint8)
+    img[:n, 0], img[:n, 1], img[:n, 2] = r_.ravel(), g_.ravel(), b_.ravel()
+    img[:, 3] = 255
+    img = img.reshape(h, w, 4)
+    for op in (oracle.HSL, oracle.S_HSL):
+        for p in ((30.0, -20.0, 10.0), (123.0, 40.0, -5.0), (-359.0, 100.0, 0.0)):
+            exact(eng.adjust(img, op, p), oracle.adjust(img, op, p), f"hsl {op} {p}")
+
+
+def test_warps_random(eng, oracle):
+    rng = np.random.default_rng(4)
+    for (w, h) in [(67, 45), (256, 192)]:
+        src = fx.random_rgba(rng, w, h)
+        disp = rng.normal(0, 6, (h, w, 2)).astype(np.float32)
+        disp[0, 0] = (1e9, -1e9); disp[1, 1] = (np.nan, 0.0); disp[2, 2] = (0.5, w + 5.0)
+        exact(eng.warp_displacement(src, disp), oracle.warp_displacement(src, disp), "warp")
+        # source of a different size than the field
+        src2 = fx.random_rgba(rng, w // 2 + 1, h + 3)
+        exact(eng.warp_displacement(src2, disp), oracle.warp_displacement(src2, disp), "warp src!=dst size")
+        for cols, rows in ((2, 2), (6, 6), (1, 3), (15, 15)):
+            orig = fx.uniform_grid(cols, rows, float(w), float(h))
+            deformed = (orig + rng.normal(0, 4, orig.shape)).astype(np.float32)
+            d_full = oracle.mesh_displacement(orig, deformed, cols, rows, w, h)
+            assert np.array_equal(eng.mesh_displacement(orig, deformed, cols, rows, w, h), d_full)
+            d_fast = oracle.mesh_displacement(None, deformed, cols, rows, w, h)
+            assert np.array_equal(eng.mesh_displacement(None, deformed, cols, rows, w, h), d_fast)
+            exact(eng.mesh_warp(src, orig, deformed, cols, rows, w, h), oracle.mesh_warp(src, orig, deformed, cols, rows, w, h),
+                  f"mesh {cols}x{rows}")
+
+
+def test_liquify_random(eng, oracle):
+    rng = np.random.default_rng(6)
+    w, h = 200, 150
+    fo = np.zeros((h, w, 2), np.float32)
+    fe = np.zeros((h, w, 2), np.float32)
+    for i in range(24):
+        kind = i % 4
+        cx, cy = float(rng.uniform(-10, w + 10)), float(rng.uniform(-10, h + 10))
+        r, s = float(rng.uniform(0.5, 60)), float(rng.uniform(0.1, 1.0))
+        a0, a1 = (float(rng.uniform(-5, 5)), float(rng.uniform(-5, 5))) if kind == 0 else (float(i % 8 < 4), 0.0)
+        assert eng.liquify(fe, kind, cx, cy, r, s, a0, a1) == oracle.liquify(fo, kind, cx, cy, r, s, a0, a1)
+    # device exp is the correctly rounded value; libm expf may differ from it by one ulp on rare inputs
+    assert np.allclose(fe, fo, rtol=3e-7, atol=1e-7)
+    assert (fe != fo).mean() < 0.02
+    src = fx.random_rgba(rng, w, h)
+    within1(eng.warp_displacement(src, fe), oracle.warp_displacement(src, fo), "liquify warp")
+
+
+def test_brush_random_strokes(eng, oracle):
+    rng = np.random.default_rng(8)
+    w, h = 200, 150
+    for trial in range(12):
+        size, hard = float(rng.uniform(1, 50)), float(rng.uniform(-0.2, 1.2))
+        aa, eraser = bool(trial & 1), bool(trial & 2)
+        color = tuple(float(v) for v in rng.uniform(0, 1, 4))
+        flow = float(rng.choice([1.0, 0.5, 0.02]))
+        img_o = fx.random_rgba(rng, w, h) if trial % 3 else fx.solid(w, h, (0, 0, 0, 0))
+        img_e = img_o.copy()
+        sel = None if trial % 4 else (rng.random((h, w)) < 0.5).astype(np.uint8)
+        bo = oracle.make_brush(size, hard, aa, color, flow=flow, is_eraser=eraser)
+        be = eng.brush_desc(size, hard, aa, color, flow=flow, is_eraser=eraser)
+        pts = rng.uniform(-20, 220, (5, 2))
+        centres = []
+        for a, b in zip(pts[:-1], pts[1:]):
+            seg = (float(a[0]), float(a[1]), float(b[0]), float(b[1]))
+            oracle.brush_line(img_o, bo, *seg, sel_mask=sel)
+            centres.append(eng.brush_line_centres(w, h, *seg))
+        centres = np.concatenate(centres) if centres else np.zeros((0, 2), np.float32)
+        eng.brush_stamps(img_e, be, centres, selection_mask=sel)
+        exact(img_e, img_o, f"stroke {trial}")
+
+
+# ---------------------------------------------------------------------------------------------
+# device tier == host tier; chained ops
+# ---------------------------------------------------------------------------------------------
+def test_device_tier_matches_host_tier(eng, oracle):
+    import torch
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(12)
+    w, h = 320, 200
+    ol, el = _stack(rng, oracle, w, h, 9, masks=True, adj=True)
+    dev = [make_layer(None if L["rgba"] is None else torch.from_numpy(L["rgba"]).cuda(),
+                      opacity=L["opacity"], blend=L["blend"], visible=L["visible"],
+                      mask=None if L["mask"] is None else torch.from_numpy(L["mask"]).cuda(), kind=L["kind"], adj=L["adj"])
+           for L in el]
+    if all(L["rgba"] is None for L in el):
+        pytest.skip("no raster layer drawn")
+    flat_dev = eng.flatten(dev, w, h)
+    exp = oracle.flatten(ol, w, h)
+    exact(flat_dev.cpu().numpy(), exp, "dev flatten")
+    blur_dev = eng.gaussian_blur(flat_dev, 3.0, exact=True)
+    exact(blur_dev.cpu().numpy(), oracle.gaussian_blur(exp, 3.0), "dev gaussian")
+    hsl_dev = eng.adjust(blur_dev, oracle.S_HSL, (10.0, 15.0, 0.0))
+    exact(hsl_dev.cpu().numpy(), oracle.adjust(oracle.gaussian_blur(exp, 3.0), oracle.S_HSL, (10.0, 15.0, 0.0)), "dev hsl")
+    exact(eng.flatten_gaussian(el, w, h, 3.0, exact=True), oracle.gaussian_blur(exp, 3.0), "fused host call")
+    launches = eng.launches
+    assert launches > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size (BASELINE config) properties
+# ---------------------------------------------------------------------------------------------
+def test_full_size_8k_flatten_and_gaussian_crops(eng, oracle):
+    """7680x4320, 16 layers cycling modes (config 2) + Gaussian sigma=20 (headline): since flatten is
+    per-pixel and the blur has finite support, any crop can be re-derived by the oracle from the
+    same crop (+halo) of the inputs."""
+    import torch
+    from paintfe_b200.engine import make_layer
+
+    w, h, n = 7680, 4320, 16
+    g = torch.Generator(device="cuda").manual_seed(0x5EED)
+    layers = [torch.randint(0, 256, (h, w, 4), dtype=torch.uint8, device="cuda", generator=g) for _ in range(n)]
+    meta = [dict(blend=i % 25, opacity=0.25 + 0.05 * i) for i in range(n)]
+    flat = eng.flatten([make_layer(t, **m) for t, m in zip(layers, meta)], w, h)
+    blur = eng.gaussian_blur(flat, 20.0, exact=True)
+    blur_fast = eng.gaussian_blur(flat, 20.0)
+    r = 60
+    rng = np.random.default_rng(1)
+    crops = [(0, 0), (w - 256, h - 256), (w - 256, 0), (0, h - 256)] + [(int(rng.integers(0, w - 256)), int(rng.integers(0, h - 256))) for _ in range(3)]
+    for (cx, cy) in crops:
+        x0, y0, x1, y1 = max(cx - r, 0), max(cy - r, 0), min(cx + 256 + r, w), min(cy + 256 + r, h)
+        sub = [oracle.make_layer(t[y0:y1, x0:x1].cpu().numpy(), **m) for t, m in zip(layers, meta)]
+        exp_flat = oracle.flatten(sub, x1 - x0, y1 - y0)
+        exact(flat[y0:y1, x0:x1].cpu().numpy(), exp_flat, f"flatten crop {cx},{cy}")
+        exp_blur = oracle.gaussian_blur(exp_flat, 20.0)
+        # pixels whose support lies inside the halo'd crop (or is clamped by a true image edge)
+        ix0, iy0 = cx - x0, cy - y0
+        got = blur[cy:cy + 256, cx:cx + 256].cpu().numpy()
+        exact(got, exp_blur[iy0:iy0 + 256, ix0:ix0 + 256], f"gaussian crop {cx},{cy}")
+        within1(blur_fast[cy:cy + 256, cx:cx + 256].cpu().numpy(), exp_blur[iy0:iy0 + 256, ix0:ix0 + 256])
+    # idempotence-style property: flattening [flat] alone with Normal/1.0 returns flat where alpha==255
+    again = eng.flatten([make_layer(flat)], w, h)
+    opaque = flat[..., 3] == 255
+    assert torch.equal(again[opaque], flat[opaque])
