@@ -50,8 +50,10 @@ typedef struct pfe_ctx pfe_ctx;
  * One context = one device + one stream + scratch buffers. */
 int pfe_ctx_create(int device, pfe_ctx **out);
 int pfe_ctx_destroy(pfe_ctx *ctx);
-/* Run on a caller-owned cudaStream_t (e.g. a framework's current stream); NULL = own stream. */
+/* Run on a caller-owned cudaStream_t (e.g. a framework's current stream). NULL is the legacy
+ * default stream, as in CUDA itself; pfe_ctx_use_own_stream switches back to the context's own. */
 int pfe_ctx_set_stream(pfe_ctx *ctx, void *cuda_stream);
+int pfe_ctx_use_own_stream(pfe_ctx *ctx);
 int pfe_ctx_sync(pfe_ctx *ctx);
 const char *pfe_last_error(const pfe_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pfe_ctx_create": (C.c_int, [C.c_int, C.POINTER(_ctx)]),
     "pfe_ctx_destroy": (C.c_int, [_ctx]),
     "pfe_ctx_set_stream": (C.c_int, [_ctx, _vp]),
+    "pfe_ctx_use_own_stream": (C.c_int, [_ctx]),
     "pfe_ctx_sync": (C.c_int, [_ctx]),
     "pfe_last_error": (C.c_char_p, [_ctx]),
     "pfe_ctx_launch_count": (C.c_uint64, [_ctx]),

@@ -21,6 +21,7 @@ HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE),
 # -fmad=false: the reference (Rust) never contracts a*b+c; bit-exactness depends on it.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    "-Werror", "cross-execution-space-call",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
 ]
 

@@ -160,7 +160,13 @@ int pfe_ctx_destroy(pfe_ctx *c) {
 
 int pfe_ctx_set_stream(pfe_ctx *c, void *s) {
     if (!c) return PFE_ERR_INVALID_ARG;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = (cudaStream_t)s;
+    return PFE_OK;
+}
+
+int pfe_ctx_use_own_stream(pfe_ctx *c) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    c->stream = c->own_stream;
     return PFE_OK;
 }
 

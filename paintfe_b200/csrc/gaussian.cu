@@ -18,7 +18,9 @@
 //     are served by L2.
 // EXACT=true keeps the reference's separate multiply and add (bit-exact, 2x the FP32 work);
 // EXACT=false uses FMA (one rounding per tap instead of two; results within +-1 level).
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ void tap(float4 &acc, const float4 &in, float w) {
         _Pragma("unroll") for (int j = 0; j < N; j++) tap<N, EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N]); \
     }
 
-__device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
+__host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
 // ---- H pass: u8 -> f32 ----------------------------------------------------------------------
 template <int N, bool EXACT, int WARPS>
@@ -126,6 +128,27 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
 }
 
 // ---- V pass: f32 -> u8 ----------------------------------------------------------------------
+// Round, clamp and store one output pixel; optionally the unsharp-mask epilogue.
+__device__ __forceinline__ void v_store(const GaussParams &P, const float4 &acc, int x, int y) {
+    uint32_t r8 = pfe_round_u8(acc.x), g8 = pfe_round_u8(acc.y), b8 = pfe_round_u8(acc.z), a8 = pfe_round_u8(acc.w);
+    uint32_t outv;
+    if (P.orig) {  // sharpen_core, stylize.rs:116-134
+        uint32_t s = reinterpret_cast<const uint32_t *>(P.orig)[(size_t)y * P.dst_pitch + x];
+        if (P.mask && P.mask[(size_t)y * P.mask_pitch + x] == 0) {
+            outv = s;
+        } else {
+            float sr = (float)(s & 255u), sg = (float)((s >> 8) & 255u), sb = (float)((s >> 16) & 255u);
+            outv = pfe_pack(pfe_round_u8(sr + P.amount * (sr - (float)r8)), pfe_round_u8(sg + P.amount * (sg - (float)g8)),
+                            pfe_round_u8(sb + P.amount * (sb - (float)b8)), s >> 24);
+        }
+    } else {
+        outv = pfe_pack(r8, g8, b8, a8);
+    }
+    reinterpret_cast<uint32_t *>(P.dst)[(size_t)y * P.dst_pitch + x] = outv;
+}
+
+// Direct variant: inputs straight from global memory (L1/L2 serve the (N+2r)/N-fold re-reads).
+// Used when the tile variant's shared-memory footprint does not fit (very large sigma).
 template <int N, bool EXACT>
 __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ GaussParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -148,27 +171,80 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
         for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(V_LOAD) }
 #undef V_LOAD
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-            const int y = y0 + j;
-            if (y >= rh) break;
-            uint32_t r8 = pfe_round_u8(acc[j].x), g8 = pfe_round_u8(acc[j].y), b8 = pfe_round_u8(acc[j].z),
-                     a8 = pfe_round_u8(acc[j].w);
-            uint32_t outv;
-            if (P.orig) {  // sharpen_core, stylize.rs:116-134
-                uint32_t s = reinterpret_cast<const uint32_t *>(P.orig)[(size_t)y * P.dst_pitch + x];
-                if (P.mask && P.mask[(size_t)y * P.mask_pitch + x] == 0) {
-                    outv = s;
-                } else {
-                    float sr = (float)(s & 255u), sg = (float)((s >> 8) & 255u), sb = (float)((s >> 16) & 255u);
-                    outv = pfe_pack(pfe_round_u8(sr + P.amount * (sr - (float)r8)),
-                                    pfe_round_u8(sg + P.amount * (sg - (float)g8)),
-                                    pfe_round_u8(sb + P.amount * (sb - (float)b8)), s >> 24);
-                }
-            } else {
-                outv = pfe_pack(r8, g8, b8, a8);
-            }
-            reinterpret_cast<uint32_t *>(P.dst)[(size_t)y * P.dst_pitch + x] = outv;
+        for (int j = 0; j < N; j++)
+            if (y0 + j < rh) v_store(P, acc[j], x, y0 + j);
+    }
+}
+
+// Tile variant.  A CTA owns a 32-pixel-wide column strip tile of WARPS*N output rows. Its input rows
+// (tile height + 2r) are brought into shared memory once, one 512-byte cp.async.bulk per row
+// (clamp-to-edge is just a clamped source row index), completion tracked by an mbarrier.  Each warp
+// then streams its N+2r rows out of shared memory with conflict-free LDS.128, so a row of the f32
+// intermediate crosses L2 ~(TH+2r)/TH times instead of (N+2r)/N times.  Two CTAs per SM: one
+// computes while the other's copies are in flight.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int N, bool EXACT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TH = WARPS * N;
+    const int rows = TH + P.steps - N;
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // rows x 32 float4
+    float *wsm = reinterpret_cast<float *>(smem_raw + (size_t)rows * 512);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)rows * 512 + (size_t)((P.wp_len + 3) & ~3) * 4);
+    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    const uint32_t bar_s = smem_addr(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rw = (int)P.rw, rh = (int)P.rh;
+    const int tx = (rw + 31) / 32, ty = (rh + TH - 1) / TH;
+    const int ntiles = tx * ty;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
+        const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
+        const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * (uint32_t)rows) : "memory");
+        for (int rr = threadIdx.x; rr < rows; rr += WARPS * 32) {
+            const int sy = min(max(y0 - P.radius + rr, 0), rh - 1);
+            const float4 *src = reinterpret_cast<const float4 *>(P.mid) + (size_t)sy * rw + x0;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_addr(tile + (size_t)rr * 32)),
+                         "l"(src), "r"(row_bytes), "r"(bar_s)
+                         : "memory");
         }
+        uint32_t done;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_s), "r"(phase) : "memory");
+        } while (!done);
+        phase ^= 1u;
+
+        float4 acc[N];
+        float R[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+        const float4 *col = tile + (size_t)warp * N * 32 + lane;
+#define VT_LOAD(i) col[(size_t)(i) * 32]
+        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(VT_LOAD) }
+#undef VT_LOAD
+        const int x = x0 + lane, yw = y0 + warp * N;
+        if (x < rw) {
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                if (yw + j < rh) v_store(P, acc[j], x, yw + j);
+        }
+        // generic-proxy reads of the tile must be ordered before the next async-proxy overwrite
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
     }
 }
 
@@ -255,14 +331,26 @@ int run_passes(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
         }
         PFE_LAUNCHED(ctx);
     }
-    // V pass
+    // V pass: tile variant when its shared-memory footprint fits, else the direct variant
     {
-        size_t smem = (size_t)wp_pad * 4;
-        if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
-        if (smem > 48 * 1024)
-            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
-        PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
+        const size_t extra = (size_t)wp_pad * 4 + 64;
+        auto tile_smem = [&](int warps) { return (size_t)(warps * N + P.steps - N) * 512 + extra; };
+        const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
+        const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.rh, 8 * N);
+        if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
+            const size_t smem = tile_smem(8);
+            const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned blocks = std::min<unsigned>(tiles8, (unsigned)(ctx->sm_count * per_sm));
+            PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8><<<blocks, 256, smem, ctx->stream>>>(P));
+        } else {
+            size_t smem = (size_t)wp_pad * 4;
+            if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+            if (smem > 48 * 1024)
+                PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
+            PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
+        }
         PFE_LAUNCHED(ctx);
     }
     return PFE_OK;
