@@ -32,7 +32,7 @@ struct GaussParams {
     const uint8_t *src;   // H: region origin inside the source image
     float *mid;           // rw*rh*4 f32 intermediate
     uint8_t *dst;         // V: region origin inside the destination image
-    const float *wp;      // padded weights, device
+    const float2 *wp;     // padded weights, each duplicated into both halves of a float2, device
     const uint8_t *orig;  // sharpen: original pixels (same geometry as dst), else null
     const uint8_t *mask;  // sharpen: selection mask plane (w*h) at region origin, or null
     float amount;         // sharpen amount
@@ -45,40 +45,50 @@ struct GaussParams {
     int wp_len;           // steps + N - 1
 };
 
-// wp[m] = w[m-(N-1)] inside the kernel support, 0 outside: lets every output use the same
-// unrolled N-step body.  Zero-weight taps are exact no-ops in both modes (x*0 + acc == acc).
-template <int N, bool EXACT>
-__device__ __forceinline__ void tap(float4 &acc, const float4 &in, float w) {
+// One RGBA accumulator as two packed f32x2 halves: sm_100's FFMA2 / FMUL2 / FADD2 retire two IEEE
+// f32 operations per issue slot, which leaves the other slot free for the loads and keeps the FMA
+// pipe (not the issue port) the limiter.  EXACT mode (separate multiply and add, as the reference
+// does) must stay scalar: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even
+// under --fmad=false, whereas scalar __fmul_rn/__fadd_rn are never fused.
+struct Acc4 {
+    float2 lo, hi;  // (r,g) (b,a)
+};
+template <bool EXACT>
+__device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2) {
+    const float2 ilo = make_float2(in.x, in.y), ihi = make_float2(in.z, in.w);
     if (EXACT) {
-        acc.x = __fadd_rn(acc.x, __fmul_rn(in.x, w));
-        acc.y = __fadd_rn(acc.y, __fmul_rn(in.y, w));
-        acc.z = __fadd_rn(acc.z, __fmul_rn(in.z, w));
-        acc.w = __fadd_rn(acc.w, __fmul_rn(in.w, w));
+        acc.lo.x = __fadd_rn(acc.lo.x, __fmul_rn(in.x, w2.x));
+        acc.lo.y = __fadd_rn(acc.lo.y, __fmul_rn(in.y, w2.x));
+        acc.hi.x = __fadd_rn(acc.hi.x, __fmul_rn(in.z, w2.x));
+        acc.hi.y = __fadd_rn(acc.hi.y, __fmul_rn(in.w, w2.x));
     } else {
-        acc.x = __fmaf_rn(in.x, w, acc.x);
-        acc.y = __fmaf_rn(in.y, w, acc.y);
-        acc.z = __fmaf_rn(in.z, w, acc.z);
-        acc.w = __fmaf_rn(in.w, w, acc.w);
+        acc.lo = __ffma2_rn(ilo, w2, acc.lo);
+        acc.hi = __ffma2_rn(ihi, w2, acc.hi);
     }
 }
 
-// One group of N steps with a static rotation phase. LOAD(i) yields the input for step i.
-#define PFE_GAUSS_GROUP(LOAD)                                                         \
-    _Pragma("unroll") for (int s = 0; s < N; s++) {                                   \
-        const int i = g + s;                                                          \
-        R[(s + N - 1) % N] = wsm[i + N - 1];                                          \
-        const float4 in = LOAD(i);                                                    \
-        _Pragma("unroll") for (int j = 0; j < N; j++) tap<N, EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N]); \
+// wp[m] = w[m-(N-1)] inside the kernel support, 0 outside: every output uses the same unrolled
+// N-step body; zero-weight taps are exact no-ops in both modes (x*0 + acc == acc).  The N live
+// weights sit in a rotating register window R[] (one uniform 8-byte smem read per step).
+// LOAD(s) yields the input for step g+s.
+#define PFE_GAUSS_GROUP(LOAD)                                                                   \
+    _Pragma("unroll") for (int s = 0; s < N; s++) {                                             \
+        R[(s + N - 1) % N] = wsm[g + s + N - 1];                                                \
+        const float4 in = LOAD(s);                                                              \
+        _Pragma("unroll") for (int j = 0; j < N; j++) tap<EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N]); \
     }
 
 __host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
 // ---- H pass: u8 -> f32 ----------------------------------------------------------------------
+// A warp owns one row segment of 32*N pixels. The u8 pixels are converted to f32 once while being
+// staged into a skewed shared-memory tile (one pad float4 every N, so lane stride N+1 keeps
+// LDS.128 conflict free); results return through the same tile for fully coalesced stores.
 template <int N, bool EXACT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *wsm = reinterpret_cast<float *>(smem_raw);
-    const int wp_pad = (P.wp_len + 3) & ~3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
+    const int wp_pad = (P.wp_len + 1) & ~1;
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
     float4 *tiles = reinterpret_cast<float4 *>(wsm + wp_pad);
@@ -104,20 +114,25 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
                                            (float)((v >> 16) & 255u), (float)(v >> 24));
         }
         __syncwarp();
-        float4 acc[N];
-        float R[N];
+        Acc4 acc[N];
+        float2 R[N];
 #pragma unroll
-        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
-        const int base = lane * N;
-#define H_LOAD(i) tile[skew(base + (i), N)]
-        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(H_LOAD) }
+        // input i of this lane sits at skew(lane*N + i) = lane*(N+1) + i + i/N
+        const float4 *tl = tile + lane * (N + 1);
+        for (int g = 0; g < P.steps; g += N) {
+            const float4 *tg = tl + g + g / N;  // within a group i/N is constant: step s is tg[s]
+#define H_LOAD(s) tg[s]
+            PFE_GAUSS_GROUP(H_LOAD)
 #undef H_LOAD
+        }
         __syncwarp();
         // results through the tile -> coalesced 512 B stores
+        float4 *to = tile + lane * (N + 1);
 #pragma unroll
-        for (int j = 0; j < N; j++) tile[skew(base + j, N)] = acc[j];
+        for (int j = 0; j < N; j++) to[j] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
         __syncwarp();
         float4 *out = reinterpret_cast<float4 *>(P.mid) + (size_t)y * P.rw;
 #pragma unroll 4
@@ -129,8 +144,8 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
 
 // ---- V pass: f32 -> u8 ----------------------------------------------------------------------
 // Round, clamp and store one output pixel; optionally the unsharp-mask epilogue.
-__device__ __forceinline__ void v_store(const GaussParams &P, const float4 &acc, int x, int y) {
-    uint32_t r8 = pfe_round_u8(acc.x), g8 = pfe_round_u8(acc.y), b8 = pfe_round_u8(acc.z), a8 = pfe_round_u8(acc.w);
+__device__ __forceinline__ void v_store(const GaussParams &P, const Acc4 &acc, int x, int y) {
+    uint32_t r8 = pfe_round_u8(acc.lo.x), g8 = pfe_round_u8(acc.lo.y), b8 = pfe_round_u8(acc.hi.x), a8 = pfe_round_u8(acc.hi.y);
     uint32_t outv;
     if (P.orig) {  // sharpen_core, stylize.rs:116-134
         uint32_t s = reinterpret_cast<const uint32_t *>(P.orig)[(size_t)y * P.dst_pitch + x];
@@ -151,8 +166,8 @@ __device__ __forceinline__ void v_store(const GaussParams &P, const float4 &acc,
 // Used when the tile variant's shared-memory footprint does not fit (very large sigma).
 template <int N, bool EXACT>
 __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ GaussParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *wsm = reinterpret_cast<float *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
     for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
     __syncthreads();
     const int x = blockIdx.x * 128 + threadIdx.x;
@@ -160,42 +175,55 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
     const int rh = (int)P.rh;
     const float4 *mid = reinterpret_cast<const float4 *>(P.mid) + x;
     for (int y0 = blockIdx.y * N; y0 < rh; y0 += gridDim.y * N) {
-        float4 acc[N];
-        float R[N];
+        Acc4 acc[N];
+        float2 R[N];
 #pragma unroll
-        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
         const int ybase = y0 - P.radius;
-#define V_LOAD(i) __ldg(mid + (size_t)min(max(ybase + (i), 0), rh - 1) * P.rw)
-        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(V_LOAD) }
+        for (int g = 0; g < P.steps; g += N) {
+#define V_LOAD(s) __ldg(mid + (size_t)min(max(ybase + g + (s), 0), rh - 1) * P.rw)
+            PFE_GAUSS_GROUP(V_LOAD)
 #undef V_LOAD
+        }
 #pragma unroll
         for (int j = 0; j < N; j++)
             if (y0 + j < rh) v_store(P, acc[j], x, y0 + j);
     }
 }
 
-// Tile variant.  A CTA owns a 32-pixel-wide column strip tile of WARPS*N output rows. Its input rows
-// (tile height + 2r) are brought into shared memory once, one 512-byte cp.async.bulk per row
-// (clamp-to-edge is just a clamped source row index), completion tracked by an mbarrier.  Each warp
-// then streams its N+2r rows out of shared memory with conflict-free LDS.128, so a row of the f32
-// intermediate crosses L2 ~(TH+2r)/TH times instead of (N+2r)/N times.  Two CTAs per SM: one
-// computes while the other's copies are in flight.
+// Tile variant.  A CTA owns a 32-pixel-wide tile of WARPS*N output rows. Its input rows (tile
+// height + 2r) are brought into shared memory once, one 512-byte cp.async.bulk per row (clamp-to-
+// edge is just a clamped source row index).  The rows are split into kChunks groups, each with its
+// own mbarrier, and every warp waits only for the chunk it is about to read, so the FMA stream
+// starts while most of the tile is still in flight.  Each warp then streams its N+2r rows out of
+// shared memory with conflict-free LDS.128, so a row of the f32 intermediate crosses L2
+// ~(TH+2r)/TH times instead of (N+2r)/N times.  Two CTAs per SM when the tile fits twice.
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+constexpr int kChunks = 8;
 
 template <int N, bool EXACT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TH = WARPS * N;
     const int rows = TH + P.steps - N;
+    const int chunk_rows = (rows + kChunks - 1) / kChunks;
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // rows x 32 float4
-    float *wsm = reinterpret_cast<float *>(smem_raw + (size_t)rows * 512);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)rows * 512 + (size_t)((P.wp_len + 3) & ~3) * 4);
+    float2 *wsm = reinterpret_cast<float2 *>(smem_raw + (size_t)rows * 512);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)rows * 512 + (size_t)((P.wp_len + 1) & ~1) * 8);
     for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
-    const uint32_t bar_s = smem_addr(bar);
+    const uint32_t bar0 = smem_addr(bars);
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+        for (int c = 0; c < kChunks; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * c), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
@@ -209,33 +237,40 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_v_tile_kernel(const __grid_c
         // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
         const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
         const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
-        if (threadIdx.x == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes * (uint32_t)rows) : "memory");
+        if (threadIdx.x < kChunks) {
+            const int c = threadIdx.x;
+            const int nrows = max(0, min(chunk_rows, rows - c * chunk_rows));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
+        }
         for (int rr = threadIdx.x; rr < rows; rr += WARPS * 32) {
             const int sy = min(max(y0 - P.radius + rr, 0), rh - 1);
             const float4 *src = reinterpret_cast<const float4 *>(P.mid) + (size_t)sy * rw + x0;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_addr(tile + (size_t)rr * 32)),
-                         "l"(src), "r"(row_bytes), "r"(bar_s)
+                         "l"(src), "r"(row_bytes), "r"(bar0 + 8u * (uint32_t)(rr / chunk_rows))
                          : "memory");
         }
-        uint32_t done;
-        do {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar_s), "r"(phase) : "memory");
-        } while (!done);
-        phase ^= 1u;
 
-        float4 acc[N];
-        float R[N];
+        Acc4 acc[N];
+        float2 R[N];
 #pragma unroll
-        for (int j = 0; j < N; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
         const float4 *col = tile + (size_t)warp * N * 32 + lane;
-#define VT_LOAD(i) col[(size_t)(i) * 32]
-        for (int g = 0; g < P.steps; g += N) { PFE_GAUSS_GROUP(VT_LOAD) }
+        int have = -1, have_rows = 0;  // chunks [0, have] = tile rows [0, have_rows) have landed
+        for (int g = 0; g < P.steps; g += N) {
+            while (warp * N + g + N > have_rows) {  // this group reads tile rows up to warp*N + g + N - 1
+                mbar_wait(bar0 + 8u * (uint32_t)(++have), phase);
+                have_rows += chunk_rows;
+            }
+            const float4 *cg = col + (size_t)g * 32;
+#define VT_LOAD(s) cg[(s) * 32]
+            PFE_GAUSS_GROUP(VT_LOAD)
 #undef VT_LOAD
+        }
+        while (have < kChunks - 1) mbar_wait(bar0 + 8u * (uint32_t)(++have), phase);  // keep every barrier's phase in step
+        phase ^= 1u;
         const int x = x0 + lane, yw = y0 + warp * N;
         if (x < rw) {
 #pragma unroll
@@ -306,45 +341,45 @@ int run_passes(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     const int taps = (int)k.size();
     P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
     P.wp_len = P.steps + N - 1;
-    std::vector<float> wp((size_t)P.wp_len, 0.0f);
-    for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = k[(size_t)t];
+    std::vector<float2> wp((size_t)P.wp_len, make_float2(0.0f, 0.0f));
+    for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
     void *wdev;
-    PFE_TRY(pfe_small_upload(ctx, wp.data(), wp.size() * sizeof(float), &wdev));
-    P.wp = (const float *)wdev;
-    const int wp_pad = (P.wp_len + 3) & ~3;
+    PFE_TRY(pfe_small_upload(ctx, wp.data(), wp.size() * sizeof(float2), &wdev));
+    P.wp = (const float2 *)wdev;
+    const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
 
     // H pass
     {
         const int tile_len = skew(31 * N + P.steps, N) + 1;
         int warps = 4;
-        size_t smem = (size_t)wp_pad * 4 + (size_t)warps * tile_len * 16;
-        if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 4 + (size_t)tile_len * 16; }
+        size_t smem = (size_t)wp_pad * 8 + (size_t)warps * tile_len * 16;
+        if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 8 + (size_t)tile_len * 16; }
         if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
         const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
-        unsigned blocks = (unsigned)std::min<uint64_t>((ntask + warps - 1) / warps, (uint64_t)ctx->sm_count * 8);
         if (warps == 4) {
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned blocks = (unsigned)std::min<uint64_t>((ntask + 3) / 4, (uint64_t)ctx->sm_count * 8);
             PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4><<<blocks, 128, smem, ctx->stream>>>(P));
         } else {
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned blocks = (unsigned)std::min<uint64_t>(ntask, (uint64_t)ctx->sm_count * 8);
             PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1><<<blocks, 32, smem, ctx->stream>>>(P));
         }
         PFE_LAUNCHED(ctx);
     }
     // V pass: tile variant when its shared-memory footprint fits, else the direct variant
     {
-        const size_t extra = (size_t)wp_pad * 4 + 64;
+        const size_t extra = (size_t)wp_pad * 8 + 8 * kChunks + 64;
         auto tile_smem = [&](int warps) { return (size_t)(warps * N + P.steps - N) * 512 + extra; };
         const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
         const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.rh, 8 * N);
         if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
             const size_t smem = tile_smem(8);
-            const int per_sm = smem <= 112 * 1024 ? 2 : 1;
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            unsigned blocks = std::min<unsigned>(tiles8, (unsigned)(ctx->sm_count * per_sm));
+            const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8>, 256, smem, tiles8);
             PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8><<<blocks, 256, smem, ctx->stream>>>(P));
         } else {
-            size_t smem = (size_t)wp_pad * 4;
+            size_t smem = (size_t)wp_pad * 8;
             if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
             if (smem > 48 * 1024)
                 PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -19,10 +19,28 @@ __global__ void __launch_bounds__(256) k(float *out, const float *wts, int iters
             float w = wts[it & 63];
 #pragma unroll
             for (int i = 0; i < 32; i++) acc[i] = __fmaf_rn(x, w, acc[i]);
+        } else if (MODE == 3) {  // packed fma.rn.f32x2 (FFMA2): 16 instructions = 32 FMAs
+            unsigned long long *a2 = reinterpret_cast<unsigned long long *>(acc);
+            unsigned long long x2, y2;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(x2) : "f"(x));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(y2) : "f"(y));
+#pragma unroll
+            for (int i = 0; i < 16; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a2[i]) : "l"(x2), "l"(y2));
+        } else if (MODE == 4) {  // FFMA2 interleaved with one integer op per FFMA2 (do spare issue slots exist?)
+            unsigned long long *a2 = reinterpret_cast<unsigned long long *>(acc);
+            unsigned long long x2, y2;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(x2) : "f"(x));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(y2) : "f"(y));
+            unsigned k0 = it, k1 = it + 1, k2 = it + 2, k3 = it + 3;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a2[i]) : "l"(x2), "l"(y2));
+                if ((i & 3) == 0) k0 = k0 * 3 + 1; else if ((i & 3) == 1) k1 = k1 * 5 + 1; else if ((i & 3) == 2) k2 ^= k0; else k3 += k1;
+            }
+            if ((k0 ^ k1 ^ k2 ^ k3) == 0x12345u) acc[0] += 1.0f;
         } else {  // separate FMUL + FADD (the bit-exact path)
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x, y));
-            x += 1e-9f;
+            for (int i = 0; i < 32; i++) acc[i] = __fadd_rn(acc[i], __fmul_rn(x, acc[(i + 7) & 31] ));
         }
     }
     unsigned long long t1 = clock64();
@@ -46,7 +64,7 @@ void run(const char *name, int sms, float *out, float *wts, unsigned long long *
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, a, b);
     unsigned long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
-    double ops = (double)blocks * 256 * iters * 32 * (MODE == 2 ? 2 : 1);
+    double ops = (double)blocks * 256 * iters * 32 * (MODE == 2 ? 2 : 1);  // scalar FP32 operations
     double mhz = (double)c / (ms * 1e-3) / 1e6;
     printf("{\"kernel\": \"%s\", \"ms\": %.3f, \"fp32_instr_per_s\": %.4e, \"lanes_per_clk_per_sm\": %.2f, \"sm_mhz_est\": %.0f}\n",
            name, ms, ops / (ms * 1e-3), ops / (double)c / sms, mhz);
@@ -62,5 +80,7 @@ int main() {
     run<0>("ffma_3reg", p.multiProcessorCount, out, wts, cyc);
     run<1>("ffma_uniform_operand", p.multiProcessorCount, out, wts, cyc);
     run<2>("fmul_fadd", p.multiProcessorCount, out, wts, cyc);
+    run<3>("ffma2_packed", p.multiProcessorCount, out, wts, cyc);
+    run<4>("ffma2_plus_int", p.multiProcessorCount, out, wts, cyc);
     return 0;
 }
