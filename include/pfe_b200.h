@@ -226,6 +226,15 @@ int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t
                       const float *original_points, const float *deformed_points, uint32_t cols,
                       uint32_t rows, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out,
                       uint8_t *dst_band);
+/* Row-band form of both warps for a canvas split across GPUs: produce output rows
+ * [y0, y0+rows_out) of the w x h result from a WINDOW of source rows [src_y0, src_y0+src_nrows) of
+ * the src_w x src_h source (own band + halo). disp_band != NULL: displacement warp with the band's
+ * rows_out*w*2 field; disp_band == NULL: fused mesh warp (points are HOST pointers). Synchronises,
+ * and fails with PFE_ERR_INVALID_ARG if any bilinear tap inside the image fell outside the window. */
+int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t src_w, uint32_t src_h, uint32_t src_y0,
+                      uint32_t src_nrows, const float *disp_band, const float *original_points,
+                      const float *deformed_points, uint32_t cols, uint32_t rows, uint32_t w, uint32_t h,
+                      uint32_t y0, uint32_t rows_out, uint8_t *dst_band);
 /* DisplacementField::apply_push / expand / contract / twirl (:1051-1200), in place on a
  * w*h*2 field. a0,a1: push = (delta_x, delta_y); twirl = (clockwise ? 1 : 0, -).
  * bbox_out (may be NULL) = (x0, y0, x1, y1) like the reference's return value. */

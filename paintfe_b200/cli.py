@@ -1,0 +1,114 @@
+"""Headless batch mode sharded over GPUs: the `cli::run` loop (src/cli.rs:105-215) with the serial
+`for input in inputs` (cli.rs:159) replaced by "image k -> rank k mod world".
+
+  python -m paintfe_b200.cli -i "shots/*.png" --script process.rhai --output-dir out/
+  torchrun --nproc-per-node 8 -m paintfe_b200.cli -i "shots/*.png" --script process.rhai --output-dir out/
+
+Same flags as the reference for the part of the pipeline that is in scope: -i/--input (glob patterns
+or literal paths, deduplicated in order, cli.rs:315-350), -s/--script, -o/--output (single input
+only), --output-dir, -f/--format, -v/--verbose.  Image decoding/encoding is harness plumbing (PIL);
+`.pfe` project I/O is listed as "next" in DESIGN.md.  A per-file failure is reported and the batch
+continues; the exit code is 1 if any file failed (cli.rs:204-215).
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import os
+import sys
+import time
+from typing import List, Optional
+
+import numpy as np
+
+
+def resolve_inputs(patterns: List[str]) -> List[str]:
+    """cli.rs:315-350: literal paths first, else glob; ordered, deduplicated; warn on empty matches."""
+    out: List[str] = []
+    for pat in patterns:
+        if os.path.exists(pat):
+            if pat not in out:
+                out.append(pat)
+            continue
+        matched = False
+        for p in sorted(glob.glob(pat)):
+            if p not in out:
+                out.append(p)
+            matched = True
+        if not matched:
+            print(f"warning: pattern '{pat}' matched no files.", file=sys.stderr)
+    return out
+
+
+def build_output_path(inp: str, output: Optional[str], output_dir: Optional[str], fmt: str) -> Optional[str]:
+    """cli.rs build_output_path: --output for a single file, else <output_dir>/<stem>.<ext>."""
+    if output:
+        return output
+    stem = os.path.splitext(os.path.basename(inp))[0]
+    if output_dir:
+        return os.path.join(output_dir, f"{stem}.{fmt}")
+    return None
+
+
+def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool) -> None:
+    """cli.rs:222-308 for single-layer raster inputs: load -> script -> encode."""
+    from PIL import Image
+
+    from .script import execute_script_sync
+
+    img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
+    if script:
+        img = execute_script_sync(eng, script, img)
+    os.makedirs(os.path.dirname(os.path.abspath(outp)), exist_ok=True)
+    Image.fromarray(np.asarray(img), "RGBA").save(outp)
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="paintfe", description="PaintFE headless batch image processor (B200 engine)")
+    ap.add_argument("-i", "--input", nargs="+", required=True)
+    ap.add_argument("-s", "--script")
+    ap.add_argument("-o", "--output")
+    ap.add_argument("--output-dir")
+    ap.add_argument("-f", "--format", default=None)
+    ap.add_argument("-v", "--verbose", action="store_true")
+    args = ap.parse_args(argv)
+
+    inputs = resolve_inputs(args.input)
+    if not inputs:
+        print("error: no input files.", file=sys.stderr)
+        return 1
+    if args.output and len(inputs) > 1:
+        print("error: --output is only valid for a single input; use --output-dir.", file=sys.stderr)
+        return 1
+    fmt = (args.format or (os.path.splitext(args.output)[1][1:] if args.output else "") or "png").lower()
+    script = open(args.script).read() if args.script else None
+
+    from .dist import shard_indices
+    from .engine import Engine
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    eng = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    total, any_failure = len(inputs), False
+    for idx in shard_indices(total, rank, world):
+        path = inputs[idx]
+        if total > 1 or args.verbose:
+            print(f"[{idx + 1}/{total}] {path}")
+        t0 = time.perf_counter()
+        outp = build_output_path(path, args.output, args.output_dir, fmt)
+        if outp is None:
+            print(f"  error: cannot determine output path for '{path}'.", file=sys.stderr)
+            any_failure = True
+            continue
+        try:
+            run_one(eng, path, outp, script, args.verbose)
+            if args.verbose or total > 1:
+                print(f"  -> {outp} ({(time.perf_counter() - t0) * 1000:.0f}ms)")
+        except Exception as e:  # per-file failure: report and continue (cli.rs:204-209)
+            print(f"  error: {e}", file=sys.stderr)
+            any_failure = True
+    eng.close()
+    return 1 if any_failure else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

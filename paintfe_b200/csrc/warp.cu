@@ -67,7 +67,11 @@ __device__ __forceinline__ void mesh_disp(const MeshParams &M, const float *sdef
 }
 
 // warp_displacement_full inner body, transform.rs:1303-1342
-__device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int sh, int x, int y, float ddx, float ddy) {
+// `src` holds source rows [sy0, sy0 + snr) of an sw x sh image (sy0 = 0, snr = sh for a whole image).
+// A tap inside the image but outside the provided rows raises *missing (band callers size their halo
+// so this never happens; the flag turns a wrong halo into an error instead of a wrong pixel).
+__device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int sh, int x, int y, float ddx, float ddy,
+                                                int sy0 = 0, int snr = 0x7fffffff, int *missing = nullptr) {
     float sx = (float)x - ddx, sy = (float)y - ddy;
     float flx = floorf(sx), fly = floorf(sy);
     // `as i32` saturates; anything outside [-1, size) leaves the pixel transparent
@@ -78,7 +82,9 @@ __device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int px = x0 + (k & 1), py = y0 + (k >> 1);
-        q[k] = (px < 0 || py < 0 || px >= sw || py >= sh) ? 0u : __ldg(src + (size_t)py * sw + px);
+        if (px < 0 || py < 0 || px >= sw || py >= sh) q[k] = 0u;
+        else if (py < sy0 || py - sy0 >= snr) { q[k] = 0u; if (missing) *missing = 1; }
+        else q[k] = __ldg(src + (size_t)(py - sy0) * sw + px);
     }
     uint32_t o[4];
 #pragma unroll
@@ -129,6 +135,27 @@ __global__ void __launch_bounds__(256) mesh_warp_kernel(const __grid_constant__ 
     float dx, dy;
     mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
     dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy);
+}
+
+// Band form shared by the displacement warp and the fused mesh warp: output rows [y0, y0+rows_out)
+// of a w x h result, source given as a row window. disp == nullptr selects the mesh path.
+__global__ void __launch_bounds__(256) warp_band_kernel(const __grid_constant__ MeshParams M, const uint32_t *src, int sw,
+                                                        int sh, int sy0, int snr, const float2 *disp, uint32_t *dst,
+                                                        uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out, int *missing) {
+    __shared__ float sdef[PFE_MESH_MAX_POINTS * 2], sorig[PFE_MESH_MAX_POINTS * 2];
+    if (!disp) {
+        const int np = (M.cols + 1) * (M.rows + 1) * 2;
+        for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
+        __syncthreads();
+    }
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t ry = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= (int)w || ry >= rows_out) return;
+    const int y = (int)(y0 + ry);
+    float dx, dy;
+    if (disp) { const float2 d = __ldg(disp + (size_t)ry * w + x); dx = d.x; dy = d.y; }
+    else mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
+    dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy, sy0, snr, missing);
 }
 
 // exp() as the reference's libm expf sees it: correctly rounded f32. Evaluated in f64 and rounded
@@ -223,6 +250,32 @@ extern "C" int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, 
     PFE_KERNEL(ctx, "mesh_warp", mesh_warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8)), 256, 0, ctx->stream>>>(
         M, (const uint32_t *)src, (int)sw, (int)sh, (uint32_t *)dst, w, h, y0, rows_out));
     PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t sw, uint32_t sh, uint32_t src_y0,
+                                 uint32_t src_nrows, const float *disp_band, const float *orig, const float *def,
+                                 uint32_t cols, uint32_t rows, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out,
+                                 uint8_t *dst_band) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src_rows || !dst_band || !sw || !sh || !w || !h || !rows_out || (uint64_t)y0 + rows_out > h ||
+        (uint64_t)src_y0 + src_nrows > sh || !src_nrows || (!disp_band && !def))
+        return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp_band: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    MeshParams M;
+    memset(&M, 0, sizeof(M));
+    if (!disp_band) PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
+    int zero = 0;
+    void *flag;
+    PFE_TRY(pfe_small_upload(ctx, &zero, sizeof(zero), &flag));
+    PFE_KERNEL(ctx, "warp_band", warp_band_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8)), 256, 0, ctx->stream>>>(
+        M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, (const float2 *)disp_band,
+        (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
+    PFE_LAUNCHED(ctx);
+    int missing = 0;
+    PFE_CUDA(ctx, cudaMemcpyAsync(&missing, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (missing) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp_band: the source row window does not cover the warp's reach");
     return PFE_OK;
 }
 

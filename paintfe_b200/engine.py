@@ -319,6 +319,17 @@ class Engine:
                                             _ptr(dst)))
         return dst
 
+    def warp_band(self, src_rows, src_h, src_y0, w, h, y0, rows_out, disp_band=None, original=None, deformed=None,
+                  cols=0, rows=0, out=None):
+        """Device tier only: rows [y0, y0+rows_out) of a warp whose source is the row window src_rows."""
+        sw = int(src_rows.shape[1])
+        self._dev(src_rows, disp_band)
+        original, deformed = self._pts(original), self._pts(deformed)
+        dst = out if out is not None else torch.empty((rows_out, w, 4), dtype=torch.uint8, device=src_rows.device)
+        self._ck(self.lib.pfe_dev_warp_band(self.h, _ptr(src_rows), sw, src_h, src_y0, int(src_rows.shape[0]), _ptr(disp_band),
+                                            _ptr(original), _ptr(deformed), cols, rows, w, h, y0, rows_out, _ptr(dst)))
+        return dst
+
     def liquify(self, field, kind, cx, cy, radius, strength, a0=0.0, a1=0.0):
         """In place on `field` ((h, w, 2) float32, numpy or CUDA tensor). Returns the bbox."""
         h, w = int(field.shape[0]), int(field.shape[1])

@@ -1,0 +1,84 @@
+"""The Rhai Effect API surface that the CLI batch mode drives (src/ops/scripting.rs:822-1165),
+as a line-oriented runner for straight-line effect scripts such as
+
+    apply_blur(4.0); apply_hsl(10.0, 15.0, 0.0); apply_vignette(0.5, 0.3);
+
+PaintFE's Rhai host itself is kept as the caller; this runner exists so the batch
+benchmark (config 5) and the parity tests can execute the same effect sequences on the device
+without a Rust toolchain.  Each binding maps to the entry point that replaces the reference function
+it calls, with the reference's fixed arguments (e.g. apply_sharpen uses radius 1.0, scripting.rs:847).
+Anything that is not a plain `apply_*(numbers...)` call raises: there is no interpreter here.
+"""
+from __future__ import annotations
+
+import math
+import re
+from typing import Callable, Dict, List, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+_CALL = re.compile(r"\s*([A-Za-z_][A-Za-z0-9_]*)\s*\(([^()]*)\)\s*$")
+
+# pfe_adjust_op ids (include/pfe_b200.h)
+S_INVERT, S_DESATURATE, S_SEPIA, S_SEPIA_STRENGTH, S_BRIGHTNESS_CONTRAST, S_HSL, S_EXPOSURE, S_LUT_RGB = range(32, 40)
+
+
+def _f32(v) -> float:
+    return float(np.float32(v))
+
+
+def bindings(eng) -> Dict[str, Callable]:
+    """name -> f(img, mask, *args) -> img, mirroring register_effect_api (scripting.rs:822)."""
+
+    def exposure_gain(ev):
+        return _f32(np.power(np.float32(2.0), np.float32(ev)))  # 2.0f32.powf(ev as f32)
+
+    return {
+        # blur family goes through apply_effect_to_context: selection mask honoured (scripting.rs:617)
+        "apply_blur": lambda im, m, sigma: eng.gaussian_blur(im, _f32(sigma), mask=m),
+        "apply_box_blur": lambda im, m, radius: eng.box_blur(im, _f32(int(radius)), mask=m),
+        "apply_motion_blur": lambda im, m, angle, distance: eng.motion_blur(im, _f32(angle), _f32(distance), mask=m),
+        "apply_sharpen": lambda im, m, amount: eng.sharpen(im, _f32(amount), 1.0, mask=m),
+        "apply_median": lambda im, m, radius: eng.median(im, max(int(radius), 1), mask=m),
+        "apply_vignette": lambda im, m, strength, softness: eng.vignette(im, _f32(strength), _f32(softness), mask=m),
+        # inline variants: truncating casts, no mask, alpha untouched (scripting.rs:869-1075)
+        "apply_invert": lambda im, m: eng.adjust(im, S_INVERT),
+        "apply_desaturate": lambda im, m: eng.adjust(im, S_DESATURATE),
+        "apply_sepia": lambda im, m, *s: (eng.adjust(im, S_SEPIA) if not s else
+                                          eng.adjust(im, S_SEPIA_STRENGTH, (min(max(float(s[0]), 0.0), 1.0),))),
+        "apply_brightness_contrast": lambda im, m, b, c: eng.adjust(im, S_BRIGHTNESS_CONTRAST, (_f32(b), _f32(c))),
+        "apply_hsl": lambda im, m, h, s, l: eng.adjust(im, S_HSL, (_f32(h), _f32(s), _f32(l))),
+        "apply_exposure": lambda im, m, ev: eng.adjust(im, S_EXPOSURE, (exposure_gain(ev),)),
+        "apply_levels": lambda im, m, black, white, gamma: eng.adjust(
+            im, S_LUT_RGB, luts=eng.levels_lut_script(_f32(black), _f32(white), _f32(gamma))),
+    }
+
+
+def parse(source: str) -> List[Tuple[str, Tuple[float, ...]]]:
+    """Split a straight-line script into (function, args). Comments (`// ...`) are ignored."""
+    calls = []
+    src = re.sub(r"//[^\n]*", "", source)
+    for stmt in src.split(";"):
+        if not stmt.strip():
+            continue
+        m = _CALL.match(stmt)
+        if not m:
+            raise ValueError(f"unsupported script statement (only apply_*(numbers) calls): {stmt.strip()!r}")
+        args = tuple(float(a) for a in m.group(2).split(",") if a.strip())
+        calls.append((m.group(1), args))
+    return calls
+
+
+def execute_script_sync(eng, source: str, pixels, mask=None):
+    """Shape of scripting::execute_script_sync (scripting.rs:1733): flat RGBA in, flat RGBA out.
+    `pixels` may be a numpy array (host tier) or a CUDA tensor (device tier: the whole script runs
+    without leaving the device)."""
+    table = bindings(eng)
+    img = pixels
+    for name, args in parse(source):
+        if name not in table:
+            raise ValueError(f"effect {name!r} is outside the B200 hot path (see DESIGN.md, out of scope)")
+        img = table[name](img, mask, *args)
+    return img
