@@ -1,0 +1,79 @@
+"""Row-band split across real GPUs (NCCL halo exchange) == single-GPU whole-image result.
+Skipped on boxes with fewer than 2 GPUs; the same logic is covered on CPU/gloo in test_dist_cpu.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from paintfe_b200 import dist as pd
+        from paintfe_b200.engine import Engine
+
+        eng = Engine(rank)
+        rng = np.random.default_rng(77)
+        w, h = 1000, 700
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        disp = rng.normal(0, 12, (h, w, 2)).astype(np.float32)
+        full = torch.from_numpy(img).cuda()
+        bounds = pd.band_bounds(h, world)
+        y0, y1 = bounds[rank]
+        band = full[y0:y1].contiguous()
+        res = {}
+        for exact in (True, False):
+            got = pd.gaussian_blur_banded(eng, band, h, 20.0, exact=exact, bounds=bounds)
+            res[f"gauss_exact={exact}"] = torch.equal(got, eng.gaussian_blur(full, 20.0, exact=exact)[y0:y1])
+        res["box"] = torch.equal(pd.box_blur_banded(eng, band, h, 9.0, bounds=bounds), eng.box_blur(full, 9.0)[y0:y1])
+        res["median"] = torch.equal(pd.median_banded(eng, band, h, 2, bounds=bounds), eng.median(full, 2)[y0:y1])
+        res["sharpen"] = torch.equal(pd.sharpen_banded(eng, band, h, 1.0, 2.0, bounds=bounds), eng.sharpen(full, 1.0, 2.0)[y0:y1])
+        dfull = torch.from_numpy(disp).cuda()
+        res["warp"] = torch.equal(pd.warp_displacement_banded(eng, band, dfull[y0:y1].contiguous(), h, bounds=bounds),
+                                  eng.warp_displacement(full, dfull)[y0:y1])
+        orig = np.array([[c / 6 * w, r / 6 * h] for r in range(7) for c in range(7)], np.float32)
+        deformed = orig + np.array([[8 * np.sin(i) * np.cos(j)] * 2 for i in range(7) for j in range(7)], np.float32)
+        res["mesh"] = torch.equal(pd.mesh_warp_banded(eng, band, orig, deformed, 6, 6, w, h, bounds=bounds),
+                                  eng.mesh_warp(full, orig, deformed, 6, 6, w, h)[y0:y1])
+        q.put((rank, res))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_bands_over_nccl_match_single_gpu():
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in results:
+        assert all(res.values()), (rank, res)

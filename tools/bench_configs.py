@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Secondary benchmarks for BASELINE.json configs 2-5 (bench.py carries the headline metric).
+
+  python tools/bench_configs.py [--config 2,3,4,5] [--steps K]
+  torchrun --nproc-per-node N tools/bench_configs.py --config 4,5      # row bands / batch shards
+
+Prints one JSON line per measurement (rank 0).  Device-resident inputs, CUDA-event timing on the
+engine's stream, max over ranks.  Numbers taken here are reported in BASELINE.md §5.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from paintfe_b200 import dist as pd
+from paintfe_b200.engine import Engine, make_layer
+from paintfe_b200.script import execute_script_sync
+
+W8K, H8K = 7680, 4320
+
+
+def timed(fn, steps, warmup=3, world=1):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="2,3,5")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--batch-per-gpu", type=int, default=128)
+    ap.add_argument("--canvas", type=int, default=16384)
+    args = ap.parse_args()
+    configs = {int(c) for c in args.config.split(",")}
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local)
+    eng.use_torch_stream()
+    peak = 6557.8
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    def emit(d):
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+
+    gen = torch.Generator(device=dev).manual_seed(0x5EED + rank)
+    px8k = W8K * H8K
+
+    if 2 in configs:  # 16-layer 8K flatten, three stacks
+        layers = [torch.randint(0, 256, (H8K, W8K, 4), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
+        out = torch.empty((H8K, W8K, 4), dtype=torch.uint8, device=dev)
+        for name, off, binary in (("modes 0-15, uniform alpha", 0, False), ("modes 16-24,0-6, uniform alpha", 16, False),
+                                  ("modes 0-15, alpha in {0,255} (fast-path regime)", 0, True)):
+            ls = layers
+            if binary:
+                ls = [t.clone() for t in layers]
+                for t in ls:
+                    t[..., 3] = torch.where(t[..., 3] > 127, 255, 0).to(torch.uint8)
+            dl = [make_layer(t, blend=(i + off) % 25, opacity=0.25 + 0.05 * i) for i, t in enumerate(ls)]
+            ms = timed(lambda: eng.flatten(dl, W8K, H8K, out=out), args.steps)
+            gbs = 68 * px8k / (ms * 1e-3) / 1e9
+            emit({"config": 2, "workload": f"8K 16-layer flatten, {name}", "ms": ms, "mpx_s": px8k / ms / 1e3,
+                  "achieved_gbs": gbs, "frac_of_hbm": gbs / peak, "n_gpus": 1})
+            del ls
+        del layers, dl
+
+    if 3 in configs:  # Gaussian sigma=50 + HSL + unsharp on 8K
+        img = torch.randint(0, 256, (H8K, W8K, 4), dtype=torch.uint8, device=dev, generator=gen)
+        a, b = torch.empty_like(img), torch.empty_like(img)
+
+        def pipe():
+            eng.gaussian_blur(img, 50.0, out=a)
+            eng.adjust(a, 5, (30.0, -20.0, 10.0), out=b)  # PFE_ADJ_HSL
+            eng.sharpen(b, 1.0, 2.0, out=a)
+
+        eng.profile(True); eng.profile_read()
+        ms = timed(pipe, args.steps)
+        prof = eng.profile_read(); eng.profile(False)
+        n = args.steps + 3
+        emit({"config": 3, "workload": "8K Gaussian sigma=50 -> HSL(30,-20,10) -> sharpen(1.0, 2.0)", "ms": ms,
+              "mpx_s": px8k / ms / 1e3, "kernels_avg_ms": {k: v["ms"] / v["launches"] for k, v in prof.items()}, "n_gpus": 1})
+        for k, alg in (("adjust", 8 * px8k),):
+            if k in prof:
+                avg = prof[k]["ms"] / prof[k]["launches"]
+                emit({"config": 3, "kernel": k, "avg_ms": avg, "achieved_gbs": alg / (avg * 1e-3) / 1e9,
+                      "frac_of_hbm": alg / (avg * 1e-3) / 1e9 / peak})
+        del img, a, b
+
+    if 4 in configs:  # mesh warp 6x6 + liquify on a big canvas, row bands across ranks
+        S = args.canvas
+        bounds = pd.band_bounds(S, world)
+        y0, y1 = bounds[rank]
+        band = torch.randint(0, 256, (y1 - y0, S, 4), dtype=torch.uint8, device=dev, generator=gen)
+        orig = np.zeros((49, 2), np.float32)
+        for r in range(7):
+            for c in range(7):
+                orig[r * 7 + c] = (np.float32(c) / np.float32(6) * S, np.float32(r) / np.float32(6) * S)
+        deformed = orig.copy()
+        for i in range(7):
+            for j in range(7):
+                deformed[i * 7 + j] += np.float32(8.0 * np.sin(i) * np.cos(j))
+        # liquify field: 64 pushes, r=200, strength 0.8; built per band on device
+        field = torch.zeros((S if world == 1 else y1 - y0, S, 2), dtype=torch.float32, device=dev)
+        prng = np.random.default_rng(0x5EED)
+        pushes = [(float(prng.uniform(0, S)), float(prng.uniform(0, S)), float(prng.uniform(-20, 20)), float(prng.uniform(-20, 20))) for _ in range(64)]
+        if world == 1:
+            for cx, cy, dx, dy in pushes:
+                eng.liquify(field, 0, cx, cy, 200.0, 0.8, dx, dy)
+            fband = field
+        else:
+            # the field of a band is the band of the field: shift brush centres into band coordinates
+            for cx, cy, dx, dy in pushes:
+                eng.liquify(field, 0, cx, cy - y0, 200.0, 0.8, dx, dy)
+            fband = field
+
+        def step():
+            m = pd.mesh_warp_banded(eng, band, orig, deformed, 6, 6, S, S, bounds=bounds)
+            return pd.warp_displacement_banded(eng, m, fband, S, bounds=bounds)
+
+        ms = timed(step, max(3, args.steps // 4), warmup=2, world=world)
+        emit({"config": 4, "workload": f"{S}x{S} mesh warp 6x6 (fused Catmull-Rom) + liquify warp, row bands + halo exchange",
+              "ms": ms, "mpx_s": S * S / ms / 1e3, "n_gpus": world, "band_rows": y1 - y0})
+        del band, field
+
+    if 5 in configs:  # batch of 4K images through process.rhai, sharded by index
+        script = "apply_blur(4.0); apply_hsl(10.0, 15.0, 0.0); apply_vignette(0.5, 0.3);"
+        w, h = 3840, 2160
+        n_total = args.batch_per_gpu * world
+        mine = pd.shard_indices(n_total, rank, world)
+        img = torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
+
+        def run_batch():
+            for k in mine:  # synthetic image generated on the fly from seed+index, no disk I/O
+                g = torch.Generator(device=dev).manual_seed(0x5EED + k)
+                img.random_(0, 256, generator=g)
+                execute_script_sync(eng, script, img)
+
+        ms = timed(run_batch, 1, warmup=1, world=world)
+        emit({"config": 5, "workload": f"{n_total} x 4K images, script: {script}", "ms_total": ms, "images_s": n_total / ms * 1e3,
+              "mpx_s": n_total * w * h / ms / 1e3, "n_gpus": world, "note": "includes on-device synthetic image generation"})
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
