@@ -102,17 +102,20 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     const uint64_t ntask = (uint64_t)nseg * P.rh;
     const int rw = (int)P.rw;
 
+    // u8 -> f32 uses PRMT + FADD against 2^23 (ALU/FMA pipes) instead of the quarter-rate I2F:
+    // 0x4B0000xx is 2^23 + xx as a float, so one PRMT per channel and an exact subtract.
+    auto to_f4 = [](uint32_t v) {
+        const float m = 8388608.0f;
+        return make_float4(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - m,
+                           __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - m);
+    };
     for (uint64_t task = (uint64_t)blockIdx.x * WARPS + warp; task < ntask; task += (uint64_t)gridDim.x * WARPS) {
         const uint32_t y = (uint32_t)(task / nseg);
         const int x0 = (int)(task % nseg) * SEG;
         const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
-        // stage + convert: tile[p] = pixel clamp(x0 - r + p)
-        for (int p = lane; p < tile_px; p += 32) {
-            int sx = min(max(x0 - P.radius + p, 0), rw - 1);
-            uint32_t v = __ldg(row + sx);
-            tile[skew(p, N)] = make_float4((float)(v & 255u), (float)((v >> 8) & 255u),
-                                           (float)((v >> 16) & 255u), (float)(v >> 24));
-        }
+        // stage + convert: tile[p] = pixel clamp(x0 - r + p); unrolled so several loads are in flight
+#pragma unroll 4
+        for (int p = lane; p < tile_px; p += 32) tile[skew(p, N)] = to_f4(__ldg(row + min(max(x0 - P.radius + p, 0), rw - 1)));
         __syncwarp();
         Acc4 acc[N];
         float2 R[N];
@@ -193,13 +196,16 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
     }
 }
 
-// Tile variant.  A CTA owns a 32-pixel-wide tile of WARPS*N output rows. Its input rows (tile
-// height + 2r) are brought into shared memory once, one 512-byte cp.async.bulk per row (clamp-to-
-// edge is just a clamped source row index).  The rows are split into kChunks groups, each with its
-// own mbarrier, and every warp waits only for the chunk it is about to read, so the FMA stream
-// starts while most of the tile is still in flight.  Each warp then streams its N+2r rows out of
-// shared memory with conflict-free LDS.128, so a row of the f32 intermediate crosses L2
-// ~(TH+2r)/TH times instead of (N+2r)/N times.  Two CTAs per SM when the tile fits twice.
+// Tile variant: warp-specialised producer/consumer pipeline.
+// A CTA owns 32-pixel-wide tiles of WARPS*N output rows. The tile's input rows (tile height + 2r)
+// live in shared memory as a ring of kChunks chunks, each guarded by a full/empty mbarrier pair:
+//   * one producer warp streams rows in with 512-byte cp.async.bulk copies (clamp-to-edge is a clamped
+//     source row index; completion is counted in bytes on the chunk's `full` barrier) and refills a
+//     chunk for the NEXT tile as soon as every consumer warp has released it, so loads run a whole
+//     tile ahead of the math and there is no end-of-tile bubble;
+//   * WARPS consumer warps each stream their N+2r rows out of the ring with conflict-free LDS.128,
+//     waiting only on the chunk they are about to read and releasing chunks behind them.
+// A row of the f32 intermediate crosses L2 ~(TH+2r)/TH times instead of (N+2r)/N times.
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -208,22 +214,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 constexpr int kChunks = 8;
 
+// Round-half-away + clamp for a NON-NEGATIVE value (blur outputs: weights and inputs are >= 0):
+// t = trunc(x) via FADD.RZ against 2^23, x - t is exact, add one when the fraction is >= 0.5.
+__device__ __forceinline__ uint32_t round_u8_nonneg(float x) {
+    const uint32_t tb = __float_as_uint(__fadd_rz(x, 8388608.0f));
+    const float t = __uint_as_float(tb) - 8388608.0f;
+    const uint32_t v = (tb & 0x3FFu) + ((x - t) >= 0.5f ? 1u : 0u);
+    return min(v, 255u);
+}
+
 template <int N, bool EXACT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P) {
+__global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TH = WARPS * N;
     const int rows = TH + P.steps - N;
     const int chunk_rows = (rows + kChunks - 1) / kChunks;
-    float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // rows x 32 float4
-    float2 *wsm = reinterpret_cast<float2 *>(smem_raw + (size_t)rows * 512);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)rows * 512 + (size_t)((P.wp_len + 1) & ~1) * 8);
+    const int ring_rows = chunk_rows * kChunks;
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // ring_rows x 32 float4
+    float2 *wsm = reinterpret_cast<float2 *>(smem_raw + (size_t)ring_rows * 512);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ring_rows * 512 + (size_t)((P.wp_len + 1) & ~1) * 8);
     for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
-    const uint32_t bar0 = smem_addr(bars);
+    const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kChunks);
     if (threadIdx.x == 0) {
-        for (int c = 0; c < kChunks; c++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * c), "r"(1));
+        for (int c = 0; c < kChunks; c++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * c), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * c), "r"(WARPS));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
@@ -232,54 +254,83 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_v_tile_kernel(const __grid_c
     const int rw = (int)P.rw, rh = (int)P.rh;
     const int tx = (rw + 31) / 32, ty = (rh + TH - 1) / TH;
     const int ntiles = tx * ty;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
-        const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
-        const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
-        if (threadIdx.x < kChunks) {
-            const int c = threadIdx.x;
-            const int nrows = max(0, min(chunk_rows, rows - c * chunk_rows));
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
-        }
-        for (int rr = threadIdx.x; rr < rows; rr += WARPS * 32) {
-            const int sy = min(max(y0 - P.radius + rr, 0), rh - 1);
-            const float4 *src = reinterpret_cast<const float4 *>(P.mid) + (size_t)sy * rw + x0;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_addr(tile + (size_t)rr * 32)),
-                         "l"(src), "r"(row_bytes), "r"(bar0 + 8u * (uint32_t)(rr / chunk_rows))
-                         : "memory");
-        }
 
+    if (warp == WARPS) {
+        // ===== producer warp =====
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+            // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
+            const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
+            const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
+            for (int c = 0; c < kChunks; c++) {
+                const int r0 = c * chunk_rows, nrows = max(0, min(chunk_rows, rows - r0));
+                if (it > 0) mbar_wait(empty0 + 8u * c, (it - 1) & 1u);  // consumers are done with the previous tile's chunk c
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
+                __syncwarp();
+                for (int rr = r0 + lane; rr < r0 + nrows; rr += 32) {
+                    const int sy = min(max(y0 - P.radius + rr, 0), rh - 1);
+                    const float4 *src = reinterpret_cast<const float4 *>(P.mid) + (size_t)sy * rw + x0;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_addr(tile + (size_t)rr * 32)),
+                                 "l"(src), "r"(row_bytes), "r"(full0 + 8u * c)
+                                 : "memory");
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const int row_first = warp * N;  // first ring row this warp reads
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
+        const uint32_t parity = it & 1u;
         Acc4 acc[N];
         float2 R[N];
 #pragma unroll
         for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
-        const float4 *col = tile + (size_t)warp * N * 32 + lane;
-        int have = -1, have_rows = 0;  // chunks [0, have] = tile rows [0, have_rows) have landed
+        const float4 *col = tile + (size_t)row_first * 32 + lane;
+        int have_rows = 0, have = 0;          // chunks [0, have) have landed = ring rows [0, have_rows)
+        int released = 0, released_rows = 0;  // chunks [0, released) handed back to the producer
         for (int g = 0; g < P.steps; g += N) {
-            while (warp * N + g + N > have_rows) {  // this group reads tile rows up to warp*N + g + N - 1
-                mbar_wait(bar0 + 8u * (uint32_t)(++have), phase);
+            while (row_first + g + N > have_rows) {  // this group reads ring rows up to row_first + g + N - 1
+                mbar_wait(full0 + 8u * (uint32_t)have, parity);
+                have++;
                 have_rows += chunk_rows;
+            }
+            // chunks that lie entirely before the first row this group reads will not be touched again
+            while (released_rows + chunk_rows <= row_first + g) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)released);
+                released++;
+                released_rows += chunk_rows;
             }
             const float4 *cg = col + (size_t)g * 32;
 #define VT_LOAD(s) cg[(s) * 32]
             PFE_GAUSS_GROUP(VT_LOAD)
 #undef VT_LOAD
         }
-        while (have < kChunks - 1) mbar_wait(bar0 + 8u * (uint32_t)(++have), phase);  // keep every barrier's phase in step
-        phase ^= 1u;
-        const int x = x0 + lane, yw = y0 + warp * N;
+        __syncwarp();
+        if (lane == 0)
+            for (; released < kChunks; released++) mbar_arrive(empty0 + 8u * (uint32_t)released);
+        const int x = x0 + lane, yw = y0 + row_first;
         if (x < rw) {
 #pragma unroll
-            for (int j = 0; j < N; j++)
-                if (yw + j < rh) v_store(P, acc[j], x, yw + j);
+            for (int j = 0; j < N; j++) {
+                if (yw + j >= rh) break;
+                if (P.orig) {
+                    v_store(P, acc[j], x, yw + j);
+                } else {
+                    reinterpret_cast<uint32_t *>(P.dst)[(size_t)(yw + j) * P.dst_pitch + x] =
+                        pfe_pack(round_u8_nonneg(acc[j].lo.x), round_u8_nonneg(acc[j].lo.y), round_u8_nonneg(acc[j].hi.x),
+                                 round_u8_nonneg(acc[j].hi.y));
+                }
+            }
         }
-        // generic-proxy reads of the tile must be ordered before the next async-proxy overwrite
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
     }
 }
 
@@ -336,8 +387,9 @@ std::vector<float> build_kernel(float sigma, int *radius_out) {
     return k;
 }
 
-template <int N, bool EXACT>
-int run_passes(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+// Padded, duplicated weights for register-block size N: wp[m] = (w, w)[m-(N-1)] inside the support.
+template <int N>
+int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k) {
     const int taps = (int)k.size();
     P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
     P.wp_len = P.steps + N - 1;
@@ -346,67 +398,93 @@ int run_passes(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     void *wdev;
     PFE_TRY(pfe_small_upload(ctx, wp.data(), wp.size() * sizeof(float2), &wdev));
     P.wp = (const float2 *)wdev;
-    const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
-
-    // H pass
-    {
-        const int tile_len = skew(31 * N + P.steps, N) + 1;
-        int warps = 4;
-        size_t smem = (size_t)wp_pad * 8 + (size_t)warps * tile_len * 16;
-        if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 8 + (size_t)tile_len * 16; }
-        if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
-        const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
-        if (warps == 4) {
-            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned blocks = (unsigned)std::min<uint64_t>((ntask + 3) / 4, (uint64_t)ctx->sm_count * 8);
-            PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4><<<blocks, 128, smem, ctx->stream>>>(P));
-        } else {
-            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned blocks = (unsigned)std::min<uint64_t>(ntask, (uint64_t)ctx->sm_count * 8);
-            PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1><<<blocks, 32, smem, ctx->stream>>>(P));
-        }
-        PFE_LAUNCHED(ctx);
-    }
-    // V pass: tile variant when its shared-memory footprint fits, else the direct variant
-    {
-        const size_t extra = (size_t)wp_pad * 8 + 8 * kChunks + 64;
-        auto tile_smem = [&](int warps) { return (size_t)(warps * N + P.steps - N) * 512 + extra; };
-        const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
-        const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.rh, 8 * N);
-        if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
-            const size_t smem = tile_smem(8);
-            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8>, 256, smem, tiles8);
-            PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8><<<blocks, 256, smem, ctx->stream>>>(P));
-        } else {
-            size_t smem = (size_t)wp_pad * 8;
-            if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
-            if (smem > 48 * 1024)
-                PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
-            PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
-        }
-        PFE_LAUNCHED(ctx);
-    }
     return PFE_OK;
 }
 
-template <bool EXACT>
-int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
-    const int taps = (int)k.size();
-    // pick the register-block size that wastes the fewest padded steps per output
-    auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + 6.0) / n; };
+template <int N, bool EXACT>
+int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+    PFE_TRY(upload_weights<N>(ctx, P, k));
+    const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
+    const int tile_len = skew(31 * N + P.steps, N) + 1;
+    int warps = 4;
+    size_t smem = (size_t)wp_pad * 8 + (size_t)warps * tile_len * 16;
+    if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 8 + (size_t)tile_len * 16; }
+    if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
+    const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
+    if (warps == 4) {
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = (unsigned)std::min<uint64_t>((ntask + 3) / 4, (uint64_t)ctx->sm_count * 8);
+        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4><<<blocks, 128, smem, ctx->stream>>>(P));
+    } else {
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = (unsigned)std::min<uint64_t>(ntask, (uint64_t)ctx->sm_count * 8);
+        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1><<<blocks, 32, smem, ctx->stream>>>(P));
+    }
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+// V pass: tile variant when its shared-memory footprint fits, else the direct variant
+template <int N, bool EXACT>
+int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+    PFE_TRY(upload_weights<N>(ctx, P, k));
+    const int wp_pad = (P.wp_len + 1) & ~1;
+    const size_t extra = (size_t)wp_pad * 8 + 16 * kChunks + 64;
+    auto tile_smem = [&](int warps) {
+        const int rows = warps * N + P.steps - N;
+        return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra;
+    };
+    const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
+    const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.rh, 8 * N);
+    if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
+        const size_t smem = tile_smem(8);
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8>, 288, smem, tiles8);
+        PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8><<<blocks, 288, smem, ctx->stream>>>(P));
+    } else {
+        size_t smem = (size_t)wp_pad * 8;
+        if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+        if (smem > 48 * 1024)
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
+        PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
+    }
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+// Register-block size per pass: the one that wastes the fewest issue slots on zero-padded steps plus
+// per-step overhead. The V pass pays more per step (ring bookkeeping), so it prefers a larger block:
+// measured at sigma=20, H is fastest with N=8 and V with N=16.
+static int pick_n(int taps, double per_step_overhead) {
+    auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + per_step_overhead) / n; };
     int best = 1;
     if (taps >= 3) {
         best = 4;
         if (taps >= 9 && cost(8) < cost(best)) best = 8;
         if (taps >= 17 && cost(16) < cost(best)) best = 16;
     }
-    switch (best) {
-        case 16: return run_passes<16, EXACT>(ctx, P, k);
-        case 8: return run_passes<8, EXACT>(ctx, P, k);
-        case 4: return run_passes<4, EXACT>(ctx, P, k);
-        default: return run_passes<1, EXACT>(ctx, P, k);
+    if (const char *force = getenv("PFE_GAUSS_N")) {  // tuning aid
+        const int n = atoi(force);
+        if ((n == 4 || n == 8 || n == 16) && taps >= n + 1) best = n;
+    }
+    return best;
+}
+
+template <bool EXACT>
+int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    const int taps = (int)k.size();
+    switch (pick_n(taps, 6.0)) {
+        case 16: PFE_TRY((run_h<16, EXACT>(ctx, P, k))); break;
+        case 8: PFE_TRY((run_h<8, EXACT>(ctx, P, k))); break;
+        case 4: PFE_TRY((run_h<4, EXACT>(ctx, P, k))); break;
+        default: PFE_TRY((run_h<1, EXACT>(ctx, P, k))); break;
+    }
+    switch (pick_n(taps, 12.0)) {
+        case 16: return run_v<16, EXACT>(ctx, P, k);
+        case 8: return run_v<8, EXACT>(ctx, P, k);
+        case 4: return run_v<4, EXACT>(ctx, P, k);
+        default: return run_v<1, EXACT>(ctx, P, k);
     }
 }
 
