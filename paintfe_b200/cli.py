@@ -7,7 +7,7 @@
 Same flags as the reference for the part of the pipeline that is in scope: -i/--input (glob patterns
 or literal paths, deduplicated in order, cli.rs:315-350), -s/--script, -o/--output (single input
 only), --output-dir, -f/--format, -v/--verbose.  Image decoding/encoding is harness plumbing (PIL);
-`.pfe` project I/O is listed as "next" in DESIGN.md.  A per-file failure is reported and the batch
+`.pfe` v0/v1/v2 projects load through paintfe_b200/pfe_io.py and are flattened on the GPU (--flatten).  A per-file failure is reported and the batch
 continues; the exit code is 1 if any file failed (cli.rs:204-215).
 """
 from __future__ import annotations
@@ -50,15 +50,31 @@ def build_output_path(inp: str, output: Optional[str], output_dir: Optional[str]
     return None
 
 
-def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool) -> None:
-    """cli.rs:222-308 for single-layer raster inputs: load -> script -> encode."""
+def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flatten: bool = True) -> None:
+    """cli.rs:222-308: load -> script on the active layer -> flatten if several layers -> encode."""
     from PIL import Image
 
+    from .engine import make_layer
     from .script import execute_script_sync
 
-    img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
-    if script:
-        img = execute_script_sync(eng, script, img)
+    if inp.lower().endswith(".pfe"):  # io::load_image_sync -> load_pfe (io.rs:693, :469)
+        from . import pfe_io
+
+        proj = pfe_io.load_pfe(inp)
+        w, h = proj.width, proj.height
+        flats = [L.to_flat(w, h) for L in proj.layers]
+        ai = min(proj.active_layer_index, len(flats) - 1)
+        if script:  # the script sees the active layer (cli.rs:239-260)
+            flats[ai] = np.asarray(execute_script_sync(eng, script, flats[ai]))
+        if flatten and len(flats) > 1:  # cli.rs:282-285 state.composite()
+            img = eng.flatten([make_layer(f, opacity=L.opacity, blend=L.blend_mode, visible=L.visible)
+                               for f, L in zip(flats, proj.layers)], w, h)
+        else:
+            img = flats[ai]
+    else:
+        img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
+        if script:
+            img = execute_script_sync(eng, script, img)
     os.makedirs(os.path.dirname(os.path.abspath(outp)), exist_ok=True)
     Image.fromarray(np.asarray(img), "RGBA").save(outp)
 
@@ -70,6 +86,7 @@ def main(argv=None) -> int:
     ap.add_argument("-o", "--output")
     ap.add_argument("--output-dir")
     ap.add_argument("-f", "--format", default=None)
+    ap.add_argument("--flatten", action=argparse.BooleanOptionalAction, default=True)
     ap.add_argument("-v", "--verbose", action="store_true")
     args = ap.parse_args(argv)
 
@@ -100,7 +117,7 @@ def main(argv=None) -> int:
             any_failure = True
             continue
         try:
-            run_one(eng, path, outp, script, args.verbose)
+            run_one(eng, path, outp, script, args.verbose, args.flatten)
             if args.verbose or total > 1:
                 print(f"  -> {outp} ({(time.perf_counter() - t0) * 1000:.0f}ms)")
         except Exception as e:  # per-file failure: report and continue (cli.rs:204-209)

@@ -451,3 +451,39 @@ def test_full_size_8k_flatten_and_gaussian_crops(eng, oracle):
     again = eng.flatten([make_layer(flat)], w, h)
     opaque = flat[..., 3] == 255
     assert torch.equal(again[opaque], flat[opaque])
+
+
+# ---------------------------------------------------------------------------------------------
+# CLI batch mode end to end (BASELINE config 1 and a small config-5 style batch)
+# ---------------------------------------------------------------------------------------------
+def test_cli_flatten_pfe_and_script_batch(eng, oracle, tmp_path):
+    from PIL import Image
+
+    from paintfe_b200 import cli, pfe_io
+    from test_pfe_io import _config1_project
+
+    proj, _ = _config1_project()
+    (tmp_path / "in").mkdir()
+    (tmp_path / "in" / "project.pfe").write_bytes(pfe_io.save_pfe_v1(proj))
+    rng = np.random.default_rng(3)
+    shots = {}
+    for i in range(3):
+        img = fx.random_rgba(rng, 200 + 17 * i, 120 + 5 * i)
+        shots[f"shot{i}"] = img
+        Image.fromarray(img, "RGBA").save(tmp_path / "in" / f"shot{i}.png")
+    script = tmp_path / "process.rhai"
+    script.write_text("apply_blur(4.0); apply_hsl(10.0, 15.0, 0.0); apply_vignette(0.5, 0.3);\n")
+    # config 1: --flatten on the 2-layer project, no script
+    assert cli.main(["-i", str(tmp_path / "in" / "project.pfe"), "-o", str(tmp_path / "flat.png")]) == 0
+    flats = [L.to_flat(1024, 1024) for L in proj.layers]
+    exp = oracle.flatten([oracle.make_layer(f, opacity=L.opacity, blend=L.blend_mode) for f, L in zip(flats, proj.layers)], 1024, 1024)
+    exact(np.array(Image.open(tmp_path / "flat.png").convert("RGBA")), exp, "cli --flatten project.pfe")
+    # batch with a script over a glob; one unreadable file must not stop the batch (cli.rs:204-215)
+    (tmp_path / "in" / "broken.png").write_bytes(b"not a png")
+    rc = cli.main(["-i", str(tmp_path / "in" / "*.png"), "--script", str(script), "--output-dir", str(tmp_path / "out")])
+    assert rc == 1
+    for name, img in shots.items():
+        e = oracle.gaussian_blur(img, 4.0)
+        e = oracle.adjust(e, oracle.S_HSL, (10.0, 15.0, 0.0))
+        e = oracle.vignette(e, 0.5, 0.3)
+        within1(np.array(Image.open(tmp_path / "out" / f"{name}.png").convert("RGBA")), e, name)
