@@ -50,7 +50,7 @@ def build_output_path(inp: str, output: Optional[str], output_dir: Optional[str]
     return None
 
 
-def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flatten: bool = True) -> None:
+def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flatten: bool = True, exact: bool = False) -> None:
     """cli.rs:222-308: load -> script on the active layer -> flatten if several layers -> encode."""
     from PIL import Image
 
@@ -65,7 +65,7 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
         flats = [L.to_flat(w, h) for L in proj.layers]
         ai = min(proj.active_layer_index, len(flats) - 1)
         if script:  # the script sees the active layer (cli.rs:239-260)
-            flats[ai] = np.asarray(execute_script_sync(eng, script, flats[ai]))
+            flats[ai] = np.asarray(execute_script_sync(eng, script, flats[ai], exact=exact))
         if flatten and len(flats) > 1:  # cli.rs:282-285 state.composite()
             img = eng.flatten([make_layer(f, opacity=L.opacity, blend=L.blend_mode, visible=L.visible)
                                for f, L in zip(flats, proj.layers)], w, h)
@@ -74,7 +74,7 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
     else:
         img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
         if script:
-            img = execute_script_sync(eng, script, img)
+            img = execute_script_sync(eng, script, img, exact=exact)
     os.makedirs(os.path.dirname(os.path.abspath(outp)), exist_ok=True)
     Image.fromarray(np.asarray(img), "RGBA").save(outp)
 
@@ -87,6 +87,7 @@ def main(argv=None) -> int:
     ap.add_argument("--output-dir")
     ap.add_argument("-f", "--format", default=None)
     ap.add_argument("--flatten", action=argparse.BooleanOptionalAction, default=True)
+    ap.add_argument("--exact", action="store_true", help="bit-exact Gaussian/sharpen (reference tap order, no FMA)")
     ap.add_argument("-v", "--verbose", action="store_true")
     args = ap.parse_args(argv)
 
@@ -117,7 +118,7 @@ def main(argv=None) -> int:
             any_failure = True
             continue
         try:
-            run_one(eng, path, outp, script, args.verbose, args.flatten)
+            run_one(eng, path, outp, script, args.verbose, args.flatten, args.exact)
             if args.verbose or total > 1:
                 print(f"  -> {outp} ({(time.perf_counter() - t0) * 1000:.0f}ms)")
         except Exception as e:  # per-file failure: report and continue (cli.rs:204-209)

@@ -29,7 +29,7 @@ def _f32(v) -> float:
     return float(np.float32(v))
 
 
-def bindings(eng) -> Dict[str, Callable]:
+def bindings(eng, exact: bool = False) -> Dict[str, Callable]:
     """name -> f(img, mask, *args) -> img, mirroring register_effect_api (scripting.rs:822)."""
 
     def exposure_gain(ev):
@@ -37,10 +37,10 @@ def bindings(eng) -> Dict[str, Callable]:
 
     return {
         # blur family goes through apply_effect_to_context: selection mask honoured (scripting.rs:617)
-        "apply_blur": lambda im, m, sigma: eng.gaussian_blur(im, _f32(sigma), mask=m),
+        "apply_blur": lambda im, m, sigma: eng.gaussian_blur(im, _f32(sigma), mask=m, exact=exact),
         "apply_box_blur": lambda im, m, radius: eng.box_blur(im, _f32(int(radius)), mask=m),
         "apply_motion_blur": lambda im, m, angle, distance: eng.motion_blur(im, _f32(angle), _f32(distance), mask=m),
-        "apply_sharpen": lambda im, m, amount: eng.sharpen(im, _f32(amount), 1.0, mask=m),
+        "apply_sharpen": lambda im, m, amount: eng.sharpen(im, _f32(amount), 1.0, mask=m, exact=exact),
         "apply_median": lambda im, m, radius: eng.median(im, max(int(radius), 1), mask=m),
         "apply_vignette": lambda im, m, strength, softness: eng.vignette(im, _f32(strength), _f32(softness), mask=m),
         # inline variants: truncating casts, no mask, alpha untouched (scripting.rs:869-1075)
@@ -71,11 +71,12 @@ def parse(source: str) -> List[Tuple[str, Tuple[float, ...]]]:
     return calls
 
 
-def execute_script_sync(eng, source: str, pixels, mask=None):
+def execute_script_sync(eng, source: str, pixels, mask=None, exact: bool = False):
     """Shape of scripting::execute_script_sync (scripting.rs:1733): flat RGBA in, flat RGBA out.
     `pixels` may be a numpy array (host tier) or a CUDA tensor (device tier: the whole script runs
-    without leaving the device)."""
-    table = bindings(eng)
+    without leaving the device). `exact` selects the bit-exact Gaussian (PFE_GAUSS_EXACT) over the
+    default FMA path (<= 1 level)."""
+    table = bindings(eng, exact)
     img = pixels
     for name, args in parse(source):
         if name not in table:

@@ -480,10 +480,10 @@ def test_cli_flatten_pfe_and_script_batch(eng, oracle, tmp_path):
     exact(np.array(Image.open(tmp_path / "flat.png").convert("RGBA")), exp, "cli --flatten project.pfe")
     # batch with a script over a glob; one unreadable file must not stop the batch (cli.rs:204-215)
     (tmp_path / "in" / "broken.png").write_bytes(b"not a png")
-    rc = cli.main(["-i", str(tmp_path / "in" / "*.png"), "--script", str(script), "--output-dir", str(tmp_path / "out")])
+    rc = cli.main(["-i", str(tmp_path / "in" / "*.png"), "--script", str(script), "--output-dir", str(tmp_path / "out"), "--exact"])
     assert rc == 1
     for name, img in shots.items():
         e = oracle.gaussian_blur(img, 4.0)
         e = oracle.adjust(e, oracle.S_HSL, (10.0, 15.0, 0.0))
         e = oracle.vignette(e, 0.5, 0.3)
-        within1(np.array(Image.open(tmp_path / "out" / f"{name}.png").convert("RGBA")), e, name)
+        exact(np.array(Image.open(tmp_path / "out" / f"{name}.png").convert("RGBA")), e, name)
