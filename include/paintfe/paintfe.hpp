@@ -343,6 +343,41 @@ inline RgbaImage vignette_core(const RgbaImage &flat, float amount, float softne
         return pfe_vignette(c, s, w, h, amount, softness, m, d);
     });
 }
+// widened scope: stylize.rs:26, distort.rs:333/396/460, noise.rs:73/172
+inline RgbaImage glow_core(const RgbaImage &flat, float radius, float intensity, const GrayImage *mask, bool exact = true) {
+    return detail::img_op(flat, mask, "pfe_glow", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_glow(c, s, w, h, radius, intensity, m, d, exact ? PFE_GAUSS_EXACT : 0u);
+    });
+}
+inline RgbaImage pixelate_core(const RgbaImage &flat, uint32_t block_size, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_pixelate", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_pixelate(c, s, w, h, block_size, m, d);
+    });
+}
+inline RgbaImage bulge_core_at(const RgbaImage &flat, float amount, std::pair<float, float> origin, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_bulge", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_bulge(c, s, w, h, amount, origin.first, origin.second, m, d);
+    });
+}
+inline RgbaImage bulge_core(const RgbaImage &flat, float amount, const GrayImage *mask) { return bulge_core_at(flat, amount, {0.5f, 0.5f}, mask); }
+inline RgbaImage twist_core_at(const RgbaImage &flat, float angle_deg, std::pair<float, float> origin, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_twist", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_twist(c, s, w, h, angle_deg, origin.first, origin.second, m, d);
+    });
+}
+inline RgbaImage twist_core(const RgbaImage &flat, float angle_deg, const GrayImage *mask) { return twist_core_at(flat, angle_deg, {0.5f, 0.5f}, mask); }
+enum class NoiseType { Uniform = 0, Gaussian = 1, Perlin = 2 };
+inline RgbaImage add_noise_core(const RgbaImage &flat, float amount, NoiseType t, bool monochrome, uint32_t seed, float scale,
+                                uint32_t octaves, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_add_noise", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_add_noise(c, s, w, h, amount, (int)t, monochrome ? 1 : 0, seed, scale, octaves, m, d);
+    });
+}
+inline RgbaImage reduce_noise_core(const RgbaImage &flat, float strength, uint32_t radius, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_reduce_noise", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_reduce_noise(c, s, w, h, strength, radius, m, d);
+    });
+}
 }  // namespace effects
 
 namespace adjustments {

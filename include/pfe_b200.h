@@ -142,6 +142,42 @@ int pfe_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float
 int pfe_dev_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount,
                      float softness, const uint8_t *mask, uint8_t *dst);
 
+/* -- further Effect-API kernels ------------------------------------------
+ * glow_core (src/ops/effects/stylize.rs:26-76): blur(sigma=radius) then screen with the source;
+ * fused into the Gaussian V pass. */
+int pfe_glow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius, float intensity,
+             const uint8_t *mask, uint8_t *dst, uint32_t flags);
+int pfe_dev_glow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius, float intensity,
+                 const uint8_t *mask, uint8_t *dst, uint32_t flags);
+/* pixelate_core (src/ops/effects/distort.rs:333-373): block centre sample; block_size < 2 -> 2. */
+int pfe_pixelate(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t block_size,
+                 const uint8_t *mask, uint8_t *dst);
+int pfe_dev_pixelate(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t block_size,
+                     const uint8_t *mask, uint8_t *dst);
+/* bulge_core_at / twist_core_at (distort.rs:400-437, :464-493); origin in 0..1 ((0.5,0.5) for the
+ * plain _core forms). bulge is bit-exact; twist needs sin/cos per pixel: within +-1 level. */
+int pfe_bulge(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float origin_x,
+              float origin_y, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_bulge(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float origin_x,
+                  float origin_y, const uint8_t *mask, uint8_t *dst);
+int pfe_twist(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg, float origin_x,
+              float origin_y, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_twist(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg, float origin_x,
+                  float origin_y, const uint8_t *mask, uint8_t *dst);
+/* add_noise_core (src/ops/effects/noise.rs:73-143). noise_type: 0 Uniform, 1 Gaussian, 2 Perlin.
+ * Uniform and Perlin are bit-exact (integer hash + strict f32); monochrome Gaussian uses ln/cos
+ * per pixel: within +-1 level. */
+int pfe_add_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, int noise_type,
+                  int monochrome, uint32_t seed, float scale, uint32_t octaves, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_add_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, int noise_type,
+                      int monochrome, uint32_t seed, float scale, uint32_t octaves, const uint8_t *mask,
+                      uint8_t *dst);
+/* reduce_noise_core (bilateral, noise.rs:172-262); exp per tap: within +-1 level. */
+int pfe_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float strength, uint32_t radius,
+                     const uint8_t *mask, uint8_t *dst);
+int pfe_dev_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float strength,
+                         uint32_t radius, const uint8_t *mask, uint8_t *dst);
+
 /* -- per-pixel adjustments ---------------------------------------------------------------
  * Ops 0..31 follow src/ops/adjustments.rs (round-to-nearest, selection mask honoured,
  * apply_pixel_transform[_from_flat] :21-108). Ops 32.. follow the inline Rhai bindings in

@@ -1125,3 +1125,214 @@ int pfo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* ========================================================================= */
+/* Widened scope: remaining Rhai Effect-API kernels        */
+/* ========================================================================= */
+
+/* glow_core, src/ops/effects/stylize.rs:26-76 */
+void pfo_glow(const uint8_t *src, uint32_t w, uint32_t h, float radius, float intensity,
+              const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    size_t n = (size_t)w * h;
+    uint8_t *bl = (uint8_t *)malloc(n * 4);
+    pfo_gaussian_blur(src, w, h, radius, bl);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        size_t si = (size_t)i * 4;
+        if (mask && mask[i] == 0) { memcpy(dst + si, src + si, 4); continue; }
+        for (int c = 0; c < 3; c++) {
+            float s = (float)src[si + c] / 255.0f, b = (float)bl[si + c] / 255.0f;
+            float result = 1.0f - (1.0f - s) * (1.0f - b * intensity);
+            dst[si + c] = round_u8(result * 255.0f);
+        }
+        dst[si + 3] = src[si + 3];
+    }
+    free(bl);
+}
+
+/* pixelate_core, src/ops/effects/distort.rs:333-373 */
+void pfo_pixelate(const uint8_t *src, uint32_t w, uint32_t h, uint32_t block_size, const uint8_t *mask,
+                  uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    uint32_t bs = block_size < 2 ? 2 : block_size;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            uint32_t bx = ((uint32_t)x / bs) * bs + bs / 2, by = ((uint32_t)y / bs) * bs + bs / 2;
+            uint32_t sx = bx < w - 1 ? bx : w - 1, sy = by < h - 1 ? by : h - 1;
+            memcpy(dst + oi, src + ((size_t)sy * w + sx) * 4, 4);
+        }
+}
+
+/* sample_clamped / sample_bilinear, src/ops/effects.rs:109-141 */
+static inline void sample_clamped(const uint8_t *src, int w, int h, int x, int y, float p[4]) {
+    int cx = clampi(x, 0, w - 1), cy = clampi(y, 0, h - 1);
+    const uint8_t *s = src + ((size_t)cy * w + cx) * 4;
+    for (int c = 0; c < 4; c++) p[c] = (float)s[c];
+}
+static inline void sample_bilinear(const uint8_t *src, int w, int h, float fx, float fy, float out[4]) {
+    int x0 = as_i32(floorf(fx)), y0 = as_i32(floorf(fy));
+    int x1 = x0 + 1, y1 = y0 + 1;
+    float dx = fx - (float)x0, dy = fy - (float)y0;
+    float p00[4], p10[4], p01[4], p11[4];
+    sample_clamped(src, w, h, x0, y0, p00); sample_clamped(src, w, h, x1, y0, p10);
+    sample_clamped(src, w, h, x0, y1, p01); sample_clamped(src, w, h, x1, y1, p11);
+    for (int c = 0; c < 4; c++)
+        out[c] = p00[c] * (1.0f - dx) * (1.0f - dy) + p10[c] * dx * (1.0f - dy) + p01[c] * (1.0f - dx) * dy + p11[c] * dx * dy;
+}
+
+/* bulge_core_at, distort.rs:400-437 */
+void pfo_bulge(const uint8_t *src, uint32_t w, uint32_t h, float amount, float ox, float oy,
+               const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float fw = (float)w, fh = (float)h;
+    float cx = clampf(ox, 0.0f, 1.0f) * maxf(fw - 1.0f, 0.0f), cy = clampf(oy, 0.0f, 1.0f) * maxf(fh - 1.0f, 0.0f);
+    float max_r = maxf(maxf(maxf(cx, fw - cx), maxf(cy, fh - cy)), 1.0f);
+    float strength = maxf(fabsf(amount), 0.0001f);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float dx = (float)x - cx, dy = (float)y - cy;
+            float dist = sqrtf(dx * dx + dy * dy);
+            float norm = minf(dist / max_r, 1.0f);
+            float p[4];
+            if (norm >= 1.0f) sample_clamped(src, (int)w, (int)h, (int)x, (int)y, p);
+            else {
+                float falloff = 1.0f - norm;
+                float factor = amount > 0.0f ? 1.0f - falloff * strength * 0.5f : (amount < 0.0f ? 1.0f + falloff * strength * 0.5f : 1.0f);
+                sample_bilinear(src, (int)w, (int)h, cx + dx * factor, cy + dy * factor, p);
+            }
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(p[c]);
+        }
+}
+
+/* twist_core_at, distort.rs:464-493 */
+void pfo_twist(const uint8_t *src, uint32_t w, uint32_t h, float angle_deg, float ox, float oy,
+               const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float fw = (float)w, fh = (float)h;
+    float cx = clampf(ox, 0.0f, 1.0f) * maxf(fw - 1.0f, 0.0f), cy = clampf(oy, 0.0f, 1.0f) * maxf(fh - 1.0f, 0.0f);
+    float mx = maxf(cx, fw - cx), my = maxf(cy, fh - cy);
+    float max_r = maxf(sqrtf(mx * mx + my * my), 1.0f);
+    float twist_amount = pfo_to_radians(angle_deg);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float dx = (float)x - cx, dy = (float)y - cy;
+            float dist = sqrtf(dx * dx + dy * dy);
+            float norm = dist / max_r;
+            float rotation = twist_amount * (1.0f - norm);
+            float cr = cosf(rotation), sr = sinf(rotation);
+            float p[4];
+            sample_bilinear(src, (int)w, (int)h, cx + dx * cr - dy * sr, cy + dx * sr + dy * cr, p);
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(p[c]);
+        }
+}
+
+/* hash_u32 / hash_f32, src/ops/effects.rs:143-161 */
+static inline uint32_t hash_u32(uint32_t x) {
+    x *= 0x9E3779B9u; x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+static inline float hash_f32(uint32_t x, uint32_t y, uint32_t seed) {
+    uint32_t hh = hash_u32(x * 374761393u + y * 668265263u + seed);
+    return (float)(hh & 0x00FFFFFFu) / 16777216.0f;
+}
+/* perlin_noise_2d, noise.rs:52-71; turbulence_2d, distort.rs:229-246 */
+static float perlin_noise_2d(float x, float y, uint32_t seed) {
+    int xi = as_i32(floorf(x)), yi = as_i32(floorf(y));
+    float xf = x - (float)xi, yf = y - (float)yi;
+    float u = xf * xf * xf * (xf * (xf * 6.0f - 15.0f) + 10.0f), v = yf * yf * yf * (yf * (yf * 6.0f - 15.0f) + 10.0f);
+    float n00 = hash_f32((uint32_t)xi, (uint32_t)yi, seed), n10 = hash_f32((uint32_t)(xi + 1), (uint32_t)yi, seed);
+    float n01 = hash_f32((uint32_t)xi, (uint32_t)(yi + 1), seed), n11 = hash_f32((uint32_t)(xi + 1), (uint32_t)(yi + 1), seed);
+    float nx0 = n00 + u * (n10 - n00), nx1 = n01 + u * (n11 - n01);
+    return nx0 + v * (nx1 - nx0);
+}
+static float turbulence_2d(float x, float y, uint32_t seed, uint32_t octaves, float roughness) {
+    float total = 0.0f, amplitude = 1.0f, frequency = 1.0f, max_amplitude = 0.0f;
+    for (uint32_t i = 0; i < octaves; i++) {
+        total += perlin_noise_2d(x * frequency, y * frequency, seed + i * 1000u) * amplitude;
+        max_amplitude += amplitude;
+        amplitude *= roughness;
+        frequency *= 2.0f;
+    }
+    return max_amplitude > 0.0f ? total / max_amplitude : 0.0f;
+}
+
+/* add_noise_core, noise.rs:73-143. noise_type: 0 Uniform, 1 Gaussian, 2 Perlin */
+void pfo_add_noise(const uint8_t *src, uint32_t w, uint32_t h, float amount, int noise_type, int monochrome,
+                   uint32_t seed, float scale, uint32_t octaves, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float inv_scale = 1.0f / maxf(scale, 0.1f);
+    uint32_t oct = octaves < 1 ? 1 : (octaves > 8 ? 8 : octaves);
+    float strength = amount * 255.0f / 100.0f;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float r = (float)src[oi], g = (float)src[oi + 1], b = (float)src[oi + 2], a = (float)src[oi + 3];
+            float sx = (float)x * inv_scale, sy = (float)y * inv_scale;
+            uint32_t qx = as_u32(floorf((float)x * inv_scale)), qy = as_u32(floorf((float)y * inv_scale));
+            float nr, ng, nb;
+            if (monochrome) {
+                float nv;
+                if (noise_type == 0) nv = hash_f32(qx, qy, seed) * 2.0f - 1.0f;
+                else if (noise_type == 1) {
+                    float u1 = maxf(hash_f32(qx, qy, seed), 0.0001f), u2 = hash_f32(qx, qy, seed + 7u);
+                    nv = sqrtf(-2.0f * logf(u1)) * cosf(2.0f * 3.14159265358979323846f * u2) * 0.33f;
+                } else nv = turbulence_2d(sx, sy, seed, oct, 0.5f) * 2.0f - 1.0f;
+                nr = ng = nb = nv * strength;
+            } else if (noise_type == 2) {
+                nr = (turbulence_2d(sx, sy, seed, oct, 0.5f) * 2.0f - 1.0f) * strength;
+                ng = (turbulence_2d(sx, sy, seed + 1u, oct, 0.5f) * 2.0f - 1.0f) * strength;
+                nb = (turbulence_2d(sx, sy, seed + 2u, oct, 0.5f) * 2.0f - 1.0f) * strength;
+            } else {  /* non-monochrome Uniform AND Gaussian both use the uniform hash per channel (:114-136) */
+                nr = (hash_f32(qx, qy, seed) * 2.0f - 1.0f) * strength;
+                ng = (hash_f32(qx, qy, seed + 1u) * 2.0f - 1.0f) * strength;
+                nb = (hash_f32(qx, qy, seed + 2u) * 2.0f - 1.0f) * strength;
+            }
+            dst[oi] = round_u8(r + nr); dst[oi + 1] = round_u8(g + ng); dst[oi + 2] = round_u8(b + nb); dst[oi + 3] = round_u8(a);
+        }
+}
+
+/* reduce_noise_core (bilateral), noise.rs:172-262 */
+void pfo_reduce_noise(const uint8_t *src, uint32_t w, uint32_t h, float strength, uint32_t radius,
+                      const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    int r = radius < 1 ? 1 : (int)radius;
+    float sigma_s = (float)r, sigma_r = strength * 2.55f;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float cr = (float)src[oi], cg = (float)src[oi + 1], cb = (float)src[oi + 2];
+            float s[4] = {0, 0, 0, 0}, wsum = 0.0f;
+            for (int dy = -r; dy <= r; dy++) {
+                int sy = clampi((int)y + dy, 0, (int)h - 1);
+                for (int dx = -r; dx <= r; dx++) {
+                    int sx = clampi((int)x + dx, 0, (int)w - 1);
+                    const uint8_t *p = src + ((size_t)sy * w + sx) * 4;
+                    float pr = (float)p[0], pg = (float)p[1], pb = (float)p[2], pa = (float)p[3];
+                    float spatial = (float)(dx * dx + dy * dy) / (2.0f * sigma_s * sigma_s);
+                    float dr = cr - pr, dg = cg - pg, db = cb - pb;
+                    float range = (dr * dr + dg * dg + db * db) / (2.0f * sigma_r * sigma_r + 0.001f);
+                    float wt = expf(-spatial - range);
+                    s[0] += pr * wt; s[1] += pg * wt; s[2] += pb * wt; s[3] += pa * wt;
+                    wsum += wt;
+                }
+            }
+            if (wsum > 0.0f) {
+                float inv = 1.0f / wsum;
+                for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(s[c] * inv);
+            } else memcpy(dst + oi, src + oi, 4);
+        }
+}

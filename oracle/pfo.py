@@ -319,3 +319,32 @@ def tiled_roundtrip(src):
     dst = np.empty_like(src)
     lib().pfo_tiled_roundtrip(_p(src), C.c_uint32(w), C.c_uint32(h), _p(occ), _p(dst))
     return dst, occ
+
+
+# -- widened scope: remaining Rhai Effect-API kernels ------------------------------------------
+def glow(src, radius, intensity, mask=None):
+    return _img_call(lib().pfo_glow, src, C.c_float(radius), C.c_float(intensity), mask=mask)
+
+
+def pixelate(src, block_size, mask=None):
+    return _img_call(lib().pfo_pixelate, src, C.c_uint32(block_size), mask=mask)
+
+
+def bulge(src, amount, origin=(0.5, 0.5), mask=None):
+    return _img_call(lib().pfo_bulge, src, C.c_float(amount), C.c_float(origin[0]), C.c_float(origin[1]), mask=mask)
+
+
+def twist(src, angle_deg, origin=(0.5, 0.5), mask=None):
+    return _img_call(lib().pfo_twist, src, C.c_float(angle_deg), C.c_float(origin[0]), C.c_float(origin[1]), mask=mask)
+
+
+NOISE_UNIFORM, NOISE_GAUSSIAN, NOISE_PERLIN = range(3)
+
+
+def add_noise(src, amount, noise_type, monochrome, seed, scale, octaves, mask=None):
+    return _img_call(lib().pfo_add_noise, src, C.c_float(amount), C.c_int(noise_type), C.c_int(1 if monochrome else 0),
+                     C.c_uint32(seed), C.c_float(scale), C.c_uint32(octaves), mask=mask)
+
+
+def reduce_noise(src, strength, radius, mask=None):
+    return _img_call(lib().pfo_reduce_noise, src, C.c_float(strength), C.c_uint32(radius), mask=mask)

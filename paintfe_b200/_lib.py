@@ -75,6 +75,18 @@ SIGNATURES = {
     "pfe_dev_sharpen": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _u32]),
     "pfe_vignette": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp]),
     "pfe_dev_vignette": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp]),
+    "pfe_glow": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _u32]),
+    "pfe_dev_glow": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp, _u32]),
+    "pfe_pixelate": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_dev_pixelate": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_bulge": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _vp]),
+    "pfe_dev_bulge": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _vp]),
+    "pfe_twist": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _vp]),
+    "pfe_dev_twist": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _vp]),
+    "pfe_add_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, C.c_int, C.c_int, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_dev_add_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, C.c_int, C.c_int, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_reduce_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_dev_reduce_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
     "pfe_adjust": (C.c_int, [_ctx, _vp, _u32, _u32, C.POINTER(AdjustDesc), _vp, _vp, _vp]),
     "pfe_dev_adjust": (C.c_int, [_ctx, _vp, _u32, _u32, C.POINTER(AdjustDesc), _vp, _vp, _vp]),
     "pfe_build_levels_lut": (None, [_f32, _f32, _f32, _f32, _f32, _vp]),

@@ -287,6 +287,31 @@ int pfe_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float
     HOST_TIER(pfe_dev_vignette(ctx, s.src, w, h, amount, softness, s.mask, s.dst));
 }
 
+int pfe_glow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius, float intensity,
+             const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    HOST_TIER(pfe_dev_glow(ctx, s.src, w, h, radius, intensity, s.mask, s.dst, flags));
+}
+int pfe_pixelate(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t block_size,
+                 const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_pixelate(ctx, s.src, w, h, block_size, s.mask, s.dst));
+}
+int pfe_bulge(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float ox, float oy,
+              const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_bulge(ctx, s.src, w, h, amount, ox, oy, s.mask, s.dst));
+}
+int pfe_twist(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg, float ox, float oy,
+              const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_twist(ctx, s.src, w, h, angle_deg, ox, oy, s.mask, s.dst));
+}
+int pfe_add_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, int noise_type,
+                  int monochrome, uint32_t seed, float scale, uint32_t octaves, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_add_noise(ctx, s.src, w, h, amount, noise_type, monochrome, seed, scale, octaves, s.mask, s.dst));
+}
+int pfe_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float strength, uint32_t radius,
+                     const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_reduce_noise(ctx, s.src, w, h, strength, radius, s.mask, s.dst));
+}
+
 int pfe_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const pfe_adjust_desc *d,
                const uint8_t *mask, const uint8_t *occupancy, uint8_t *dst) {
     if (!ctx || !d) return PFE_ERR_INVALID_ARG;

@@ -35,7 +35,8 @@ struct GaussParams {
     const float2 *wp;     // padded weights, each duplicated into both halves of a float2, device
     const uint8_t *orig;  // sharpen: original pixels (same geometry as dst), else null
     const uint8_t *mask;  // sharpen: selection mask plane (w*h) at region origin, or null
-    float amount;         // sharpen amount
+    float amount;         // sharpen amount / glow intensity
+    int epilogue;         // 0 store the blur, 1 unsharp mask (sharpen_core), 2 screen glow (glow_core)
     uint32_t src_pitch;   // pixels per source row
     uint32_t dst_pitch;   // pixels per destination row
     uint32_t mask_pitch;
@@ -154,6 +155,15 @@ __device__ __forceinline__ void v_store(const GaussParams &P, const Acc4 &acc, i
         uint32_t s = reinterpret_cast<const uint32_t *>(P.orig)[(size_t)y * P.dst_pitch + x];
         if (P.mask && P.mask[(size_t)y * P.mask_pitch + x] == 0) {
             outv = s;
+        } else if (P.epilogue == 2) {  // glow_core, stylize.rs:62-70: screen of the source with blur*intensity
+            uint32_t o[3];
+            const uint32_t bl[3] = {r8, g8, b8};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float sv = (float)((s >> (8 * c)) & 255u) / 255.0f, bv = (float)bl[c] / 255.0f;
+                o[c] = pfe_round_u8((1.0f - (1.0f - sv) * (1.0f - bv * P.amount)) * 255.0f);
+            }
+            outv = pfe_pack(o[0], o[1], o[2], s >> 24);
         } else {
             float sr = (float)(s & 255u), sg = (float)((s >> 8) & 255u), sb = (float)((s >> 16) & 255u);
             outv = pfe_pack(pfe_round_u8(sr + P.amount * (sr - (float)r8)), pfe_round_u8(sg + P.amount * (sg - (float)g8)),
@@ -490,7 +500,7 @@ int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
 
 int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pitch, uint32_t dst_pitch,
                  uint32_t rw, uint32_t rh, float sigma, uint32_t flags, const uint8_t *orig, float amount,
-                 const uint8_t *mask, uint32_t mask_pitch) {
+                 const uint8_t *mask, uint32_t mask_pitch, int epilogue = 1) {
     int radius;
     std::vector<float> k = build_kernel(sigma, &radius);
     if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
@@ -499,7 +509,7 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     GaussParams P;
     memset(&P, 0, sizeof(P));
     P.src = src; P.mid = (float *)mid; P.dst = dst;
-    P.orig = orig; P.mask = mask; P.amount = amount;
+    P.orig = orig; P.mask = mask; P.amount = amount; P.epilogue = orig ? epilogue : 0;
     P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
     P.rw = rw; P.rh = rh; P.radius = radius;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_n<true>(ctx, P, k) : dispatch_n<false>(ctx, P, k);
@@ -557,4 +567,13 @@ extern "C" int pfe_dev_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uin
     // blur(sigma = radius) with the unsharp epilogue fused into the V pass: the blurred image is
     // quantised to u8 in registers exactly as the reference stores it, never written to memory.
     return gauss_common(ctx, src, dst, w, w, w, h, radius, flags, src, amount, mask, w);
+}
+
+extern "C" int pfe_dev_glow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius, float intensity,
+                            const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !dst || !w || !h || src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "glow: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // blur(sigma = radius) with the screen-glow epilogue fused into the V pass (stylize.rs:26-76)
+    return gauss_common(ctx, src, dst, w, w, w, h, radius, flags, src, intensity, mask, w, 2);
 }

@@ -217,6 +217,29 @@ class Engine:
         return self._img_op(self.lib.pfe_vignette, self.lib.pfe_dev_vignette, src, mask, out, C.c_float(amount),
                             C.c_float(softness))
 
+    def glow(self, src, radius, intensity, mask=None, exact=False, out=None):
+        return self._img_op(self.lib.pfe_glow, self.lib.pfe_dev_glow, src, mask, out, C.c_float(radius),
+                            C.c_float(intensity), tail=(L.GAUSS_EXACT if exact else 0,))
+
+    def pixelate(self, src, block_size, mask=None, out=None):
+        return self._img_op(self.lib.pfe_pixelate, self.lib.pfe_dev_pixelate, src, mask, out, C.c_uint32(block_size))
+
+    def bulge(self, src, amount, origin=(0.5, 0.5), mask=None, out=None):
+        return self._img_op(self.lib.pfe_bulge, self.lib.pfe_dev_bulge, src, mask, out, C.c_float(amount),
+                            C.c_float(origin[0]), C.c_float(origin[1]))
+
+    def twist(self, src, angle_deg, origin=(0.5, 0.5), mask=None, out=None):
+        return self._img_op(self.lib.pfe_twist, self.lib.pfe_dev_twist, src, mask, out, C.c_float(angle_deg),
+                            C.c_float(origin[0]), C.c_float(origin[1]))
+
+    def add_noise(self, src, amount, noise_type, monochrome, seed, scale, octaves, mask=None, out=None):
+        return self._img_op(self.lib.pfe_add_noise, self.lib.pfe_dev_add_noise, src, mask, out, C.c_float(amount),
+                            int(noise_type), 1 if monochrome else 0, C.c_uint32(seed), C.c_float(scale), C.c_uint32(octaves))
+
+    def reduce_noise(self, src, strength, radius, mask=None, out=None):
+        return self._img_op(self.lib.pfe_reduce_noise, self.lib.pfe_dev_reduce_noise, src, mask, out,
+                            C.c_float(strength), C.c_uint32(radius))
+
     def adjust(self, src, op, params=(), luts=None, mask=None, occupancy=None, out=None):
         src = self._prep(src)
         h, w = self._hw(src)

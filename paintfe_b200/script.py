@@ -43,6 +43,14 @@ def bindings(eng, exact: bool = False) -> Dict[str, Callable]:
         "apply_sharpen": lambda im, m, amount: eng.sharpen(im, _f32(amount), 1.0, mask=m, exact=exact),
         "apply_median": lambda im, m, radius: eng.median(im, max(int(radius), 1), mask=m),
         "apply_vignette": lambda im, m, strength, softness: eng.vignette(im, _f32(strength), _f32(softness), mask=m),
+        # scripting.rs:1077-1131: fixed arguments of the bindings (noise: Gaussian, seed 42, scale 1, 1 octave;
+        # reduce_noise radius 2)
+        "apply_glow": lambda im, m, radius, intensity: eng.glow(im, _f32(radius), _f32(intensity), mask=m, exact=exact),
+        "apply_pixelate": lambda im, m, size: eng.pixelate(im, max(int(size), 1), mask=m),
+        "apply_bulge": lambda im, m, amount: eng.bulge(im, _f32(amount), mask=m),
+        "apply_twist": lambda im, m, angle: eng.twist(im, _f32(angle), mask=m),
+        "apply_noise": lambda im, m, amount, mono: eng.add_noise(im, _f32(amount), 1, bool(mono), 42, 1.0, 1, mask=m),
+        "apply_reduce_noise": lambda im, m, strength: eng.reduce_noise(im, _f32(strength), 2, mask=m),
         # inline variants: truncating casts, no mask, alpha untouched (scripting.rs:869-1075)
         "apply_invert": lambda im, m: eng.adjust(im, S_INVERT),
         "apply_desaturate": lambda im, m: eng.adjust(im, S_DESATURATE),
@@ -66,7 +74,8 @@ def parse(source: str) -> List[Tuple[str, Tuple[float, ...]]]:
         m = _CALL.match(stmt)
         if not m:
             raise ValueError(f"unsupported script statement (only apply_*(numbers) calls): {stmt.strip()!r}")
-        args = tuple(float(a) for a in m.group(2).split(",") if a.strip())
+        lit = {"true": 1.0, "false": 0.0}
+        args = tuple(lit[a.strip()] if a.strip() in lit else float(a) for a in m.group(2).split(",") if a.strip())
         calls.append((m.group(1), args))
     return calls
 

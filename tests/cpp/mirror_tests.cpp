@@ -147,6 +147,14 @@ int main(int argc, char **argv) {
     run("median_r2", [&] { assert_golden("filters", "median_r2", ops::effects::median_core(img, 2, nullptr)); });
     run("sharpen_a1_r1", [&] { assert_golden("filters", "sharpen_a1_r1", ops::effects::sharpen_core(img, 1.0f, 1.0f, nullptr)); });
     run("vignette_08_05", [&] { assert_golden("filters", "vignette_08_05", ops::effects::vignette_core(img, 0.8f, 0.5f, nullptr)); });
+    run("glow_r3_i05", [&] { assert_golden("filters", "glow_r3_i05", ops::effects::glow_core(img, 3.0f, 0.5f, nullptr)); });
+    run("pixelate_8", [&] { assert_golden("filters", "pixelate_8", ops::effects::pixelate_core(img, 8, nullptr)); });
+    run("bulge_05", [&] { assert_golden("filters", "bulge_05", ops::effects::bulge_core(img, 0.5f, nullptr)); });
+    run("twist_45", [&] { assert_golden("filters", "twist_45", ops::effects::twist_core(img, 45.0f, nullptr), 1); });
+    run("add_noise_uniform", [&] { assert_golden("filters", "add_noise_uniform", ops::effects::add_noise_core(img, 30.0f, ops::effects::NoiseType::Uniform, false, 42, 1.0f, 1, nullptr)); });
+    run("add_noise_gaussian", [&] { assert_golden("filters", "add_noise_gaussian_mono", ops::effects::add_noise_core(img, 30.0f, ops::effects::NoiseType::Gaussian, true, 42, 1.0f, 1, nullptr), 1); });
+    run("add_noise_perlin", [&] { assert_golden("filters", "add_noise_perlin", ops::effects::add_noise_core(img, 50.0f, ops::effects::NoiseType::Perlin, false, 42, 5.0f, 3, nullptr)); });
+    run("reduce_noise", [&] { assert_golden("filters", "reduce_noise", ops::effects::reduce_noise_core(img, 0.5f, 2, nullptr), 1); });
     run("gaussian_sigma0_identity", [&] { check(ops::filters::parallel_gaussian_blur_pub(img, 0.0f) == img, "sigma 0 must be identity"); });  // visual_filters.rs:296
     run("sharpen_amount0_identity", [&] { check(ops::effects::sharpen_core(img, 0.0f, 1.0f, nullptr) == img, "amount 0 must be identity"); });
     run("selection_mask_limits_blur", [&] {

@@ -47,6 +47,15 @@ FILTERS = {
     "median_r2": lambda o, im: o.median(im, 2),
     "sharpen_a1_r1": lambda o, im: o.sharpen(im, 1.0, 1.0),
     "vignette_08_05": lambda o, im: o.vignette(im, 0.8, 0.5),
+    # widened scope, tests/visual_filters.rs:88-160
+    "glow_r3_i05": lambda o, im: o.glow(im, 3.0, 0.5),
+    "pixelate_8": lambda o, im: o.pixelate(im, 8),
+    "bulge_05": lambda o, im: o.bulge(im, 0.5),
+    "twist_45": lambda o, im: o.twist(im, 45.0),
+    "add_noise_uniform": lambda o, im: o.add_noise(im, 30.0, o.NOISE_UNIFORM, False, 42, 1.0, 1),
+    "add_noise_gaussian_mono": lambda o, im: o.add_noise(im, 30.0, o.NOISE_GAUSSIAN, True, 42, 1.0, 1),
+    "add_noise_perlin": lambda o, im: o.add_noise(im, 50.0, o.NOISE_PERLIN, False, 42, 5.0, 3),
+    "reduce_noise": lambda o, im: o.reduce_noise(im, 0.5, 2),
 }
 
 
@@ -96,6 +105,7 @@ SCRIPT = {
     "apply_sepia": lambda o, im: o.adjust(im, o.S_SEPIA),
     "apply_desaturate": lambda o, im: o.adjust(im, o.S_DESATURATE),
     "apply_brightness_contrast": lambda o, im: o.adjust(im, o.S_BRIGHTNESS_CONTRAST, (20.0, 10.0)),
+    "apply_pixelate": lambda o, im: o.pixelate(im, 4),
 }
 
 
