@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -132,6 +133,7 @@ int pfe_ctx_create(int device, pfe_ctx **out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&c->pinned, PFE_SMALL_BYTES) == cudaSuccess &&
               cudaMalloc(&c->dev_small, PFE_SMALL_BYTES) == cudaSuccess;
@@ -153,6 +155,7 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return PFE_OK;
@@ -411,76 +414,135 @@ int pfe_brush_stamps(pfe_ctx *ctx, uint8_t *image, uint32_t w, uint32_t h, const
     return PFE_OK;
 }
 
-// ---- flatten host tier: upload every raster layer (and mask), run, download ----------------
-static int flatten_upload(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
-                          const uint8_t *active, std::vector<pfe_layer_desc> *dev_layers,
-                          uint8_t **active_dev, uint8_t **dst_dev) {
-    if (!ctx || (!layers && n) || !w || !h) return ctx ? pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: bad args") : PFE_ERR_INVALID_ARG;
+// ---- flatten host tier --------------------------------------------------------------------------
+// The call is PCIe-bound (4 bytes per layer per pixel in, 4 out), so it is pipelined in 64-row-
+// aligned bands on three streams: while band k+1 of every layer is uploading (copy_stream), band k
+// is flattened and H-blurred (ctx->stream); a band's V pass runs as soon as the H rows within
+// +-radius of it exist, and its result starts downloading (d2h_stream) while later bands are still
+// in flight. Only the last band's compute and download are exposed.
+static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
+                            const uint8_t *active, bool blur, float sigma, uint32_t flags, uint8_t *dst) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if ((!layers && n) || !w || !h || !dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: bad args");
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
-    size_t n4 = (size_t)w * h * 4, n1 = (size_t)w * h;
-    size_t a4 = (n4 + 255) & ~size_t(255), a1 = (n1 + 255) & ~size_t(255);
-    size_t total = a4;  // dst
+    const size_t n4 = (size_t)w * h * 4, n1 = (size_t)w * h;
+    const size_t a4 = (n4 + 255) & ~size_t(255), a1 = (n1 + 255) & ~size_t(255);
+    size_t total = a4;  // flattened image
     for (uint32_t i = 0; i < n; i++) {
-        if (!layers[i].visible) continue;
-        if (layers[i].kind == PFE_LAYER_RASTER) {
-            if (!layers[i].rgba) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: raster layer without pixels");
-            total += a4;
-            if (layers[i].mask) total += a1;
-        }
+        if (!layers[i].visible || layers[i].kind != PFE_LAYER_RASTER) continue;
+        if (!layers[i].rgba) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "flatten: raster layer without pixels");
+        total += a4 + (layers[i].mask ? a1 : 0);
     }
-    size_t nb = (size_t)pfe_div_up(w, PFE_CHUNK_SIZE) * pfe_div_up(h, PFE_CHUNK_SIZE);
+    const uint32_t chunks_x = pfe_div_up(w, PFE_CHUNK_SIZE);
+    const size_t nb = (size_t)chunks_x * pfe_div_up(h, PFE_CHUNK_SIZE);
     if (active) total += (nb + 255) & ~size_t(255);
     void *base;
     PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, total, &base));
     char *cur = (char *)base;
-    *dst_dev = (uint8_t *)cur;
+    uint8_t *flat = (uint8_t *)cur;
     cur += a4;
-    dev_layers->assign(layers, layers + n);
+    std::vector<pfe_layer_desc> dl(layers, layers + n);
     for (uint32_t i = 0; i < n; i++) {
-        pfe_layer_desc &L = (*dev_layers)[i];
+        pfe_layer_desc &L = dl[i];
         if (!L.visible || L.kind != PFE_LAYER_RASTER) { L.rgba = nullptr; L.mask = nullptr; continue; }
-        PFE_CUDA(ctx, cudaMemcpyAsync(cur, layers[i].rgba, n4, cudaMemcpyHostToDevice, ctx->stream));
         L.rgba = (uint8_t *)cur;
         cur += a4;
-        if (layers[i].mask) {
-            PFE_CUDA(ctx, cudaMemcpyAsync(cur, layers[i].mask, n1, cudaMemcpyHostToDevice, ctx->stream));
-            L.mask = (uint8_t *)cur;
-            cur += a1;
+        if (layers[i].mask) { L.mask = (uint8_t *)cur; cur += a1; }
+    }
+    uint8_t *active_dev = nullptr;
+    if (active) active_dev = (uint8_t *)cur;
+    uint8_t *out = flat;
+    float *mid = nullptr;
+    int radius = 0;
+    if (blur) {
+        void *b, *m;
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, n4, &b));
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)w * h * 16, &m));
+        out = (uint8_t *)b;
+        mid = (float *)m;
+        radius = pfe_gauss_radius(sigma);
+        if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+    }
+    // band height: ~8 bands, 64-row aligned; small images go through in one band
+    uint32_t band_h = h;
+    if (n4 >= (size_t)8 << 20) band_h = std::max<uint32_t>(PFE_CHUNK_SIZE, ((h / 8 + PFE_CHUNK_SIZE - 1) / PFE_CHUNK_SIZE) * PFE_CHUNK_SIZE);
+    const uint32_t nbands = pfe_div_up(h, band_h);
+
+    // the upload stream must not overwrite buffers that earlier work on ctx->stream still reads
+    PFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_copy, 0));
+    if (active) PFE_CUDA(ctx, cudaMemcpyAsync(active_dev, active, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+
+    std::vector<cudaEvent_t> events;
+    auto new_event = [&]() -> cudaEvent_t {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        events.push_back(e);
+        return e;
+    };
+    int rc = PFE_OK;
+    uint32_t v_next = 0;  // first band whose V pass (or download) has not been issued yet
+    auto download_band = [&](uint32_t k) -> int {
+        const uint32_t y0 = k * band_h, rows = std::min(band_h, h - y0);
+        cudaEvent_t e = new_event();
+        if (!e) return pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate");
+        PFE_CUDA(ctx, cudaEventRecord(e, ctx->stream));
+        PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+        PFE_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)y0 * w * 4, out + (size_t)y0 * w * 4, (size_t)rows * w * 4,
+                                      cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        return PFE_OK;
+    };
+    for (uint32_t b = 0; b < nbands && rc == PFE_OK; b++) {
+        const uint32_t y0 = b * band_h, rows = std::min(band_h, h - y0);
+        const size_t off4 = (size_t)y0 * w * 4, off1 = (size_t)y0 * w;
+        std::vector<pfe_layer_desc> bl(dl);
+        for (uint32_t i = 0; i < n; i++) {
+            if (!dl[i].rgba) continue;
+            PFE_CUDA(ctx, cudaMemcpyAsync((void *)(dl[i].rgba + off4), layers[i].rgba + off4, (size_t)rows * w * 4,
+                                          cudaMemcpyHostToDevice, ctx->copy_stream));
+            bl[i].rgba = dl[i].rgba + off4;
+            if (dl[i].mask) {
+                PFE_CUDA(ctx, cudaMemcpyAsync((void *)(dl[i].mask + off1), layers[i].mask + off1, (size_t)rows * w,
+                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+                bl[i].mask = dl[i].mask + off1;
+            }
+        }
+        cudaEvent_t up = new_event();
+        if (!up) { rc = pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate"); break; }
+        PFE_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
+        PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+        rc = pfe_dev_flatten(ctx, bl.data(), n, w, rows, active_dev ? active_dev + (size_t)(y0 / PFE_CHUNK_SIZE) * chunks_x : nullptr,
+                             flat + off4);
+        if (rc != PFE_OK) break;
+        if (!blur) { rc = download_band(b); continue; }
+        rc = pfe_gauss_h_rows(ctx, flat, mid, w, h, y0, rows, sigma, flags);
+        const uint32_t h_done = y0 + rows;
+        while (rc == PFE_OK && v_next < nbands) {
+            const uint32_t vy0 = v_next * band_h, vrows = std::min(band_h, h - vy0);
+            if (h_done < h && vy0 + vrows + (uint32_t)radius > h_done) break;  // its lower halo is not blurred yet
+            rc = pfe_gauss_v_rows(ctx, mid, out, w, h, vy0, vrows, sigma, flags);
+            if (rc == PFE_OK) rc = download_band(v_next);
+            v_next++;
         }
     }
-    *active_dev = nullptr;
-    if (active) {
-        PFE_CUDA(ctx, cudaMemcpyAsync(cur, active, nb, cudaMemcpyHostToDevice, ctx->stream));
-        *active_dev = (uint8_t *)cur;
-    }
+    cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream),
+                e3 = cudaStreamSynchronize(ctx->d2h_stream);
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    if (rc != PFE_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return pfe_fail(ctx, PFE_ERR_CUDA, "flatten pipeline", e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3));
     return PFE_OK;
 }
 
 int pfe_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
                 const uint8_t *active, uint8_t *dst) {
-    if (!dst) return PFE_ERR_INVALID_ARG;
-    std::vector<pfe_layer_desc> dl;
-    uint8_t *act, *d;
-    PFE_TRY(flatten_upload(ctx, layers, n, w, h, active, &dl, &act, &d));
-    PFE_TRY(pfe_dev_flatten(ctx, dl.data(), n, w, h, act, d));
-    PFE_CUDA(ctx, cudaMemcpyAsync(dst, d, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PFE_OK;
+    return flatten_pipeline(ctx, layers, n, w, h, active, false, 0.0f, 0, dst);
 }
 
 int pfe_flatten_gaussian(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n, uint32_t w, uint32_t h,
                          const uint8_t *active, float sigma, uint8_t *dst, uint32_t flags) {
-    if (!dst) return PFE_ERR_INVALID_ARG;
-    std::vector<pfe_layer_desc> dl;
-    uint8_t *act, *d;
-    PFE_TRY(flatten_upload(ctx, layers, n, w, h, active, &dl, &act, &d));
-    PFE_TRY(pfe_dev_flatten(ctx, dl.data(), n, w, h, act, d));
-    void *b;
-    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, (size_t)w * h * 4, &b));
-    PFE_TRY(pfe_dev_gaussian_blur(ctx, d, w, h, sigma, nullptr, (uint8_t *)b, flags));
-    PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return PFE_OK;
+    return flatten_pipeline(ctx, layers, n, w, h, active, true, sigma, flags, dst);
 }
 
 }  // extern "C"

@@ -41,6 +41,7 @@ struct GaussParams {
     uint32_t dst_pitch;   // pixels per destination row
     uint32_t mask_pitch;
     uint32_t rw, rh;      // region size
+    uint32_t v_y0, v_rows; // V pass: produce output rows [v_y0, v_y0 + v_rows) only (band pipelining)
     int radius;
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
     if (x >= (int)P.rw) return;
     const int rh = (int)P.rh;
     const float4 *mid = reinterpret_cast<const float4 *>(P.mid) + x;
-    for (int y0 = blockIdx.y * N; y0 < rh; y0 += gridDim.y * N) {
+    const int y_end = (int)(P.v_y0 + P.v_rows);
+    for (int y0 = (int)P.v_y0 + blockIdx.y * N; y0 < y_end; y0 += gridDim.y * N) {
         Acc4 acc[N];
         float2 R[N];
 #pragma unroll
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
         }
 #pragma unroll
         for (int j = 0; j < N; j++)
-            if (y0 + j < rh) v_store(P, acc[j], x, y0 + j);
+            if (y0 + j < y_end) v_store(P, acc[j], x, y0 + j);
     }
 }
 
@@ -262,7 +264,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rw = (int)P.rw, rh = (int)P.rh;
-    const int tx = (rw + 31) / 32, ty = (rh + TH - 1) / TH;
+    const int y_end = (int)(P.v_y0 + P.v_rows);
+    const int tx = (rw + 31) / 32, ty = ((int)P.v_rows + TH - 1) / TH;
     const int ntiles = tx * ty;
 
     if (warp == WARPS) {
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         uint32_t it = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
             // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
-            const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
+            const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
             const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
             for (int c = 0; c < kChunks; c++) {
                 const int r0 = c * chunk_rows, nrows = max(0, min(chunk_rows, rows - r0));
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     const int row_first = warp * N;  // first ring row this warp reads
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
-        const int x0 = (t / ty) * 32, y0 = (t % ty) * TH;
+        const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
         const uint32_t parity = it & 1u;
         Acc4 acc[N];
         float2 R[N];
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         if (x < rw) {
 #pragma unroll
             for (int j = 0; j < N; j++) {
-                if (yw + j >= rh) break;
+                if (yw + j >= y_end) break;
                 if (P.orig) {
                     v_store(P, acc[j], x, yw + j);
                 } else {
@@ -445,7 +448,7 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
         return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra;
     };
     const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
-    const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.rh, 8 * N);
+    const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 8 * N);
     if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
         const size_t smem = tile_smem(8);
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -456,7 +459,7 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
         if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
         if (smem > 48 * 1024)
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.rh, N), 65535u));
+        dim3 grid(pfe_div_up(P.rw, 128), std::min<unsigned>(pfe_div_up(P.v_rows, N), 65535u));
         PFE_KERNEL(ctx, "gauss_v", gauss_v_kernel<N, EXACT><<<grid, 128, smem, ctx->stream>>>(P));
     }
     PFE_LAUNCHED(ctx);
@@ -482,20 +485,30 @@ static int pick_n(int taps, double per_step_overhead) {
 }
 
 template <bool EXACT>
-int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
-    const int taps = (int)k.size();
-    switch (pick_n(taps, 6.0)) {
-        case 16: PFE_TRY((run_h<16, EXACT>(ctx, P, k))); break;
-        case 8: PFE_TRY((run_h<8, EXACT>(ctx, P, k))); break;
-        case 4: PFE_TRY((run_h<4, EXACT>(ctx, P, k))); break;
-        default: PFE_TRY((run_h<1, EXACT>(ctx, P, k))); break;
+int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    switch (pick_n((int)k.size(), 6.0)) {
+        case 16: return run_h<16, EXACT>(ctx, P, k);
+        case 8: return run_h<8, EXACT>(ctx, P, k);
+        case 4: return run_h<4, EXACT>(ctx, P, k);
+        default: return run_h<1, EXACT>(ctx, P, k);
     }
+}
+
+template <bool EXACT>
+int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    const int taps = (int)k.size();
     switch (pick_n(taps, 12.0)) {
         case 16: return run_v<16, EXACT>(ctx, P, k);
         case 8: return run_v<8, EXACT>(ctx, P, k);
         case 4: return run_v<4, EXACT>(ctx, P, k);
         default: return run_v<1, EXACT>(ctx, P, k);
     }
+}
+
+template <bool EXACT>
+int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    PFE_TRY(dispatch_h<EXACT>(ctx, P, k));
+    return dispatch_v<EXACT>(ctx, P, k);
 }
 
 int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pitch, uint32_t dst_pitch,
@@ -512,10 +525,42 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     P.orig = orig; P.mask = mask; P.amount = amount; P.epilogue = orig ? epilogue : 0;
     P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
     P.rw = rw; P.rh = rh; P.radius = radius;
+    P.v_y0 = 0; P.v_rows = rh;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_n<true>(ctx, P, k) : dispatch_n<false>(ctx, P, k);
 }
 
 }  // namespace
+
+// Band-pipelining hooks (csrc/ctx.cu): the H pass is row-local, so it can run on rows [y0, y0+rows)
+// as soon as they exist; the V pass of rows [y0, y0+rows) needs the H rows within +-radius of them.
+// `mid` is the caller-provided w*h*4 f32 intermediate of the whole image.
+int pfe_gauss_h_rows(pfe_ctx *ctx, const uint8_t *src, float *mid, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows,
+                     float sigma, uint32_t flags) {
+    int radius;
+    std::vector<float> k = build_kernel(sigma, &radius);
+    if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+    GaussParams P;
+    memset(&P, 0, sizeof(P));
+    P.src = src + (size_t)y0 * w * 4; P.mid = mid + (size_t)y0 * w * 4;
+    P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = rows; P.radius = radius;
+    (void)h;
+    return (flags & PFE_GAUSS_EXACT) ? dispatch_h<true>(ctx, P, k) : dispatch_h<false>(ctx, P, k);
+}
+int pfe_gauss_v_rows(pfe_ctx *ctx, float *mid, uint8_t *dst, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows,
+                     float sigma, uint32_t flags) {
+    int radius;
+    std::vector<float> k = build_kernel(sigma, &radius);
+    GaussParams P;
+    memset(&P, 0, sizeof(P));
+    P.mid = mid; P.dst = dst; P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius;
+    P.v_y0 = y0; P.v_rows = rows;
+    return (flags & PFE_GAUSS_EXACT) ? dispatch_v<true>(ctx, P, k) : dispatch_v<false>(ctx, P, k);
+}
+int pfe_gauss_radius(float sigma) {
+    int radius;
+    build_kernel(sigma, &radius);
+    return radius;
+}
 
 int pfe_gauss_region(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t pitch_px, uint32_t x0, uint32_t y0,
                      uint32_t rw, uint32_t rh, float sigma, uint32_t flags) {

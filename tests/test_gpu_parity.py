@@ -550,3 +550,32 @@ def test_script_runner_covers_effect_api(eng, oracle):
           oracle.motion_blur(oracle.box_blur(oracle.median(img, 2), 3.0), 45.0, 10.0))
     with pytest.raises(ValueError):
         execute_script_sync(eng, "apply_oil_painting(3);", img)
+
+
+def test_host_tier_band_pipeline(eng, oracle):
+    """pfe_flatten / pfe_flatten_gaussian pipeline uploads, compute and downloads in row bands once the
+    image exceeds 8 MB; the result must equal the unpipelined device tier, including a blur radius larger
+    than a band and masks / adjustment layers / the active-chunk bitmap crossing band boundaries."""
+    import torch
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(31)
+    w, h = 2048, 1100  # 9 MB per layer -> 6 bands of 192 rows, ragged last band
+    imgs = [fx.random_rgba(rng, w, h) for _ in range(4)]
+    imgs[1][:640, :1024] = 0
+    mask = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    specs = [dict(rgba=imgs[0], blend=0, opacity=1.0), dict(rgba=imgs[1], blend=8, opacity=0.6, mask=mask),
+             dict(kind=3, opacity=0.5), dict(rgba=imgs[2], blend=21, opacity=0.9), dict(rgba=imgs[3], blend=13, opacity=0.4)]
+    host_layers = [make_layer(**s) for s in specs]
+    dev_layers = [make_layer(**{k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in s.items()}) for s in specs]
+    active = np.ones(((h + 63) // 64, (w + 63) // 64), np.uint8)
+    active[3:9, 5:20] = 0
+    flat_dev = eng.flatten(dev_layers, w, h, active=torch.from_numpy(active).cuda())
+    exact(eng.flatten(host_layers, w, h, active=active), flat_dev.cpu().numpy(), "pipelined flatten")
+    exact(flat_dev[:320, :256].cpu().numpy(),
+          oracle.flatten([oracle.make_layer(**{k: (v[:320, :256] if isinstance(v, np.ndarray) else v) for k, v in s.items()}) for s in specs],
+                         256, 320, active=active[:5, :4]), "flatten crop vs oracle")
+    for sigma in (20.0, 80.0):  # radius 60 < band height 192 < radius 240
+        for ex in (True, False):
+            want = eng.gaussian_blur(flat_dev, sigma, exact=ex).cpu().numpy()
+            exact(eng.flatten_gaussian(host_layers, w, h, sigma, active=active, exact=ex), want, f"pipelined flatten+gaussian s={sigma} exact={ex}")

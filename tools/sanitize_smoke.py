@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Small pass over every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
+Sizes are tiny on purpose (the sanitizer slows kernels 10-100x); results are still compared to the oracle."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+from oracle import pfo
+from paintfe_b200.engine import Engine, make_layer
+
+eng = Engine(0)
+rng = np.random.default_rng(5)
+w, h = 200, 150
+img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+mask = (rng.random((h, w)) < 0.6).astype(np.uint8) * 255
+layers = [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(6)]
+meta = [dict(blend=(5 * i + 1) % 25, opacity=0.3 + 0.1 * i) for i in range(6)]
+ok = True
+
+
+def check(name, got, exp, tol=0):
+    global ok
+    d = int(np.abs(np.asarray(got).astype(int) - np.asarray(exp).astype(int)).max())
+    print(f"{name:28s} max diff {d}")
+    ok = ok and d <= tol
+
+
+check("flatten", eng.flatten([make_layer(im, **m) for im, m in zip(layers, meta)], w, h),
+      pfo.flatten([pfo.make_layer(im, **m) for im, m in zip(layers, meta)], w, h))
+for s in (2.0, 20.0):
+    check(f"gaussian exact s={s}", eng.gaussian_blur(img, s, exact=True), pfo.gaussian_blur(img, s))
+    check(f"gaussian fast s={s}", eng.gaussian_blur(img, s), pfo.gaussian_blur(img, s), 1)
+check("gaussian masked", eng.gaussian_blur(img, 3.0, mask=mask, exact=True), pfo.gaussian_blur(img, 3.0, mask=mask))
+check("sharpen", eng.sharpen(img, 1.0, 2.0, exact=True), pfo.sharpen(img, 1.0, 2.0))
+check("glow", eng.glow(img, 3.0, 0.5, exact=True), pfo.glow(img, 3.0, 0.5))
+check("box", eng.box_blur(img, 5.0), pfo.box_blur(img, 5.0))
+check("motion", eng.motion_blur(img, 30.0, 8.0), pfo.motion_blur(img, 30.0, 8.0))
+check("median", eng.median(img, 2), pfo.median(img, 2))
+check("vignette", eng.vignette(img, 0.8, 0.5), pfo.vignette(img, 0.8, 0.5))
+check("hsl", eng.adjust(img, pfo.HSL, (30.0, -20.0, 10.0)), pfo.adjust(img, pfo.HSL, (30.0, -20.0, 10.0)))
+disp = rng.normal(0, 5, (h, w, 2)).astype(np.float32)
+check("warp", eng.warp_displacement(img, disp), pfo.warp_displacement(img, disp))
+orig = np.array([[c / 3 * w, r / 3 * h] for r in range(4) for c in range(4)], np.float32)
+deformed = (orig + rng.normal(0, 3, orig.shape)).astype(np.float32)
+check("mesh warp", eng.mesh_warp(img, orig, deformed, 3, 3, w, h), pfo.mesh_warp(img, orig, deformed, 3, 3, w, h))
+check("pixelate", eng.pixelate(img, 7), pfo.pixelate(img, 7))
+check("bulge", eng.bulge(img, 0.5), pfo.bulge(img, 0.5))
+check("twist", eng.twist(img, 45.0), pfo.twist(img, 45.0), 1)
+check("noise perlin", eng.add_noise(img, 50.0, 2, False, 42, 5.0, 3), pfo.add_noise(img, 50.0, 2, False, 42, 5.0, 3))
+check("bilateral", eng.reduce_noise(img, 10.0, 2), pfo.reduce_noise(img, 10.0, 2), 1)
+a, b = img.copy(), img.copy()
+br = pfo.make_brush(12.0, 0.8, True, (1, 0, 0, 1))
+pfo.brush_line(a, br, 10.0, 10.0, 150.0, 120.0)
+eng.brush_stamps(b, eng.brush_desc(12.0, 0.8, True, (1, 0, 0, 1)), eng.brush_line_centres(w, h, 10.0, 10.0, 150.0, 120.0))
+check("brush", b, a)
+eng.close()
+print("SANITIZE_SMOKE", "OK" if ok else "MISMATCH")
+sys.exit(0 if ok else 1)
