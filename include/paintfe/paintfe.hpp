@@ -378,6 +378,94 @@ inline RgbaImage reduce_noise_core(const RgbaImage &flat, float strength, uint32
         return pfe_reduce_noise(c, s, w, h, strength, radius, m, d);
     });
 }
+// the rest of src/ops/effects/: artistic.rs:31/123/266, contours.rs:56, distort.rs:26/248, stylize.rs:242,
+// blur.rs:22/322, render.rs:52/114/220/403, glitch.rs:44/142
+inline RgbaImage ink_core(const RgbaImage &flat, float edge_strength, float threshold, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_ink", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_ink(c, s, w, h, edge_strength, threshold, m, d);
+    });
+}
+inline RgbaImage oil_painting_core(const RgbaImage &flat, uint32_t radius, uint32_t levels, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_oil_painting", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_oil_painting(c, s, w, h, radius, levels, m, d);
+    });
+}
+enum class ColorFilterMode { Multiply = 0, Screen = 1, Overlay = 2, SoftLight = 3 };
+inline RgbaImage color_filter_core(const RgbaImage &flat, std::array<uint8_t, 4> filter_color, float intensity, ColorFilterMode mode, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_color_filter", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_color_filter(c, s, w, h, filter_color.data(), intensity, (int)mode, m, d);
+    });
+}
+inline RgbaImage contours_core(const RgbaImage &flat, float scale, float frequency, float line_width, std::array<uint8_t, 4> line_color, uint32_t seed,
+                              uint32_t octaves, float blend, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_contours", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_contours(c, s, w, h, scale, frequency, line_width, line_color.data(), seed, octaves, blend, m, d);
+    });
+}
+inline RgbaImage crystallize_core(const RgbaImage &flat, float cell_size, uint32_t seed, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_crystallize", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_crystallize(c, s, w, h, cell_size, seed, m, d);
+    });
+}
+inline RgbaImage dents_core(const RgbaImage &flat, float scale, float amount, uint32_t seed, uint32_t octaves, float roughness, bool pinch, bool wrap,
+                           const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_dents", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_dents(c, s, w, h, scale, amount, seed, octaves, roughness, pinch ? 1 : 0, wrap ? 1 : 0, m, d);
+    });
+}
+enum class HalftoneShape { Circle = 0, Square = 1, Diamond = 2, Line = 3 };
+inline RgbaImage halftone_core(const RgbaImage &flat, float dot_size, float angle_deg, HalftoneShape shape, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_halftone", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_halftone(c, s, w, h, dot_size, angle_deg, (int)shape, m, d);
+    });
+}
+inline RgbaImage bokeh_blur_core(const RgbaImage &flat, float radius, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_bokeh_blur", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_bokeh_blur(c, s, w, h, radius, m, d);
+    });
+}
+inline RgbaImage zoom_blur_core(const RgbaImage &flat, float center_x, float center_y, float strength, uint32_t samples, std::array<float, 4> tint_color,
+                               float tint_strength, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_zoom_blur", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_zoom_blur(c, s, w, h, center_x, center_y, strength, samples, tint_color.data(), tint_strength, m, d);
+    });
+}
+enum class GridStyle { Lines = 0, Checkerboard = 1 };
+inline RgbaImage grid_core(const RgbaImage &flat, uint32_t cell_w, uint32_t cell_h, uint32_t line_width, std::array<uint8_t, 4> color, GridStyle style,
+                          float opacity, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_grid", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_grid(c, s, w, h, cell_w, cell_h, line_width, color.data(), (int)style, opacity, m, d);
+    });
+}
+inline RgbaImage canvas_border_core(const RgbaImage &flat, uint32_t width, std::array<uint8_t, 4> color, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_canvas_border", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_canvas_border(c, s, w, h, width, color.data(), m, d);
+    });
+}
+inline RgbaImage shadow_core(const RgbaImage &flat, int32_t offset_x, int32_t offset_y, float blur_radius, bool widen_radius, std::array<uint8_t, 4> color,
+                            float opacity, const GrayImage *mask, bool exact = true) {
+    return detail::img_op(flat, mask, "pfe_drop_shadow", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_drop_shadow(c, s, w, h, offset_x, offset_y, blur_radius, widen_radius ? 1 : 0, color.data(), opacity, m, d, exact ? PFE_GAUSS_EXACT : 0u);
+    });
+}
+enum class OutlineMode { Outside = 0, Inside = 1, Center = 2 };
+inline RgbaImage outline_core(const RgbaImage &flat, uint32_t width, std::array<uint8_t, 4> color, OutlineMode mode, bool anti_alias, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_outline", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_outline(c, s, w, h, width, color.data(), (int)mode, anti_alias ? 1 : 0, m, d);
+    });
+}
+inline RgbaImage pixel_drag_core(const RgbaImage &flat, uint32_t seed, float amount, uint32_t distance, float direction, const GrayImage *mask) {
+    return detail::img_op(flat, mask, "pfe_pixel_drag", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_pixel_drag(c, s, w, h, seed, amount, distance, direction, m, d);
+    });
+}
+inline RgbaImage rgb_displace_core(const RgbaImage &flat, std::pair<int32_t, int32_t> r_off, std::pair<int32_t, int32_t> g_off,
+                                   std::pair<int32_t, int32_t> b_off, const GrayImage *mask) {
+    const int32_t off[6] = {r_off.first, r_off.second, g_off.first, g_off.second, b_off.first, b_off.second};
+    return detail::img_op(flat, mask, "pfe_rgb_displace", [&](pfe_ctx *c, const uint8_t *s, uint32_t w, uint32_t h, const uint8_t *m, uint8_t *d) {
+        return pfe_rgb_displace(c, s, w, h, off, m, d);
+    });
+}
 }  // namespace effects
 
 namespace adjustments {

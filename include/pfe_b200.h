@@ -178,6 +178,96 @@ int pfe_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, f
 int pfe_dev_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float strength,
                          uint32_t radius, const uint8_t *mask, uint8_t *dst);
 
+/* -- the rest of src/ops/effects/ (each pinned by a golden in tests/visual_filters.rs) --------------- */
+/* ink_core (src/ops/effects/artistic.rs:31-99): Sobel on Rec.709 luminance, thresholded to black/white. */
+int pfe_ink(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float edge_strength, float threshold,
+            const uint8_t *mask, uint8_t *dst);
+int pfe_dev_ink(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float edge_strength,
+                float threshold, const uint8_t *mask, uint8_t *dst);
+/* oil_painting_core (artistic.rs:123-217): most common intensity bin in a (2r+1)^2 window; radius clamps to
+ * 1..10, levels to 2..64; integer arithmetic. */
+int pfe_oil_painting(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+                     uint32_t levels, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_oil_painting(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+                         uint32_t levels, const uint8_t *mask, uint8_t *dst);
+/* color_filter_core (artistic.rs:266-307). color = RGBA; mode: 0 Multiply, 1 Screen, 2 Overlay, 3 SoftLight. */
+int pfe_color_filter(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const uint8_t *color,
+                     float intensity, int mode, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_color_filter(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const uint8_t *color,
+                         float intensity, int mode, const uint8_t *mask, uint8_t *dst);
+/* contours_core (src/ops/effects/contours.rs:56-112): iso-lines of a turbulence field blended over the image. */
+int pfe_contours(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale, float frequency,
+                 float line_width, const uint8_t *color, uint32_t seed, uint32_t octaves, float blend,
+                 const uint8_t *mask, uint8_t *dst);
+int pfe_dev_contours(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale,
+                     float frequency, float line_width, const uint8_t *color, uint32_t seed,
+                     uint32_t octaves, float blend, const uint8_t *mask, uint8_t *dst);
+/* crystallize_core (src/ops/effects/distort.rs:26-169): jittered-grid Voronoi cells filled with their mean colour. */
+int pfe_crystallize(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float cell_size,
+                    uint32_t seed, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_crystallize(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float cell_size,
+                        uint32_t seed, const uint8_t *mask, uint8_t *dst);
+/* dents_core (distort.rs:248-310): turbulence displacement, bilinear sample. */
+int pfe_dents(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale, float amount,
+              uint32_t seed, uint32_t octaves, float roughness, int pinch, int wrap, const uint8_t *mask,
+              uint8_t *dst);
+int pfe_dev_dents(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale, float amount,
+                  uint32_t seed, uint32_t octaves, float roughness, int pinch, int wrap,
+                  const uint8_t *mask, uint8_t *dst);
+/* halftone_core (src/ops/effects/stylize.rs:242-277). shape: 0 Circle, 1 Square, 2 Diamond, 3 Line. */
+int pfe_halftone(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float dot_size, float angle_deg,
+                 int shape, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_halftone(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float dot_size,
+                     float angle_deg, int shape, const uint8_t *mask, uint8_t *dst);
+/* bokeh_blur_core (src/ops/effects/blur.rs:22-115): equal-weight disc, integer sums; radius < 0.5 copies. */
+int pfe_bokeh_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                   const uint8_t *mask, uint8_t *dst);
+int pfe_dev_bokeh_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                       const uint8_t *mask, uint8_t *dst);
+/* zoom_blur_core (blur.rs:322-427): nearest-neighbour samples toward (center_x, center_y) in 0..1; tint_rgba =
+ * 4 floats in 0..1 or NULL. */
+int pfe_zoom_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float center_x, float center_y,
+                  float strength, uint32_t samples, const float *tint_rgba, float tint_strength,
+                  const uint8_t *mask, uint8_t *dst);
+int pfe_dev_zoom_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float center_x,
+                      float center_y, float strength, uint32_t samples, const float *tint_rgba,
+                      float tint_strength, const uint8_t *mask, uint8_t *dst);
+/* grid_core (src/ops/effects/render.rs:52-92). style: 0 Lines, 1 Checkerboard. */
+int pfe_grid(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t cell_w, uint32_t cell_h,
+             uint32_t line_width, const uint8_t *color, int style, float opacity, const uint8_t *mask,
+             uint8_t *dst);
+int pfe_dev_grid(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t cell_w,
+                 uint32_t cell_h, uint32_t line_width, const uint8_t *color, int style, float opacity,
+                 const uint8_t *mask, uint8_t *dst);
+/* canvas_border_core (render.rs:114-165). */
+int pfe_canvas_border(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                      const uint8_t *color, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_canvas_border(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                          const uint8_t *color, const uint8_t *mask, uint8_t *dst);
+/* shadow_core (render.rs:220-352): offset alpha, optional max-spread, Gaussian blur, shadow under the source.
+ * flags as for pfe_gaussian_blur (PFE_GAUSS_EXACT = bit-exact blur). */
+int pfe_drop_shadow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, int32_t offset_x,
+                    int32_t offset_y, float blur_radius, int widen_radius, const uint8_t *color,
+                    float opacity, const uint8_t *mask, uint8_t *dst, uint32_t flags);
+int pfe_dev_drop_shadow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, int32_t offset_x,
+                        int32_t offset_y, float blur_radius, int widen_radius, const uint8_t *color,
+                        float opacity, const uint8_t *mask, uint8_t *dst, uint32_t flags);
+/* outline_core (render.rs:403-572). mode: 0 Outside, 1 Inside, 2 Center. */
+int pfe_outline(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                const uint8_t *color, int mode, int anti_alias, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_outline(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                    const uint8_t *color, int mode, int anti_alias, const uint8_t *mask, uint8_t *dst);
+/* pixel_drag_core (src/ops/effects/glitch.rs:44-99). */
+int pfe_pixel_drag(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t seed, float amount,
+                   uint32_t distance, float direction, const uint8_t *mask, uint8_t *dst);
+int pfe_dev_pixel_drag(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t seed,
+                       float amount, uint32_t distance, float direction, const uint8_t *mask, uint8_t *dst);
+/* rgb_displace_core (glitch.rs:142-197). offsets = {r_dx, r_dy, g_dx, g_dy, b_dx, b_dy}. */
+int pfe_rgb_displace(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const int32_t *offsets,
+                     const uint8_t *mask, uint8_t *dst);
+int pfe_dev_rgb_displace(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const int32_t *offsets,
+                         const uint8_t *mask, uint8_t *dst);
+
 /* -- per-pixel adjustments ---------------------------------------------------------------
  * Ops 0..31 follow src/ops/adjustments.rs (round-to-nearest, selection mask honoured,
  * apply_pixel_transform[_from_flat] :21-108). Ops 32.. follow the inline Rhai bindings in

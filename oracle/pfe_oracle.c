@@ -1336,3 +1336,536 @@ void pfo_reduce_noise(const uint8_t *src, uint32_t w, uint32_t h, float strength
             } else memcpy(dst + oi, src + oi, 4);
         }
 }
+
+/* ========================================================================= */
+/* Widened scope, part 2: the rest of src/ops/effects/ (every effect the      */
+/* reference pins with a golden in tests/visual_filters.rs)                    */
+/* ========================================================================= */
+
+/* ink_core, src/ops/effects/artistic.rs:31-99 (Sobel on Rec.709 luminance) */
+static inline float ink_lum(const uint8_t *src, int w, int h, int px, int py) {
+    const uint8_t *s = src + ((size_t)clampi(py, 0, h - 1) * w + clampi(px, 0, w - 1)) * 4;
+    return 0.2126f * (float)s[0] + 0.7152f * (float)s[1] + 0.0722f * (float)s[2];
+}
+void pfo_ink(const uint8_t *src, uint32_t w, uint32_t h, float edge_strength, float threshold,
+             const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    int iw = (int)w, ih = (int)h;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            int ix = (int)x, iy = (int)y;
+#define L(a, b) ink_lum(src, iw, ih, (a), (b))
+            float gx = -L(ix - 1, iy - 1) - 2.0f * L(ix - 1, iy) - L(ix - 1, iy + 1) + L(ix + 1, iy - 1) +
+                       2.0f * L(ix + 1, iy) + L(ix + 1, iy + 1);
+            float gy = -L(ix - 1, iy - 1) - 2.0f * L(ix, iy - 1) - L(ix + 1, iy - 1) + L(ix - 1, iy + 1) +
+                       2.0f * L(ix, iy + 1) + L(ix + 1, iy + 1);
+#undef L
+            float edge = sqrtf(gx * gx + gy * gy) * edge_strength / 100.0f;
+            uint8_t val = edge > threshold ? 0 : 255;
+            dst[oi] = dst[oi + 1] = dst[oi + 2] = val;
+            dst[oi + 3] = src[oi + 3];
+        }
+}
+
+/* oil_painting_core, artistic.rs:123-217 (integer histogram of intensity bins) */
+void pfo_oil_painting(const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius, uint32_t levels,
+                      const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    int r = (int)(radius < 1 ? 1 : (radius > 10 ? 10 : radius));
+    uint32_t nl = levels < 2 ? 2 : (levels > 64 ? 64 : levels);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++) {
+        uint32_t cnt[64], sr[64], sg[64], sb[64];
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            for (uint32_t i = 0; i < nl; i++) cnt[i] = sr[i] = sg[i] = sb[i] = 0;
+            for (int dy = -r; dy <= r; dy++) {
+                int sy = clampi((int)y + dy, 0, (int)h - 1);
+                for (int dx = -r; dx <= r; dx++) {
+                    int sx = clampi((int)x + dx, 0, (int)w - 1);
+                    const uint8_t *p = src + ((size_t)sy * w + sx) * 4;
+                    uint32_t pr = p[0], pg = p[1], pb = p[2];
+                    uint32_t bin = (pr + pg + pb) / 3 * nl / 256;
+                    if (bin > nl - 1) bin = nl - 1;
+                    cnt[bin]++; sr[bin] += pr; sg[bin] += pg; sb[bin] += pb;
+                }
+            }
+            uint32_t max_count = 0, max_idx = 0;
+            for (uint32_t i = 0; i < nl; i++)
+                if (cnt[i] > max_count) { max_count = cnt[i]; max_idx = i; }
+            dst[oi] = (uint8_t)(sr[max_idx] / max_count);
+            dst[oi + 1] = (uint8_t)(sg[max_idx] / max_count);
+            dst[oi + 2] = (uint8_t)(sb[max_idx] / max_count);
+            dst[oi + 3] = src[oi + 3];
+        }
+    }
+}
+
+/* color_filter_core, artistic.rs:266-307. mode: 0 Multiply, 1 Screen, 2 Overlay, 3 SoftLight */
+static inline float color_filter_blend(int mode, float s, float f) {
+    switch (mode) {
+    case 0: return s * f;
+    case 1: return 1.0f - (1.0f - s) * (1.0f - f);
+    case 2: return s < 0.5f ? 2.0f * s * f : 1.0f - 2.0f * (1.0f - s) * (1.0f - f);
+    default: return f < 0.5f ? s - (1.0f - 2.0f * f) * s * (1.0f - s) : s + (2.0f * f - 1.0f) * (sqrtf(s) - s);
+    }
+}
+void pfo_color_filter(const uint8_t *src, uint32_t w, uint32_t h, const uint8_t color[4], float intensity, int mode,
+                      const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float fc[3] = {(float)color[0] / 255.0f, (float)color[1] / 255.0f, (float)color[2] / 255.0f};
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)((size_t)w * h); i++) {
+        size_t oi = (size_t)i * 4;
+        if (mask && mask[i] == 0) { memcpy(dst + oi, src + oi, 4); continue; }
+        for (int c = 0; c < 3; c++) {
+            float s = (float)src[oi + c] / 255.0f;
+            dst[oi + c] = round_u8((s * (1.0f - intensity) + color_filter_blend(mode, s, fc[c]) * intensity) * 255.0f);
+        }
+        dst[oi + 3] = src[oi + 3];
+    }
+}
+
+/* contours_core, src/ops/effects/contours.rs:56-112 */
+void pfo_contours(const uint8_t *src, uint32_t w, uint32_t h, float scale, float frequency, float line_width,
+                  const uint8_t color[4], uint32_t seed, uint32_t octaves, float blend, const uint8_t *mask,
+                  uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float inv_scale = 1.0f / maxf(scale, 0.5f);
+    uint32_t oct = octaves < 1 ? 1 : (octaves > 8 ? 8 : octaves);
+    float half_lw = maxf(line_width * 0.5f, 0.3f);
+    float lr = (float)color[0], lg = (float)color[1], lb = (float)color[2], la = (float)color[3] / 255.0f;
+    float freq = maxf(frequency, 0.5f);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float r = (float)src[oi], g = (float)src[oi + 1], b = (float)src[oi + 2];
+            float noise_val = turbulence_2d((float)x * inv_scale, (float)y * inv_scale, seed, oct, 0.5f);
+            float level = noise_val * freq;
+            float dist = fabsf(level - roundf(level)) / freq;
+            float edge = half_lw * inv_scale * 0.5f;
+            float line_alpha = dist < edge ? 1.0f : (dist < edge * 2.0f ? 1.0f - (dist - edge) / edge : 0.0f);
+            float alpha = line_alpha * la * blend;
+            dst[oi] = round_u8(r * (1.0f - alpha) + lr * alpha);
+            dst[oi + 1] = round_u8(g * (1.0f - alpha) + lg * alpha);
+            dst[oi + 2] = round_u8(b * (1.0f - alpha) + lb * alpha);
+            dst[oi + 3] = src[oi + 3];
+        }
+}
+
+/* crystallize_core, src/ops/effects/distort.rs:26-169 (jittered-grid Voronoi, f64 cell means) */
+static inline size_t crystal_cell(const float *seeds, int cells_x, int cells_y, float cs, long x, long y) {
+    int gcx = as_i32((float)x / cs), gcy = as_i32((float)y / cs);
+    float px = (float)x + 0.5f, py = (float)y + 0.5f;
+    float best = 3.40282347e+38f;
+    size_t best_idx = 0;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            int nx = gcx + dx, ny = gcy + dy;
+            if (nx < 0 || ny < 0 || nx >= cells_x || ny >= cells_y) continue;
+            size_t idx = (size_t)ny * cells_x + nx;
+            float sx = seeds[idx * 2], sy = seeds[idx * 2 + 1];
+            float d = (px - sx) * (px - sx) + (py - sy) * (py - sy);
+            if (d < best) { best = d; best_idx = idx; }
+        }
+    return best_idx;
+}
+void pfo_crystallize(const uint8_t *src, uint32_t w, uint32_t h, float cell_size, uint32_t seed,
+                     const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float cs = maxf(cell_size, 2.0f);
+    int cells_x = as_i32(ceilf((float)w / cs)), cells_y = as_i32(ceilf((float)h / cs));
+    if (cells_x < 1) cells_x = 1;
+    if (cells_y < 1) cells_y = 1;
+    size_t nc = (size_t)cells_x * cells_y;
+    float *seeds = (float *)malloc(nc * 2 * sizeof(float));
+    double *sums = (double *)calloc(nc * 4, sizeof(double));
+    uint32_t *counts = (uint32_t *)calloc(nc, sizeof(uint32_t));
+    uint8_t *avg = (uint8_t *)calloc(nc, 4);
+    for (int cy = 0; cy < cells_y; cy++)
+        for (int cx = 0; cx < cells_x; cx++) {
+            float jx = hash_f32((uint32_t)cx, (uint32_t)cy, seed), jy = hash_f32((uint32_t)cx, (uint32_t)cy, seed + 77u);
+            seeds[((size_t)cy * cells_x + cx) * 2] = (float)cx * cs + jx * cs;
+            seeds[((size_t)cy * cells_x + cx) * 2 + 1] = (float)cy * cs + jy * cs;
+        }
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t b = crystal_cell(seeds, cells_x, cells_y, cs, x, y), si = ((size_t)y * w + x) * 4;
+            for (int c = 0; c < 4; c++) sums[b * 4 + c] += (double)src[si + c];
+            counts[b]++;
+        }
+    for (size_t i = 0; i < nc; i++)
+        if (counts[i] > 0) {
+            double inv = 1.0 / (double)counts[i];
+            for (int c = 0; c < 4; c++) {
+                double v = round(sums[i * 4 + c] * inv);
+                avg[i * 4 + c] = (uint8_t)(v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v));
+            }
+        }
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            memcpy(dst + oi, avg + crystal_cell(seeds, cells_x, cells_y, cs, x, y) * 4, 4);
+        }
+    free(seeds); free(sums); free(counts); free(avg);
+}
+
+/* f32::rem_euclid */
+static inline float rem_euclid_f(float a, float b) {
+    float r = fmodf(a, b);
+    return r < 0.0f ? r + fabsf(b) : r;
+}
+/* dents_core, distort.rs:248-310 */
+void pfo_dents(const uint8_t *src, uint32_t w, uint32_t h, float scale, float amount, uint32_t seed, uint32_t octaves,
+               float roughness, int pinch, int wrap, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    uint32_t oct = octaves < 1 ? 1 : (octaves > 8 ? 8 : octaves);
+    float inv_scale = 1.0f / maxf(scale, 0.5f);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float nx = turbulence_2d((float)x * inv_scale, (float)y * inv_scale, seed, oct, roughness) * 2.0f - 1.0f;
+            float ny = turbulence_2d((float)x * inv_scale, (float)y * inv_scale, seed + 9999u, oct, roughness) * 2.0f - 1.0f;
+            if (pinch) {
+                float cx = (float)w * 0.5f, cy = (float)h * 0.5f;
+                float dx = (float)x - cx, dy = (float)y - cy;
+                float dist = maxf(sqrtf(dx * dx + dy * dy), 1.0f);
+                float factor = (1.0f - dist / maxf(cx, cy)) * 0.5f;
+                nx = nx + dx / dist * factor;
+                ny = ny + dy / dist * factor;
+            }
+            float sx = (float)x + nx * amount * scale, sy = (float)y + ny * amount * scale;
+            if (wrap) { sx = rem_euclid_f(sx, (float)w); sy = rem_euclid_f(sy, (float)h); }
+            float p[4];
+            sample_bilinear(src, (int)w, (int)h, sx, sy, p);
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(p[c]);
+        }
+}
+
+/* halftone_core, src/ops/effects/stylize.rs:242-277. shape: 0 Circle, 1 Square, 2 Diamond, 3 Line */
+void pfo_halftone(const uint8_t *src, uint32_t w, uint32_t h, float dot_size, float angle_deg, int shape,
+                  const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    float ds = maxf(dot_size, 2.0f);
+    float angle = pfo_to_radians(angle_deg);
+    float cos_a = cosf(angle), sin_a = sinf(angle);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float r = (float)src[oi], g = (float)src[oi + 1], b = (float)src[oi + 2];
+            float lum = (0.2126f * r + 0.7152f * g + 0.0722f * b) / 255.0f;
+            float fx = (float)x * cos_a + (float)y * sin_a;
+            float fy = -((float)x) * sin_a + (float)y * cos_a;
+            float qx = fx / ds, qy = fy / ds;
+            float cx = fabsf(qx - truncf(qx)) - 0.5f, cy = fabsf(qy - truncf(qy)) - 0.5f;
+            float thr;
+            switch (shape) {
+            case 0: thr = sqrtf(cx * cx + cy * cy) * 2.0f; break;
+            case 1: thr = maxf(fabsf(cx), fabsf(cy)) * 2.0f; break;
+            case 2: thr = fabsf(cx) + fabsf(cy); break;
+            default: thr = fabsf(cy) * 2.0f; break;
+            }
+            uint8_t val = thr < lum ? 255 : 0;
+            dst[oi] = dst[oi + 1] = dst[oi + 2] = val;
+            dst[oi + 3] = src[oi + 3];
+        }
+}
+
+/* bokeh_blur_core, src/ops/effects/blur.rs:22-115: equal-weight disc, integer sums (the reference's
+ * sliding row sums equal the direct clamped-coordinate sum). Fills spans[] (<= 2r+1) for the caller. */
+int pfo_bokeh_spans(float radius, int *spans, int cap, uint32_t *sample_count) {
+    int r = as_i32(ceilf(radius)), n = 0;
+    float r2 = radius * radius;
+    uint32_t cnt = 0;
+    for (int dy = -r; dy <= r; dy++) {
+        float remaining = r2 - (float)(dy * dy);
+        if (remaining >= 0.0f) {
+            int span = as_i32(floorf(sqrtf(remaining)));
+            if (n < cap) { spans[2 * n] = dy; spans[2 * n + 1] = span; }
+            n++;
+            cnt += (uint32_t)(span * 2 + 1);
+        }
+    }
+    *sample_count = cnt;
+    return n;
+}
+void pfo_bokeh_blur(const uint8_t *src, uint32_t w, uint32_t h, float radius, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    if (radius < 0.5f) { memcpy(dst, src, (size_t)w * h * 4); return; }
+    int r = as_i32(ceilf(radius));
+    int *spans = (int *)malloc(sizeof(int) * 2 * (size_t)(2 * r + 1));
+    uint32_t sample_count;
+    int ns = pfo_bokeh_spans(radius, spans, 2 * r + 1, &sample_count);
+    float inv_count = 1.0f / (float)sample_count;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            uint64_t tot[4] = {0, 0, 0, 0};
+            for (int s = 0; s < ns; s++) {
+                int sy = clampi((int)y + spans[2 * s], 0, (int)h - 1), span = spans[2 * s + 1];
+                for (int dx = -span; dx <= span; dx++) {
+                    const uint8_t *p = src + ((size_t)sy * w + clampi((int)x + dx, 0, (int)w - 1)) * 4;
+                    for (int c = 0; c < 4; c++) tot[c] += p[c];
+                }
+            }
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8((float)tot[c] * inv_count);
+        }
+    free(spans);
+}
+
+/* zoom_blur_core, blur.rs:322-427 */
+void pfo_zoom_blur(const uint8_t *src, uint32_t w, uint32_t h, float center_x, float center_y, float strength,
+                   uint32_t samples, const float tint[4], float tint_strength, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    if (strength < 0.001f) { memcpy(dst, src, (size_t)w * h * 4); return; }
+    float cx = center_x * (float)w, cy = center_y * (float)h;
+    float s = clampf(strength, 0.0f, 0.99f);
+    uint32_t n = samples < 2 ? 2 : samples;
+    float inv_n = 1.0f / (float)n;
+    float cdx[4] = {cx, (float)w - cx, cx, (float)w - cx}, cdy[4] = {cy, cy, (float)h - cy, (float)h - cy};
+    float max_dist = 0.0f;
+    for (int i = 0; i < 4; i++) max_dist = maxf(max_dist, sqrtf(cdx[i] * cdx[i] + cdy[i] * cdy[i]));
+    max_dist = maxf(max_dist, 1.0f);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            float dx = (float)x - cx, dy = (float)y - cy;
+            float sum[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < n; i++) {
+                float t = 1.0f - s * ((float)i / (float)(n - 1));
+                int sx = clampi(as_i32(roundf(cx + dx * t)), 0, (int)w - 1);
+                int sy = clampi(as_i32(roundf(cy + dy * t)), 0, (int)h - 1);
+                const uint8_t *p = src + ((size_t)sy * w + sx) * 4;
+                for (int c = 0; c < 4; c++) sum[c] += (float)p[c];
+            }
+            float v[4];
+            for (int c = 0; c < 4; c++) v[c] = sum[c] * inv_n;
+            if (tint_strength > 0.001f) {
+                float dist = sqrtf(dx * dx + dy * dy);
+                float t = maxf(1.0f - dist / max_dist, 0.0f) * tint_strength;
+                for (int c = 0; c < 4; c++) v[c] = v[c] + (tint[c] * 255.0f - v[c]) * t;
+            }
+            for (int c = 0; c < 4; c++) dst[oi + c] = round_u8(v[c]);
+        }
+}
+
+/* grid_core, src/ops/effects/render.rs:52-92. style: 0 Lines, 1 Checkerboard */
+void pfo_grid(const uint8_t *src, uint32_t w, uint32_t h, uint32_t cell_w, uint32_t cell_h, uint32_t line_width,
+              const uint8_t color[4], int style, float opacity, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    uint32_t cw = cell_w < 2 ? 2 : cell_w, ch = cell_h < 2 ? 2 : cell_h, lw = line_width < 1 ? 1 : line_width;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            int draw = style == 0 ? (((uint32_t)x % cw) < lw || ((uint32_t)y % ch) < lw)
+                                  : ((((uint32_t)x / cw) + ((uint32_t)y / ch)) % 2 == 0);
+            for (int c = 0; c < 4; c++) {
+                float v = (float)src[oi + c];
+                dst[oi + c] = round_u8(draw ? v * (1.0f - opacity) + (float)color[c] * opacity : v);
+            }
+        }
+}
+
+/* canvas_border_core, render.rs:114-165 */
+void pfo_canvas_border(const uint8_t *src, uint32_t w, uint32_t h, uint32_t width, const uint8_t color[4],
+                       const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    uint32_t bw = width < 1 ? 1 : width, m = w < h ? w : h;
+    if (bw > m) bw = m;
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            int border = x < bw || y < bw || x >= w - bw || y >= h - bw;
+            if (masked_out(mask, w, x, y) || !border) memcpy(dst + oi, src + oi, 4);
+            else memcpy(dst + oi, color, 4);
+        }
+}
+
+/* shadow_core (drop shadow), render.rs:220-352 */
+void pfo_drop_shadow(const uint8_t *src, uint32_t w, uint32_t h, int32_t offset_x, int32_t offset_y, float blur_radius,
+                     int widen_radius, const uint8_t color[4], float opacity, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    size_t n = (size_t)w * h;
+    uint8_t *sa = (uint8_t *)calloc(n, 1);
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            long sx = x - offset_x, sy = y - offset_y;
+            if (sx >= 0 && sx < (long)w && sy >= 0 && sy < (long)h) sa[(size_t)y * w + x] = src[((size_t)sy * w + sx) * 4 + 3];
+        }
+    if (widen_radius) {
+        int spread = as_i32(roundf(maxf(blur_radius, 1.0f)));
+        if (spread > 0) {
+            uint8_t *hz = (uint8_t *)calloc(n, 1);
+            for (long y = 0; y < (long)h; y++)
+                for (long x = 0; x < (long)w; x++) {
+                    long x0 = x - spread < 0 ? 0 : x - spread, x1 = x + spread > (long)w - 1 ? (long)w - 1 : x + spread;
+                    uint8_t m = 0;
+                    for (long s = x0; s <= x1; s++) if (sa[(size_t)y * w + s] > m) m = sa[(size_t)y * w + s];
+                    hz[(size_t)y * w + x] = m;
+                }
+            for (long y = 0; y < (long)h; y++) {
+                long y0 = y - spread < 0 ? 0 : y - spread, y1 = y + spread > (long)h - 1 ? (long)h - 1 : y + spread;
+                for (long x = 0; x < (long)w; x++) {
+                    uint8_t m = 0;
+                    for (long s = y0; s <= y1; s++) if (hz[(size_t)s * w + x] > m) m = hz[(size_t)s * w + x];
+                    sa[(size_t)y * w + x] = m;
+                }
+            }
+            free(hz);
+        }
+    }
+    uint8_t *argba = (uint8_t *)malloc(n * 4), *blur = argba;
+    for (size_t i = 0; i < n; i++) argba[i * 4] = argba[i * 4 + 1] = argba[i * 4 + 2] = argba[i * 4 + 3] = sa[i];
+    if (blur_radius > 0.5f) {
+        blur = (uint8_t *)malloc(n * 4);
+        pfo_gaussian_blur(argba, w, h, blur_radius, blur);
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; i++) {
+        size_t si = (size_t)i * 4;
+        if (mask && mask[i] == 0) { memcpy(dst + si, src + si, 4); continue; }
+        float shadow_a = ((float)blur[si] / 255.0f) * opacity * ((float)color[3] / 255.0f);
+        float src_a = (float)src[si + 3] / 255.0f;
+        float out_a = src_a + shadow_a * (1.0f - src_a);
+        for (int c = 0; c < 3; c++) {
+            float shadow_c = (float)color[c] / 255.0f, src_c = (float)src[si + c] / 255.0f;
+            float out_c = out_a > 0.0f ? (src_c * src_a + shadow_c * shadow_a * (1.0f - src_a)) / out_a : 0.0f;
+            dst[si + c] = round_u8(out_c * 255.0f);
+        }
+        dst[si + 3] = round_u8(out_a * 255.0f);
+    }
+    if (blur != argba) free(blur);
+    free(argba); free(sa);
+}
+
+/* outline_core, render.rs:403-572. mode: 0 Outside, 1 Inside, 2 Center */
+static inline float outline_cov(float distance, float radius, int aa) {
+    if (aa) {
+        float t = clampf((radius + 0.5f - distance) / 1.0f, 0.0f, 1.0f);
+        return t * t * (3.0f - 2.0f * t);
+    }
+    return distance <= radius ? 1.0f : 0.0f;
+}
+static inline int outline_nearest_sq(const uint8_t *src, int w, int h, int x, int y, int sr, int want_filled) {
+    int best = -1;
+    for (int dy = -sr; dy <= sr; dy++)
+        for (int dx = -sr; dx <= sr; dx++) {
+            int d = dx * dx + dy * dy;
+            if (best >= 0 && d > best) continue;
+            int sx = x + dx, sy = y + dy;
+            if (sx < 0 || sy < 0 || sx >= w || sy >= h) continue;
+            uint8_t a = src[((size_t)sy * w + sx) * 4 + 3];
+            if (want_filled ? a > 0 : a == 0) best = d;
+        }
+    return best;
+}
+void pfo_outline(const uint8_t *src, uint32_t w, uint32_t h, uint32_t width, const uint8_t color[4], int mode,
+                 int anti_alias, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    memcpy(dst, src, (size_t)w * h * 4);
+    float radius = (float)(width < 1 ? 1 : width);
+    int sr = as_i32(ceilf(radius)) + 1;
+    long minx = w, miny = h, maxx = 0, maxy = 0;
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++)
+            if (src[((size_t)y * w + x) * 4 + 3] > 0) {
+                if (x < minx) minx = x;
+                if (y < miny) miny = y;
+                if (x > maxx) maxx = x;
+                if (y > maxy) maxy = y;
+            }
+    if (minx == (long)w) return;
+    long pminx = minx - (sr + 1) < 0 ? 0 : minx - (sr + 1), pminy = miny - (sr + 1) < 0 ? 0 : miny - (sr + 1);
+    long pmaxx = maxx + sr + 1 > (long)w - 1 ? (long)w - 1 : maxx + sr + 1;
+    long pmaxy = maxy + sr + 1 > (long)h - 1 ? (long)h - 1 : maxy + sr + 1;
+    float ca = (float)color[3] / 255.0f;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (long y = pminy; y <= pmaxy; y++)
+        for (long x = pminx; x <= pmaxx; x++) {
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) continue;
+            size_t oi = ((size_t)y * w + x) * 4;
+            float src_a = (float)src[oi + 3] / 255.0f;
+            int dfo = outline_nearest_sq(src, (int)w, (int)h, (int)x, (int)y, sr, 1);
+            int dfi = outline_nearest_sq(src, (int)w, (int)h, (int)x, (int)y, sr, 0);
+            float outside_cov = (dfo >= 0 ? outline_cov(maxf(sqrtf((float)dfo) - 1.0f, 0.0f), radius, anti_alias) : 0.0f) * (1.0f - src_a);
+            float inside_cov = (dfi >= 0 ? outline_cov(sqrtf((float)dfi), radius, anti_alias) : 0.0f) * src_a;
+            float under_cov = mode == 1 ? 0.0f : outside_cov, over_cov = mode == 0 ? 0.0f : inside_cov;
+            float a_under = ca * under_cov, a_over = ca * over_cov;
+            float comp[3] = {(float)src[oi] / 255.0f, (float)src[oi + 1] / 255.0f, (float)src[oi + 2] / 255.0f};
+            float comp_a = (float)src[oi + 3] / 255.0f;
+            if (a_under > 0.0f) {
+                float out_a = comp_a + a_under * (1.0f - comp_a);
+                if (out_a > 0.0f)
+                    for (int c = 0; c < 3; c++)
+                        comp[c] = (comp[c] * comp_a + ((float)color[c] / 255.0f) * a_under * (1.0f - comp_a)) / out_a;
+                comp_a = out_a;
+            }
+            if (a_over > 0.0f) {
+                float out_a = a_over + comp_a * (1.0f - a_over);
+                if (out_a > 0.0f)
+                    for (int c = 0; c < 3; c++)
+                        comp[c] = (((float)color[c] / 255.0f) * a_over + comp[c] * comp_a * (1.0f - a_over)) / out_a;
+                comp_a = out_a;
+            }
+            for (int c = 0; c < 3; c++) dst[oi + c] = as_u8(roundf(clampf(comp[c], 0.0f, 1.0f) * 255.0f));
+            dst[oi + 3] = as_u8(roundf(clampf(comp_a, 0.0f, 1.0f) * 255.0f));
+        }
+}
+
+/* pixel_drag_core, src/ops/effects/glitch.rs:44-99 */
+void pfo_pixel_drag(const uint8_t *src, uint32_t w, uint32_t h, uint32_t seed, float amount, uint32_t distance,
+                    float direction, const uint8_t *mask, uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+    memcpy(dst, src, (size_t)w * h * 4);
+    float dir = pfo_to_radians(direction);
+    float dx_dir = cosf(dir), dy_dir = sinf(dir);
+    float dist = (float)(distance < 1 ? 1 : distance);
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++) {
+        if (hash_f32((uint32_t)y, 0, seed) > amount / 100.0f) continue;
+        int drag = as_i32(hash_f32((uint32_t)y, 1, seed) * dist);
+        for (long x = 0; x < (long)w; x++) {
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) continue;
+            int sx = clampi(as_i32(roundf((float)x - (float)drag * dx_dir)), 0, (int)w - 1);
+            int sy = clampi(as_i32(roundf((float)y - (float)drag * dy_dir)), 0, (int)h - 1);
+            memcpy(dst + ((size_t)y * w + x) * 4, src + ((size_t)sy * w + sx) * 4, 4);
+        }
+    }
+}
+
+/* rgb_displace_core, glitch.rs:142-197. off = {rx, ry, gx, gy, bx, by} */
+void pfo_rgb_displace(const uint8_t *src, uint32_t w, uint32_t h, const int32_t off[6], const uint8_t *mask,
+                      uint8_t *dst) {
+    if (w == 0 || h == 0) return;
+#pragma omp parallel for schedule(static)
+    for (long y = 0; y < (long)h; y++)
+        for (long x = 0; x < (long)w; x++) {
+            size_t oi = ((size_t)y * w + x) * 4;
+            if (masked_out(mask, w, (size_t)x, (size_t)y)) { memcpy(dst + oi, src + oi, 4); continue; }
+            for (int c = 0; c < 3; c++) {
+                long sx = x + off[2 * c], sy = y + off[2 * c + 1];
+                sx = sx < 0 ? 0 : (sx > (long)w - 1 ? (long)w - 1 : sx);
+                sy = sy < 0 ? 0 : (sy > (long)h - 1 ? (long)h - 1 : sy);
+                dst[oi + c] = src[((size_t)sy * w + sx) * 4 + c];
+            }
+            dst[oi + 3] = src[oi + 3];
+        }
+}

@@ -348,3 +348,89 @@ def add_noise(src, amount, noise_type, monochrome, seed, scale, octaves, mask=No
 
 def reduce_noise(src, strength, radius, mask=None):
     return _img_call(lib().pfo_reduce_noise, src, C.c_float(strength), C.c_uint32(radius), mask=mask)
+
+
+# -- widened scope, part 2: the rest of src/ops/effects/ -------------------------------------------
+def _rgba4(color):
+    return (C.c_uint8 * 4)(*[int(v) for v in color])
+
+
+def ink(src, edge_strength, threshold, mask=None):
+    return _img_call(lib().pfo_ink, src, C.c_float(edge_strength), C.c_float(threshold), mask=mask)
+
+
+def oil_painting(src, radius, levels, mask=None):
+    return _img_call(lib().pfo_oil_painting, src, C.c_uint32(radius), C.c_uint32(levels), mask=mask)
+
+
+CF_MULTIPLY, CF_SCREEN, CF_OVERLAY, CF_SOFT_LIGHT = range(4)
+
+
+def color_filter(src, color, intensity, mode, mask=None):
+    return _img_call(lib().pfo_color_filter, src, _rgba4(color), C.c_float(intensity), C.c_int(mode), mask=mask)
+
+
+def contours(src, scale, frequency, line_width, color, seed, octaves, blend, mask=None):
+    return _img_call(lib().pfo_contours, src, C.c_float(scale), C.c_float(frequency), C.c_float(line_width),
+                     _rgba4(color), C.c_uint32(seed), C.c_uint32(octaves), C.c_float(blend), mask=mask)
+
+
+def crystallize(src, cell_size, seed, mask=None):
+    return _img_call(lib().pfo_crystallize, src, C.c_float(cell_size), C.c_uint32(seed), mask=mask)
+
+
+def dents(src, scale, amount, seed, octaves, roughness, pinch, wrap, mask=None):
+    return _img_call(lib().pfo_dents, src, C.c_float(scale), C.c_float(amount), C.c_uint32(seed), C.c_uint32(octaves),
+                     C.c_float(roughness), C.c_int(1 if pinch else 0), C.c_int(1 if wrap else 0), mask=mask)
+
+
+HT_CIRCLE, HT_SQUARE, HT_DIAMOND, HT_LINE = range(4)
+
+
+def halftone(src, dot_size, angle_deg, shape, mask=None):
+    return _img_call(lib().pfo_halftone, src, C.c_float(dot_size), C.c_float(angle_deg), C.c_int(shape), mask=mask)
+
+
+def bokeh_blur(src, radius, mask=None):
+    return _img_call(lib().pfo_bokeh_blur, src, C.c_float(radius), mask=mask)
+
+
+def zoom_blur(src, center_x, center_y, strength, samples, tint=(0.0, 0.0, 0.0, 0.0), tint_strength=0.0, mask=None):
+    t = (C.c_float * 4)(*tint)
+    return _img_call(lib().pfo_zoom_blur, src, C.c_float(center_x), C.c_float(center_y), C.c_float(strength),
+                     C.c_uint32(samples), t, C.c_float(tint_strength), mask=mask)
+
+
+GRID_LINES, GRID_CHECKERBOARD = range(2)
+
+
+def grid(src, cell_w, cell_h, line_width, color, style, opacity, mask=None):
+    return _img_call(lib().pfo_grid, src, C.c_uint32(cell_w), C.c_uint32(cell_h), C.c_uint32(line_width),
+                     _rgba4(color), C.c_int(style), C.c_float(opacity), mask=mask)
+
+
+def canvas_border(src, width, color, mask=None):
+    return _img_call(lib().pfo_canvas_border, src, C.c_uint32(width), _rgba4(color), mask=mask)
+
+
+def drop_shadow(src, offset_x, offset_y, blur_radius, widen_radius, color, opacity, mask=None):
+    return _img_call(lib().pfo_drop_shadow, src, C.c_int32(offset_x), C.c_int32(offset_y), C.c_float(blur_radius),
+                     C.c_int(1 if widen_radius else 0), _rgba4(color), C.c_float(opacity), mask=mask)
+
+
+OUTLINE_OUTSIDE, OUTLINE_INSIDE, OUTLINE_CENTER = range(3)
+
+
+def outline(src, width, color, mode, anti_alias, mask=None):
+    return _img_call(lib().pfo_outline, src, C.c_uint32(width), _rgba4(color), C.c_int(mode),
+                     C.c_int(1 if anti_alias else 0), mask=mask)
+
+
+def pixel_drag(src, seed, amount, distance, direction, mask=None):
+    return _img_call(lib().pfo_pixel_drag, src, C.c_uint32(seed), C.c_float(amount), C.c_uint32(distance),
+                     C.c_float(direction), mask=mask)
+
+
+def rgb_displace(src, r_off, g_off, b_off, mask=None):
+    off = (C.c_int32 * 6)(r_off[0], r_off[1], g_off[0], g_off[1], b_off[0], b_off[1])
+    return _img_call(lib().pfo_rgb_displace, src, off, mask=mask)

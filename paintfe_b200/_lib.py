@@ -87,6 +87,36 @@ SIGNATURES = {
     "pfe_dev_add_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, C.c_int, C.c_int, _u32, _f32, _u32, _vp, _vp]),
     "pfe_reduce_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
     "pfe_dev_reduce_noise": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_ink": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp]),
+    "pfe_dev_ink": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _vp, _vp]),
+    "pfe_oil_painting": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_dev_oil_painting": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_color_filter": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _f32, C.c_int, _vp, _vp]),
+    "pfe_dev_color_filter": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _f32, C.c_int, _vp, _vp]),
+    "pfe_contours": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _u32, _u32, _f32, _vp, _vp]),
+    "pfe_dev_contours": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _vp, _u32, _u32, _f32, _vp, _vp]),
+    "pfe_crystallize": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_dev_crystallize": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _u32, _vp, _vp]),
+    "pfe_dents": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _u32, _u32, _f32, C.c_int, C.c_int, _vp, _vp]),
+    "pfe_dev_dents": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _u32, _u32, _f32, C.c_int, C.c_int, _vp, _vp]),
+    "pfe_halftone": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, C.c_int, _vp, _vp]),
+    "pfe_dev_halftone": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, C.c_int, _vp, _vp]),
+    "pfe_bokeh_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _vp, _vp]),
+    "pfe_dev_bokeh_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _vp, _vp]),
+    "pfe_zoom_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _u32, _vp, _f32, _vp, _vp]),
+    "pfe_dev_zoom_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _f32, _f32, _u32, _vp, _f32, _vp, _vp]),
+    "pfe_grid": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _u32, _vp, C.c_int, _f32, _vp, _vp]),
+    "pfe_dev_grid": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _u32, _vp, C.c_int, _f32, _vp, _vp]),
+    "pfe_canvas_border": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "pfe_dev_canvas_border": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "pfe_drop_shadow": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int32, C.c_int32, _f32, C.c_int, _vp, _f32, _vp, _vp, _u32]),
+    "pfe_dev_drop_shadow": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int32, C.c_int32, _f32, C.c_int, _vp, _f32, _vp, _vp, _u32]),
+    "pfe_outline": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "pfe_dev_outline": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "pfe_pixel_drag": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _f32, _u32, _f32, _vp, _vp]),
+    "pfe_dev_pixel_drag": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _f32, _u32, _f32, _vp, _vp]),
+    "pfe_rgb_displace": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "pfe_dev_rgb_displace": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _vp]),
     "pfe_adjust": (C.c_int, [_ctx, _vp, _u32, _u32, C.POINTER(AdjustDesc), _vp, _vp, _vp]),
     "pfe_dev_adjust": (C.c_int, [_ctx, _vp, _u32, _u32, C.POINTER(AdjustDesc), _vp, _vp, _vp]),
     "pfe_build_levels_lut": (None, [_f32, _f32, _f32, _f32, _f32, _vp]),

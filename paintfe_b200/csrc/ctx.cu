@@ -315,6 +315,73 @@ int pfe_reduce_noise(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, f
     HOST_TIER(pfe_dev_reduce_noise(ctx, s.src, w, h, strength, radius, s.mask, s.dst));
 }
 
+// the rest of src/ops/effects/ (effects3.cu)
+int pfe_ink(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float edge_strength, float threshold,
+            const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_ink(ctx, s.src, w, h, edge_strength, threshold, s.mask, s.dst));
+}
+int pfe_oil_painting(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
+                     uint32_t levels, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_oil_painting(ctx, s.src, w, h, radius, levels, s.mask, s.dst));
+}
+int pfe_color_filter(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const uint8_t *color,
+                     float intensity, int mode, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_color_filter(ctx, s.src, w, h, color, intensity, mode, s.mask, s.dst));
+}
+int pfe_contours(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale, float frequency,
+                 float line_width, const uint8_t *color, uint32_t seed, uint32_t octaves, float blend,
+                 const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_contours(ctx, s.src, w, h, scale, frequency, line_width, color, seed, octaves, blend, s.mask, s.dst));
+}
+int pfe_crystallize(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float cell_size,
+                    uint32_t seed, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_crystallize(ctx, s.src, w, h, cell_size, seed, s.mask, s.dst));
+}
+int pfe_dents(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float scale, float amount,
+              uint32_t seed, uint32_t octaves, float roughness, int pinch, int wrap, const uint8_t *mask,
+              uint8_t *dst) {
+    HOST_TIER(pfe_dev_dents(ctx, s.src, w, h, scale, amount, seed, octaves, roughness, pinch, wrap, s.mask, s.dst));
+}
+int pfe_halftone(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float dot_size, float angle_deg,
+                 int shape, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_halftone(ctx, s.src, w, h, dot_size, angle_deg, shape, s.mask, s.dst));
+}
+int pfe_bokeh_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
+                   const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_bokeh_blur(ctx, s.src, w, h, radius, s.mask, s.dst));
+}
+int pfe_zoom_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float center_x, float center_y,
+                  float strength, uint32_t samples, const float *tint_rgba, float tint_strength,
+                  const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_zoom_blur(ctx, s.src, w, h, center_x, center_y, strength, samples, tint_rgba, tint_strength, s.mask, s.dst));
+}
+int pfe_grid(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t cell_w, uint32_t cell_h,
+             uint32_t line_width, const uint8_t *color, int style, float opacity, const uint8_t *mask,
+             uint8_t *dst) {
+    HOST_TIER(pfe_dev_grid(ctx, s.src, w, h, cell_w, cell_h, line_width, color, style, opacity, s.mask, s.dst));
+}
+int pfe_canvas_border(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                      const uint8_t *color, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_canvas_border(ctx, s.src, w, h, width, color, s.mask, s.dst));
+}
+int pfe_drop_shadow(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, int32_t offset_x,
+                    int32_t offset_y, float blur_radius, int widen_radius, const uint8_t *color,
+                    float opacity, const uint8_t *mask, uint8_t *dst, uint32_t flags) {
+    HOST_TIER(pfe_dev_drop_shadow(ctx, s.src, w, h, offset_x, offset_y, blur_radius, widen_radius, color, opacity, s.mask, s.dst, flags));
+}
+int pfe_outline(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t width,
+                const uint8_t *color, int mode, int anti_alias, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_outline(ctx, s.src, w, h, width, color, mode, anti_alias, s.mask, s.dst));
+}
+int pfe_pixel_drag(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t seed, float amount,
+                   uint32_t distance, float direction, const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_pixel_drag(ctx, s.src, w, h, seed, amount, distance, direction, s.mask, s.dst));
+}
+int pfe_rgb_displace(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const int32_t *offsets,
+                     const uint8_t *mask, uint8_t *dst) {
+    HOST_TIER(pfe_dev_rgb_displace(ctx, s.src, w, h, offsets, s.mask, s.dst));
+}
+
 int pfe_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, const pfe_adjust_desc *d,
                const uint8_t *mask, const uint8_t *occupancy, uint8_t *dst) {
     if (!ctx || !d) return PFE_ERR_INVALID_ARG;

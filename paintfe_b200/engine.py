@@ -240,6 +240,73 @@ class Engine:
         return self._img_op(self.lib.pfe_reduce_noise, self.lib.pfe_dev_reduce_noise, src, mask, out,
                             C.c_float(strength), C.c_uint32(radius))
 
+    # -- the rest of src/ops/effects/ (effects3.cu) ---------------------------------------------------
+    @staticmethod
+    def _rgba(color):
+        return (C.c_uint8 * 4)(*[int(v) for v in color])
+
+    def ink(self, src, edge_strength, threshold, mask=None, out=None):
+        return self._img_op(self.lib.pfe_ink, self.lib.pfe_dev_ink, src, mask, out, C.c_float(edge_strength), C.c_float(threshold))
+
+    def oil_painting(self, src, radius, levels, mask=None, out=None):
+        return self._img_op(self.lib.pfe_oil_painting, self.lib.pfe_dev_oil_painting, src, mask, out,
+                            C.c_uint32(radius), C.c_uint32(levels))
+
+    def color_filter(self, src, color, intensity, mode, mask=None, out=None):
+        return self._img_op(self.lib.pfe_color_filter, self.lib.pfe_dev_color_filter, src, mask, out, self._rgba(color),
+                            C.c_float(intensity), int(mode))
+
+    def contours(self, src, scale, frequency, line_width, color, seed, octaves, blend, mask=None, out=None):
+        return self._img_op(self.lib.pfe_contours, self.lib.pfe_dev_contours, src, mask, out, C.c_float(scale),
+                            C.c_float(frequency), C.c_float(line_width), self._rgba(color), C.c_uint32(seed),
+                            C.c_uint32(octaves), C.c_float(blend))
+
+    def crystallize(self, src, cell_size, seed, mask=None, out=None):
+        return self._img_op(self.lib.pfe_crystallize, self.lib.pfe_dev_crystallize, src, mask, out, C.c_float(cell_size),
+                            C.c_uint32(seed))
+
+    def dents(self, src, scale, amount, seed, octaves, roughness, pinch, wrap, mask=None, out=None):
+        return self._img_op(self.lib.pfe_dents, self.lib.pfe_dev_dents, src, mask, out, C.c_float(scale), C.c_float(amount),
+                            C.c_uint32(seed), C.c_uint32(octaves), C.c_float(roughness), 1 if pinch else 0, 1 if wrap else 0)
+
+    def halftone(self, src, dot_size, angle_deg, shape, mask=None, out=None):
+        return self._img_op(self.lib.pfe_halftone, self.lib.pfe_dev_halftone, src, mask, out, C.c_float(dot_size),
+                            C.c_float(angle_deg), int(shape))
+
+    def bokeh_blur(self, src, radius, mask=None, out=None):
+        return self._img_op(self.lib.pfe_bokeh_blur, self.lib.pfe_dev_bokeh_blur, src, mask, out, C.c_float(radius))
+
+    def zoom_blur(self, src, center_x, center_y, strength, samples, tint=(0.0, 0.0, 0.0, 0.0), tint_strength=0.0,
+                  mask=None, out=None):
+        t = (C.c_float * 4)(*tint)
+        return self._img_op(self.lib.pfe_zoom_blur, self.lib.pfe_dev_zoom_blur, src, mask, out, C.c_float(center_x),
+                            C.c_float(center_y), C.c_float(strength), C.c_uint32(samples), t, C.c_float(tint_strength))
+
+    def grid(self, src, cell_w, cell_h, line_width, color, style, opacity, mask=None, out=None):
+        return self._img_op(self.lib.pfe_grid, self.lib.pfe_dev_grid, src, mask, out, C.c_uint32(cell_w), C.c_uint32(cell_h),
+                            C.c_uint32(line_width), self._rgba(color), int(style), C.c_float(opacity))
+
+    def canvas_border(self, src, width, color, mask=None, out=None):
+        return self._img_op(self.lib.pfe_canvas_border, self.lib.pfe_dev_canvas_border, src, mask, out, C.c_uint32(width),
+                            self._rgba(color))
+
+    def drop_shadow(self, src, offset_x, offset_y, blur_radius, widen_radius, color, opacity, mask=None, exact=False, out=None):
+        return self._img_op(self.lib.pfe_drop_shadow, self.lib.pfe_dev_drop_shadow, src, mask, out, C.c_int32(offset_x),
+                            C.c_int32(offset_y), C.c_float(blur_radius), 1 if widen_radius else 0, self._rgba(color),
+                            C.c_float(opacity), tail=(L.GAUSS_EXACT if exact else 0,))
+
+    def outline(self, src, width, color, mode, anti_alias, mask=None, out=None):
+        return self._img_op(self.lib.pfe_outline, self.lib.pfe_dev_outline, src, mask, out, C.c_uint32(width),
+                            self._rgba(color), int(mode), 1 if anti_alias else 0)
+
+    def pixel_drag(self, src, seed, amount, distance, direction, mask=None, out=None):
+        return self._img_op(self.lib.pfe_pixel_drag, self.lib.pfe_dev_pixel_drag, src, mask, out, C.c_uint32(seed),
+                            C.c_float(amount), C.c_uint32(distance), C.c_float(direction))
+
+    def rgb_displace(self, src, r_off, g_off, b_off, mask=None, out=None):
+        off = (C.c_int32 * 6)(r_off[0], r_off[1], g_off[0], g_off[1], b_off[0], b_off[1])
+        return self._img_op(self.lib.pfe_rgb_displace, self.lib.pfe_dev_rgb_displace, src, mask, out, off)
+
     def adjust(self, src, op, params=(), luts=None, mask=None, occupancy=None, out=None):
         src = self._prep(src)
         h, w = self._hw(src)

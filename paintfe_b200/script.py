@@ -51,6 +51,11 @@ def bindings(eng, exact: bool = False) -> Dict[str, Callable]:
         "apply_twist": lambda im, m, angle: eng.twist(im, _f32(angle), mask=m),
         "apply_noise": lambda im, m, amount, mono: eng.add_noise(im, _f32(amount), 1, bool(mono), 42, 1.0, 1, mask=m),
         "apply_reduce_noise": lambda im, m, strength: eng.reduce_noise(im, _f32(strength), 2, mask=m),
+        # scripting.rs:1103-1164: fixed seed 42, 45 degree circle screen, 20 levels
+        "apply_crystallize": lambda im, m, size: eng.crystallize(im, _f32(max(int(size), 1)), 42, mask=m),
+        "apply_halftone": lambda im, m, dot_size: eng.halftone(im, _f32(dot_size), 45.0, 0, mask=m),
+        "apply_ink": lambda im, m, strength, threshold: eng.ink(im, _f32(strength), _f32(threshold), mask=m),
+        "apply_oil_painting": lambda im, m, radius: eng.oil_painting(im, max(int(radius), 1), 20, mask=m),
         # inline variants: truncating casts, no mask, alpha untouched (scripting.rs:869-1075)
         "apply_invert": lambda im, m: eng.adjust(im, S_INVERT),
         "apply_desaturate": lambda im, m: eng.adjust(im, S_DESATURATE),

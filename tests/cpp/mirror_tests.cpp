@@ -50,6 +50,12 @@ static RgbaImage create_test_gradient(uint32_t w, uint32_t h) {
         }
     return img;
 }
+static RgbaImage create_solid(uint32_t w, uint32_t h, Rgba c) {
+    RgbaImage img(w, h);
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) img.put_pixel(x, y, c);
+    return img;
+}
 static RgbaImage create_test_checkerboard(uint32_t w, uint32_t h) {
     RgbaImage img(w, h);
     for (uint32_t y = 0; y < h; y++)
@@ -155,6 +161,36 @@ int main(int argc, char **argv) {
     run("add_noise_gaussian", [&] { assert_golden("filters", "add_noise_gaussian_mono", ops::effects::add_noise_core(img, 30.0f, ops::effects::NoiseType::Gaussian, true, 42, 1.0f, 1, nullptr), 1); });
     run("add_noise_perlin", [&] { assert_golden("filters", "add_noise_perlin", ops::effects::add_noise_core(img, 50.0f, ops::effects::NoiseType::Perlin, false, 42, 5.0f, 3, nullptr)); });
     run("reduce_noise", [&] { assert_golden("filters", "reduce_noise", ops::effects::reduce_noise_core(img, 0.5f, 2, nullptr), 1); });
+    // the rest of visual_filters.rs (:44-283)
+    using namespace ops::effects;
+    run("bokeh_blur_r5", [&] { assert_golden("filters", "bokeh_blur_r5", bokeh_blur_core(img, 5.0f, nullptr)); });
+    run("zoom_blur", [&] { assert_golden("filters", "zoom_blur", zoom_blur_core(img, 0.5f, 0.5f, 0.3f, 8, {0.0f, 0.0f, 0.0f, 0.0f}, 0.0f, nullptr)); });
+    run("crystallize_s16", [&] { assert_golden("filters", "crystallize_s16", crystallize_core(img, 16.0f, 42, nullptr)); });
+    run("dents", [&] { assert_golden("filters", "dents", dents_core(img, 20.0f, 10.0f, 42, 2, 0.5f, false, false, nullptr)); });
+    run("halftone_circle", [&] { assert_golden("filters", "halftone_circle", halftone_core(img, 4.0f, 45.0f, HalftoneShape::Circle, nullptr)); });
+    run("grid_lines_16", [&] { assert_golden("filters", "grid_lines_16", grid_core(img, 16, 16, 1, {0, 0, 0, 255}, GridStyle::Lines, 1.0f, nullptr)); });
+    run("drop_shadow", [&] {
+        RgbaImage sq = create_solid(64, 64, Rgba{{0, 0, 0, 0}});
+        for (uint32_t y = 16; y < 48; y++) for (uint32_t x = 16; x < 48; x++) sq.put_pixel(x, y, Rgba{{255, 255, 255, 255}});
+        assert_golden("filters", "drop_shadow", shadow_core(sq, 5, 5, 3.0f, false, {0, 0, 0, 255}, 0.8f, nullptr));
+    });
+    run("outline_outside", [&] {
+        RgbaImage sq = create_solid(64, 64, Rgba{{0, 0, 0, 0}});
+        for (uint32_t y = 16; y < 48; y++) for (uint32_t x = 16; x < 48; x++) sq.put_pixel(x, y, Rgba{{255, 0, 0, 255}});
+        assert_golden("filters", "outline_outside", outline_core(sq, 2, {0, 0, 255, 255}, OutlineMode::Outside, true, nullptr));
+    });
+    run("contours", [&] { assert_golden("filters", "contours", contours_core(img, 10.0f, 5.0f, 1.0f, {0, 0, 0, 255}, 42, 2, 0.5f, nullptr)); });
+    run("canvas_border_core_applies_edges_only", [&] {
+        RgbaImage out = canvas_border_core(create_solid(8, 8, Rgba{{10, 20, 30, 255}}), 2, {200, 100, 50, 255}, nullptr);
+        check(out.get_pixel(0, 0) == Rgba{{200, 100, 50, 255}}, "edge pixel should be the border colour");
+        check(out.get_pixel(3, 3) == Rgba{{10, 20, 30, 255}}, "interior pixel should be unchanged");
+    });
+    run("pixel_drag", [&] { assert_golden("filters", "pixel_drag", pixel_drag_core(img, 42, 50.0f, 20, 0.0f, nullptr)); });
+    run("rgb_displace", [&] { assert_golden("filters", "rgb_displace", rgb_displace_core(img, {5, 0}, {0, 0}, {-5, 0}, nullptr)); });
+    run("ink", [&] { assert_golden("filters", "ink", ink_core(img, 1.0f, 0.5f, nullptr)); });
+    run("oil_painting", [&] { assert_golden("filters", "oil_painting", oil_painting_core(img, 3, 20, nullptr)); });
+    run("color_filter_multiply", [&] { assert_golden("filters", "color_filter_multiply", color_filter_core(img, {255, 128, 0, 255}, 0.5f, ColorFilterMode::Multiply, nullptr)); });
+    run("color_filter_identity", [&] { check(color_filter_core(img, {255, 255, 255, 255}, 0.0f, ColorFilterMode::Multiply, nullptr) == img, "intensity 0 must be identity"); });
     run("gaussian_sigma0_identity", [&] { check(ops::filters::parallel_gaussian_blur_pub(img, 0.0f) == img, "sigma 0 must be identity"); });  // visual_filters.rs:296
     run("sharpen_amount0_identity", [&] { check(ops::effects::sharpen_core(img, 0.0f, 1.0f, nullptr) == img, "amount 0 must be identity"); });
     run("selection_mask_limits_blur", [&] {

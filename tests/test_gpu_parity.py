@@ -77,6 +77,13 @@ class _EngAsOracle:
     def add_noise(self, im, amount, t, mono, seed, scale, octaves, mask=None):
         return self.e.add_noise(im, amount, t, mono, seed, scale, octaves, mask=mask)
     def reduce_noise(self, im, s, r, mask=None): return self.e.reduce_noise(im, s, r, mask=mask)
+    def drop_shadow(self, im, ox, oy, br, widen, color, op, mask=None):
+        return self.e.drop_shadow(im, ox, oy, br, widen, color, op, mask=mask, exact=self.x)
+    def __getattr__(self, name):  # the remaining effects take the oracle's arguments unchanged
+        if name in ("ink", "oil_painting", "color_filter", "contours", "crystallize", "dents", "halftone", "bokeh_blur",
+                    "zoom_blur", "grid", "canvas_border", "outline", "pixel_drag", "rgb_displace"):
+            return getattr(self.e, name)
+        raise AttributeError(name)
     def adjust(self, im, op, params=(), luts=None, mask=None, occupancy=None):
         return self.e.adjust(im, op, params, luts=luts, mask=mask, occupancy=occupancy)
     def levels_lut(self, *a): return self.e.levels_lut(*a)
@@ -535,6 +542,94 @@ def test_widened_effects_random(eng, oracle, w, h):
     assert within1(eng.reduce_noise(img, 20.0, 2, mask=mask), oracle.reduce_noise(img, 20.0, 2, mask=mask), "bilateral mask") < 0.02
 
 
+def test_effects3_goldens_and_known_answers(eng):
+    """tests/visual_filters.rs:193-236, :338-352 through the engine."""
+    from test_oracle_golden import _square
+
+    o = _EngAsOracle(eng, True)
+    exact(o.drop_shadow(_square((255, 255, 255, 255)), 5, 5, 3.0, False, (0, 0, 0, 255), 0.8), fx.golden("filters", "drop_shadow"))
+    within1(_EngAsOracle(eng, False).drop_shadow(_square((255, 255, 255, 255)), 5, 5, 3.0, False, (0, 0, 0, 255), 0.8),
+            fx.golden("filters", "drop_shadow"))
+    exact(o.outline(_square((255, 0, 0, 255)), 2, (0, 0, 255, 255), o.OUTLINE_OUTSIDE, True), fx.golden("filters", "outline_outside"))
+    out = eng.canvas_border(fx.solid(8, 8, (10, 20, 30, 255)), 2, (200, 100, 50, 255))
+    assert tuple(out[0, 0]) == (200, 100, 50, 255) and tuple(out[3, 3]) == (10, 20, 30, 255)
+    g = fx.gradient(64, 64)
+    exact(eng.color_filter(g, (255, 255, 255, 255), 0.0, 0), g, "colour filter identity")
+
+
+@pytest.mark.parametrize("w,h", [(64, 64), (67, 45), (1, 1), (300, 200)])
+def test_effects3_random(eng, oracle, w, h):
+    """Every effect of effects3.cu against the oracle on random images (so alpha, clamping and the mask
+    rule are exercised), ragged sizes, parameter extremes."""
+    rng = np.random.default_rng(w * 17 + h)
+    img = fx.random_rgba(rng, w, h)
+    mask = (rng.random((h, w)) < 0.7).astype(np.uint8) * 255
+    sparse = img.copy()
+    sparse[rng.random((h, w)) < 0.6] = 0  # holes in alpha for shadow / outline
+    col = (200, 40, 90, 180)
+
+    def both(name, *a, src=img):
+        exact(getattr(eng, name)(src, *a), getattr(oracle, name)(src, *a), f"{name}{a}")
+        exact(getattr(eng, name)(src, *a, mask=mask), getattr(oracle, name)(src, *a, mask=mask), f"{name}{a} mask")
+
+    for es, th in ((1.0, 0.5), (50.0, 3.0), (0.0, 0.0)):
+        both("ink", es, th)
+    for r, lv in ((3, 20), (1, 2), (10, 64), (0, 0), (25, 300)):
+        both("oil_painting", r, lv)
+    for mode in range(4):
+        both("color_filter", col, 0.6, mode)
+    both("color_filter", (255, 128, 0, 255), 1.5, 3)
+    both("contours", 10.0, 5.0, 1.0, (0, 0, 0, 255), 42, 2, 0.5)
+    both("contours", 0.1, 0.2, 6.0, col, 7, 9, 1.0)
+    for cs, seed in ((16.0, 42), (2.0, 1), (0.5, 3), (7.3, 99), (500.0, 5)):
+        both("crystallize", cs, seed)
+    for args in ((20.0, 10.0, 42, 2, 0.5, False, False), (5.0, 30.0, 7, 4, 0.8, True, False), (8.0, 50.0, 3, 1, 0.3, True, True),
+                 (0.1, 5.0, 1, 9, 0.5, False, True)):
+        both("dents", *args)
+    for shape in range(4):
+        both("halftone", 4.0, 45.0, shape)
+    both("halftone", 0.5, -30.0, 0)
+    for r in (5.0, 0.4, 0.5, 1.0, 2.7, 12.0):
+        both("bokeh_blur", r)
+    both("zoom_blur", 0.5, 0.5, 0.3, 8)
+    both("zoom_blur", 0.2, 0.9, 5.0, 1, (1.0, 0.5, 0.0, 1.0), 0.7)
+    both("zoom_blur", 0.5, 0.5, 0.0005, 16)
+    both("grid", 16, 16, 1, (0, 0, 0, 255), 0, 1.0)
+    both("grid", 0, 5, 0, col, 1, 0.4)
+    both("grid", 7, 3, 2, col, 0, 0.5)
+    for bw in (0, 2, 1000):
+        both("canvas_border", bw, col)
+    for args in ((5, 5, 3.0, False, (0, 0, 0, 255), 0.8), (-3, 7, 2.0, True, col, 1.0), (0, 0, 0.4, False, col, 0.5),
+                 (1000, 0, 1.0, True, col, 0.9), (2, -2, 0.2, True, col, 0.7)):
+        exact(eng.drop_shadow(sparse, *args, exact=True), oracle.drop_shadow(sparse, *args), f"drop_shadow{args}")
+        exact(eng.drop_shadow(sparse, *args, mask=mask, exact=True), oracle.drop_shadow(sparse, *args, mask=mask), f"drop_shadow{args} mask")
+    for args in ((2, (0, 0, 255, 255), 0, True), (1, col, 1, False), (4, col, 2, True), (0, col, 2, False)):
+        both("outline", *args, src=sparse)
+    both("outline", 2, col, 0, True, src=np.zeros_like(img))  # nothing opaque: clone
+    for args in ((42, 50.0, 20, 0.0), (7, 100.0, 1, 45.0), (3, 0.0, 9, 90.0), (9, 80.0, 500, 200.0)):
+        both("pixel_drag", *args)
+    both("rgb_displace", (5, 0), (0, 0), (-5, 0))
+    both("rgb_displace", (-1000, 3), (2, -2), (0, 100000))
+
+
+def test_effects3_device_tier_and_large(eng, oracle):
+    """Device-pointer tier equals the host tier; an image larger than one block grid row / several cells."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    img = fx.random_rgba(rng, 1031, 517)
+    dev = torch.from_numpy(img).cuda()
+    for name, a in (("ink", (2.0, 0.5)), ("oil_painting", (4, 32)), ("crystallize", (23.0, 42)), ("bokeh_blur", (9.5,)),
+                    ("halftone", (6.0, 15.0, 0)), ("zoom_blur", (0.4, 0.6, 0.5, 32)), ("dents", (20.0, 10.0, 42, 3, 0.5, True, True)),
+                    ("pixel_drag", (42, 50.0, 40, 10.0)), ("contours", (30.0, 8.0, 2.0, (10, 20, 30, 200), 1, 4, 0.8))):
+        want = getattr(oracle, name)(img, *a)
+        exact(getattr(eng, name)(dev, *a).cpu().numpy(), want, f"{name} device tier")
+        exact(getattr(eng, name)(img, *a), want, f"{name} host tier")
+    exact(eng.drop_shadow(dev, 9, -4, 6.0, True, (5, 5, 5, 255), 0.9, exact=True).cpu().numpy(),
+          oracle.drop_shadow(img, 9, -4, 6.0, True, (5, 5, 5, 255), 0.9), "drop_shadow device tier")
+    exact(eng.outline(dev, 3, (1, 2, 3, 255), 2, True).cpu().numpy(), oracle.outline(img, 3, (1, 2, 3, 255), 2, True), "outline device")
+
+
 def test_script_runner_covers_effect_api(eng, oracle):
     """The Rhai bindings' fixed arguments (scripting.rs:822-1165) through the script runner."""
     from paintfe_b200.script import execute_script_sync
@@ -548,8 +643,12 @@ def test_script_runner_covers_effect_api(eng, oracle):
     within1(execute_script_sync(eng, "apply_reduce_noise(0.5);", img), fx.golden("filters", "reduce_noise"))
     exact(execute_script_sync(eng, "apply_median(2); apply_box_blur(3); apply_motion_blur(45.0, 10.0);", img),
           oracle.motion_blur(oracle.box_blur(oracle.median(img, 2), 3.0), 45.0, 10.0))
+    exact(execute_script_sync(eng, "apply_oil_painting(3);", img), fx.golden("filters", "oil_painting"))
+    exact(execute_script_sync(eng, "apply_ink(1.0, 0.5);", img), fx.golden("filters", "ink"))
+    exact(execute_script_sync(eng, "apply_crystallize(16);", img), fx.golden("filters", "crystallize_s16"))
+    exact(execute_script_sync(eng, "apply_halftone(4.0);", img), fx.golden("filters", "halftone_circle"))
     with pytest.raises(ValueError):
-        execute_script_sync(eng, "apply_oil_painting(3);", img)
+        execute_script_sync(eng, "resize_image(3, 3);", img)
 
 
 def test_host_tier_band_pipeline(eng, oracle):

@@ -56,12 +56,51 @@ FILTERS = {
     "add_noise_gaussian_mono": lambda o, im: o.add_noise(im, 30.0, o.NOISE_GAUSSIAN, True, 42, 1.0, 1),
     "add_noise_perlin": lambda o, im: o.add_noise(im, 50.0, o.NOISE_PERLIN, False, 42, 5.0, 3),
     "reduce_noise": lambda o, im: o.reduce_noise(im, 0.5, 2),
+    # widened scope, part 2: the rest of src/ops/effects/ (tests/visual_filters.rs:44-283)
+    "bokeh_blur_r5": lambda o, im: o.bokeh_blur(im, 5.0),
+    "zoom_blur": lambda o, im: o.zoom_blur(im, 0.5, 0.5, 0.3, 8),
+    "crystallize_s16": lambda o, im: o.crystallize(im, 16.0, 42),
+    "dents": lambda o, im: o.dents(im, 20.0, 10.0, 42, 2, 0.5, False, False),
+    "halftone_circle": lambda o, im: o.halftone(im, 4.0, 45.0, o.HT_CIRCLE),
+    "grid_lines_16": lambda o, im: o.grid(im, 16, 16, 1, (0, 0, 0, 255), o.GRID_LINES, 1.0),
+    "contours": lambda o, im: o.contours(im, 10.0, 5.0, 1.0, (0, 0, 0, 255), 42, 2, 0.5),
+    "pixel_drag": lambda o, im: o.pixel_drag(im, 42, 50.0, 20, 0.0),
+    "rgb_displace": lambda o, im: o.rgb_displace(im, (5, 0), (0, 0), (-5, 0)),
+    "ink": lambda o, im: o.ink(im, 1.0, 0.5),
+    "oil_painting": lambda o, im: o.oil_painting(im, 3, 20),
+    "color_filter_multiply": lambda o, im: o.color_filter(im, (255, 128, 0, 255), 0.5, o.CF_MULTIPLY),
 }
 
 
 @pytest.mark.parametrize("name", sorted(FILTERS))
 def test_filter_golden(oracle, name):
     assert_exact(FILTERS[name](oracle, fx.gradient(64, 64)), "filters", name)
+
+
+def _square(fill):
+    """tests/visual_filters.rs:193-214: transparent 64x64 with a solid 32x32 square in the centre."""
+    img = fx.solid(64, 64, (0, 0, 0, 0))
+    img[16:48, 16:48] = fill
+    return img
+
+
+def test_drop_shadow_golden(oracle):
+    out = oracle.drop_shadow(_square((255, 255, 255, 255)), 5, 5, 3.0, False, (0, 0, 0, 255), 0.8)
+    assert_exact(out, "filters", "drop_shadow")
+
+
+def test_outline_outside_golden(oracle):
+    out = oracle.outline(_square((255, 0, 0, 255)), 2, (0, 0, 255, 255), oracle.OUTLINE_OUTSIDE, True)
+    assert_exact(out, "filters", "outline_outside")
+
+
+def test_effect_known_answers(oracle):
+    """tests/visual_filters.rs:226-236 (canvas border), :338-352 (colour filter identity)."""
+    img = fx.solid(8, 8, (10, 20, 30, 255))
+    out = oracle.canvas_border(img, 2, (200, 100, 50, 255))
+    assert tuple(out[0, 0]) == (200, 100, 50, 255) and tuple(out[3, 3]) == (10, 20, 30, 255)
+    g = fx.gradient(64, 64)
+    assert np.array_equal(oracle.color_filter(g, (255, 255, 255, 255), 0.0, oracle.CF_MULTIPLY), g)
 
 
 # ---- adjustments (tests/visual_adjustments.rs:50-216) ---------------------------------
