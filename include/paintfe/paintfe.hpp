@@ -528,6 +528,26 @@ inline void levels_from_flat(CanvasState &s, size_t i, float ib, float iw, float
     pfe_build_levels_lut(ib, iw, g, ob, ow, lut);
     detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_LUT_RGB, {}, lut));
 }
+// adjustments.rs:374-421, :517-545, :1240-1444
+inline void highlights_shadows(CanvasState &s, size_t i, float shadows, float highlights) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_HIGHLIGHTS_SHADOWS, {shadows, highlights})); }
+inline void highlights_shadows_from_flat(CanvasState &s, size_t i, float shadows, float highlights, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_HIGHLIGHTS_SHADOWS, {shadows, highlights})); }
+inline void temperature_tint(CanvasState &s, size_t i, float t, float tint) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_TEMPERATURE_TINT, {t, tint})); }
+inline void temperature_tint_from_flat(CanvasState &s, size_t i, float t, float tint, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_TEMPERATURE_TINT, {t, tint})); }
+inline void threshold(CanvasState &s, size_t i, float level) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_THRESHOLD, {level})); }
+inline void threshold_from_flat(CanvasState &s, size_t i, float level, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_THRESHOLD, {level})); }
+inline void posterize(CanvasState &s, size_t i, uint32_t levels) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_POSTERIZE, {(float)std::max(levels, 2u)})); }
+inline void posterize_from_flat(CanvasState &s, size_t i, uint32_t levels, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_POSTERIZE, {(float)std::max(levels, 2u)})); }
+using Rgb3 = std::array<float, 3>;
+inline pfe_adjust_desc color_balance_desc(Rgb3 sh, Rgb3 mid, Rgb3 hi) { return detail2::desc(PFE_ADJ_COLOR_BALANCE, {sh[0], sh[1], sh[2], mid[0], mid[1], mid[2], hi[0], hi[1], hi[2]}); }
+inline void color_balance(CanvasState &s, size_t i, Rgb3 sh, Rgb3 mid, Rgb3 hi) { detail2::in_place(s, i, color_balance_desc(sh, mid, hi)); }
+inline void color_balance_from_flat(CanvasState &s, size_t i, Rgb3 sh, Rgb3 mid, Rgb3 hi, const RgbaImage &flat) { detail2::from_flat(s, i, flat, color_balance_desc(sh, mid, hi)); }
+using GradientLut = std::array<std::array<uint8_t, 4>, 256>;
+inline void gradient_map(CanvasState &s, size_t i, const GradientLut &lut) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_GRADIENT_MAP, {}, &lut[0][0])); }
+inline void gradient_map_from_flat(CanvasState &s, size_t i, const GradientLut &lut, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_GRADIENT_MAP, {}, &lut[0][0])); }
+inline void black_and_white(CanvasState &s, size_t i, float rw, float gw, float bw) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_BLACK_AND_WHITE, {rw, gw, bw})); }
+inline void black_and_white_from_flat(CanvasState &s, size_t i, float rw, float gw, float bw, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_BLACK_AND_WHITE, {rw, gw, bw})); }
+inline void vibrance(CanvasState &s, size_t i, float amount) { detail2::in_place(s, i, detail2::desc(PFE_ADJ_VIBRANCE, {amount / 100.0f})); }
+inline void vibrance_from_flat(CanvasState &s, size_t i, float amount, const RgbaImage &flat) { detail2::from_flat(s, i, flat, detail2::desc(PFE_ADJ_VIBRANCE, {amount / 100.0f})); }
 // curves_from_flat_multi, :563: channel_points = [RGB, R, G, B, A], each (points, enabled)
 using CurvePoints = std::vector<std::pair<float, float>>;
 inline void curves_from_flat_multi(CanvasState &s, size_t i, const std::array<std::pair<CurvePoints, bool>, 5> &ch, const RgbaImage &flat) {
@@ -596,6 +616,77 @@ inline void flatten_image(CanvasState &state) {
     state.layers.clear();
     state.layers.emplace_back("Background", state.width, state.height, Rgba{{0, 0, 0, 0}});
     state.layers[0].pixels = TiledImage::from_rgba_image(comp);
+}
+
+// ---- geometry: src/ops/transform.rs:14-131, :134-186, :347-463, :750-820 (selection-region variants
+// `try_transform_selected_region` / `flip_layer_selected_region_*` are GUI paths and not mirrored)
+enum class Interpolation { Nearest = 0, Bilinear = 1, Bicubic = 2, Lanczos3 = 3 };
+namespace detail3 {
+template <class F>
+inline RgbaImage reshape(const RgbaImage &flat, uint32_t nw, uint32_t nh, const char *what, F f) {
+    RgbaImage out(nw, nh);
+    if (flat.width() == 0 || flat.height() == 0 || nw == 0 || nh == 0) return out;
+    Engine &e = Engine::current();
+    e.check(f(e.ctx(), flat.as_raw().data(), out.as_mut().data()), what);
+    return out;
+}
+inline RgbaImage orient(const RgbaImage &flat, int op) {
+    const bool turn = op == PFE_ORIENT_ROTATE_90CW || op == PFE_ORIENT_ROTATE_90CCW;
+    return reshape(flat, turn ? flat.height() : flat.width(), turn ? flat.width() : flat.height(), "pfe_orient",
+                   [&](pfe_ctx *c, const uint8_t *s, uint8_t *d) { return pfe_orient(c, s, flat.width(), flat.height(), op, d); });
+}
+inline void orient_all(CanvasState &s, int op) {
+    for (auto &l : s.layers) l.pixels = TiledImage::from_rgba_image(orient(l.pixels.to_rgba_image(), op));
+    if (op == PFE_ORIENT_ROTATE_90CW || op == PFE_ORIENT_ROTATE_90CCW) std::swap(s.width, s.height);
+}
+inline RgbaImage apply_affine(const RgbaImage &src, uint32_t cw, uint32_t ch, float rz, float rx, float ry, float scale,
+                              std::pair<float, float> offset, Interpolation interp) {
+    return reshape(src, cw, ch, "pfe_affine", [&](pfe_ctx *c, const uint8_t *s, uint8_t *d) {
+        return pfe_affine(c, s, src.width(), src.height(), cw, ch, rz, rx, ry, scale, offset.first, offset.second, interp == Interpolation::Nearest ? 1 : 0, d);
+    });
+}
+}  // namespace detail3
+inline void flip_canvas_horizontal(CanvasState &s) { detail3::orient_all(s, PFE_ORIENT_FLIP_H); }
+inline void flip_canvas_vertical(CanvasState &s) { detail3::orient_all(s, PFE_ORIENT_FLIP_V); }
+inline void rotate_canvas_90cw(CanvasState &s) { detail3::orient_all(s, PFE_ORIENT_ROTATE_90CW); }
+inline void rotate_canvas_90ccw(CanvasState &s) { detail3::orient_all(s, PFE_ORIENT_ROTATE_90CCW); }
+inline void rotate_canvas_180(CanvasState &s) { detail3::orient_all(s, PFE_ORIENT_ROTATE_180); }
+inline void flip_layer_horizontal(CanvasState &s, size_t i) { if (i < s.layers.size()) s.layers[i].pixels = TiledImage::from_rgba_image(detail3::orient(s.layers[i].pixels.to_rgba_image(), PFE_ORIENT_FLIP_H)); }
+inline void flip_layer_vertical(CanvasState &s, size_t i) { if (i < s.layers.size()) s.layers[i].pixels = TiledImage::from_rgba_image(detail3::orient(s.layers[i].pixels.to_rgba_image(), PFE_ORIENT_FLIP_V)); }
+inline void resize_image(CanvasState &s, uint32_t nw, uint32_t nh, Interpolation interp) {
+    for (auto &l : s.layers) {
+        RgbaImage flat = l.pixels.to_rgba_image();
+        l.pixels = TiledImage::from_rgba_image(detail3::reshape(flat, nw, nh, "pfe_resize", [&](pfe_ctx *c, const uint8_t *src, uint8_t *d) {
+            return pfe_resize(c, src, flat.width(), flat.height(), nw, nh, (int)interp, d);
+        }));
+    }
+    s.width = nw;
+    s.height = nh;
+}
+inline void resize_canvas(CanvasState &s, uint32_t nw, uint32_t nh, std::pair<uint32_t, uint32_t> anchor, Rgba fill) {
+    for (auto &l : s.layers) {
+        RgbaImage flat = l.pixels.to_rgba_image();
+        l.pixels = TiledImage::from_rgba_image(detail3::reshape(flat, nw, nh, "pfe_resize_canvas", [&](pfe_ctx *c, const uint8_t *src, uint8_t *d) {
+            return pfe_resize_canvas(c, src, flat.width(), flat.height(), nw, nh, anchor.first, anchor.second, fill.v, d);
+        }));
+    }
+    s.width = nw;
+    s.height = nh;
+}
+inline void affine_transform_layer(CanvasState &s, size_t i, float rz, float rx, float ry, float scale, std::pair<float, float> offset) {
+    if (i >= s.layers.size()) return;
+    s.layers[i].pixels = TiledImage::from_rgba_image(detail3::apply_affine(s.layers[i].pixels.to_rgba_image(), s.width, s.height, rz, rx, ry, scale, offset, Interpolation::Bilinear));
+}
+inline void affine_transform_layer_from_flat(CanvasState &s, size_t i, float rz, float rx, float ry, float scale, std::pair<float, float> offset, const RgbaImage &flat) {
+    if (i >= s.layers.size()) return;
+    s.layers[i].pixels = TiledImage::from_rgba_image(detail3::apply_affine(flat, s.width, s.height, rz, rx, ry, scale, offset, Interpolation::Bilinear));
+}
+inline void rotate_canvas_arbitrary(CanvasState &s, float degrees, Interpolation interp) {
+    if (std::fabs(degrees) < 0.001f) return;
+    for (auto &l : s.layers) {
+        l.pixels = TiledImage::from_rgba_image(detail3::apply_affine(l.pixels.to_rgba_image(), s.width, s.height, degrees, 0, 0, 1.0f, {0, 0}, interp));
+        if (l.mask) l.mask = TiledImage::from_rgba_image(detail3::apply_affine(l.mask->to_rgba_image(), s.width, s.height, degrees, 0, 0, 1.0f, {0, 0}, interp));
+    }
 }
 }  // namespace transform
 }  // namespace ops

@@ -285,6 +285,12 @@ typedef enum pfe_adjust_op {
     PFE_ADJ_LUT_RGBA = 8,            /* curves :549-626, per-channel levels :490; luts = 4*256 */
     PFE_ADJ_TEMPERATURE_TINT = 9,    /* :518; params = {temperature, tint} */
     PFE_ADJ_HIGHLIGHTS_SHADOWS = 10, /* :371; params = {shadows, highlights} */
+    PFE_ADJ_THRESHOLD = 11,          /* :1240; params = {level} */
+    PFE_ADJ_POSTERIZE = 12,          /* :1267; params = {max(levels, 2)} */
+    PFE_ADJ_COLOR_BALANCE = 13,      /* :1294; params = {shadows r,g,b, midtones r,g,b, highlights r,g,b} */
+    PFE_ADJ_GRADIENT_MAP = 14,       /* :1344; luts = 256 RGBA entries (1024 bytes) indexed by luminance */
+    PFE_ADJ_BLACK_AND_WHITE = 15,    /* :1373; params = {r_weight, g_weight, b_weight} */
+    PFE_ADJ_VIBRANCE = 16,           /* :1408; params = {amount / 100} */
     PFE_ADJ_S_INVERT = 32,              /* apply_invert, scripting.rs:869 */
     PFE_ADJ_S_DESATURATE = 33,          /* apply_desaturate :883 */
     PFE_ADJ_S_SEPIA = 34,               /* apply_sepia() :900 */
@@ -297,7 +303,7 @@ typedef enum pfe_adjust_op {
 
 typedef struct pfe_adjust_desc {
     int32_t op;          /* pfe_adjust_op */
-    float params[8];
+    float params[12];
     const uint8_t *luts; /* HOST pointer in both tiers (<= 1 KiB, copied with the launch) */
 } pfe_adjust_desc;
 
@@ -324,6 +330,50 @@ int pfe_channel_minmax(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h,
                        const uint8_t *mask, uint8_t out[6]);
 int pfe_dev_channel_minmax(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h,
                            const uint8_t *mask, uint8_t out_host[6]);
+
+/* -- geometry ----------------------------------------------------------------
+ * Flips and quarter turns: imageops::{flip_horizontal, flip_vertical, rotate90, rotate270, rotate180} as
+ * called from src/ops/transform.rs:326-334 and the Rhai bindings src/ops/scripting.rs:645-740; the same
+ * pixels as TiledImage::{flip,rotate}_*_chunked behind flip_canvas_* / rotate_canvas_* (transform.rs:62-131).
+ * dst is w*h, or h wide and w tall for the quarter turns. No selection mask (the reference has none here). */
+typedef enum pfe_orient_op {
+    PFE_ORIENT_FLIP_H = 0,
+    PFE_ORIENT_FLIP_V = 1,
+    PFE_ORIENT_ROTATE_90CW = 2,
+    PFE_ORIENT_ROTATE_90CCW = 3,
+    PFE_ORIENT_ROTATE_180 = 4
+} pfe_orient_op;
+int pfe_orient(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, int op, uint8_t *dst);
+int pfe_dev_orient(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, int op, uint8_t *dst);
+/* resize_canvas / resize_canvas_layers (transform.rs:382-463): anchor_x/y in {0 start, 1 centre, 2 end}. */
+int pfe_resize_canvas(pfe_ctx *ctx, const uint8_t *src, uint32_t old_w, uint32_t old_h, uint32_t new_w,
+                      uint32_t new_h, uint32_t anchor_x, uint32_t anchor_y, const uint8_t fill_rgba[4],
+                      uint8_t *dst);
+int pfe_dev_resize_canvas(pfe_ctx *ctx, const uint8_t *src, uint32_t old_w, uint32_t old_h, uint32_t new_w,
+                          uint32_t new_h, uint32_t anchor_x, uint32_t anchor_y, const uint8_t fill_rgba[4],
+                          uint8_t *dst);
+/* apply_affine (transform.rs:826-946) behind affine_transform_layer[_from_flat] (:750-820) and
+ * rotate_canvas_arbitrary (:134-186): rotations in degrees, perspective focal = 1.5 * max(canvas);
+ * nearest != 0 is Interpolation::Nearest, anything else the bilinear branch. dst = canvas_w * canvas_h. */
+int pfe_affine(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h, uint32_t canvas_w,
+               uint32_t canvas_h, float rotation_z, float rotation_x, float rotation_y, float scale,
+               float offset_x, float offset_y, int nearest, uint8_t *dst);
+int pfe_dev_affine(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h, uint32_t canvas_w,
+                   uint32_t canvas_h, float rotation_z, float rotation_x, float rotation_y, float scale,
+                   float offset_x, float offset_y, int nearest, uint8_t *dst);
+/* imageops::resize as resize_image / resize_layers call it (transform.rs:347-378; Interpolation::to_filter
+ * :47-55). `image` crate 0.25.9 arithmetic (not vendored in the reference; restated from its published
+ * source and pinned by golden/transforms/resize_*.png). */
+typedef enum pfe_resize_filter {
+    PFE_RESIZE_NEAREST = 0,     /* Interpolation::Nearest  -> FilterType::Nearest */
+    PFE_RESIZE_TRIANGLE = 1,    /* Interpolation::Bilinear -> FilterType::Triangle */
+    PFE_RESIZE_CATMULL_ROM = 2, /* Interpolation::Bicubic  -> FilterType::CatmullRom */
+    PFE_RESIZE_LANCZOS3 = 3     /* Interpolation::Lanczos3 -> FilterType::Lanczos3 */
+} pfe_resize_filter;
+int pfe_resize(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t new_w, uint32_t new_h,
+               int filter, uint8_t *dst);
+int pfe_dev_resize(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t new_w, uint32_t new_h,
+                   int filter, uint8_t *dst);
 
 /* -- warps -----------------------------------------------------------------------------
  * warp_displacement_full (src/ops/transform.rs:1288-1345) / GpuLiquifyPipeline::warp_into

@@ -669,6 +669,12 @@ enum {
     PFO_LUT_RGBA = 8,       /* curves :549 — four LUTs; per-channel levels :490 */
     PFO_TEMPERATURE_TINT = 9,   /* :518  p=[temperature, tint] */
     PFO_HIGHLIGHTS_SHADOWS = 10,/* :371  p=[shadows, highlights] */
+    PFO_THRESHOLD = 11,     /* :1240 p=[level] */
+    PFO_POSTERIZE = 12,     /* :1267 p=[factor = max(levels, 2)] */
+    PFO_COLOR_BALANCE = 13, /* :1294 p=[shadows rgb, midtones rgb, highlights rgb] */
+    PFO_GRADIENT_MAP = 14,  /* :1344 luts = 256 RGBA entries */
+    PFO_BLACK_AND_WHITE = 15, /* :1373 p=[r_weight, g_weight, b_weight] */
+    PFO_VIBRANCE = 16,      /* :1408 p=[amount / 100] */
     /* scripting.rs inline variants: truncating casts, no mask, alpha untouched */
     PFO_S_INVERT = 32,      /* scripting.rs:869 */
     PFO_S_DESATURATE = 33,  /* :883 integer 299/587/114 */
@@ -736,6 +742,43 @@ static inline void adjust_pixel(int op, const float *p, const uint8_t *luts, con
         float hw = lum * lum;
         float adj = sw * shadow_amt * 128.0f + hw * highlight_amt * 128.0f;
         nr = r + adj; ng = g + adj; nb = b + adj;
+    } break;
+    case PFO_THRESHOLD: {
+        float lum = 0.2126f * r + 0.7152f * g + 0.0722f * b;
+        nr = ng = nb = lum >= p[0] ? 255.0f : 0.0f;
+    } break;
+    case PFO_POSTERIZE: {
+        float f1 = p[0] - 1.0f;
+        nr = roundf(r / 255.0f * f1) / f1 * 255.0f;
+        ng = roundf(g / 255.0f * f1) / f1 * 255.0f;
+        nb = roundf(b / 255.0f * f1) / f1 * 255.0f;
+    } break;
+    case PFO_COLOR_BALANCE: { /* color_balance_pixel :1321-1338; powi(2) == x*x */
+        float lum = (0.2126f * r + 0.7152f * g + 0.0722f * b) / 255.0f;
+        float s0 = maxf(1.0f - lum * 2.0f, 0.0f), h0 = maxf(lum * 2.0f - 1.0f, 0.0f);
+        float sw = s0 * s0, hw = h0 * h0;
+        float mw = maxf(1.0f - sw - hw, 0.0f);
+        nr = r + (sw * p[0] + mw * p[3] + hw * p[6]) * 1.28f;
+        ng = g + (sw * p[1] + mw * p[4] + hw * p[7]) * 1.28f;
+        nb = b + (sw * p[2] + mw * p[5] + hw * p[8]) * 1.28f;
+    } break;
+    case PFO_GRADIENT_MAP: {
+        uint32_t lum = as_u32(0.2126f * r + 0.7152f * g + 0.0722f * b);
+        if (lum > 255) lum = 255;
+        nr = (float)luts[lum * 4]; ng = (float)luts[lum * 4 + 1]; nb = (float)luts[lum * 4 + 2];
+    } break;
+    case PFO_BLACK_AND_WHITE: {
+        float v = clampf((r * p[0] + g * p[1] + b * p[2]) / 100.0f, 0.0f, 255.0f);
+        nr = ng = nb = v;
+    } break;
+    case PFO_VIBRANCE: { /* vibrance_pixel :1431-1444 */
+        float hh, sat, l;
+        rgb_to_hsl(r / 255.0f, g / 255.0f, b / 255.0f, &hh, &sat, &l);
+        float boost = p[0] >= 0.0f ? p[0] * ((1.0f - sat) * (1.0f - sat)) : p[0] * (sat * sat);
+        float ns = clampf(sat + boost, 0.0f, 1.0f);
+        float rr, gg, bb;
+        hsl_to_rgb(hh, ns, l, &rr, &gg, &bb);
+        nr = rr * 255.0f; ng = gg * 255.0f; nb = bb * 255.0f;
     } break;
     /* ---- scripting variants: write u8 directly ---- */
     case PFO_S_INVERT: out[0] = 255 - in[0]; out[1] = 255 - in[1]; out[2] = 255 - in[2]; out[3] = in[3]; return;
@@ -1868,4 +1911,207 @@ void pfo_rgb_displace(const uint8_t *src, uint32_t w, uint32_t h, const int32_t 
             }
             dst[oi + 3] = src[oi + 3];
         }
+}
+
+/* ========================================================================= */
+/* Geometry: flips / quarter turns, resize_canvas,         */
+/* apply_affine, and imageops::resize                                          */
+/* ========================================================================= */
+
+/* imageops::flip_horizontal / flip_vertical / rotate90 / rotate270 / rotate180 as called from
+ * src/ops/transform.rs:326-334 and src/ops/scripting.rs:645-740; identical to
+ * TiledImage::{flip_*,rotate_*}_chunked (transform.rs:62-131) on the flattened layer.
+ * op: 0 flip H, 1 flip V, 2 rotate 90 cw, 3 rotate 90 ccw, 4 rotate 180. dst is w*h or h*w. */
+void pfo_orient(const uint8_t *src, uint32_t w, uint32_t h, int op, uint8_t *dst) {
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) {
+            size_t si = ((size_t)y * w + x) * 4, di;
+            switch (op) {
+            case 0: di = ((size_t)y * w + (w - 1 - x)) * 4; break;
+            case 1: di = ((size_t)(h - 1 - y) * w + x) * 4; break;
+            case 2: di = ((size_t)x * h + (h - 1 - y)) * 4; break;       /* out(h-1-y, x), width h */
+            case 3: di = ((size_t)(w - 1 - x) * h + y) * 4; break;       /* out(y, w-1-x), width h */
+            default: di = ((size_t)(h - 1 - y) * w + (w - 1 - x)) * 4; break;
+            }
+            memcpy(dst + di, src + si, 4);
+        }
+}
+
+/* resize_canvas / resize_canvas_layers, transform.rs:382-463. anchor in {0,1,2}^2. */
+void pfo_resize_canvas(const uint8_t *src, uint32_t ow, uint32_t oh, uint32_t nw, uint32_t nh, uint32_t ax, uint32_t ay,
+                       const uint8_t fill[4], uint8_t *dst) {
+    int32_t offx = ax == 0 ? 0 : (ax == 1 ? ((int32_t)nw - (int32_t)ow) / 2 : (int32_t)nw - (int32_t)ow);
+    int32_t offy = ay == 0 ? 0 : (ay == 1 ? ((int32_t)nh - (int32_t)oh) / 2 : (int32_t)nh - (int32_t)oh);
+    for (size_t i = 0; i < (size_t)nw * nh; i++) memcpy(dst + i * 4, fill, 4);
+    for (uint32_t y = 0; y < oh; y++)
+        for (uint32_t x = 0; x < ow; x++) {
+            int32_t nx = (int32_t)x + offx, ny = (int32_t)y + offy;
+            if (nx >= 0 && ny >= 0 && (uint32_t)nx < nw && (uint32_t)ny < nh)
+                memcpy(dst + ((size_t)ny * nw + nx) * 4, src + ((size_t)y * ow + x) * 4, 4);
+        }
+}
+
+/* invert_3x3, transform.rs:949-976 */
+static void invert_3x3(const float m[3][3], float o[3][3]) {
+    float a = m[0][0], b = m[0][1], c = m[0][2], d = m[1][0], e = m[1][1], f = m[1][2], g = m[2][0], h = m[2][1], i = m[2][2];
+    float det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (fabsf(det) < 1e-12f) {
+        float id[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        memcpy(o, id, sizeof(id));
+        return;
+    }
+    float inv = 1.0f / det;
+    o[0][0] = (e * i - f * h) * inv; o[0][1] = (c * h - b * i) * inv; o[0][2] = (b * f - c * e) * inv;
+    o[1][0] = (f * g - d * i) * inv; o[1][1] = (a * i - c * g) * inv; o[1][2] = (c * d - a * f) * inv;
+    o[2][0] = (d * h - e * g) * inv; o[2][1] = (b * g - a * h) * inv; o[2][2] = (a * e - b * d) * inv;
+}
+/* The inverse homography of apply_affine (transform.rs:838-876): out[0..8] = hi row-major,
+ * out[9] = inv_scale. Host arithmetic (libm sinf/cosf), shared by the oracle and its callers. */
+void pfo_affine_matrix(uint32_t canvas_w, uint32_t canvas_h, float rotation_z, float rotation_x, float rotation_y,
+                       float scale, float out[10]) {
+    float focal = (float)(canvas_w > canvas_h ? canvas_w : canvas_h) * 1.5f;
+    float rz = pfo_to_radians(rotation_z), rx = pfo_to_radians(rotation_x), ry = pfo_to_radians(rotation_y);
+    float sz = sinf(rz), cz = cosf(rz), sxr = sinf(rx), cxr = cosf(rx), syr = sinf(ry), cyr = cosf(ry);
+    float r00 = cz * cyr, r01 = cz * syr * sxr - sz * cxr, r10 = sz * cyr, r11 = sz * syr * sxr + cz * cxr;
+    float r20 = -syr, r21 = cyr * sxr;
+    float hm[3][3] = {{focal * r00, focal * r01, 0.0f}, {focal * r10, focal * r11, 0.0f}, {r20, r21, focal}}, hi[3][3];
+    invert_3x3(hm, hi);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) out[r * 3 + c] = hi[r][c];
+    out[9] = fabsf(scale) > 1e-6f ? 1.0f / scale : 1.0f;
+}
+/* apply_affine, transform.rs:826-946. nearest != 0 selects Interpolation::Nearest; every other
+ * interpolation is the bilinear branch. dst = canvas_w x canvas_h, transparent where unmapped. */
+void pfo_affine(const uint8_t *src, uint32_t sw, uint32_t sh, uint32_t canvas_w, uint32_t canvas_h, float rotation_z,
+                float rotation_x, float rotation_y, float scale, float off_x, float off_y, int nearest, uint8_t *dst) {
+    memset(dst, 0, (size_t)canvas_w * canvas_h * 4);
+    if (canvas_w == 0 || canvas_h == 0) return;
+    float m[10];
+    pfo_affine_matrix(canvas_w, canvas_h, rotation_z, rotation_x, rotation_y, scale, m);
+    float cx = (float)canvas_w * 0.5f, cy = (float)canvas_h * 0.5f, inv_scale = m[9];
+    int src_w = (int)sw, src_h = (int)sh;
+#pragma omp parallel for schedule(static)
+    for (long dy = 0; dy < (long)canvas_h; dy++) {
+        float v = ((float)dy - cy - off_y) * inv_scale;
+        float base_sx = m[1] * v + m[2], base_sy = m[4] * v + m[5], base_sw = m[7] * v + m[8];
+        for (long dx = 0; dx < (long)canvas_w; dx++) {
+            float u = ((float)dx - cx - off_x) * inv_scale;
+            float wq = m[6] * u + base_sw;
+            if (fabsf(wq) < 1e-8f) continue;
+            float inv_w = 1.0f / wq;
+            float src_x = (m[0] * u + base_sx) * inv_w + cx, src_y = (m[3] * u + base_sy) * inv_w + cy;
+            uint8_t *o = dst + ((size_t)dy * canvas_w + dx) * 4;
+            if (nearest) {
+                int nx = as_i32(roundf(src_x)), ny = as_i32(roundf(src_y));
+                if (nx >= 0 && ny >= 0 && nx < src_w && ny < src_h) memcpy(o, src + ((size_t)ny * sw + nx) * 4, 4);
+                continue;
+            }
+            int x0 = as_i32(floorf(src_x)), y0 = as_i32(floorf(src_y));
+            if (x0 < -1 || y0 < -1 || x0 >= src_w || y0 >= src_h) continue;
+            float fx = src_x - (float)x0, fy = src_y - (float)y0;
+            float t[4][4];
+            for (int k = 0; k < 4; k++) {
+                int sx = x0 + (k & 1), sy = y0 + (k >> 1);
+                for (int c = 0; c < 4; c++)
+                    t[k][c] = (sx < 0 || sy < 0 || sx >= src_w || sy >= src_h) ? 0.0f : (float)src[((size_t)sy * sw + sx) * 4 + c];
+            }
+            for (int c = 0; c < 4; c++) {
+                float top = t[0][c] + (t[1][c] - t[0][c]) * fx, bot = t[2][c] + (t[3][c] - t[2][c]) * fx;
+                o[c] = round_u8(top + (bot - top) * fy);
+            }
+        }
+    }
+}
+
+/* imageops::resize of the `image` crate 0.25.9 (Cargo.lock; the crate is NOT vendored under
+ * /root/reference, so this restates its published algorithm: imageops/sample.rs `resize` =
+ * vertical_sample into an f32 image, then horizontal_sample with FloatNearest rounding and a clamp to
+ * [0, 255]).  Called by resize_image / resize_layers (transform.rs:347-378).  Pinned by the reference's
+ * goldens transforms/resize_{2x_nearest,half_bilinear,half_lanczos}.png; CatmullRom has no golden.
+ * filter: 0 Nearest (box, support 0), 1 Triangle, 2 CatmullRom, 3 Lanczos3. */
+static float rs_sinc(float t) {
+    float a = t * 3.14159265358979323846f;
+    return t == 0.0f ? 1.0f : sinf(a) / a;
+}
+static float rs_kernel(int filter, float x) {
+    switch (filter) {
+    case 0: return 1.0f; /* box_kernel over a window of one sample */
+    case 1: return fabsf(x) < 1.0f ? 1.0f - fabsf(x) : 0.0f;
+    case 2: { /* bc_cubic_spline(x, b = 0, c = 0.5) */
+        float a = fabsf(x), b = 0.0f, c = 0.5f, k;
+        if (a < 1.0f) k = (12.0f - 9.0f * b - 6.0f * c) * a * a * a + (-18.0f + 12.0f * b + 6.0f * c) * a * a + (6.0f - 2.0f * b);
+        else if (a < 2.0f) k = (-b - 6.0f * c) * a * a * a + (6.0f * b + 30.0f * c) * a * a + (-12.0f * b - 48.0f * c) * a + (8.0f * b + 24.0f * c);
+        else k = 0.0f;
+        return k / 6.0f;
+    }
+    default: return fabsf(x) < 3.0f ? rs_sinc(x) * rs_sinc(x / 3.0f) : 0.0f;
+    }
+}
+static float rs_support(int filter) { return filter == 0 ? 0.0f : (filter == 1 ? 1.0f : (filter == 2 ? 2.0f : 3.0f)); }
+/* One axis of sample weights: for every output index, `left[o]`, `count[o]` and count normalised
+ * weights at weights[offset[o] ...]. Returns the total number of weights (call with weights == NULL
+ * to size the buffer). */
+size_t pfo_resize_weights(uint32_t n_in, uint32_t n_out, int filter, uint32_t *left_out, uint32_t *count_out,
+                          uint32_t *offset_out, float *weights) {
+    float ratio = (float)n_in / (float)n_out;
+    float sratio = ratio < 1.0f ? 1.0f : ratio;
+    float src_support = rs_support(filter) * sratio;
+    size_t total = 0;
+    for (uint32_t o = 0; o < n_out; o++) {
+        float inp = ((float)o + 0.5f) * ratio;
+        int64_t left = (int64_t)floorf(inp - src_support);
+        if (left < 0) left = 0;
+        if (left > (int64_t)n_in - 1) left = (int64_t)n_in - 1;
+        int64_t right = (int64_t)ceilf(inp + src_support);
+        if (right < left + 1) right = left + 1;
+        if (right > (int64_t)n_in) right = (int64_t)n_in;
+        inp = inp - 0.5f;
+        uint32_t cnt = (uint32_t)(right - left);
+        if (left_out) { left_out[o] = (uint32_t)left; count_out[o] = cnt; offset_out[o] = (uint32_t)total; }
+        if (weights) {
+            float sum = 0.0f;
+            for (uint32_t i = 0; i < cnt; i++) {
+                float wv = rs_kernel(filter, ((float)(left + i) - inp) / sratio);
+                weights[total + i] = wv;
+                sum += wv;
+            }
+            for (uint32_t i = 0; i < cnt; i++) weights[total + i] /= sum;
+        }
+        total += cnt;
+    }
+    return total;
+}
+void pfo_resize(const uint8_t *src, uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, int filter, uint8_t *dst) {
+    if (nw == 0 || nh == 0) return;
+    if (w == 0 || h == 0) { memset(dst, 0, (size_t)nw * nh * 4); return; }
+    if (nw == w && nh == h) { memcpy(dst, src, (size_t)w * h * 4); return; }
+    uint32_t *vl = (uint32_t *)malloc(sizeof(uint32_t) * 3 * nh), *hl = (uint32_t *)malloc(sizeof(uint32_t) * 3 * nw);
+    size_t nvw = pfo_resize_weights(h, nh, filter, NULL, NULL, NULL, NULL), nhw = pfo_resize_weights(w, nw, filter, NULL, NULL, NULL, NULL);
+    float *vw = (float *)malloc(sizeof(float) * nvw), *hw = (float *)malloc(sizeof(float) * nhw);
+    pfo_resize_weights(h, nh, filter, vl, vl + nh, vl + 2 * nh, vw);
+    pfo_resize_weights(w, nw, filter, hl, hl + nw, hl + 2 * nw, hw);
+    float *tmp = (float *)malloc(sizeof(float) * 4 * (size_t)w * nh);
+#pragma omp parallel for schedule(static)
+    for (long oy = 0; oy < (long)nh; oy++)
+        for (uint32_t x = 0; x < w; x++) {
+            float t[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < vl[nh + oy]; i++) {
+                const uint8_t *p = src + ((size_t)(vl[oy] + i) * w + x) * 4;
+                float wt = vw[vl[2 * nh + oy] + i];
+                for (int c = 0; c < 4; c++) t[c] += (float)p[c] * wt;
+            }
+            memcpy(tmp + ((size_t)oy * w + x) * 4, t, sizeof(t));
+        }
+#pragma omp parallel for schedule(static)
+    for (long oy = 0; oy < (long)nh; oy++)
+        for (uint32_t ox = 0; ox < nw; ox++) {
+            float t[4] = {0, 0, 0, 0};
+            for (uint32_t i = 0; i < hl[nw + ox]; i++) {
+                const float *p = tmp + ((size_t)oy * w + hl[ox] + i) * 4;
+                float wt = hw[hl[2 * nw + ox] + i];
+                for (int c = 0; c < 4; c++) t[c] += p[c] * wt;
+            }
+            for (int c = 0; c < 4; c++) dst[((size_t)oy * nw + ox) * 4 + c] = as_u8(roundf(clampf(t[c], 0.0f, 255.0f)));
+        }
+    free(tmp); free(vw); free(hw); free(vl); free(hl);
 }

@@ -160,7 +160,8 @@ def vignette(src, amount, softness, mask=None):
 
 # -- adjustments ------------------------------------------------------------------------
 INVERT, INVERT_ALPHA, SEPIA, DESATURATE, BRIGHTNESS_CONTRAST, HSL, EXPOSURE, LUT_RGB, LUT_RGBA, \
-    TEMPERATURE_TINT, HIGHLIGHTS_SHADOWS = range(11)
+    TEMPERATURE_TINT, HIGHLIGHTS_SHADOWS, THRESHOLD, POSTERIZE, COLOR_BALANCE, GRADIENT_MAP, BLACK_AND_WHITE, \
+    VIBRANCE = range(17)
 S_INVERT, S_DESATURATE, S_SEPIA, S_SEPIA_STRENGTH, S_BRIGHTNESS_CONTRAST, S_HSL, S_EXPOSURE, \
     S_LUT_RGB = range(32, 40)
 
@@ -169,7 +170,7 @@ def adjust(src, op, params=(), luts=None, mask=None, occupancy=None):
     src = _u8(src)
     h, w = src.shape[:2]
     dst = np.empty_like(src)
-    p = np.zeros(8, np.float32)
+    p = np.zeros(12, np.float32)
     p[: len(params)] = params
     luts = _u8(luts)
     mask = _u8(mask)
@@ -434,3 +435,45 @@ def pixel_drag(src, seed, amount, distance, direction, mask=None):
 def rgb_displace(src, r_off, g_off, b_off, mask=None):
     off = (C.c_int32 * 6)(r_off[0], r_off[1], g_off[0], g_off[1], b_off[0], b_off[1])
     return _img_call(lib().pfo_rgb_displace, src, off, mask=mask)
+
+
+# -- geometry: flips / quarter turns, resize_canvas, apply_affine, imageops::resize ----------------
+FLIP_H, FLIP_V, ROT90CW, ROT90CCW, ROT180 = range(5)
+
+
+def orient(src, op):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty((w, h, 4) if op in (ROT90CW, ROT90CCW) else (h, w, 4), np.uint8)
+    lib().pfo_orient(_p(src), C.c_uint32(w), C.c_uint32(h), C.c_int(op), _p(dst))
+    return dst
+
+
+def resize_canvas(src, new_w, new_h, anchor, fill):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty((new_h, new_w, 4), np.uint8)
+    lib().pfo_resize_canvas(_p(src), C.c_uint32(w), C.c_uint32(h), C.c_uint32(new_w), C.c_uint32(new_h),
+                            C.c_uint32(anchor[0]), C.c_uint32(anchor[1]), _rgba4(fill), _p(dst))
+    return dst
+
+
+def affine(src, canvas_w, canvas_h, rotation_z, rotation_x=0.0, rotation_y=0.0, scale=1.0, offset=(0.0, 0.0), nearest=False):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty((canvas_h, canvas_w, 4), np.uint8)
+    lib().pfo_affine(_p(src), C.c_uint32(w), C.c_uint32(h), C.c_uint32(canvas_w), C.c_uint32(canvas_h),
+                     C.c_float(rotation_z), C.c_float(rotation_x), C.c_float(rotation_y), C.c_float(scale),
+                     C.c_float(offset[0]), C.c_float(offset[1]), C.c_int(1 if nearest else 0), _p(dst))
+    return dst
+
+
+RS_NEAREST, RS_TRIANGLE, RS_CATMULL_ROM, RS_LANCZOS3 = range(4)
+
+
+def resize(src, new_w, new_h, filter):
+    src = _u8(src)
+    h, w = src.shape[:2]
+    dst = np.empty((new_h, new_w, 4), np.uint8)
+    lib().pfo_resize(_p(src), C.c_uint32(w), C.c_uint32(h), C.c_uint32(new_w), C.c_uint32(new_h), C.c_int(filter), _p(dst))
+    return dst

@@ -31,7 +31,7 @@ class LayerDesc(C.Structure):
 
 
 class AdjustDesc(C.Structure):
-    _fields_ = [("op", C.c_int32), ("params", C.c_float * 8), ("luts", C.c_void_p)]
+    _fields_ = [("op", C.c_int32), ("params", C.c_float * 12), ("luts", C.c_void_p)]
 
 
 class BrushDesc(C.Structure):
@@ -126,6 +126,14 @@ SIGNATURES = {
     "pfe_compose_curve_luts": (None, [_vp, _vp]),
     "pfe_channel_minmax": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp]),
     "pfe_dev_channel_minmax": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp]),
+    "pfe_orient": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _vp]),
+    "pfe_dev_orient": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _vp]),
+    "pfe_resize_canvas": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_dev_resize_canvas": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "pfe_affine": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int, _vp]),
+    "pfe_dev_affine": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int, _vp]),
+    "pfe_resize": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, C.c_int, _vp]),
+    "pfe_dev_resize": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, C.c_int, _vp]),
     "pfe_warp_displacement": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _u32, _u32, _vp]),
     "pfe_dev_warp_displacement": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _u32, _u32, _vp]),
     "pfe_mesh_displacement": (C.c_int, [_ctx, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),

@@ -14,7 +14,7 @@ struct AdjParams {
     const uint8_t *mask;       // w*h or null (ignored by the scripting family)
     const uint8_t *occupancy;  // chunk bitmap or null
     const uint8_t *luts;       // device, 256 or 1024 bytes, or null
-    float p[8];
+    float p[12];
     uint32_t w, h, chunks_x;
     int op;
     uint64_t n;
@@ -100,6 +100,40 @@ __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint
         float adj = sw * shadow_amt * 128.0f + hw * highlight_amt * 128.0f;
         return round_px(r + adj, g + adj, b + adj, a);
     }
+    case PFE_ADJ_THRESHOLD: {
+        const float v1 = (0.2126f * r + 0.7152f * g + 0.0722f * b) >= p[0] ? 255.0f : 0.0f;
+        return round_px(v1, v1, v1, a);
+    }
+    case PFE_ADJ_POSTERIZE: {
+        const float f1 = p[0] - 1.0f;
+        return round_px(roundf(r / 255.0f * f1) / f1 * 255.0f, roundf(g / 255.0f * f1) / f1 * 255.0f,
+                        roundf(b / 255.0f * f1) / f1 * 255.0f, a);
+    }
+    case PFE_ADJ_COLOR_BALANCE: {  // color_balance_pixel, adjustments.rs:1321-1338
+        const float lum = (0.2126f * r + 0.7152f * g + 0.0722f * b) / 255.0f;
+        const float s0 = fmaxf(1.0f - lum * 2.0f, 0.0f), h0 = fmaxf(lum * 2.0f - 1.0f, 0.0f);
+        const float sw = s0 * s0, hw = h0 * h0;
+        const float mw = fmaxf(1.0f - sw - hw, 0.0f);
+        return round_px(r + (sw * p[0] + mw * p[3] + hw * p[6]) * 1.28f, g + (sw * p[1] + mw * p[4] + hw * p[7]) * 1.28f,
+                        b + (sw * p[2] + mw * p[5] + hw * p[8]) * 1.28f, a);
+    }
+    case PFE_ADJ_GRADIENT_MAP: {
+        const uint32_t lum = min((uint32_t)__float2int_rz(0.2126f * r + 0.7152f * g + 0.0722f * b), 255u);
+        return pfe_pack(lut[lum * 4], lut[lum * 4 + 1], lut[lum * 4 + 2], a8);
+    }
+    case PFE_ADJ_BLACK_AND_WHITE: {
+        const float v1 = pfe_clampf((r * p[0] + g * p[1] + b * p[2]) / 100.0f, 0.0f, 255.0f);
+        return round_px(v1, v1, v1, a);
+    }
+    case PFE_ADJ_VIBRANCE: {  // vibrance_pixel, adjustments.rs:1431-1444
+        float hh, sat, l;
+        rgb_to_hsl(r / 255.0f, g / 255.0f, b / 255.0f, hh, sat, l);
+        const float boost = p[0] >= 0.0f ? p[0] * ((1.0f - sat) * (1.0f - sat)) : p[0] * (sat * sat);
+        const float ns = pfe_clampf(sat + boost, 0.0f, 1.0f);
+        float rr, gg, bb;
+        hsl_to_rgb(hh, ns, l, 1e-6f, rr, gg, bb);
+        return round_px(rr * 255.0f, gg * 255.0f, bb * 255.0f, a);
+    }
     // ---- scripting.rs inline variants ----
     case PFE_ADJ_S_INVERT: return pfe_pack(255u - r8, 255u - g8, 255u - b8, a8);
     case PFE_ADJ_S_DESATURATE: {
@@ -157,7 +191,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256) adjust_kernel(const __grid_constant__ AdjParams P) {
     __shared__ uint8_t lut[1024];
     if (P.luts) {
-        const int nl = (P.op == PFE_ADJ_LUT_RGBA) ? 1024 : 256;
+        const int nl = (P.op == PFE_ADJ_LUT_RGBA || P.op == PFE_ADJ_GRADIENT_MAP) ? 1024 : 256;
         for (int i = threadIdx.x; i < nl; i += blockDim.x) lut[i] = P.luts[i];
         __syncthreads();
     }
@@ -215,8 +249,8 @@ extern "C" int pfe_dev_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint
     if (!ctx) return PFE_ERR_INVALID_ARG;
     if (!src || !dst || !d || !w || !h) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "adjust: bad args");
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
-    const bool lut_op = d->op == PFE_ADJ_LUT_RGB || d->op == PFE_ADJ_LUT_RGBA || d->op == PFE_ADJ_S_LUT_RGB;
-    const bool known = (d->op >= 0 && d->op <= PFE_ADJ_HIGHLIGHTS_SHADOWS) || (d->op >= 32 && d->op <= PFE_ADJ_S_LUT_RGB);
+    const bool lut_op = d->op == PFE_ADJ_LUT_RGB || d->op == PFE_ADJ_LUT_RGBA || d->op == PFE_ADJ_S_LUT_RGB || d->op == PFE_ADJ_GRADIENT_MAP;
+    const bool known = (d->op >= 0 && d->op <= PFE_ADJ_VIBRANCE) || (d->op >= 32 && d->op <= PFE_ADJ_S_LUT_RGB);
     if (!known) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "adjust: unknown op");
     if (lut_op && !d->luts) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "adjust: LUT op without luts");
     AdjParams P;
@@ -226,7 +260,7 @@ extern "C" int pfe_dev_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint
     P.w = w; P.h = h; P.chunks_x = pfe_div_up(w, PFE_CHUNK_SIZE); P.op = d->op; P.n = (uint64_t)w * h;
     if (lut_op) {
         void *ld;
-        PFE_TRY(pfe_small_upload(ctx, d->luts, d->op == PFE_ADJ_LUT_RGBA ? 1024 : 256, &ld));
+        PFE_TRY(pfe_small_upload(ctx, d->luts, (d->op == PFE_ADJ_LUT_RGBA || d->op == PFE_ADJ_GRADIENT_MAP) ? 1024 : 256, &ld));
         P.luts = (const uint8_t *)ld;
     }
     const bool vec = (P.n % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;

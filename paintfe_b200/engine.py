@@ -307,6 +307,38 @@ class Engine:
         off = (C.c_int32 * 6)(r_off[0], r_off[1], g_off[0], g_off[1], b_off[0], b_off[1])
         return self._img_op(self.lib.pfe_rgb_displace, self.lib.pfe_dev_rgb_displace, src, mask, out, off)
 
+    # -- geometry (geometry.cu): source and result shapes may differ --------------------------------
+    def _reshape_op(self, host_fn, dev_fn, src, out_hw, out, *args):
+        src = self._prep(src)
+        dev = _is_tensor(src)
+        if out is None:
+            out = torch.empty((out_hw[0], out_hw[1], 4), dtype=torch.uint8, device=src.device) if dev \
+                else np.empty((out_hw[0], out_hw[1], 4), np.uint8)
+        self._ck((dev_fn if dev else host_fn)(self.h, _ptr(src), *args, _ptr(out)))
+        return out
+
+    def orient(self, src, op, out=None):
+        h, w = self._hw(src)
+        return self._reshape_op(self.lib.pfe_orient, self.lib.pfe_dev_orient, src, (w, h) if op in (2, 3) else (h, w), out,
+                                w, h, int(op))
+
+    def resize_canvas(self, src, new_w, new_h, anchor, fill, out=None):
+        h, w = self._hw(src)
+        return self._reshape_op(self.lib.pfe_resize_canvas, self.lib.pfe_dev_resize_canvas, src, (new_h, new_w), out,
+                                w, h, new_w, new_h, anchor[0], anchor[1], self._rgba(fill))
+
+    def affine(self, src, canvas_w, canvas_h, rotation_z, rotation_x=0.0, rotation_y=0.0, scale=1.0, offset=(0.0, 0.0),
+               nearest=False, out=None):
+        h, w = self._hw(src)
+        return self._reshape_op(self.lib.pfe_affine, self.lib.pfe_dev_affine, src, (canvas_h, canvas_w), out, w, h,
+                                canvas_w, canvas_h, C.c_float(rotation_z), C.c_float(rotation_x), C.c_float(rotation_y),
+                                C.c_float(scale), C.c_float(offset[0]), C.c_float(offset[1]), 1 if nearest else 0)
+
+    def resize(self, src, new_w, new_h, filter, out=None):
+        h, w = self._hw(src)
+        return self._reshape_op(self.lib.pfe_resize, self.lib.pfe_dev_resize, src, (new_h, new_w), out, w, h, new_w, new_h,
+                                int(filter))
+
     def adjust(self, src, op, params=(), luts=None, mask=None, occupancy=None, out=None):
         src = self._prep(src)
         h, w = self._hw(src)

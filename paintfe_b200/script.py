@@ -59,6 +59,17 @@ def bindings(eng, exact: bool = False) -> Dict[str, Callable]:
         # inline variants: truncating casts, no mask, alpha untouched (scripting.rs:869-1075)
         "apply_invert": lambda im, m: eng.adjust(im, S_INVERT),
         "apply_desaturate": lambda im, m: eng.adjust(im, S_DESATURATE),
+        # scripting.rs:645-745: whole-buffer flips / turns (the selection mask does not apply); the
+        # canvas-wide forms transform the script's buffer the same way and leave the replay on the other
+        # layers to the caller (CanvasOpRequest)
+        "flip_horizontal": lambda im, m: eng.orient(im, 0),
+        "flip_vertical": lambda im, m: eng.orient(im, 1),
+        "rotate_180": lambda im, m: eng.orient(im, 4),
+        "flip_canvas_horizontal": lambda im, m: eng.orient(im, 0),
+        "flip_canvas_vertical": lambda im, m: eng.orient(im, 1),
+        "rotate_canvas_90cw": lambda im, m: eng.orient(im, 2),
+        "rotate_canvas_90ccw": lambda im, m: eng.orient(im, 3),
+        "rotate_canvas_180": lambda im, m: eng.orient(im, 4),
         "apply_sepia": lambda im, m, *s: (eng.adjust(im, S_SEPIA) if not s else
                                           eng.adjust(im, S_SEPIA_STRENGTH, (min(max(float(s[0]), 0.0), 1.0),))),
         "apply_brightness_contrast": lambda im, m, b, c: eng.adjust(im, S_BRIGHTNESS_CONTRAST, (_f32(b), _f32(c))),

@@ -211,6 +211,32 @@ int main(int argc, char **argv) {
     run("hsl_adjustment", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::hue_saturation_lightness_from_flat(s, 0, 30.0f, -20.0f, 10.0f, img); assert_golden("adjustments", "hsl_h30_s-20_l10", extract(s)); });
     run("exposure", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::exposure_from_flat(s, 0, 1.0f, img); assert_golden("adjustments", "exposure_1ev", extract(s)); });
     run("levels", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::levels_from_flat(s, 0, 20.0f, 235.0f, 1.2f, 0.0f, 255.0f, img); assert_golden("adjustments", "levels", extract(s)); });
+    run("highlights_shadows", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::highlights_shadows_from_flat(s, 0, 30.0f, -20.0f, img); assert_golden("adjustments", "highlights_shadows", extract(s)); });
+    run("temperature_tint", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::temperature_tint_from_flat(s, 0, 30.0f, 10.0f, img); assert_golden("adjustments", "temperature_tint", extract(s)); });
+    run("threshold", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::threshold_from_flat(s, 0, 128.0f, img); assert_golden("adjustments", "threshold_128", extract(s)); });
+    run("posterize", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::posterize_from_flat(s, 0, 4, img); assert_golden("adjustments", "posterize_4", extract(s)); });
+    run("color_balance", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::color_balance_from_flat(s, 0, {10.0f, 0.0f, -10.0f}, {0.0f, 0.0f, 0.0f}, {-10.0f, 0.0f, 10.0f}, img); assert_golden("adjustments", "color_balance", extract(s)); });
+    run("color_balance_identity", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::color_balance_from_flat(s, 0, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}, img); check(extract(s) == img, "all-zero colour balance must be identity"); });
+    run("gradient_map", [&] {  // visual_adjustments.rs:299-316
+        ops::adjustments::GradientLut lut;
+        for (int i = 0; i < 256; i++) {
+            float t = (float)i / 255.0f;
+            lut[i] = {(uint8_t)(t * 255.0f), (uint8_t)(t * t * 200.0f), (uint8_t)(t * t * t * 150.0f), 255};
+        }
+        CanvasState s = canvas_from_image(img);
+        ops::adjustments::gradient_map_from_flat(s, 0, lut, img);
+        assert_golden("adjustments", "gradient_map", extract(s));
+    });
+    run("black_and_white", [&] {
+        RgbaImage bands(64, 64);
+        const Rgba colors[8] = {{{255, 0, 0, 255}}, {{0, 255, 0, 255}}, {{0, 0, 255, 255}}, {{0, 255, 255, 255}}, {{255, 0, 255, 255}}, {{255, 255, 0, 255}}, {{255, 255, 255, 255}}, {{0, 0, 0, 255}}};
+        for (uint32_t y = 0; y < 64; y++) for (uint32_t x = 0; x < 64; x++) bands.put_pixel(x, y, colors[std::min<uint32_t>(x * 8 / 64, 7)]);
+        CanvasState s = canvas_from_image(bands);
+        ops::adjustments::black_and_white_from_flat(s, 0, 0.3f, 0.59f, 0.11f, bands);
+        assert_golden("adjustments", "black_and_white", extract(s));
+    });
+    run("vibrance", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::vibrance_from_flat(s, 0, 50.0f, img); assert_golden("adjustments", "vibrance_50", extract(s)); });
+    run("vibrance_identity", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::vibrance_from_flat(s, 0, 0.0f, img); check(extract(s) == img, "vibrance 0 must be identity"); });
     run("curves_identity", [&] {  // visual_adjustments.rs:228-246
         CanvasState s = canvas_from_image(img);
         std::array<std::pair<ops::adjustments::CurvePoints, bool>, 5> ch;
@@ -220,6 +246,39 @@ int main(int argc, char **argv) {
     });
     run("bad_layer_index_is_noop", [&] { CanvasState s = canvas_from_image(img); ops::adjustments::invert_colors(s, 7); ops::filters::gaussian_blur_layer(s, 7, 2.0f); check(extract(s) == img, "out-of-range layer index"); });
 
+
+    // visual_transforms.rs
+    {
+        using namespace ops::transform;
+        const RgbaImage ti = create_test_gradient(64, 48);
+        auto ex0 = [](const CanvasState &s) { return s.layers[0].pixels.to_rgba_image(); };
+        run("flip_canvas_h", [&] { CanvasState s = canvas_from_image(ti); flip_canvas_horizontal(s); assert_golden("transforms", "flip_canvas_h", ex0(s)); });
+        run("flip_canvas_v", [&] { CanvasState s = canvas_from_image(ti); flip_canvas_vertical(s); assert_golden("transforms", "flip_canvas_v", ex0(s)); });
+        run("flip_canvas_h_roundtrip", [&] { CanvasState s = canvas_from_image(ti); flip_canvas_horizontal(s); flip_canvas_horizontal(s); check(ex0(s) == ti, "flip h x 2 should be identity"); });
+        run("rotate_90cw", [&] {
+            CanvasState s = canvas_from_image(ti);
+            rotate_canvas_90cw(s);
+            check(ex0(s).width() == 48 && ex0(s).height() == 64 && s.width == 48 && s.height == 64, "90cw swaps the dimensions");
+            assert_golden("transforms", "rotate_90cw", ex0(s));
+        });
+        run("rotate_90ccw", [&] { CanvasState s = canvas_from_image(ti); rotate_canvas_90ccw(s); assert_golden("transforms", "rotate_90ccw", ex0(s)); });
+        run("rotate_180", [&] { CanvasState s = canvas_from_image(ti); rotate_canvas_180(s); assert_golden("transforms", "rotate_180", ex0(s)); });
+        run("rotate_90cw_x4_identity", [&] { CanvasState s = canvas_from_image(ti); for (int i = 0; i < 4; i++) rotate_canvas_90cw(s); check(ex0(s) == ti, "4 x 90cw should be identity"); });
+        run("rotate_90cw_then_ccw_identity", [&] { CanvasState s = canvas_from_image(ti); rotate_canvas_90cw(s); rotate_canvas_90ccw(s); check(ex0(s) == ti, "90cw + 90ccw should be identity"); });
+        run("resize_2x_nearest", [&] { CanvasState s = canvas_from_image(ti); resize_image(s, 128, 96, Interpolation::Nearest); assert_golden("transforms", "resize_2x_nearest", ex0(s)); });
+        run("resize_half_bilinear", [&] { CanvasState s = canvas_from_image(ti); resize_image(s, 32, 24, Interpolation::Bilinear); assert_golden("transforms", "resize_half_bilinear", ex0(s)); });
+        run("resize_half_lanczos", [&] { CanvasState s = canvas_from_image(ti); resize_image(s, 32, 24, Interpolation::Lanczos3); assert_golden("transforms", "resize_half_lanczos", ex0(s)); });
+        run("resize_canvas_center", [&] { CanvasState s = canvas_from_image(ti); resize_canvas(s, 96, 80, {1, 1}, Rgba{{0, 0, 0, 0}}); assert_golden("transforms", "resize_canvas_center", ex0(s)); });
+        run("resize_canvas_topleft", [&] { CanvasState s = canvas_from_image(ti); resize_canvas(s, 80, 64, {0, 0}, Rgba{{255, 0, 0, 255}}); assert_golden("transforms", "resize_canvas_topleft", ex0(s)); });
+        run("flip_layer_h", [&] { CanvasState s = canvas_from_image(ti); flip_layer_horizontal(s, 0); assert_golden("transforms", "flip_layer_h", ex0(s)); });
+        run("flip_layer_v", [&] { CanvasState s = canvas_from_image(ti); flip_layer_vertical(s, 0); assert_golden("transforms", "flip_layer_v", ex0(s)); });
+        run("affine_rotate_45", [&] { CanvasState s = canvas_from_image(ti); affine_transform_layer(s, 0, 45.0f * (3.14159265358979323846f / 180.0f), 0.0f, 0.0f, 1.0f, {0.0f, 0.0f}); assert_golden("transforms", "affine_rotate_45", ex0(s)); });
+        run("affine_identity", [&] { CanvasState s = canvas_from_image(ti); affine_transform_layer(s, 0, 0.0f, 0.0f, 0.0f, 1.0f, {0.0f, 0.0f}); check(max_diff(ex0(s), ti) <= 1, "identity affine within 1 level"); });
+        // transform_ops.rs:280-303
+        const RgbaImage g32 = create_test_gradient(32, 32);
+        run("affine_rotate_90_golden", [&] { CanvasState s = canvas_from_image(g32); affine_transform_layer(s, 0, 1.57079632679489661923f, 0.0f, 0.0f, 1.0f, {0.0f, 0.0f}); assert_golden("transform", "affine_rotate_90", s.composite()); });
+        run("affine_scale_half_golden", [&] { CanvasState s = canvas_from_image(g32); affine_transform_layer(s, 0, 0.0f, 0.0f, 0.0f, 0.5f, {0.0f, 0.0f}); assert_golden("transform", "affine_scale_half", s.composite()); });
+    }
     // transform_ops.rs
     using namespace ops::transform;
     run("displacement_identity_preserves_image", [] { check(warp_displacement_full(gradient_32(), DisplacementField(32, 32)) == gradient_32(), "identity warp"); });

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import fixtures as fx
-from test_oracle_golden import ADJUST, BLEND_IDS, FILTERS, SCRIPT, STROKES, BLACK
+from test_oracle_golden import ADJUST, BLEND_IDS, FILTERS, GEOMETRY, SCRIPT, STROKES, BLACK
 
 pytestmark = pytest.mark.gpu
 
@@ -79,8 +79,12 @@ class _EngAsOracle:
     def reduce_noise(self, im, s, r, mask=None): return self.e.reduce_noise(im, s, r, mask=mask)
     def drop_shadow(self, im, ox, oy, br, widen, color, op, mask=None):
         return self.e.drop_shadow(im, ox, oy, br, widen, color, op, mask=mask, exact=self.x)
+    def flatten(self, layers, w, h): return self.e.flatten(layers, w, h)
+    def make_layer(self, *a, **k):
+        from paintfe_b200.engine import make_layer
+        return make_layer(*a, **k)
     def __getattr__(self, name):  # the remaining effects take the oracle's arguments unchanged
-        if name in ("ink", "oil_painting", "color_filter", "contours", "crystallize", "dents", "halftone", "bokeh_blur",
+        if name in ("orient", "resize_canvas", "affine", "resize", "ink", "oil_painting", "color_filter", "contours", "crystallize", "dents", "halftone", "bokeh_blur",
                     "zoom_blur", "grid", "canvas_border", "outline", "pixel_drag", "rgb_displace"):
             return getattr(self.e, name)
         raise AttributeError(name)
@@ -312,7 +316,13 @@ def test_adjust_all_ops_random(eng, oracle):
                  (oracle.HSL, (-170.0, 80.0, -30.0), None), (oracle.HSL, (0.0, 0.0, 0.0), None),
                  (oracle.EXPOSURE, (2.0,), None), (oracle.EXPOSURE, (0.3,), None), (oracle.LUT_RGB, (), lut1),
                  (oracle.LUT_RGBA, (), lut4), (oracle.TEMPERATURE_TINT, (30.0, 10.0), None),
-                 (oracle.HIGHLIGHTS_SHADOWS, (30.0, -20.0), None), (oracle.S_INVERT, (), None),
+                 (oracle.HIGHLIGHTS_SHADOWS, (30.0, -20.0), None), (oracle.THRESHOLD, (128.0,), None),
+                 (oracle.THRESHOLD, (0.0,), None), (oracle.POSTERIZE, (4.0,), None), (oracle.POSTERIZE, (2.0,), None),
+                 (oracle.POSTERIZE, (16.0,), None), (oracle.COLOR_BALANCE, (10.0, 0.0, -10.0, 0.0, 0.0, 0.0, -10.0, 0.0, 10.0), None),
+                 (oracle.COLOR_BALANCE, (-100.0, 50.0, 100.0, 30.0, -60.0, 90.0, 100.0, -100.0, 5.0), None),
+                 (oracle.GRADIENT_MAP, (), lut4.T.copy()), (oracle.BLACK_AND_WHITE, (0.3, 0.59, 0.11), None),
+                 (oracle.BLACK_AND_WHITE, (200.0, 150.0, 40.0), None), (oracle.VIBRANCE, (0.5,), None),
+                 (oracle.VIBRANCE, (-1.0,), None), (oracle.VIBRANCE, (1.0,), None), (oracle.S_INVERT, (), None),
                  (oracle.S_DESATURATE, (), None), (oracle.S_SEPIA, (), None), (oracle.S_SEPIA_STRENGTH, (0.4,), None),
                  (oracle.S_BRIGHTNESS_CONTRAST, (20.0, 10.0), None), (oracle.S_HSL, (10.0, 15.0, 0.0), None),
                  (oracle.S_HSL, (-200.0, -50.0, 20.0), None), (oracle.S_EXPOSURE, (1.7,), None),
@@ -344,6 +354,10 @@ def test_adjust_exhaustive_hsl_inputs(eng, oracle):
     for op in (oracle.HSL, oracle.S_HSL):
         for p in ((30.0, -20.0, 10.0), (123.0, 40.0, -5.0), (-359.0, 100.0, 0.0)):
             exact(eng.adjust(img, op, p), oracle.adjust(img, op, p), f"hsl {op} {p}")
+    for v in (0.5, -0.5, 0.0, 1.0):
+        exact(eng.adjust(img, oracle.VIBRANCE, (v,)), oracle.adjust(img, oracle.VIBRANCE, (v,)), f"vibrance {v}")
+    exact(eng.adjust(img, oracle.COLOR_BALANCE, (40.0, -10.0, 5.0, 1.0, 2.0, 3.0, -30.0, 20.0, 60.0)),
+          oracle.adjust(img, oracle.COLOR_BALANCE, (40.0, -10.0, 5.0, 1.0, 2.0, 3.0, -30.0, 20.0, 60.0)), "colour balance lattice")
 
 
 def test_warps_random(eng, oracle):
@@ -630,6 +644,55 @@ def test_effects3_device_tier_and_large(eng, oracle):
     exact(eng.outline(dev, 3, (1, 2, 3, 255), 2, True).cpu().numpy(), oracle.outline(img, 3, (1, 2, 3, 255), 2, True), "outline device")
 
 
+# ---------------------------------------------------------------------------------------------
+# geometry: flips / quarter turns / resize_canvas / affine / imageops::resize
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(GEOMETRY))
+def test_geometry_golden(eng, oracle, name):
+    out = GEOMETRY[name](_EngAsOracle(eng), fx.gradient(64, 48))
+    if name != "flatten_single":
+        out, _ = oracle.tiled_roundtrip(out)
+    exact(out, fx.golden("transforms", name), name)
+
+
+def test_geometry_more_goldens(eng):
+    from paintfe_b200.engine import make_layer
+
+    src = fx.gradient(32, 32)
+    for name, rz, sc in (("affine_rotate_90", float(np.float32(np.pi / 2)), 1.0), ("affine_scale_half", 0.0, 0.5)):
+        exact(eng.flatten([make_layer(eng.affine(src, 32, 32, rz, scale=sc))], 32, 32), fx.golden("transform", name), name)
+    g = fx.gradient(64, 64)
+    exact(eng.orient(g, 0), fx.golden("scripting", "flip_horizontal"))
+    exact(eng.orient(g, 1), fx.golden("scripting", "flip_vertical"))
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (67, 45), (1, 1), (1, 9), (300, 200), (33, 1031)])
+def test_geometry_random(eng, oracle, w, h):
+    import torch
+
+    rng = np.random.default_rng(w * 19 + h)
+    img = fx.random_rgba(rng, w, h)
+    dev = torch.from_numpy(img).cuda()
+    for op in range(5):
+        want = oracle.orient(img, op)
+        exact(eng.orient(img, op), want, f"orient {op}")
+        exact(eng.orient(dev, op).cpu().numpy(), want, f"orient {op} device tier")
+    for nw, nh, anchor in ((w + 32, h + 32, (1, 1)), (w + 16, h + 16, (0, 0)), (max(w // 2, 1), max(h // 2, 1), (2, 2)),
+                           (w + 5, max(h - 3, 1), (1, 2)), (max(w - 7, 1), h + 9, (2, 0))):
+        exact(eng.resize_canvas(img, nw, nh, anchor, (9, 8, 7, 200)), oracle.resize_canvas(img, nw, nh, anchor, (9, 8, 7, 200)),
+              f"resize_canvas {nw}x{nh} {anchor}")
+    for args in ((0.0, 0.0, 0.0, 1.0, (0.0, 0.0)), (33.0, 0.0, 0.0, 1.0, (0.0, 0.0)), (-120.0, 20.0, -35.0, 0.7, (5.5, -3.25)),
+                 (90.0, 0.0, 0.0, 2.5, (0.0, 0.0)), (10.0, 89.0, 0.0, 1.0, (0.0, 0.0)), (0.0, 0.0, 0.0, 0.0, (1.0, 1.0))):
+        for nearest in (False, True):
+            exact(eng.affine(img, w, h, *args, nearest=nearest), oracle.affine(img, w, h, *args, nearest=nearest), f"affine {args} {nearest}")
+    exact(eng.affine(dev, w + 11, h + 3, 17.0, 5.0, 5.0, 1.2, (2.0, 2.0)).cpu().numpy(),
+          oracle.affine(img, w + 11, h + 3, 17.0, 5.0, 5.0, 1.2, (2.0, 2.0)), "affine other canvas, device tier")
+    for nw, nh in ((w * 2, h * 2), (max(w // 2, 1), max(h // 2, 1)), (w + 3, max(h - 1, 1)), (max(w // 7, 1), h * 3), (w, h), (1, 1)):
+        for f in range(4):
+            exact(eng.resize(img, nw, nh, f), oracle.resize(img, nw, nh, f), f"resize {nw}x{nh} filter {f}")
+    exact(eng.resize(dev, w + 9, h + 4, 3).cpu().numpy(), oracle.resize(img, w + 9, h + 4, 3), "resize device tier")
+
+
 def test_script_runner_covers_effect_api(eng, oracle):
     """The Rhai bindings' fixed arguments (scripting.rs:822-1165) through the script runner."""
     from paintfe_b200.script import execute_script_sync
@@ -647,8 +710,14 @@ def test_script_runner_covers_effect_api(eng, oracle):
     exact(execute_script_sync(eng, "apply_ink(1.0, 0.5);", img), fx.golden("filters", "ink"))
     exact(execute_script_sync(eng, "apply_crystallize(16);", img), fx.golden("filters", "crystallize_s16"))
     exact(execute_script_sync(eng, "apply_halftone(4.0);", img), fx.golden("filters", "halftone_circle"))
+    exact(execute_script_sync(eng, "flip_horizontal();", img), fx.golden("scripting", "flip_horizontal"))
+    exact(execute_script_sync(eng, "flip_vertical();", img), fx.golden("scripting", "flip_vertical"))
+    exact(execute_script_sync(eng, "rotate_180(); flip_canvas_horizontal(); flip_canvas_vertical();", img), img)
+    g = fx.gradient(64, 48)
+    exact(execute_script_sync(eng, "rotate_canvas_90cw();", g), oracle.orient(g, oracle.ROT90CW))
+    exact(execute_script_sync(eng, "rotate_canvas_90ccw(); rotate_canvas_180();", g), oracle.orient(g, oracle.ROT90CW))
     with pytest.raises(ValueError):
-        execute_script_sync(eng, "resize_image(3, 3);", img)
+        execute_script_sync(eng, "for_each_pixel(3);", img)
 
 
 def test_host_tier_band_pipeline(eng, oracle):

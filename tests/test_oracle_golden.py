@@ -126,7 +126,25 @@ ADJUST = {
     "highlights_shadows": lambda o, im: o.adjust(im, o.HIGHLIGHTS_SHADOWS, (30.0, -20.0)),
     "levels": lambda o, im: o.adjust(im, o.LUT_RGB, luts=o.levels_lut(20.0, 235.0, 1.2, 0.0, 255.0)),
     "temperature_tint": lambda o, im: o.adjust(im, o.TEMPERATURE_TINT, (30.0, 10.0)),
+    # tests/visual_adjustments.rs:249-333
+    "threshold_128": lambda o, im: o.adjust(im, o.THRESHOLD, (128.0,)),
+    "posterize_4": lambda o, im: o.adjust(im, o.POSTERIZE, (4.0,)),
+    "color_balance": lambda o, im: o.adjust(im, o.COLOR_BALANCE, (10.0, 0.0, -10.0, 0.0, 0.0, 0.0, -10.0, 0.0, 10.0)),
+    "gradient_map": lambda o, im: o.adjust(im, o.GRADIENT_MAP, luts=warm_gradient_lut()),
+    "black_and_white": lambda o, im: o.adjust(fx.color_bands(64, 64), o.BLACK_AND_WHITE, (0.3, 0.59, 0.11)),
+    "vibrance_50": lambda o, im: o.adjust(im, o.VIBRANCE, (np.float32(50.0) / np.float32(100.0),)),
 }
+
+
+def warm_gradient_lut():
+    """tests/visual_adjustments.rs:302-311, f32 arithmetic with truncating casts."""
+    t = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    lut = np.empty((256, 4), np.uint8)
+    lut[:, 0] = (t * np.float32(255.0)).astype(np.uint8)
+    lut[:, 1] = (t * t * np.float32(200.0)).astype(np.uint8)
+    lut[:, 2] = (t * t * t * np.float32(150.0)).astype(np.uint8)
+    lut[:, 3] = 255
+    return lut
 
 
 @pytest.mark.parametrize("name", sorted(ADJUST))
@@ -151,6 +169,13 @@ SCRIPT = {
 @pytest.mark.parametrize("name", sorted(SCRIPT))
 def test_scripting_golden(oracle, name):
     assert_exact(SCRIPT[name](oracle, fx.gradient(64, 64)), "scripting", name)
+
+
+def test_adjust_identities(oracle):
+    """tests/visual_adjustments.rs:283-296, :337-343"""
+    g = fx.gradient(64, 64)
+    assert np.array_equal(oracle.adjust(g, oracle.COLOR_BALANCE, (0.0,) * 9), g)
+    assert np.array_equal(oracle.adjust(g, oracle.VIBRANCE, (0.0,)), g)
 
 
 def test_scripting_bc_is_truncating(oracle):
@@ -258,3 +283,67 @@ def test_stroke_selection_mask(oracle):
     mask[:, :32] = 255
     oracle.brush_stamp(img, oracle.make_brush(40.0, 1.0, True, BLACK), 32.0, 32.0, sel_mask=mask)
     assert_exact(img, "tools", "brush_with_selection_mask")
+
+
+# ---- geometry (tests/visual_transforms.rs, tests/transform_ops.rs:280-303, tests/scripting.rs) -----
+def _img_64x48():
+    return fx.gradient(64, 48)
+
+
+GEOMETRY = {
+    "flip_canvas_h": lambda o, im: o.orient(im, o.FLIP_H),
+    "flip_canvas_v": lambda o, im: o.orient(im, o.FLIP_V),
+    "flip_layer_h": lambda o, im: o.orient(im, o.FLIP_H),
+    "flip_layer_v": lambda o, im: o.orient(im, o.FLIP_V),
+    "rotate_90cw": lambda o, im: o.orient(im, o.ROT90CW),
+    "rotate_90ccw": lambda o, im: o.orient(im, o.ROT90CCW),
+    "rotate_180": lambda o, im: o.orient(im, o.ROT180),
+    "resize_canvas_center": lambda o, im: o.resize_canvas(im, 96, 80, (1, 1), (0, 0, 0, 0)),
+    "resize_canvas_topleft": lambda o, im: o.resize_canvas(im, 80, 64, (0, 0), (255, 0, 0, 255)),
+    "resize_2x_nearest": lambda o, im: o.resize(im, 128, 96, o.RS_NEAREST),
+    "resize_half_bilinear": lambda o, im: o.resize(im, 32, 24, o.RS_TRIANGLE),
+    "resize_half_lanczos": lambda o, im: o.resize(im, 32, 24, o.RS_LANCZOS3),
+    # the reference test passes 45 degrees *already converted to radians* as the degree argument
+    "affine_rotate_45": lambda o, im: o.affine(im, 64, 48, float(np.float32(45.0) * (np.float32(np.pi) / np.float32(180.0)))),
+    "flatten_single": lambda o, im: o.flatten([o.make_layer(im)], 64, 48),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GEOMETRY))
+def test_geometry_golden(oracle, name):
+    out = GEOMETRY[name](oracle, _img_64x48())
+    if name != "flatten_single":
+        out, _ = oracle.tiled_roundtrip(out)  # results are stored as tiles and read back (extract_layer)
+    assert_exact(out, "transforms", name)
+
+
+def test_affine_goldens(oracle):
+    """tests/transform_ops.rs:280-303: affine then composite over a transparent canvas."""
+    src = fx.gradient(32, 32)
+    for name, rz, sc in (("affine_rotate_90", float(np.float32(np.pi / 2)), 1.0), ("affine_scale_half", 0.0, 0.5)):
+        out = oracle.affine(src, 32, 32, rz, scale=sc)
+        assert_exact(oracle.flatten([oracle.make_layer(out)], 32, 32), "transform", name)
+
+
+def test_scripting_flip_goldens(oracle):
+    """tests/scripting.rs: flip_horizontal() / flip_vertical() on the script's pixel buffer."""
+    g = fx.gradient(64, 64)
+    assert_exact(oracle.orient(g, oracle.FLIP_H), "scripting", "flip_horizontal")
+    assert_exact(oracle.orient(g, oracle.FLIP_V), "scripting", "flip_vertical")
+
+
+def test_geometry_identities(oracle):
+    """tests/visual_transforms.rs:43-130, :250-262; transform_ops.rs:254-277."""
+    im = _img_64x48()
+    for op in (oracle.FLIP_H, oracle.FLIP_V, oracle.ROT180):
+        assert np.array_equal(oracle.orient(oracle.orient(im, op), op), im)
+    r = im
+    for _ in range(4):
+        r = oracle.orient(r, oracle.ROT90CW)
+    assert np.array_equal(r, im)
+    assert np.array_equal(oracle.orient(oracle.orient(im, oracle.ROT90CW), oracle.ROT90CCW), im)
+    assert np.abs(oracle.affine(im, 64, 48, 0.0).astype(int) - im.astype(int)).max() <= 1
+    dot = np.zeros((32, 32, 4), np.uint8)
+    dot[16, 16] = (255, 0, 0, 255)
+    assert np.array_equal(oracle.affine(dot, 32, 32, 0.0), dot)
+    assert np.array_equal(oracle.resize(im, 64, 48, oracle.RS_LANCZOS3), im)
