@@ -423,7 +423,7 @@ int pfe_dev_liquify(pfe_ctx *ctx, float *field_dev, uint32_t w, uint32_t h, int 
 
 /* -- brush stamps ------------------------------------------------------------------------
  * ToolsPanel::draw_circle_no_dirty (src/ui/panels/tools/behavior/raster/brush_render.rs:135-400)
- * for the circle tip in BrushMode::Normal and the eraser, plus rebuild_brush_lut (:27-50) and
+ * for the circle tip in every BrushMode and the eraser, plus rebuild_brush_lut (:27-50) and
  * draw_line_no_dirty's stamp placement (:762-838). One launch applies a whole list of stamps
  * in order, in place. */
 typedef struct pfe_brush_desc {
@@ -433,6 +433,7 @@ typedef struct pfe_brush_desc {
     int32_t anti_aliased;
     float color[4];      /* straight RGBA, 0..1 (primary or secondary, chosen by the caller) */
     int32_t is_eraser;
+    int32_t mode;        /* BrushMode: 0 Normal, 1 Dodge, 2 Burn, 3 Sponge (brush_render.rs:362-395) */
 } pfe_brush_desc;
 int pfe_brush_stamps(pfe_ctx *ctx, uint8_t *image, uint32_t w, uint32_t h, const pfe_brush_desc *brush,
                      const float *centres_xy, uint32_t n_stamps, const uint8_t *selection_mask);

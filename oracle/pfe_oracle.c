@@ -1026,6 +1026,7 @@ typedef struct pfo_brush {
     int anti_aliased;
     float color[4];               /* brush colour, straight RGBA in 0..1 */
     int is_eraser;
+    int mode;                     /* BrushMode: 0 Normal, 1 Dodge, 2 Burn, 3 Sponge (:362-395) */
 } pfo_brush;
 
 /* compute_brush_alpha :54-82 */
@@ -1055,7 +1056,7 @@ void pfo_brush_lut(const pfo_brush *b, uint8_t lut[256]) {
         lut[i] = as_u8(minf(roundf(alpha * 255.0f), 255.0f));
     }
 }
-/* draw_circle_no_dirty :135-400, circle tip, BrushMode::Normal or eraser, no scatter/jitter,
+/* draw_circle_no_dirty :135-400, circle tip, every BrushMode and the eraser, no scatter/jitter,
  * on a flat w*h RGBA8 target (the chunk walk only decides which tiles get allocated). */
 void pfo_brush_stamp(uint8_t *img, uint32_t w, uint32_t h, const pfo_brush *b, float cx, float cy,
                      const uint8_t *sel_mask) {
@@ -1093,8 +1094,18 @@ void pfo_brush_stamp(uint8_t *img, uint32_t w, uint32_t h, const pfo_brush *b, f
                 float old_mask = (float)p[3] / 255.0f;
                 if (strength > old_mask) { p[0] = p[1] = p[2] = 0; p[3] = as_u8(strength * 255.0f); }
             } else {
-                uint8_t a8 = as_u8(strength * 255.0f);
-                if (a8 >= p[3]) { p[0] = r8; p[1] = g8; p[2] = b8; p[3] = a8; }
+                if (b->mode == 0) {
+                    uint8_t a8 = as_u8(strength * 255.0f);
+                    if (a8 >= p[3]) { p[0] = r8; p[1] = g8; p[2] = b8; p[3] = a8; }
+                } else { /* Dodge / Burn / Sponge :374-394: HSL edit of the existing pixel, alpha kept */
+                    float hh, sat, l, nr, ng, nb, st = strength * 0.5f;
+                    rgb_to_hsl((float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f, &hh, &sat, &l);
+                    if (b->mode == 1) l = clampf(l + st, 0.0f, 1.0f);
+                    else if (b->mode == 2) l = clampf(l - st, 0.0f, 1.0f);
+                    else if (b->mode == 3) sat = clampf(sat - st, 0.0f, 1.0f);
+                    hsl_to_rgb(hh, sat, l, &nr, &ng, &nb);
+                    p[0] = as_u8(nr * 255.0f); p[1] = as_u8(ng * 255.0f); p[2] = as_u8(nb * 255.0f);
+                }
             }
         }
     }

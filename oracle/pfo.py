@@ -43,6 +43,7 @@ class Brush(C.Structure):
         ("anti_aliased", C.c_int),
         ("color", C.c_float * 4),
         ("is_eraser", C.c_int),
+        ("mode", C.c_int),
     ]
 
 
@@ -272,13 +273,17 @@ def liquify(field, kind, cx, cy, radius, strength, a0=0.0, a1=0.0):
 
 
 # -- brush ------------------------------------------------------------------------------
-def make_brush(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False):
+BRUSH_NORMAL, BRUSH_DODGE, BRUSH_BURN, BRUSH_SPONGE = range(4)
+
+
+def make_brush(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False, mode=0):
     b = Brush()
     b.size, b.hardness, b.flow = size, hardness, flow
     b.anti_aliased = 1 if anti_aliased else 0
     for i in range(4):
         b.color[i] = color[i]
     b.is_eraser = 1 if is_eraser else 0
+    b.mode = int(mode)
     return b
 
 

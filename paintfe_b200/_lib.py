@@ -36,7 +36,7 @@ class AdjustDesc(C.Structure):
 
 class BrushDesc(C.Structure):
     _fields_ = [("size", C.c_float), ("hardness", C.c_float), ("flow", C.c_float), ("anti_aliased", C.c_int32),
-                ("color", C.c_float * 4), ("is_eraser", C.c_int32)]
+                ("color", C.c_float * 4), ("is_eraser", C.c_int32), ("mode", C.c_int32)]
 
 
 _u32, _f32, _vp, _i32 = C.c_uint32, C.c_float, C.c_void_p, C.c_int32

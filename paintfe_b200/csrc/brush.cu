@@ -1,6 +1,6 @@
 // Brush-stamp inner loop: a whole stroke's stamps in one launch.
 // Reference: ToolsPanel::draw_circle_no_dirty (src/ui/panels/tools/behavior/raster/brush_render.rs:
-// 135-400) for the circle tip in BrushMode::Normal and the eraser; rebuild_brush_lut (:27-50);
+// 135-400) for the circle tip in every BrushMode and the eraser; rebuild_brush_lut (:27-50);
 // compute_brush_alpha (:54-82); draw_line_no_dirty's stamp placement (:762-838).
 //
 // The reference stamps sequentially, one circle per pixel of stroke length, each a read-modify-
@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hsl.cuh"
 
 namespace {
 
@@ -20,7 +21,7 @@ struct BrushParams {
     float radius, radius_sq, draw_radius_sq, inv_radius_sq;
     float hardness;  // clamped to [0,1]
     float src_a, flow;
-    int anti_aliased, direct, is_eraser;
+    int anti_aliased, direct, is_eraser, mode;
     uint32_t rgb;  // packed r8 | g8<<8 | b8<<16
     uint8_t lut[256];
 };
@@ -85,9 +86,18 @@ __global__ void __launch_bounds__(256) brush_kernel(const __grid_constant__ Brus
         if (B.is_eraser) {
             float old_mask = (float)(px >> 24) / 255.0f;
             if (strength > old_mask) px = pfe_as_u8(strength * 255.0f) << 24; // :352-357
-        } else {
+        } else if (B.mode == 0) {
             uint32_t a8 = pfe_as_u8(strength * 255.0f);
             if (a8 >= (px >> 24)) px = B.rgb | (a8 << 24);                    // :366-372
+        } else {                                                              // Dodge / Burn / Sponge :374-394
+            float hh, sat, l, nr, ng, nb;
+            const float st = strength * 0.5f;
+            rgb_to_hsl((float)(px & 255u) / 255.0f, (float)((px >> 8) & 255u) / 255.0f, (float)((px >> 16) & 255u) / 255.0f, hh, sat, l);
+            if (B.mode == 1) l = pfe_clampf(l + st, 0.0f, 1.0f);
+            else if (B.mode == 2) l = pfe_clampf(l - st, 0.0f, 1.0f);
+            else if (B.mode == 3) sat = pfe_clampf(sat - st, 0.0f, 1.0f);
+            hsl_to_rgb(hh, sat, l, 1e-6f, nr, ng, nb);
+            px = pfe_pack(pfe_as_u8(nr * 255.0f), pfe_as_u8(ng * 255.0f), pfe_as_u8(nb * 255.0f), px >> 24);
         }
     }
     if (px != before) img[o] = px;
@@ -107,6 +117,7 @@ void fill_params(const pfe_brush_desc *b, BrushParams *P) {
     P->flow = b->flow;
     P->anti_aliased = b->anti_aliased ? 1 : 0;
     P->is_eraser = b->is_eraser ? 1 : 0;
+    P->mode = (b->mode >= 0 && b->mode <= 3) ? b->mode : 0;  // unknown modes leave the pixel as Normal would
     auto as_u8 = [](float v) -> uint32_t { return v != v || v <= 0.0f ? 0u : (v >= 255.0f ? 255u : (uint32_t)v); };
     P->rgb = as_u8(b->color[0] * 255.0f) | (as_u8(b->color[1] * 255.0f) << 8) | (as_u8(b->color[2] * 255.0f) << 16);
     pfe_brush_lut(b, P->lut);

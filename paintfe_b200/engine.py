@@ -468,13 +468,14 @@ class Engine:
 
     # -- brush --------------------------------------------------------------------------------
     @staticmethod
-    def brush_desc(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False):
+    def brush_desc(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False, mode=0):
         b = L.BrushDesc()
         b.size, b.hardness, b.flow = size, hardness, flow
         b.anti_aliased = 1 if anti_aliased else 0
         for i in range(4):
             b.color[i] = color[i]
         b.is_eraser = 1 if is_eraser else 0
+        b.mode = int(mode)  # BrushMode: 0 Normal, 1 Dodge, 2 Burn, 3 Sponge
         return b
 
     def brush_lut(self, brush):

@@ -57,7 +57,7 @@ def test_struct_layouts_match_oracle_and_header():
     from paintfe_b200 import _lib
 
     assert C.sizeof(_lib.LayerDesc) == C.sizeof(pfo.LayerDesc) == 88
-    assert C.sizeof(_lib.BrushDesc) == C.sizeof(pfo.Brush) == 36
+    assert C.sizeof(_lib.BrushDesc) == C.sizeof(pfo.Brush) == 40
     assert C.sizeof(_lib.AdjustDesc) == 64  # i32 op, 12 f32 params, pad, luts pointer
 
 

@@ -156,6 +156,29 @@ def test_stroke_golden(eng, name):
     exact(img, fx.golden("tools", name), name)
 
 
+@pytest.mark.parametrize("name,mode", [("brush_dodge_mode", 1), ("brush_burn_mode", 2)])
+def test_stroke_mode_golden(eng, name, mode):
+    img = fx.gradient(64, 64)
+    eng.brush_stamps(img, eng.brush_desc(24.0, 1.0, True, BLACK, mode=mode), [(32.0, 32.0)])
+    exact(img, fx.golden("tools", name), name)
+
+
+def test_stroke_modes_random(eng, oracle):
+    """Dodge / burn / sponge over overlapping stamps (each stamp re-reads what the previous one wrote)."""
+    rng = np.random.default_rng(77)
+    for mode in (1, 2, 3):
+        for aa in (True, False):
+            img = fx.random_rgba(rng, 97, 61)
+            want = img.copy()
+            color = (0.2, 0.4, 0.6, float(rng.uniform(0.3, 1.0)))
+            centres = np.stack([np.linspace(5, 90, 40), np.linspace(50, 8, 40)], 1).astype(np.float32)
+            ob = oracle.make_brush(17.0, 0.6, aa, color, flow=0.8, mode=mode)
+            for cx, cy in centres:
+                oracle.brush_stamp(want, ob, float(cx), float(cy))
+            eng.brush_stamps(img, eng.brush_desc(17.0, 0.6, aa, color, flow=0.8, mode=mode), centres)
+            exact(img, want, f"brush mode {mode} aa {aa}")
+
+
 def test_stroke_selection_mask_golden(eng):
     img = fx.solid(64, 64, (0, 0, 0, 0))
     mask = np.zeros((64, 64), np.uint8)

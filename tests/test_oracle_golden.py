@@ -261,6 +261,9 @@ STROKES = {
     "brush_at_origin": (10.0, 1.0, True, BLACK, False, "blank", "stamp", [(0.0, 0.0)]),
     "brush_at_corner": (20.0, 1.0, True, BLACK, False, "blank", "stamp", [(63.0, 63.0)]),
     "line_zero_length": (12.0, 1.0, True, BLACK, False, "blank", "line", (32.0, 32.0, 32.0, 32.0)),
+    # tests/tool_strokes.rs:521-571: pencil = hard brush without anti-aliasing
+    "pencil_circle": (12.0, 1.0, False, BLACK, False, "blank", "stamp", [(32.0, 32.0)]),
+    "pencil_line": (4.0, 1.0, False, RED, False, "blank", "line", (4.0, 4.0, 60.0, 60.0)),
 }
 
 
@@ -274,6 +277,14 @@ def test_stroke_golden(oracle, name):
             oracle.brush_stamp(img, b, x, y)
     else:
         oracle.brush_line(img, b, *args)
+    assert_exact(img, "tools", name)
+
+
+@pytest.mark.parametrize("name,mode", [("brush_dodge_mode", 1), ("brush_burn_mode", 2)])
+def test_stroke_mode_golden(oracle, name, mode):
+    """tests/tool_strokes.rs:472-515: dodge / burn edit the existing pixels in HSL space."""
+    img = fx.gradient(64, 64)
+    oracle.brush_stamp(img, oracle.make_brush(24.0, 1.0, True, BLACK, mode=mode), 32.0, 32.0)
     assert_exact(img, "tools", name)
 
 
