@@ -187,6 +187,11 @@ public:
             if (chunks_[i]) k.emplace_back((uint32_t)(i % chunks_per_row_), (uint32_t)(i / chunks_per_row_));
         return k;
     }
+    std::vector<const uint8_t *> chunk_table() const {  // `chunk.as_raw().as_ptr()` per entry, null where None
+        std::vector<const uint8_t *> t(chunks_.size());
+        for (size_t i = 0; i < chunks_.size(); i++) t[i] = chunks_[i] ? chunks_[i]->data() : nullptr;
+        return t;
+    }
     std::vector<uint8_t> occupancy() const {
         std::vector<uint8_t> o(chunks_.size());
         for (size_t i = 0; i < chunks_.size(); i++) o[i] = chunks_[i] ? 1 : 0;
@@ -230,8 +235,44 @@ public:
     CanvasState(uint32_t w, uint32_t h) : width(w), height(h) {  // CanvasState::new: one white background layer
         layers.emplace_back("Background", w, h, Rgba{{255, 255, 255, 255}});
     }
-    // CanvasState::composite, canvas_state.rs:482-698
+    // CanvasState::composite, canvas_state.rs:482-698: the chunk tables go to the library as they are
+    // (no densification on the host); only populated chunks are uploaded.
     RgbaImage composite() const {
+        std::vector<std::vector<const uint8_t *>> tables;
+        tables.reserve(layers.size() * 2);
+        std::vector<pfe_tile_layer_desc> descs;
+        for (const Layer &L : layers) {
+            pfe_tile_layer_desc d{};
+            d.opacity = L.opacity;
+            d.blend = to_u8(L.blend_mode);
+            d.visible = L.visible ? 1 : 0;
+            if (L.adjustment) {
+                const auto &a = *L.adjustment;
+                d.kind = (uint8_t)a.kind;
+                if (a.kind == AdjustmentLayerData::Exposure) d.adj[0] = std::pow(2.0f, a.ev);  // 2.0f32.powf(ev)
+                if (a.kind == AdjustmentLayerData::BrightnessContrast) { d.adj[0] = a.brightness; d.adj[1] = a.contrast; }
+                if (a.kind == AdjustmentLayerData::ChannelMixer)
+                    for (int i = 0; i < 4; i++) { d.adj[i] = a.red[i]; d.adj[4 + i] = a.green[i]; d.adj[8 + i] = a.blue[i]; d.adj[12 + i] = a.alpha[i]; }
+            } else if (L.visible) {
+                tables.push_back(L.pixels.chunk_table());
+                d.chunks = tables.back().data();
+                if (L.mask_enabled && L.mask) {
+                    tables.push_back(L.mask->chunk_table());
+                    d.mask_chunks = tables.back().data();
+                }
+            } else {
+                d.visible = 0;
+            }
+            descs.push_back(d);
+        }
+        RgbaImage out(width, height);
+        Engine &e = Engine::current();
+        e.check(pfe_flatten_tiles(e.ctx(), descs.data(), (uint32_t)descs.size(), width, height, out.as_mut().data()), "pfe_flatten_tiles");
+        return out;
+    }
+    // The same composite through the dense entry point (pfe_flatten + active-chunk bitmap): what a caller
+    // that already holds flat layers uses; kept so both boundaries stay covered by the ported tests.
+    RgbaImage composite_dense() const {
         const size_t nch = (size_t)((width + CHUNK_SIZE - 1) / CHUNK_SIZE) * ((height + CHUNK_SIZE - 1) / CHUNK_SIZE);
         std::vector<uint8_t> active(nch, 0);
         std::vector<RgbaImage> flats;

@@ -104,6 +104,47 @@ int pfe_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n_layers, u
 int pfe_dev_flatten(pfe_ctx *ctx, const pfe_layer_desc *layers_with_dev_ptrs, uint32_t n_layers,
                     uint32_t w, uint32_t h, const uint8_t *active_chunks_dev, uint8_t *dst_dev);
 
+/* -- tile-native flatten and device-resident TiledImage --------------------------
+ * The compositor's own data structure: a layer is a row-major table of ceil(w/64)*ceil(h/64) chunk
+ * pointers, each to 64*64*4 bytes (row-major RGBA8, zero padded past the canvas edge) or NULL for an
+ * unpopulated chunk - `Vec<Option<Arc<RgbaImage>>>`, src/canvas/tiled_image.rs:2-7, with
+ * `chunk.as_raw().as_ptr()` per entry.  pfe_flatten_tiles is CanvasState::composite
+ * (src/canvas/canvas_state.rs:482-698) on those tables: chunks no visible raster layer populates stay
+ * transparent and are never read (:529-550), a layer without a chunk at a position is skipped there
+ * (:596-598), `mask_chunks` is Layer::mask (its alpha conceals, :660-665; NULL = none / mask disabled).
+ * Host tier: tables are host arrays of host pointers; only populated chunks are copied to the device.
+ * Device tier: tables are device arrays of device pointers (pfe_tiled_table). dst is the flat w*h image. */
+typedef struct pfe_tile_layer_desc {
+    const uint8_t *const *chunks;      /* NULL for adjustment layers */
+    const uint8_t *const *mask_chunks; /* or NULL */
+    float opacity;
+    uint8_t blend;
+    uint8_t visible;
+    uint8_t kind; /* pfe_layer_kind */
+    uint8_t _pad;
+    float adj[16];
+} pfe_tile_layer_desc;
+int pfe_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers, uint32_t n_layers, uint32_t w,
+                      uint32_t h, uint8_t *dst);
+int pfe_dev_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers_with_dev_tables,
+                          uint32_t n_layers, uint32_t w, uint32_t h, uint8_t *dst_dev);
+/* A TiledImage resident on the device: chunk pool + pointer table + occupancy bytes.
+ * upload     TiledImage -> device; only populated chunks cross PCIe.
+ * from_flat  TiledImage::from_rgba_image (tiled_image.rs:50-104) on the device: a chunk is populated iff
+ *            some pixel in it has alpha != 0.
+ * to_flat    TiledImage::to_rgba_image (:271-293).
+ * download   occupancy (one byte per chunk) and, if `tiles` != NULL, the populated chunks at
+ *            tiles + index * 16384 (the layout pfe_flat_to_tiles produces). */
+typedef struct pfe_tiled pfe_tiled;
+int pfe_tiled_create(pfe_ctx *ctx, uint32_t w, uint32_t h, pfe_tiled **out);
+int pfe_tiled_destroy(pfe_ctx *ctx, pfe_tiled *t);
+int pfe_tiled_upload(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *const *host_chunk_table);
+int pfe_tiled_from_flat(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *flat_dev);
+int pfe_tiled_to_flat(pfe_ctx *ctx, const pfe_tiled *t, uint8_t *flat_dev);
+int pfe_tiled_download(pfe_ctx *ctx, const pfe_tiled *t, uint8_t *occupancy, uint8_t *tiles);
+const uint8_t *const *pfe_tiled_table(const pfe_tiled *t);
+const uint8_t *pfe_tiled_occupancy(const pfe_tiled *t);
+
 /* -- blurs -----------------------------------------------------------------------------
  * flags for the Gaussian family: */
 #define PFE_GAUSS_EXACT 1u /* reference tap order with separate mul/add: bit-exact with the CPU

@@ -34,6 +34,11 @@ class AdjustDesc(C.Structure):
     _fields_ = [("op", C.c_int32), ("params", C.c_float * 12), ("luts", C.c_void_p)]
 
 
+class TileLayerDesc(C.Structure):
+    _fields_ = [("chunks", C.c_void_p), ("mask_chunks", C.c_void_p), ("opacity", C.c_float), ("blend", C.c_uint8),
+                ("visible", C.c_uint8), ("kind", C.c_uint8), ("_pad", C.c_uint8), ("adj", C.c_float * 16)]
+
+
 class BrushDesc(C.Structure):
     _fields_ = [("size", C.c_float), ("hardness", C.c_float), ("flow", C.c_float), ("anti_aliased", C.c_int32),
                 ("color", C.c_float * 4), ("is_eraser", C.c_int32), ("mode", C.c_int32)]
@@ -63,6 +68,16 @@ SIGNATURES = {
     "pfe_dev_download": (C.c_int, [_ctx, _vp, _vp, C.c_size_t]),
     "pfe_flatten": (C.c_int, [_ctx, C.POINTER(LayerDesc), _u32, _u32, _u32, _vp, _vp]),
     "pfe_dev_flatten": (C.c_int, [_ctx, C.POINTER(LayerDesc), _u32, _u32, _u32, _vp, _vp]),
+    "pfe_flatten_tiles": (C.c_int, [_ctx, C.POINTER(TileLayerDesc), _u32, _u32, _u32, _vp]),
+    "pfe_dev_flatten_tiles": (C.c_int, [_ctx, C.POINTER(TileLayerDesc), _u32, _u32, _u32, _vp]),
+    "pfe_tiled_create": (C.c_int, [_ctx, _u32, _u32, C.POINTER(_vp)]),
+    "pfe_tiled_destroy": (C.c_int, [_ctx, _vp]),
+    "pfe_tiled_upload": (C.c_int, [_ctx, _vp, _vp]),
+    "pfe_tiled_from_flat": (C.c_int, [_ctx, _vp, _vp]),
+    "pfe_tiled_to_flat": (C.c_int, [_ctx, _vp, _vp]),
+    "pfe_tiled_download": (C.c_int, [_ctx, _vp, _vp, _vp]),
+    "pfe_tiled_table": (_vp, [_vp]),
+    "pfe_tiled_occupancy": (_vp, [_vp]),
     "pfe_gaussian_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _vp, _vp, _u32]),
     "pfe_dev_gaussian_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _vp, _vp, _u32]),
     "pfe_box_blur": (C.c_int, [_ctx, _vp, _u32, _u32, _f32, _vp, _vp]),

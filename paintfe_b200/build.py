@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpfe_b200.so")
-SOURCES = ["ctx.cu", "flatten.cu", "gaussian.cu", "filters.cu", "adjust.cu", "warp.cu", "brush.cu", "hostops.cu", "effects2.cu", "effects3.cu", "geometry.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "fx_common.cuh"), os.path.join(CSRC, "hsl.cuh"), os.path.join(os.path.dirname(HERE), "include", "pfe_b200.h")]
+SOURCES = ["ctx.cu", "flatten.cu", "gaussian.cu", "filters.cu", "adjust.cu", "warp.cu", "brush.cu", "hostops.cu", "effects2.cu", "effects3.cu", "geometry.cu", "tiles.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "fx_common.cuh"), os.path.join(CSRC, "hsl.cuh"), os.path.join(CSRC, "blend.cuh"), os.path.join(os.path.dirname(HERE), "include", "pfe_b200.h")]
 
 # -fmad=false: the reference (Rust) never contracts a*b+c; bit-exactness depends on it.
 NVCC_FLAGS = [

@@ -153,6 +153,10 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->dev_small) cudaFree(c->dev_small);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < 2; i++) {
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+        if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+    }
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);

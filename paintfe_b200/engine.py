@@ -48,6 +48,56 @@ def make_layer(rgba=None, opacity=1.0, blend=0, visible=True, mask=None, kind=0,
                  kind=int(kind), adj=tuple(float(v) for v in adj))
 
 
+class DeviceTiled:
+    """A TiledImage resident on the device (`pfe_tiled`): chunk pool, pointer table, occupancy."""
+
+    def __init__(self, eng, w, h):
+        self.eng, self.w, self.h = eng, int(w), int(h)
+        hnd = C.c_void_p()
+        eng._ck(eng.lib.pfe_tiled_create(eng.h, self.w, self.h, C.byref(hnd)))
+        self.hnd = hnd
+        self.n_chunks = ((self.w + 63) // 64) * ((self.h + 63) // 64)
+
+    @property
+    def table(self):
+        return self.eng.lib.pfe_tiled_table(self.hnd)
+
+    def upload(self, table):
+        """table: row-major chunk grid of (64,64,4) uint8 arrays or None."""
+        arr, keep = Engine._chunk_table(table)
+        self.eng._ck(self.eng.lib.pfe_tiled_upload(self.eng.h, self.hnd, arr))
+        return self
+
+    def from_flat(self, flat_dev):
+        self.eng.use_torch_stream()
+        self.eng._ck(self.eng.lib.pfe_tiled_from_flat(self.eng.h, self.hnd, _ptr(flat_dev)))
+        return self
+
+    def to_flat(self, out=None):
+        self.eng.use_torch_stream()
+        out = out if out is not None else torch.empty((self.h, self.w, 4), dtype=torch.uint8, device=f"cuda:{self.eng.device}")
+        self.eng._ck(self.eng.lib.pfe_tiled_to_flat(self.eng.h, self.hnd, _ptr(out)))
+        return out
+
+    def download(self, want_tiles=True):
+        occ = np.empty(self.n_chunks, np.uint8)
+        tiles = np.zeros((self.n_chunks, 64, 64, 4), np.uint8) if want_tiles else None
+        self.eng.use_torch_stream()
+        self.eng._ck(self.eng.lib.pfe_tiled_download(self.eng.h, self.hnd, _ptr(occ), _ptr(tiles)))
+        return occ, tiles
+
+    def close(self):
+        if getattr(self, "hnd", None) and getattr(self.eng, "h", None):
+            self.eng.lib.pfe_tiled_destroy(self.eng.h, self.hnd)
+        self.hnd = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One CUDA device, one stream, scratch buffers (`pfe_ctx`)."""
 
@@ -184,6 +234,58 @@ class Engine:
         self._ck(self.lib.pfe_flatten_gaussian(self.h, arr, len(layers), w, h, _ptr(active), C.c_float(sigma),
                                                _ptr(dst), L.GAUSS_EXACT if exact else 0))
         return dst
+
+    # -- tile-native flatten / device-resident TiledImage (tiles.cu) --------------------------------
+    @staticmethod
+    def _chunk_table(table):
+        """list (row-major chunk grid) of (64,64,4) uint8 arrays or None -> ctypes pointer array."""
+        arr = (C.c_void_p * max(len(table), 1))()
+        keep = []
+        for i, t in enumerate(table):
+            if t is not None:
+                t = _np_u8(t, (64, 64, 4))
+                keep.append(t)
+                arr[i] = t.ctypes.data
+        return arr, keep
+
+    def flatten_tiles(self, layers, w, h, out=None):
+        """CanvasState::composite on chunk tables. Each layer is a dict like make_layer()'s with `tiles`
+        (and optionally `mask_tiles`) = a chunk table (host tier: list of arrays / None) or a DeviceTiled."""
+        arr = (L.TileLayerDesc * max(len(layers), 1))()
+        keep = []
+        dev = None
+        for i, Ly in enumerate(layers):
+            for key, field in (("tiles", "chunks"), ("mask_tiles", "mask_chunks")):
+                t = Ly.get(key)
+                if t is None:
+                    continue
+                is_dev = isinstance(t, DeviceTiled)
+                dev = is_dev if dev is None else dev
+                if is_dev != dev:
+                    raise ValueError("all layers must be on the same side (host chunk tables or DeviceTiled)")
+                if is_dev:
+                    setattr(arr[i], field, t.table)
+                else:
+                    a, k = self._chunk_table(t)
+                    keep += [a, k]
+                    setattr(arr[i], field, C.cast(a, C.c_void_p).value)
+            arr[i].opacity = Ly.get("opacity", 1.0)
+            arr[i].blend = Ly.get("blend", 0) & 0xFF
+            arr[i].visible = 1 if Ly.get("visible", True) else 0
+            arr[i].kind = Ly.get("kind", 0)
+            for j, v in enumerate(Ly.get("adj", ())):
+                arr[i].adj[j] = v
+        if dev:
+            self.use_torch_stream()
+            dst = out if out is not None else torch.empty((h, w, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+            self._ck(self.lib.pfe_dev_flatten_tiles(self.h, arr, len(layers), w, h, _ptr(dst)))
+        else:
+            dst = out if out is not None else np.empty((h, w, 4), np.uint8)
+            self._ck(self.lib.pfe_flatten_tiles(self.h, arr, len(layers), w, h, _ptr(dst)))
+        return dst
+
+    def tiled(self, w, h):
+        return DeviceTiled(self, w, h)
 
     # -- single-image ops -----------------------------------------------------------------------
     def _img_op(self, host_fn, dev_fn, src, mask, out, *mid, tail=()):

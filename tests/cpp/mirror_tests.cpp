@@ -139,6 +139,7 @@ int main(int argc, char **argv) {
         adj.adjustment = AdjustmentLayerData{};
         state.layers.push_back(std::move(adj));
         RgbaImage out = state.composite();
+        check(out == state.composite_dense(), "tile-native and dense composites differ");
         check(out.get_pixel(5, 5) == Rgba{{0, 0, 0, 255}}, "concealed half: white background inverted");
         check(out.get_pixel(40, 5) == Rgba{{255, 255, 0, 255}}, "revealed half: blue inverted");
     });

@@ -716,6 +716,88 @@ def test_geometry_random(eng, oracle, w, h):
     exact(eng.resize(dev, w + 9, h + 4, 3).cpu().numpy(), oracle.resize(img, w + 9, h + 4, 3), "resize device tier")
 
 
+# ---------------------------------------------------------------------------------------------
+# tile-native flatten and the device-resident TiledImage
+# ---------------------------------------------------------------------------------------------
+def _sparse_stack(rng, w, h, n):
+    """Random layers with holes: whole chunks cleared, plus some chunks that are populated but fully
+    transparent in one layer only."""
+    cyn, cxn = (h + 63) // 64, (w + 63) // 64
+    imgs, specs = [], []
+    for i in range(n):
+        im = fx.random_rgba(rng, w, h)
+        keep = rng.random((cyn, cxn)) < (0.5 if i else 0.8)
+        big = np.kron(keep, np.ones((64, 64), bool))[:h, :w]
+        im[~big] = 0
+        imgs.append(im)
+    return imgs
+
+
+@pytest.mark.parametrize("w,h,n", [(64, 64, 2), (200, 130, 5), (67, 45, 3), (1, 1, 1), (260, 257, 40), (512, 384, 16)])
+def test_flatten_tiles_matches_oracle(eng, oracle, w, h, n):
+    import torch
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(w * 23 + h + n)
+    imgs = _sparse_stack(rng, w, h, n)
+    cyn, cxn = (h + 63) // 64, (w + 63) // 64
+    o_layers, t_layers, d_layers, active = [], [], [], np.zeros((cyn, cxn), np.uint8)
+    handles = []
+    for i, im in enumerate(imgs):
+        meta = dict(blend=int(rng.integers(0, 25)), opacity=float(rng.choice([1.0, rng.uniform(0, 1)])), visible=bool(rng.random() < 0.9))
+        if i % 7 == 3:  # adjustment layer: only chunks some raster layer populates are touched
+            meta.update(kind=int(rng.integers(1, 5)), adj=tuple(float(v) for v in rng.uniform(-0.5, 1.2, 16)))
+            o_layers.append(oracle.make_layer(None, **meta))
+            t_layers.append(dict(meta))
+            d_layers.append(dict(meta))
+            continue
+        occ, tiles = eng.flat_to_tiles(im)
+        table = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
+        mask_img = mask_plane = mask_table = None
+        if i % 3 == 1:
+            mask_img = fx.random_rgba(rng, w, h)
+            mask_img[rng.random((h, w)) < 0.5] = 0
+            mocc, mtiles = eng.flat_to_tiles(mask_img)
+            mask_table = [mtiles[k] if mocc.reshape(-1)[k] else None for k in range(mocc.size)]
+            mask_plane = np.ascontiguousarray(mask_img[..., 3])
+        if meta["visible"]:
+            active |= occ
+        o_layers.append(oracle.make_layer(im, mask=mask_plane, **meta))
+        t_layers.append(dict(meta, tiles=table, mask_tiles=mask_table))
+        dt = eng.tiled(w, h).upload(table)
+        dm = eng.tiled(w, h).from_flat(torch.from_numpy(mask_img).cuda()) if mask_img is not None else None
+        handles += [dt, dm]
+        d_layers.append(dict(meta, tiles=dt, mask_tiles=dm))
+    want = oracle.flatten(o_layers, w, h, active=active)
+    exact(eng.flatten_tiles(t_layers, w, h), want, "host tier chunk tables")
+    exact(eng.flatten_tiles(d_layers, w, h).cpu().numpy(), want, "device-resident tiles")
+    for hnd in handles:
+        if hnd is not None:
+            hnd.close()
+
+
+def test_device_tiled_roundtrip(eng, oracle):
+    """from_rgba_image / to_rgba_image on the device: occupancy and pixels equal the host marshalling."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    for (w, h) in [(64, 64), (65, 63), (200, 130), (1, 1), (129, 64)]:
+        img = fx.random_rgba(rng, w, h)
+        img[: h // 2, : w // 2, 3] = 0  # a fully transparent region with non-zero RGB
+        t = eng.tiled(w, h).from_flat(torch.from_numpy(img).cuda())
+        exp, exp_occ = oracle.tiled_roundtrip(img)
+        occ, tiles = t.download()
+        assert np.array_equal(occ.reshape(exp_occ.shape), exp_occ)
+        exact(t.to_flat().cpu().numpy(), exp, "to_flat")
+        hocc, htiles = eng.flat_to_tiles(img)
+        for k in range(occ.size):
+            if occ[k]:
+                assert np.array_equal(tiles[k], htiles[k])
+        t2 = eng.tiled(w, h).upload([htiles[k] if hocc.reshape(-1)[k] else None for k in range(hocc.size)])
+        exact(t2.to_flat().cpu().numpy(), exp, "upload + to_flat")
+        t.close(); t2.close()
+
+
 def test_script_runner_covers_effect_api(eng, oracle):
     """The Rhai bindings' fixed arguments (scripting.rs:822-1165) through the script runner."""
     from paintfe_b200.script import execute_script_sync
