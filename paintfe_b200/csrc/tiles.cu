@@ -47,7 +47,7 @@ __global__ void tile_active_kernel(const uint8_t *const *table, uint8_t *active,
     if (i < n && table[i] != nullptr) active[i] = 1;
 }
 
-__global__ void __launch_bounds__(256) flatten_tiles_kernel(const __grid_constant__ TileParams P) {
+__global__ void __launch_bounds__(256, 3) flatten_tiles_kernel(const __grid_constant__ TileParams P) {
     __shared__ const uint8_t *s_px[kMaxLayers], *s_mask[kMaxLayers];
     __shared__ int s_list[kMaxLayers], s_n;
     blend_lut_init();

@@ -169,6 +169,53 @@ def main():
         emit({"config": 5, "workload": f"{n_total} x 4K images, script: {script}", "ms_total": ms, "images_s": n_total / ms * 1e3,
               "mpx_s": n_total * w * h / ms / 1e3, "n_gpus": world, "note": "includes on-device synthetic image generation"})
 
+    if 6 in configs:  # tile-native flatten: dense and sparse 8K stacks, device-resident and host tier
+        import time
+
+        cyn, cxn = (H8K + 63) // 64, (W8K + 63) // 64
+        out = torch.empty((H8K, W8K, 4), dtype=torch.uint8, device=dev)
+        for name, fill in (("every chunk populated", 1.0), ("25% of each layer's chunks populated", 0.25)):
+            prng = np.random.default_rng(7)
+            flat_layers, tiled, metas = [], [], []
+            for i in range(16):
+                t = torch.randint(0, 256, (H8K, W8K, 4), dtype=torch.uint8, device=dev, generator=gen)
+                if fill < 1.0:
+                    keep = torch.from_numpy(prng.random((cyn, cxn)) < fill).to(dev)
+                    big = keep.repeat_interleave(64, 0).repeat_interleave(64, 1)[:H8K, :W8K]
+                    t[~big] = 0
+                flat_layers.append(t)
+                tiled.append(eng.tiled(W8K, H8K).from_flat(t))
+                metas.append(dict(blend=i % 25, opacity=0.25 + 0.05 * i))
+            dl = [make_layer(t, **m) for t, m in zip(flat_layers, metas)]
+            tl = [dict(m, tiles=t) for t, m in zip(tiled, metas)]
+            ms_dense = timed(lambda: eng.flatten(dl, W8K, H8K, out=out), args.steps)
+            ref = out.clone()
+            ms_tiles = timed(lambda: eng.flatten_tiles(tl, W8K, H8K, out=out), args.steps)
+            same = bool(torch.equal(ref, out))
+            populated = sum(int(t.download(False)[0].sum()) for t in tiled)
+            emit({"config": 6, "workload": f"8K 16-layer flatten, {name}", "dense_kernel_ms": ms_dense, "tile_kernel_ms": ms_tiles,
+                  "mpx_s_tiles": px8k / ms_tiles / 1e3, "populated_chunks": populated, "identical": same, "n_gpus": 1})
+            # host tier: chunk tables of host pointers vs. dense host layers (pageable numpy memory on both sides)
+            host_tabs = []
+            for t in tiled:
+                occ, tiles = t.download(True)
+                host_tabs.append([tiles[k] if occ[k] else None for k in range(occ.size)])
+            host_flat = [t.cpu().numpy() for t in flat_layers]
+            hl_t = [dict(m, tiles=tab) for tab, m in zip(host_tabs, metas)]
+            hl_d = [make_layer(a, **m) for a, m in zip(host_flat, metas)]
+            res = {}
+            for key, fn in (("host_tier_tiles_ms", lambda: eng.flatten_tiles(hl_t, W8K, H8K)), ("host_tier_dense_ms", lambda: eng.flatten(hl_d, W8K, H8K))):
+                fn()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    r = fn()
+                res[key] = (time.perf_counter() - t0) / 3 * 1e3
+            emit({"config": 6, "workload": f"host tier, {name}", **res, "h2d_bytes_tiles": populated * 16384, "h2d_bytes_dense": 16 * px8k * 4,
+                  "note": "pageable host memory; wall clock incl. the Python marshalling of the chunk tables"})
+            for t in tiled:
+                t.close()
+            del flat_layers, tiled, dl, tl, host_tabs, host_flat, hl_t, hl_d
+
     if world > 1:
         dist.destroy_process_group()
 
