@@ -173,6 +173,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; rank 0's stdout must be ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     from paintfe_b200.engine import Engine, make_layer
@@ -221,6 +224,9 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the host-pointer C ABI call (pinned host buffers) -----------------
+    from paintfe_b200.dist import bind_to_gpu_numa
+
+    numa = bind_to_gpu_numa(local)  # pinned buffers next to this GPU's root port (matters for N > 1)
     host_layers = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(NLAYERS)]
     for hl, t in zip(host_layers, layers):
         hl.copy_(t)
@@ -300,7 +306,8 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": NLAYERS * px * 4,
                     "d2h_bytes_per_step": px * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "pfe_flatten_gaussian (host pointers, pinned)", "matches_device_tier": same},
+                    "api": "pfe_flatten_gaussian (host pointers, pinned)", "matches_device_tier": same,
+                    "numa_rank0": numa},
             "gpu_launches": launches,
             "roofline": roofline, "roofline_whole_step": whole, "kernels": per_kernel,
             "cpu_baseline": cpu,

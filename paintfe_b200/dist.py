@@ -45,6 +45,38 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process (CPU affinity + preferred memory node) to the NUMA node its GPU hangs off, so the
+    pinned staging buffers of the host tier are allocated next to the GPU's PCIe root port.  With one
+    process per GPU on a two-socket box this keeps every rank's H2D traffic off the inter-socket link.
+    Best effort: returns what was done, never raises."""
+    import ctypes
+    import os
+
+    info = {"node": None, "cpus": None}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL(None, use_errno=True)
+        if libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64)) == 0:  # set_mempolicy(MPOL_PREFERRED)
+            info["node"] = node
+    except Exception:
+        pass
+    return info
+
+
 def _world(group=None) -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(group), dist.get_world_size(group)
@@ -149,6 +181,44 @@ def sharpen_banded(eng, band, h_total: int, amount: float, radius: float, exact:
     _, world = _world(group)
     bounds = bounds or band_bounds(h_total, world)
     return _windowed(eng, lambda ext: eng.sharpen(ext, amount, radius, exact=exact), band, gaussian_radius(radius), bounds, group)
+
+
+def neighbourhood_banded(eng, band, h_total: int, op: str, args: tuple = (), halo: int = 0, group=None, bounds=None, **kw):
+    """Any translation-invariant windowed effect of a row-split image: exchange `halo` input rows, run
+    `eng.<op>(extended band, *args)`, keep the core rows.  Valid for effects whose result at a pixel
+    depends only on the pixels within `halo` rows of it and not on absolute coordinates - ink (halo 1),
+    oil painting (halo = radius), bokeh (ceil(radius)), bilateral reduce_noise (radius), motion blur
+    (ceil(distance) + 1), glow (ceil(3 sigma)), rgb_displace (max |dy|).  Effects that use absolute
+    coordinates (vignette, halftone, zoom, noise, contours, crystallize, pixel_drag, dents) do not split
+    this way; whole images shard across GPUs instead."""
+    _, world = _world(group)
+    bounds = bounds or band_bounds(h_total, world)
+    return _windowed(eng, lambda ext: getattr(eng, op)(ext, *args, **kw), band, int(halo), bounds, group)
+
+
+def ink_banded(eng, band, h_total, edge_strength, threshold, group=None, bounds=None):
+    """ink_core (effects/artistic.rs:31-99): 3x3 Sobel."""
+    return neighbourhood_banded(eng, band, h_total, "ink", (edge_strength, threshold), 1, group, bounds)
+
+
+def oil_painting_banded(eng, band, h_total, radius, levels, group=None, bounds=None):
+    """oil_painting_core (artistic.rs:123-217): window radius clamps to 1..10."""
+    return neighbourhood_banded(eng, band, h_total, "oil_painting", (radius, levels), min(max(int(radius), 1), 10), group, bounds)
+
+
+def bokeh_blur_banded(eng, band, h_total, radius, group=None, bounds=None):
+    """bokeh_blur_core (effects/blur.rs:22-115): disc of ceil(radius) rows either side."""
+    return neighbourhood_banded(eng, band, h_total, "bokeh_blur", (radius,), int(math.ceil(radius)) if radius >= 0.5 else 0, group, bounds)
+
+
+def reduce_noise_banded(eng, band, h_total, strength, radius, group=None, bounds=None):
+    """reduce_noise_core (effects/noise.rs:172-262)."""
+    return neighbourhood_banded(eng, band, h_total, "reduce_noise", (strength, radius), max(int(radius), 1), group, bounds)
+
+
+def motion_blur_banded(eng, band, h_total, angle_deg, distance, group=None, bounds=None):
+    """motion_blur_core (effects/blur.rs:144-210): samples reach ceil(distance) pixels along the direction."""
+    return neighbourhood_banded(eng, band, h_total, "motion_blur", (angle_deg, distance), int(math.ceil(abs(distance))) + 1, group, bounds)
 
 
 def flatten_banded(eng, layer_bands, w: int, band_rows: int, active=None):

@@ -24,6 +24,11 @@ class OracleEngine:
     def box_blur(self, img, radius, mask=None, out=None): return self.o.box_blur(img, radius, mask=mask)
     def median(self, img, radius, mask=None, out=None): return self.o.median(img, radius, mask=mask)
     def sharpen(self, img, amount, radius, mask=None, exact=False, out=None): return self.o.sharpen(img, amount, radius, mask=mask)
+    def ink(self, img, es, th, mask=None, out=None): return self.o.ink(img, es, th, mask=mask)
+    def oil_painting(self, img, r, lv, mask=None, out=None): return self.o.oil_painting(img, r, lv, mask=mask)
+    def bokeh_blur(self, img, r, mask=None, out=None): return self.o.bokeh_blur(img, r, mask=mask)
+    def reduce_noise(self, img, s, r, mask=None, out=None): return self.o.reduce_noise(img, s, r, mask=mask)
+    def motion_blur(self, img, a, d, mask=None, out=None): return self.o.motion_blur(img, a, d, mask=mask)
     def flatten(self, layers, w, h, active=None, out=None):
         return self.o.flatten([self.o.make_layer(**{k: (np.asarray(v) if k in ("rgba", "mask") and v is not None else v)
                                                     for k, v in L.items()}) for L in layers], w, h, active=active)
@@ -87,6 +92,14 @@ def _worker(rank, world, port, case, q):
         elif case == "sharpen":
             out = pd.sharpen_banded(eng, band, h, 1.5, 2.0, exact=True, bounds=bounds)
             exp = eng.sharpen(img, 1.5, 2.0)
+        elif case == "effects":  # translation-invariant neighbourhood effects through the generic halo path
+            out = pd.ink_banded(eng, band, h, 2.0, 0.5, bounds=bounds)
+            exp = eng.ink(img, 2.0, 0.5)
+            for got, want in ((pd.oil_painting_banded(eng, band, h, 4, 24, bounds=bounds), eng.oil_painting(img, 4, 24)),
+                              (pd.bokeh_blur_banded(eng, band, h, 6.5, bounds=bounds), eng.bokeh_blur(img, 6.5)),
+                              (pd.reduce_noise_banded(eng, band, h, 12.0, 3, bounds=bounds), eng.reduce_noise(img, 12.0, 3)),
+                              (pd.motion_blur_banded(eng, band, h, 70.0, 9.0, bounds=bounds), eng.motion_blur(img, 70.0, 9.0))):
+                assert np.array_equal(np.asarray(got), want[y0:y1])
         elif case == "flatten":
             imgs = [fx.random_rgba(rng, w, h) for _ in range(5)]
             meta = [dict(blend=(3 * i) % 25, opacity=0.3 + 0.15 * i) for i in range(5)]
@@ -129,7 +142,7 @@ def _run(case, world):
         assert ok, f"{case}: rank {rank} band differs from the whole-image result"
 
 
-@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "flatten", "warp", "mesh"])
+@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "effects", "flatten", "warp", "mesh"])
 def test_band_split_equals_whole_world2(case):
     _run(case, 2)
 

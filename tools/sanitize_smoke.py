@@ -52,6 +52,48 @@ check("bulge", eng.bulge(img, 0.5), pfo.bulge(img, 0.5))
 check("twist", eng.twist(img, 45.0), pfo.twist(img, 45.0), 1)
 check("noise perlin", eng.add_noise(img, 50.0, 2, False, 42, 5.0, 3), pfo.add_noise(img, 50.0, 2, False, 42, 5.0, 3))
 check("bilateral", eng.reduce_noise(img, 10.0, 2), pfo.reduce_noise(img, 10.0, 2), 1)
+# effects3.cu
+col = (200, 40, 90, 180)
+sparse = img.copy()
+sparse[rng.random((h, w)) < 0.6] = 0
+for name, args, src in (("ink", (2.0, 0.5), img), ("oil_painting", (10, 64), img), ("color_filter", (col, 0.6, 3), img),
+                        ("contours", (10.0, 5.0, 1.0, col, 42, 2, 0.5), img), ("crystallize", (16.0, 42), img),
+                        ("dents", (20.0, 10.0, 42, 2, 0.5, True, True), img), ("halftone", (4.0, 45.0, 0), img),
+                        ("bokeh_blur", (6.5,), img), ("zoom_blur", (0.5, 0.5, 0.3, 8), img), ("grid", (16, 16, 1, col, 0, 0.7), img),
+                        ("canvas_border", (3, col), img), ("outline", (3, col, 2, True), sparse), ("pixel_drag", (42, 50.0, 20, 30.0), img),
+                        ("rgb_displace", ((5, 0), (0, 0), (-5, 3)), img)):
+    check(name, getattr(eng, name)(src, *args, mask=mask), getattr(pfo, name)(src, *args, mask=mask))
+check("drop_shadow", eng.drop_shadow(sparse, 5, -3, 3.0, True, col, 0.8, exact=True), pfo.drop_shadow(sparse, 5, -3, 3.0, True, col, 0.8))
+# geometry.cu
+for op in range(5):
+    check(f"orient {op}", eng.orient(img, op), pfo.orient(img, op))
+check("resize_canvas", eng.resize_canvas(img, w + 13, h - 7, (1, 2), col), pfo.resize_canvas(img, w + 13, h - 7, (1, 2), col))
+check("affine", eng.affine(img, w, h, 33.0, 10.0, -5.0, 0.8, (3.0, 2.0)), pfo.affine(img, w, h, 33.0, 10.0, -5.0, 0.8, (3.0, 2.0)))
+check("resize lanczos", eng.resize(img, 77, 201, 3), pfo.resize(img, 77, 201, 3))
+# adjust ops 11-16
+for op, prm, luts in ((pfo.THRESHOLD, (128.0,), None), (pfo.POSTERIZE, (4.0,), None), (pfo.COLOR_BALANCE, (10.0, 0.0, -10.0, 0.0, 0.0, 0.0, -10.0, 0.0, 10.0), None),
+                      (pfo.GRADIENT_MAP, (), rng.integers(0, 256, (256, 4), dtype=np.uint8)), (pfo.BLACK_AND_WHITE, (30.0, 59.0, 11.0), None), (pfo.VIBRANCE, (0.5,), None)):
+    check(f"adjust op {op}", eng.adjust(img, op, prm, luts=luts), pfo.adjust(img, op, prm, luts=luts))
+# tiles.cu: host chunk tables and device-resident tiles
+occ, tiles = eng.flat_to_tiles(sparse)
+table = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
+occ2, tiles2 = eng.flat_to_tiles(layers[0])
+table2 = [tiles2[k] if occ2.reshape(-1)[k] else None for k in range(occ2.size)]
+tl = [dict(tiles=table2, blend=0, opacity=1.0), dict(tiles=table, mask_tiles=table2, blend=8, opacity=0.7), dict(kind=3, opacity=0.5)]
+want = pfo.flatten([pfo.make_layer(layers[0]), pfo.make_layer(sparse, blend=8, opacity=0.7, mask=np.ascontiguousarray(layers[0][..., 3])),
+                    pfo.make_layer(None, kind=3, opacity=0.5)], w, h, active=occ | occ2)
+check("flatten_tiles host", eng.flatten_tiles(tl, w, h), want)
+dt = [eng.tiled(w, h).upload(table2), eng.tiled(w, h).upload(table)]
+check("flatten_tiles device", eng.flatten_tiles([dict(tiles=dt[0], blend=0, opacity=1.0), dict(tiles=dt[1], mask_tiles=dt[0], blend=8, opacity=0.7),
+                                                 dict(kind=3, opacity=0.5)], w, h).cpu().numpy(), want)
+for t in dt:
+    t.close()
+# dodge / burn / sponge
+for mode in (1, 2, 3):
+    a, b = img.copy(), img.copy()
+    pfo.brush_line(a, pfo.make_brush(12.0, 0.8, True, (1, 0, 0, 1), mode=mode), 10.0, 10.0, 150.0, 120.0)
+    eng.brush_stamps(b, eng.brush_desc(12.0, 0.8, True, (1, 0, 0, 1), mode=mode), eng.brush_line_centres(w, h, 10.0, 10.0, 150.0, 120.0))
+    check(f"brush mode {mode}", b, a)
 a, b = img.copy(), img.copy()
 br = pfo.make_brush(12.0, 0.8, True, (1, 0, 0, 1))
 pfo.brush_line(a, br, 10.0, 10.0, 150.0, 120.0)
