@@ -282,6 +282,26 @@ def run_b200(args):
                         "traffic": traffic, "peak_source": peak_src,
                         "note": "algorithmic bytes / CUDA-event kernel time; the kernel is FP32-issue bound when "
                                 "bit-exact (DESIGN.md §4), so frac << 1 is expected"}
+        # what actually bounds each kernel: warp-instruction issue for the flatten, FP32 FMA lanes
+        # for the Gaussian passes. Static counts from the committed ncu capture, live kernel times.
+        compute = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            sm_clock_hz = (clocks or {}).get("sm_mhz", 1965.0) * 1e6
+            issue_peak = 148 * 4 * sm_clock_hz  # one warp instruction per scheduler per clock
+            for k, n_inst in tj.get("warp_instructions", {}).items():
+                if k in per_kernel:
+                    ach = n_inst / (per_kernel[k]["avg_ms"] * 1e-3)
+                    compute[k] = {"bound": "warp-instruction issue", "achieved_ginst_s": ach / 1e9, "peak_ginst_s": issue_peak / 1e9,
+                                  "frac": ach / issue_peak}
+            for k, lanes in tj.get("fma_lanes", {}).items():
+                if k in per_kernel:
+                    ach = lanes / (per_kernel[k]["avg_ms"] * 1e-3)
+                    compute[k].update({"fma_bound": "fp32 FMA lanes", "achieved_tfma_s": ach / 1e12,
+                                       "peak_tfma_s": tj["fp32_fma_lanes_per_s_peak"] / 1e12, "fma_frac": ach / tj["fp32_fma_lanes_per_s_peak"]})
+        except Exception:
+            pass
         whole = {"achieved": 76 * px / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_px": 76}
         whole["frac"] = whole["achieved"] / peak
 
@@ -309,7 +329,7 @@ def run_b200(args):
                     "api": "pfe_flatten_gaussian (host pointers, pinned)", "matches_device_tier": same,
                     "numa_rank0": numa},
             "gpu_launches": launches,
-            "roofline": roofline, "roofline_whole_step": whole, "kernels": per_kernel,
+            "roofline": roofline, "roofline_whole_step": whole, "roofline_compute": compute, "kernels": per_kernel,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

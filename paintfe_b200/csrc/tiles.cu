@@ -39,6 +39,7 @@ struct TileParams {
     const uint8_t *active;  // one byte per chunk: some visible raster layer populates it
     uint8_t *dst;           // flat w*h RGBA8
     uint32_t n_layers, w, h, chunks_x, n_chunks, init_from_dst, vec_store;
+    PackedConsts pc;
 };
 
 // active |= "this layer has a chunk here" (canvas_state.rs:529-550)
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256, 3) flatten_tiles_kernel(const __grid_cons
     __shared__ const uint8_t *s_px[kMaxLayers], *s_mask[kMaxLayers];
     __shared__ int s_list[kMaxLayers], s_n;
     blend_lut_init();
-    const Lut lut{(threadIdx.x & 31) * 4u};
+    const Lut lut = make_lut(P.pc);
     for (uint32_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
         __syncthreads();  // table ready (first pass) / previous chunk's list no longer in use
         const uint32_t cy = chunk / P.chunks_x, cx = chunk - cy * P.chunks_x;
@@ -197,6 +198,7 @@ int run_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers, uint32_t 
                       uint8_t *dst) {
     TileParams P;
     memset(&P, 0, sizeof(P));
+    P.pc = packed_consts();
     P.active = active_dev;
     P.dst = dst;
     P.w = w; P.h = h;
