@@ -111,10 +111,7 @@ __global__ void __launch_bounds__(256, 3) flatten_tiles_kernel(const __grid_cons
                         for (int k = 0; k < 4; k++)
                             if (mv[k] > 0) top[k] = (top[k] & 0x00FFFFFFu) | ((((top[k] >> 24) * (255u - mv[k])) / 255u) << 24);
                     }
-                    bool all_clear = true;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) all_clear = all_clear && (top[k] >> 24) == 0;
-                    if (__all_sync(__activemask(), all_clear)) continue;
+                    if (__all_sync(__activemask(), (top[0] | top[1] | top[2] | top[3]) <= 0x00FFFFFFu)) continue;
                     blend_k<4>(acc, top, L.blend, L.opacity, pfe_clampf(L.opacity, 0.0f, 1.0f), lut);
                 }
             } else if (P.init_from_dst) {
