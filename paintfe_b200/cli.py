@@ -62,15 +62,26 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
 
         proj = pfe_io.load_pfe(inp)
         w, h = proj.width, proj.height
-        flats = [L.to_flat(w, h) for L in proj.layers]
-        ai = min(proj.active_layer_index, len(flats) - 1)
-        if script:  # the script sees the active layer (cli.rs:239-260)
-            flats[ai] = np.asarray(execute_script_sync(eng, script, flats[ai], exact=exact))
-        if flatten and len(flats) > 1:  # cli.rs:282-285 state.composite()
-            img = eng.flatten([make_layer(f, opacity=L.opacity, blend=L.blend_mode, visible=L.visible)
-                               for f, L in zip(flats, proj.layers)], w, h)
+        ai = min(proj.active_layer_index, len(proj.layers) - 1)
+        cxn, cyn = (w + 63) // 64, (h + 63) // 64
+
+        def table(L):  # the project's sparse chunks as a TiledImage chunk table (row-major, None = unpopulated)
+            t = [None] * (cxn * cyn)
+            for (cx, cy), px in L.chunks.items():
+                if cx < cxn and cy < cyn:
+                    t[cy * cxn + cx] = px
+            return t
+
+        tables = [table(L) for L in proj.layers]
+        if script:  # the script sees the active layer as a flat image and commits it back as tiles (cli.rs:239-260)
+            res = np.asarray(execute_script_sync(eng, script, proj.layers[ai].to_flat(w, h), exact=exact))
+            occ, tiles = eng.flat_to_tiles(res)
+            tables[ai] = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
+        if flatten and len(tables) > 1:  # cli.rs:282-285 state.composite(): straight from the chunk tables
+            img = eng.flatten_tiles([dict(tiles=t, opacity=L.opacity, blend=L.blend_mode, visible=L.visible)
+                                     for t, L in zip(tables, proj.layers)], w, h)
         else:
-            img = flats[ai]
+            img = eng.tiles_to_flat(tables[ai], w, h)
     else:
         img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
         if script:
