@@ -682,7 +682,7 @@ extern "C" int pfe_dev_outline(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uin
                                int mode, int anti_alias, const uint8_t *mask, uint8_t *dst) {
     PFE_TRY(check(ctx, src, dst, w, h, "outline: bad args"));
     if (!color || mode < 0 || mode > 2) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "outline: bad colour or mode");
-    if (width > 4096) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "outline: width too large");
+    if (width > 512) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "outline: width too large");  // the search is O(width^2) per pixel
     const float radius = (float)std::max(width, 1u);
     const int sr = (int)ceilf(radius) + 1;
     void *bbd;

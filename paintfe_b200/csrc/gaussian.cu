@@ -309,6 +309,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         const float4 *col = tile + (size_t)row_first * 32 + lane;
         int have_rows = 0, have = 0;          // chunks [0, have) have landed = ring rows [0, have_rows)
         int released = 0, released_rows = 0;  // chunks [0, released) handed back to the producer
+
         for (int g = 0; g < P.steps; g += N) {
             while (row_first + g + N > have_rows) {  // this group reads ring rows up to row_first + g + N - 1
                 mbar_wait(full0 + 8u * (uint32_t)have, parity);
