@@ -255,8 +255,15 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kChunks);
     if (threadIdx.x == 0) {
         for (int c = 0; c < kChunks; c++) {
+            // `empty` counts only the warps that READ the chunk (warp w reads ring rows [w*N, w*N + steps)):
+            // a reader arrives for tile t after it has seen full[c] of tile t, which the producer only
+            // signals after empty[c] of tile t-1 completed - so no warp, however far it runs ahead, can
+            // contribute two arrivals to one phase. Warps that never touch a chunk take no part in it.
+            int readers = 0;
+            for (int w = 0; w < WARPS; w++)
+                if (w * N < (c + 1) * chunk_rows && w * N + P.steps > c * chunk_rows) readers++;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * c), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * c), "r"(WARPS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * c), "r"(max(readers, 1)));
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
             const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
             for (int c = 0; c < kChunks; c++) {
                 const int r0 = c * chunk_rows, nrows = max(0, min(chunk_rows, rows - r0));
-                if (it > 0) mbar_wait(empty0 + 8u * c, (it - 1) & 1u);  // consumers are done with the previous tile's chunk c
+                if (it > 0 && nrows > 0) mbar_wait(empty0 + 8u * c, (it - 1) & 1u);  // its readers are done with the previous tile's chunk c
                 if (lane == 0)
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
                 __syncwarp();
@@ -307,8 +314,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 #pragma unroll
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
         const float4 *col = tile + (size_t)row_first * 32 + lane;
-        int have_rows = 0, have = 0;          // chunks [0, have) have landed = ring rows [0, have_rows)
-        int released = 0, released_rows = 0;  // chunks [0, released) handed back to the producer
+        // this warp reads ring rows [row_first, row_first + steps): chunks before c_first are none of its
+        // business - it neither waits for them nor releases them (a warp may only watch barriers it also
+        // gates, or it could fall two phases behind one and mis-read its parity)
+        const int c_first = row_first / chunk_rows;
+        int have = c_first, have_rows = c_first * chunk_rows;          // chunks [c_first, have) have landed
+        int released = c_first, released_rows = c_first * chunk_rows;  // chunks [c_first, released) handed back
 
         for (int g = 0; g < P.steps; g += N) {
             while (row_first + g + N > have_rows) {  // this group reads ring rows up to row_first + g + N - 1
@@ -329,8 +340,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 #undef VT_LOAD
         }
         __syncwarp();
-        if (lane == 0)
-            for (; released < kChunks; released++) mbar_arrive(empty0 + 8u * (uint32_t)released);
+        if (lane == 0)  // the chunks this warp was still reading at the end (those past its last row it never touched)
+            for (; released < kChunks && released * chunk_rows < row_first + P.steps; released++)
+                mbar_arrive(empty0 + 8u * (uint32_t)released);
         const int x = x0 + lane, yw = y0 + row_first;
         if (x < rw) {
 #pragma unroll

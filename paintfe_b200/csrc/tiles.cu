@@ -57,21 +57,28 @@ __global__ void __launch_bounds__(256, 3) flatten_tiles_kernel(const __grid_cons
         __syncthreads();  // table ready (first pass) / previous chunk's list no longer in use
         const uint32_t cy = chunk / P.chunks_x, cx = chunk - cy * P.chunks_x;
         const bool active = P.active[chunk] != 0;
-        if (threadIdx.x == 0) {
-            // the layers that do something in this chunk, bottom to top: raster layers with a chunk here
-            // and adjustment layers (:579-600)
-            int n = 0;
-            if (active)
-                for (uint32_t li = 0; li < P.n_layers; li++) {
-                    const TileLayer &L = P.layers[li];
-                    if (L.kind != PFE_LAYER_RASTER) { s_list[n++] = (int)li; continue; }
-                    const uint8_t *p = L.chunks[chunk];
-                    if (!p) continue;
-                    s_px[li] = p;
-                    s_mask[li] = L.mask_chunks ? L.mask_chunks[chunk] : nullptr;
-                    s_list[n++] = (int)li;
+        if (threadIdx.x < 32) {
+            // the layers that do something in this chunk, bottom to top: raster layers with a chunk here and
+            // adjustment layers (:579-600). One lane per layer (kMaxLayers == 32) so the table reads of all
+            // layers are in flight together; a ballot compacts the survivors in layer order.
+            const uint32_t li = threadIdx.x;
+            const uint8_t *p = nullptr, *m = nullptr;
+            bool use = false;
+            if (active && li < P.n_layers) {
+                const TileLayer &L = P.layers[li];
+                if (L.kind != PFE_LAYER_RASTER) use = true;
+                else if ((p = L.chunks[chunk]) != nullptr) {
+                    use = true;
+                    m = L.mask_chunks ? L.mask_chunks[chunk] : nullptr;
                 }
-            s_n = n;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, use);
+            if (use) {
+                s_list[__popc(b & ((1u << li) - 1u))] = (int)li;
+                s_px[li] = p;
+                s_mask[li] = m;
+            }
+            if (li == 0) s_n = __popc(b);
         }
         __syncthreads();
         const int n = s_n;

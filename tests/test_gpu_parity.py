@@ -798,6 +798,24 @@ def test_device_tiled_roundtrip(eng, oracle):
         t.close(); t2.close()
 
 
+def test_gaussian_ring_pipeline_full_8k(eng, monkeypatch):
+    """The V pass's producer/consumer ring (one CTA walks ~56 tiles back to back at 8K) against the
+    direct-from-global V kernel on EVERY pixel of an 8K image, repeatedly: a chunk refilled while a slow
+    warp still reads it would show up here and nowhere at test sizes where a CTA sees one or two tiles."""
+    import torch
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    img = torch.randint(0, 256, (4320, 7680, 4), dtype=torch.uint8, device="cuda", generator=g)
+    for sigma in (20.0, 5.0, 50.0):
+        monkeypatch.setenv("PFE_GAUSS_V_DIRECT", "1")
+        ref = eng.gaussian_blur(img, sigma).clone()
+        monkeypatch.delenv("PFE_GAUSS_V_DIRECT")
+        for rep in range(6):
+            out = eng.gaussian_blur(img, sigma)
+            bad = int((out != ref).any(dim=-1).sum())
+            assert bad == 0, f"sigma {sigma} rep {rep}: {bad} pixels differ between the ring and the direct V pass"
+
+
 def test_script_runner_covers_effect_api(eng, oracle):
     """The Rhai bindings' fixed arguments (scripting.rs:822-1165) through the script runner."""
     from paintfe_b200.script import execute_script_sync
