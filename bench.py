@@ -268,6 +268,8 @@ def run_b200(args):
                 ent["achieved_gbs"] = alg[k] / (avg_ms * 1e-3) / 1e9
                 ent["frac_of_hbm"] = ent["achieved_gbs"] / peak
             per_kernel[k] = ent
+        # the per-kernel event spans must add up to (just under) the step time measured around the whole loop
+        span_share = sum(v["share_of_step"] for v in per_kernel.values())
         dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
         traffic = None
         try:
@@ -330,6 +332,7 @@ def run_b200(args):
                     "numa_rank0": numa},
             "gpu_launches": launches,
             "roofline": roofline, "roofline_whole_step": whole, "roofline_compute": compute, "kernels": per_kernel,
+            "kernel_spans_share_of_step": span_share,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -158,15 +158,17 @@ __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint
     }
 }
 
-template <int VEC>
+// One instantiation per op: the switch in adjust_px folds away, so each op gets the registers and code
+// size of its own arithmetic only (the HSL family is ~100 instructions per pixel, invert is 4).
+template <int VEC, int OP>
 __global__ void __launch_bounds__(256) adjust_kernel(const __grid_constant__ AdjParams P) {
     __shared__ uint8_t lut[1024];
     if (P.luts) {
-        const int nl = (P.op == PFE_ADJ_LUT_RGBA || P.op == PFE_ADJ_GRADIENT_MAP) ? 1024 : 256;
+        const int nl = (OP == PFE_ADJ_LUT_RGBA || OP == PFE_ADJ_GRADIENT_MAP) ? 1024 : 256;
         for (int i = threadIdx.x; i < nl; i += blockDim.x) lut[i] = P.luts[i];
         __syncthreads();
     }
-    const bool use_mask = P.mask != nullptr && P.op < 32;
+    const bool use_mask = P.mask != nullptr && OP < 32;
     for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g * VEC < P.n; g += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t px = g * VEC;
         uint32_t v[VEC];
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256) adjust_kernel(const __grid_constant__ Adj
                 uint32_t y = (uint32_t)(i / P.w), x = (uint32_t)(i - (uint64_t)y * P.w);
                 skip = skip || P.occupancy[(size_t)(y / PFE_CHUNK_SIZE) * P.chunks_x + x / PFE_CHUNK_SIZE] == 0;
             }
-            if (!skip) v[k] = adjust_px(P.op, P.p, lut, v[k]);
+            if (!skip) v[k] = adjust_px(OP, P.p, lut, v[k]);
         }
         if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(P.dst + px) = make_uint4(v[0], v[1], v[2], v[3]);
         else P.dst[px] = v[0];
@@ -237,8 +239,22 @@ extern "C" int pfe_dev_adjust(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint
     const bool vec = (P.n % 4 == 0) && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
     const uint64_t groups = vec ? P.n / 4 : P.n;
     unsigned blocks = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->sm_count * 16);
-    if (vec) PFE_KERNEL(ctx, "adjust", adjust_kernel<4><<<blocks, 256, 0, ctx->stream>>>(P));
-    else PFE_KERNEL(ctx, "adjust", adjust_kernel<1><<<blocks, 256, 0, ctx->stream>>>(P));
+#define PFE_ADJ_CASE(OPV)                                                                              \
+    case OPV:                                                                                          \
+        if (vec) PFE_KERNEL(ctx, "adjust", adjust_kernel<4, OPV><<<blocks, 256, 0, ctx->stream>>>(P)); \
+        else PFE_KERNEL(ctx, "adjust", adjust_kernel<1, OPV><<<blocks, 256, 0, ctx->stream>>>(P));     \
+        break;
+    switch (d->op) {
+        PFE_ADJ_CASE(PFE_ADJ_INVERT) PFE_ADJ_CASE(PFE_ADJ_INVERT_ALPHA) PFE_ADJ_CASE(PFE_ADJ_SEPIA) PFE_ADJ_CASE(PFE_ADJ_DESATURATE)
+        PFE_ADJ_CASE(PFE_ADJ_BRIGHTNESS_CONTRAST) PFE_ADJ_CASE(PFE_ADJ_HSL) PFE_ADJ_CASE(PFE_ADJ_EXPOSURE) PFE_ADJ_CASE(PFE_ADJ_LUT_RGB)
+        PFE_ADJ_CASE(PFE_ADJ_LUT_RGBA) PFE_ADJ_CASE(PFE_ADJ_TEMPERATURE_TINT) PFE_ADJ_CASE(PFE_ADJ_HIGHLIGHTS_SHADOWS)
+        PFE_ADJ_CASE(PFE_ADJ_THRESHOLD) PFE_ADJ_CASE(PFE_ADJ_POSTERIZE) PFE_ADJ_CASE(PFE_ADJ_COLOR_BALANCE) PFE_ADJ_CASE(PFE_ADJ_GRADIENT_MAP)
+        PFE_ADJ_CASE(PFE_ADJ_BLACK_AND_WHITE) PFE_ADJ_CASE(PFE_ADJ_VIBRANCE) PFE_ADJ_CASE(PFE_ADJ_S_INVERT) PFE_ADJ_CASE(PFE_ADJ_S_DESATURATE)
+        PFE_ADJ_CASE(PFE_ADJ_S_SEPIA) PFE_ADJ_CASE(PFE_ADJ_S_SEPIA_STRENGTH) PFE_ADJ_CASE(PFE_ADJ_S_BRIGHTNESS_CONTRAST)
+        PFE_ADJ_CASE(PFE_ADJ_S_HSL) PFE_ADJ_CASE(PFE_ADJ_S_EXPOSURE) PFE_ADJ_CASE(PFE_ADJ_S_LUT_RGB)
+        default: return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "adjust: unknown op");
+    }
+#undef PFE_ADJ_CASE
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
