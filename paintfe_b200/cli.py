@@ -7,7 +7,7 @@
 Same flags as the reference for the part of the pipeline that is in scope: -i/--input (glob patterns
 or literal paths, deduplicated in order, cli.rs:315-350), -s/--script, -o/--output (single input
 only), --output-dir, -f/--format, -v/--verbose.  Image decoding/encoding is harness plumbing (PIL);
-`.pfe` v0/v1/v2 projects load through paintfe_b200/pfe_io.py and are flattened on the GPU (--flatten).  A per-file failure is reported and the batch
+`.pfe` v0/v1/v2/v3 projects load through paintfe_b200/pfe_io.py and are flattened on the GPU (--flatten).  A per-file failure is reported and the batch
 continues; the exit code is 1 if any file failed (cli.rs:204-215).
 """
 from __future__ import annotations
@@ -78,8 +78,16 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
             occ, tiles = eng.flat_to_tiles(res)
             tables[ai] = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
         if flatten and len(tables) > 1:  # cli.rs:282-285 state.composite(): straight from the chunk tables
-            img = eng.flatten_tiles([dict(tiles=t, opacity=L.opacity, blend=L.blend_mode, visible=L.visible)
-                                     for t, L in zip(tables, proj.layers)], w, h)
+            descs = []
+            for i, (t, L) in enumerate(zip(tables, proj.layers)):
+                vis = proj.layer_effectively_visible(i)  # a hidden folder hides its layers (canvas_state.rs:216)
+                if L.adjustment is not None:             # v3 adjustment layer (layers.rs:276-325)
+                    kind, prm = L.adjustment
+                    adj = (float(np.float32(2.0) ** np.float32(prm[0])),) if kind == 1 else prm  # Exposure: 2^ev on the host
+                    descs.append(dict(opacity=L.opacity, blend=L.blend_mode, visible=vis, kind=kind, adj=adj))
+                else:
+                    descs.append(dict(tiles=t, opacity=L.opacity, blend=L.blend_mode, visible=vis))
+            img = eng.flatten_tiles(descs, w, h)
         else:
             img = eng.tiles_to_flat(tables[ai], w, h)
     else:

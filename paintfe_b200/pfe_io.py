@@ -1,4 +1,4 @@
-"""`.pfe` project files: reader for v0/v1/v2 raster layers and writer for v1.
+"""`.pfe` project files: reader for v0/v1/v2/v3 and writers for v1 and v3.
 
 Reference: src/io.rs:85-208 (structures), :296-340 (v1 writer), :477-497 (magic dispatch),
 :1110-1146 (v1 loader and its validation).  The files are bincode 1.3.3 with the default options:
@@ -6,8 +6,11 @@ little-endian fixed-width integers, `u64` length prefixes for String / Vec, `usi
 as one byte, `Option` as a one-byte tag.  The magic string "PFE<n>" therefore sits at bytes 8..12.
 
 This is harness plumbing on either side of the hot path: it lets the CLI run
-`--flatten` on a multi-layer project (BASELINE config 1).  v3 (adjustment layers, HDR metadata) is
-rejected with a clear error rather than half-parsed.
+`--flatten` on a multi-layer project (BASELINE config 1).  v3 (io.rs:171-208, :405-460, :812-900) adds
+layer folders, adjustment layers (`content_data` = bincode of AdjustmentLayerData, layers.rs:244-273) and
+per-layer format / HDR / source metadata, which is parsed and carried but does not affect compositing.
+The reference has no .pfe fixtures (its tests round-trip through its own writer), so the v3 layout here
+follows the serde derive order of the structs and is checked against this module's own writer only.
 """
 from __future__ import annotations
 
@@ -34,6 +37,11 @@ class PfeLayer:
     opacity: float
     blend_mode: int
     chunks: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)  # (cx, cy) -> (64, 64, 4) u8
+    # v3 only
+    folder_id: object = None          # Option<u64>
+    layer_type: int = 0               # 0 Raster, 1 Text, 2 Adjustment
+    adjustment: object = None         # (kind, params): kind 1 Exposure, 2 BrightnessContrast, 3 Invert, 4 ChannelMixer
+    extra: object = None              # raw (pixel_format, hdr, source metadata, webp, deep pixels) for a faithful rewrite
 
     def to_flat(self, w: int, h: int) -> np.ndarray:
         """TiledImage::to_rgba_image (tiled_image.rs:271-293)."""
@@ -60,6 +68,20 @@ class PfeProject:
     height: int
     active_layer_index: int
     layers: List[PfeLayer]
+    folders: list = field(default_factory=list)  # v3: dicts {id, name, visible, collapsed, insert_above_layer, color_index}
+    next_layer_folder_id: int = 1
+
+    def layer_effectively_visible(self, i: int) -> bool:
+        """canvas_state.rs:216-227: a layer in a hidden folder does not composite."""
+        L = self.layers[i]
+        if not L.visible:
+            return False
+        if L.folder_id is None:
+            return True
+        for f in self.folders:
+            if f["id"] == L.folder_id:
+                return bool(f["visible"])
+        return True
 
 
 class _Reader:
@@ -79,6 +101,7 @@ class _Reader:
     def f32(self): return struct.unpack("<f", self.take(4))[0]
     def string(self): return self.take(self.u64()).decode("utf-8")
     def blob(self): return self.take(self.u64())
+    def opt(self, fn): return fn() if self.u8() else None
 
 
 def load_pfe_from_bytes(raw: bytes) -> PfeProject:
@@ -86,9 +109,9 @@ def load_pfe_from_bytes(raw: bytes) -> PfeProject:
     if len(raw) < 12:
         raise PfeError("File too small")
     magic = raw[8:12].decode("utf-8", "replace")
+    if magic == "PFE3":
+        return _load_v3(raw)
     if magic not in ("PFE0", "PFE1", "PFE2"):
-        if magic == "PFE3":
-            raise PfeError("PFE3 projects (adjustment layers / HDR metadata) are not supported by this reader")
         raise PfeError(f"Unknown magic '{magic}'")
     r = _Reader(raw)
     r.string()
@@ -132,6 +155,121 @@ def load_pfe_from_bytes(raw: bytes) -> PfeProject:
                 del layer_type
         layers.append(L)
     return PfeProject(w, h, active, layers)
+
+
+# AdjustmentKind (layers.rs:244-262): bincode writes the variant index as u32, then the fields in order
+_ADJ_FIELDS = {0: 1, 1: 2, 2: 0, 3: 16}  # Exposure{ev}, BrightnessContrast{b, c}, Invert, ChannelMixer{4 x [f32; 4]}
+
+
+def _read_adjustment(blob: bytes):
+    r = _Reader(blob)
+    variant = r.u32()
+    if variant not in _ADJ_FIELDS:
+        raise PfeError(f"unknown AdjustmentKind variant {variant}")
+    return variant + 1, tuple(r.f32() for _ in range(_ADJ_FIELDS[variant]))  # kind ids of pfe_layer_kind
+
+
+def _write_adjustment(adj) -> bytes:
+    kind, params = adj
+    return struct.pack("<I", kind - 1) + b"".join(struct.pack("<f", float(v)) for v in params)
+
+
+def _load_v3(raw: bytes) -> PfeProject:
+    """load_pfe_v3, io.rs:812-900."""
+    r = _Reader(raw)
+    r.string()
+    w, h = r.u32(), r.u32()
+    if w == 0 or h == 0:
+        raise PfeError("Image dimensions cannot be zero")
+    if w > MAX_CANVAS_DIM or h > MAX_CANVAS_DIM:
+        raise PfeError(f"Image size {w}x{h} exceeds maximum allowed {MAX_CANVAS_DIM}x{MAX_CANVAS_DIM}")
+    active = r.u64()
+    folders = [dict(id=r.u64(), name=r.string(), visible=r.u8() != 0, collapsed=r.u8() != 0,
+                    insert_above_layer=r.opt(r.u64), color_index=r.opt(r.u8)) for _ in range(r.u64())]
+    next_folder = r.u64()
+    n_layers = r.u64()
+    if n_layers > MAX_LAYERS:
+        raise PfeError(f"Project contains {n_layers} layers, which exceeds the maximum of {MAX_LAYERS}")
+    layers = []
+    for _ in range(n_layers):
+        name, visible = r.string(), r.u8() != 0
+        folder_id = r.opt(r.u64)
+        opacity, blend, layer_type = r.f32(), r.u8(), r.u8()
+        L = PfeLayer(name, visible, opacity, blend, folder_id=folder_id, layer_type=layer_type)
+        for _ in range(r.u64()):
+            cx, cy = r.u32(), r.u32()
+            px = r.blob()
+            if len(px) != CHUNK_BYTES:
+                raise PfeError(f"Chunk ({cx},{cy}) in layer '{name}' has {len(px)} bytes, expected {CHUNK_BYTES}")
+            L.chunks[(cx, cy)] = np.frombuffer(px, np.uint8).reshape(CHUNK, CHUNK, 4).copy()
+        content = r.opt(r.blob)
+        if layer_type == 2 and content is not None:
+            try:
+                L.adjustment = _read_adjustment(content)
+            except PfeError:
+                L.adjustment = None  # `.ok()` -> falls back to LayerContent::Raster (io.rs:868-874)
+        start = r.o
+        r.u32()                                                        # pixel_format
+        r.u8(); r.opt(r.f32); r.opt(r.f32); r.opt(r.string)            # hdr_metadata
+        r.opt(r.string); r.opt(r.string); r.opt(r.string)              # source_metadata
+        for _ in range(r.u64()):
+            r.string(); r.string()
+        for _ in range(r.u64()):
+            r.blob()
+        r.u32()                                                        # webp_frame_compression
+        if r.u8():                                                     # deep_pixels: Option<DeepRgbaBuffer>
+            variant = r.u32()
+            r.take(r.u64() * {0: 1, 1: 2, 2: 2, 3: 4}.get(variant, 1))
+        L.extra = (content if layer_type != 2 else None, raw[start:r.o])
+        layers.append(L)
+    if not layers:
+        raise PfeError("Project contains no layers")
+    return PfeProject(w, h, min(active, len(layers) - 1), layers, folders, next_folder)
+
+
+def save_pfe_v3(project: PfeProject) -> bytes:
+    """build_pfe_v3 + write_pfe_v3 (io.rs:405-475)."""
+    out = bytearray()
+
+    def string(s: str):
+        b = s.encode("utf-8")
+        out.extend(struct.pack("<Q", len(b)))
+        out.extend(b)
+
+    def opt(v, fmt):
+        out.extend(b"\x00" if v is None else b"\x01" + struct.pack(fmt, v))
+
+    string("PFE3")
+    out.extend(struct.pack("<IIQ", project.width, project.height, project.active_layer_index))
+    out.extend(struct.pack("<Q", len(project.folders)))
+    for f in project.folders:
+        out.extend(struct.pack("<Q", f["id"]))
+        string(f["name"])
+        out.extend(struct.pack("<BB", 1 if f["visible"] else 0, 1 if f.get("collapsed") else 0))
+        opt(f.get("insert_above_layer"), "<Q")
+        opt(f.get("color_index"), "<B")
+    out.extend(struct.pack("<Q", project.next_layer_folder_id))
+    out.extend(struct.pack("<Q", len(project.layers)))
+    # default tail: RgbaU8, HdrMetadata::default, ImageMetadata::default, Lossless, no deep pixels
+    default_tail = struct.pack("<I", 0) + b"\x00" * 4 + b"\x00" * 3 + struct.pack("<QQ", 0, 0) + struct.pack("<I", 1) + b"\x00"
+    for L in project.layers:
+        string(L.name)
+        out.extend(b"\x01" if L.visible else b"\x00")
+        opt(L.folder_id, "<Q")
+        layer_type = 2 if L.adjustment is not None else L.layer_type
+        out.extend(struct.pack("<fBB", L.opacity, L.blend_mode & 0xFF, layer_type))
+        keys = sorted(L.chunks, key=lambda k: (k[1], k[0]))
+        out.extend(struct.pack("<Q", len(keys)))
+        for (cx, cy) in keys:
+            out.extend(struct.pack("<IIQ", cx, cy, CHUNK_BYTES))
+            out.extend(np.ascontiguousarray(L.chunks[(cx, cy)], np.uint8).tobytes())
+        content = _write_adjustment(L.adjustment) if L.adjustment is not None else (L.extra[0] if L.extra else None)
+        if content is None:
+            out.extend(b"\x00")
+        else:
+            out.extend(b"\x01" + struct.pack("<Q", len(content)) + content)
+        out.extend(L.extra[1] if L.extra else default_tail)
+    return bytes(out)
 
 
 def load_pfe(path: str) -> PfeProject:

@@ -536,6 +536,25 @@ def test_cli_flatten_pfe_and_script_batch(eng, oracle, tmp_path):
     flats = [L.to_flat(1024, 1024) for L in proj.layers]
     exp = oracle.flatten([oracle.make_layer(f, opacity=L.opacity, blend=L.blend_mode) for f, L in zip(flats, proj.layers)], 1024, 1024)
     exact(np.array(Image.open(tmp_path / "flat.png").convert("RGBA")), exp, "cli --flatten project.pfe")
+    # a v3 project: sparse layers, a hidden folder, adjustment layers - flattened from its chunk tables
+    w3, h3 = 333, 200
+    bg, top, hid = fx.random_rgba(rng, w3, h3, alpha="opaque"), fx.random_rgba(rng, w3, h3), fx.random_rgba(rng, w3, h3)
+    top[:128, :192] = 0
+    v3_layers = [pfe_io.layer_from_flat("bg", bg), pfe_io.layer_from_flat("hidden", hid),
+                 pfe_io.PfeLayer("invert", True, 0.6, 0, adjustment=(3, ())),
+                 pfe_io.layer_from_flat("top", top, opacity=0.8, blend_mode=21),
+                 pfe_io.PfeLayer("exposure", True, 0.5, 0, adjustment=(1, (0.7,)))]
+    v3_layers[1].folder_id = 7
+    v3 = pfe_io.PfeProject(w3, h3, 0, v3_layers, folders=[dict(id=7, name="off", visible=False, collapsed=False,
+                                                                insert_above_layer=None, color_index=None)])
+    (tmp_path / "v3.pfe").write_bytes(pfe_io.save_pfe_v3(v3))
+    assert cli.main(["-i", str(tmp_path / "v3.pfe"), "-o", str(tmp_path / "v3.png")]) == 0
+    occ = v3_layers[0].occupancy(w3, h3) | v3_layers[3].occupancy(w3, h3)
+    exp3 = oracle.flatten([oracle.make_layer(bg), oracle.make_layer(hid, visible=False), oracle.make_layer(None, opacity=0.6, kind=3),
+                           oracle.make_layer(v3_layers[3].to_flat(w3, h3), opacity=0.8, blend=21),
+                           oracle.make_layer(None, opacity=0.5, kind=1, adj=(float(np.float32(2.0) ** np.float32(0.7)),))],
+                          w3, h3, active=occ)
+    exact(np.array(Image.open(tmp_path / "v3.png").convert("RGBA")), exp3, "cli --flatten v3 project")
     # batch with a script over a glob; one unreadable file must not stop the batch (cli.rs:204-215)
     (tmp_path / "in" / "broken.png").write_bytes(b"not a png")
     rc = cli.main(["-i", str(tmp_path / "in" / "*.png"), "--script", str(script), "--output-dir", str(tmp_path / "out"), "--exact"])
@@ -814,6 +833,33 @@ def test_gaussian_ring_pipeline_full_8k(eng, monkeypatch):
             out = eng.gaussian_blur(img, sigma)
             bad = int((out != ref).any(dim=-1).sum())
             assert bad == 0, f"sigma {sigma} rep {rep}: {bad} pixels differ between the ring and the direct V pass"
+
+
+def test_error_statuses_of_widened_entry_points(eng):
+    """Bad enums / unsupported sizes come back as statuses (the ABI never unwinds, never falls back) and the
+    context stays usable afterwards."""
+    from paintfe_b200._lib import PfeError
+
+    img = fx.gradient(64, 48)
+
+    def code(fn, *a, **k):
+        with pytest.raises(PfeError) as e:
+            fn(*a, **k)
+        return e.value.code
+
+    assert code(eng.halftone, img, 4.0, 45.0, 9) == -1            # unknown HalftoneShape
+    assert code(eng.color_filter, img, (1, 2, 3, 4), 0.5, 7) == -1  # unknown ColorFilterMode
+    assert code(eng.grid, img, 8, 8, 1, (0, 0, 0, 255), 5, 1.0) == -1
+    assert code(eng.outline, img, 2, (0, 0, 0, 255), 3, True) == -1
+    assert code(eng.outline, img, 100000, (0, 0, 0, 255), 0, True) == -2  # O(width^2) search refused
+    assert code(eng.bokeh_blur, img, 1.0e6) == -2
+    assert code(eng.orient, img, 9) == -1
+    assert code(eng.resize, img, 10, 10, 9) == -1
+    assert code(eng.resize, img, 0, 10, 1) == -1
+    assert code(eng.adjust, img, 17) == -1                         # between the two op families
+    assert code(eng.adjust, img, 14) == -1                         # gradient map without its LUT
+    assert code(eng.flatten_tiles, [dict(kind=9)], 64, 48) == -1
+    exact(eng.orient(eng.orient(img, 0), 0), img, "context still usable")
 
 
 def test_script_runner_covers_effect_api(eng, oracle):

@@ -59,7 +59,7 @@ def test_v0_and_v2_readers_and_validation():
     v2 = (s(b"PFE2") + struct.pack("<IIQQ", w, h, 0, 1) + s(b"t") + struct.pack("<BfBB", 1, 1.0, 0, 1) +
           struct.pack("<Q", len(L.chunks)) + body + b"\x01" + s(b"textdata"))
     assert np.array_equal(pfe_io.load_pfe_from_bytes(v2).layers[0].to_flat(w, h), flat)
-    for bad, msg in [(b"short", "too small"), (s(b"XXXX") + b"\0" * 8, "Unknown magic"), (s(b"PFE3") + b"\0" * 8, "PFE3"),
+    for bad, msg in [(b"short", "too small"), (s(b"XXXX") + b"\0" * 8, "Unknown magic"), (s(b"PFE3") + b"\0" * 8, "zero"), (s(b"PFE3") + struct.pack("<IIQ", 5, 5, 0), "end of file"),
                      (s(b"PFE1") + struct.pack("<IIQQ", 0, 5, 0, 0), "zero"),
                      (s(b"PFE1") + struct.pack("<IIQQ", 30000, 5, 0, 0), "exceeds"),
                      (s(b"PFE1") + struct.pack("<IIQQ", 5, 5, 0, 300), "layers"),
@@ -67,3 +67,48 @@ def test_v0_and_v2_readers_and_validation():
                       struct.pack("<Q", 1) + struct.pack("<IIQ", 0, 0, 3) + b"abc", "expected")]:
         with pytest.raises(pfe_io.PfeError, match=msg):
             pfe_io.load_pfe_from_bytes(bad)
+
+
+def test_v3_roundtrip_adjustment_layers_and_folders(oracle):
+    """v3 (io.rs:171-208): folders, an adjustment layer and per-layer metadata survive a round trip, and
+    the composite honours folder visibility and the adjustment layer (checked against the oracle)."""
+    w, h = 130, 70
+    rng = np.random.default_rng(2)
+    bg = fx.random_rgba(rng, w, h, alpha="opaque")
+    top = fx.random_rgba(rng, w, h)
+    hidden = fx.random_rgba(rng, w, h)
+    layers = [pfe_io.layer_from_flat("bg", bg), pfe_io.layer_from_flat("in hidden folder", hidden),
+              pfe_io.PfeLayer("invert", True, 0.6, 0, adjustment=(3, ())),
+              pfe_io.layer_from_flat("top", top, opacity=0.8, blend_mode=8),
+              pfe_io.PfeLayer("mixer", True, 1.0, 0, adjustment=(4, tuple(float(v) for v in rng.uniform(-0.2, 1.1, 16)))),
+              pfe_io.PfeLayer("exposure", True, 0.5, 0, adjustment=(1, (0.7,)))]
+    layers[1].folder_id = 7
+    layers[3].folder_id = 9
+    proj = pfe_io.PfeProject(w, h, 3, layers, folders=[dict(id=7, name="off", visible=False, collapsed=True, insert_above_layer=None, color_index=2),
+                                                      dict(id=9, name="on", visible=True, collapsed=False, insert_above_layer=1, color_index=None)],
+                             next_layer_folder_id=10)
+    raw = pfe_io.save_pfe_v3(proj)
+    assert raw[8:12] == b"PFE3"
+    back = pfe_io.load_pfe_from_bytes(raw)
+    assert pfe_io.save_pfe_v3(back) == raw  # byte-stable, metadata tail carried verbatim
+    assert [L.layer_type for L in back.layers] == [0, 0, 2, 0, 2, 2] and back.next_layer_folder_id == 10
+    assert back.layers[2].adjustment == (3, ()) and back.layers[4].adjustment[0] == 4 and len(back.layers[4].adjustment[1]) == 16
+    assert back.layers[5].adjustment[1][0] == pytest.approx(0.7)
+    assert [back.layer_effectively_visible(i) for i in range(6)] == [True, False, True, True, True, True]
+    o_layers = []
+    active = np.zeros(((h + 63) // 64, (w + 63) // 64), np.uint8)
+    for i, L in enumerate(back.layers):
+        vis = back.layer_effectively_visible(i)
+        if L.adjustment is not None:
+            kind, prm = L.adjustment
+            adj = (float(np.float32(2.0) ** np.float32(prm[0])),) if kind == 1 else prm
+            o_layers.append(oracle.make_layer(None, opacity=L.opacity, visible=vis, kind=kind, adj=adj))
+        else:
+            o_layers.append(oracle.make_layer(L.to_flat(w, h), opacity=L.opacity, blend=L.blend_mode, visible=vis))
+            if vis:
+                active |= L.occupancy(w, h)
+    out = oracle.flatten(o_layers, w, h, active=active)
+    assert out.shape == (h, w, 4)
+    # the hidden-folder layer must not show: same result with that layer removed altogether
+    out2 = oracle.flatten([l for i, l in enumerate(o_layers) if i != 1], w, h, active=active)
+    assert np.array_equal(out, out2)
