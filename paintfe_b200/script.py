@@ -21,6 +21,18 @@ from . import _lib as L
 
 _CALL = re.compile(r"\s*([A-Za-z_][A-Za-z0-9_]*)\s*\(([^()]*)\)\s*$")
 
+# parse_script_filter / parse_anchor, scripting.rs:60-82
+_FILTERS = {"nearest": 0, "nn": 0, "bicubic": 2, "catmull": 2, "catmullrom": 2, "lanczos": 3, "lanczos3": 3}
+_ANCHORS = {"top-left": (0, 0), "tl": (0, 0), "nw": (0, 0), "top-center": (1, 0), "tc": (1, 0), "n": (1, 0), "top": (1, 0),
+            "top-right": (2, 0), "tr": (2, 0), "ne": (2, 0), "center-left": (0, 1), "cl": (0, 1), "w": (0, 1), "left": (0, 1),
+            "center": (1, 1), "c": (1, 1), "middle": (1, 1), "center-right": (2, 1), "cr": (2, 1), "e": (2, 1), "right": (2, 1),
+            "bottom-left": (0, 2), "bl": (0, 2), "sw": (0, 2), "bottom-center": (1, 2), "bc": (1, 2), "s": (1, 2), "bottom": (1, 2),
+            "bottom-right": (2, 2), "br": (2, 2), "se": (2, 2)}
+
+
+def _dim(v) -> int:
+    return min(max(int(v), 1), 32768)  # `(new_w.max(1) as u32).min(32768)`, scripting.rs:750
+
 # pfe_adjust_op ids (include/pfe_b200.h)
 S_INVERT, S_DESATURATE, S_SEPIA, S_SEPIA_STRENGTH, S_BRIGHTNESS_CONTRAST, S_HSL, S_EXPOSURE, S_LUT_RGB = range(32, 40)
 
@@ -70,6 +82,12 @@ def bindings(eng, exact: bool = False) -> Dict[str, Callable]:
         "rotate_canvas_90cw": lambda im, m: eng.orient(im, 2),
         "rotate_canvas_90ccw": lambda im, m: eng.orient(im, 3),
         "rotate_canvas_180": lambda im, m: eng.orient(im, 4),
+        # scripting.rs:744-815: imageops::resize of the buffer / re-anchored copy on a transparent canvas
+        "resize_image": lambda im, m, w, h, method="bilinear": (
+            im if (_dim(w), _dim(h)) == (im.shape[1], im.shape[0])
+            else eng.resize(im, _dim(w), _dim(h), _FILTERS.get(str(method).lower(), 1))),
+        "resize_canvas": lambda im, m, w, h, anchor="top-left": eng.resize_canvas(
+            im, _dim(w), _dim(h), _ANCHORS.get(str(anchor).lower(), (0, 0)), (0, 0, 0, 0)),
         "apply_sepia": lambda im, m, *s: (eng.adjust(im, S_SEPIA) if not s else
                                           eng.adjust(im, S_SEPIA_STRENGTH, (min(max(float(s[0]), 0.0), 1.0),))),
         "apply_brightness_contrast": lambda im, m, b, c: eng.adjust(im, S_BRIGHTNESS_CONTRAST, (_f32(b), _f32(c))),
@@ -91,7 +109,14 @@ def parse(source: str) -> List[Tuple[str, Tuple[float, ...]]]:
         if not m:
             raise ValueError(f"unsupported script statement (only apply_*(numbers) calls): {stmt.strip()!r}")
         lit = {"true": 1.0, "false": 0.0}
-        args = tuple(lit[a.strip()] if a.strip() in lit else float(a) for a in m.group(2).split(",") if a.strip())
+
+        def arg(a):
+            a = a.strip()
+            if len(a) >= 2 and a[0] == a[-1] == '"':
+                return a[1:-1]  # string literal (resize_image's method, resize_canvas' anchor)
+            return lit[a] if a in lit else float(a)
+
+        args = tuple(arg(a) for a in m.group(2).split(",") if a.strip())
         calls.append((m.group(1), args))
     return calls
 

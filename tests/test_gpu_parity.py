@@ -885,6 +885,10 @@ def test_script_runner_covers_effect_api(eng, oracle):
     g = fx.gradient(64, 48)
     exact(execute_script_sync(eng, "rotate_canvas_90cw();", g), oracle.orient(g, oracle.ROT90CW))
     exact(execute_script_sync(eng, "rotate_canvas_90ccw(); rotate_canvas_180();", g), oracle.orient(g, oracle.ROT90CW))
+    exact(execute_script_sync(eng, 'resize_image(32, 24, "lanczos");', g), fx.golden("transforms", "resize_half_lanczos"))
+    exact(execute_script_sync(eng, 'resize_image(128, 96, "nn"); resize_image(128, 96, "bicubic");', g), fx.golden("transforms", "resize_2x_nearest"))
+    exact(execute_script_sync(eng, 'resize_canvas(96, 80, "center");', g), fx.golden("transforms", "resize_canvas_center"))
+    exact(execute_script_sync(eng, 'resize_canvas(70, 50, "se");', g), oracle.resize_canvas(g, 70, 50, (2, 2), (0, 0, 0, 0)))
     with pytest.raises(ValueError):
         execute_script_sync(eng, "for_each_pixel(3);", img)
 
