@@ -452,6 +452,12 @@ int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t src_w, uin
                       uint32_t src_nrows, const float *disp_band, const float *original_points,
                       const float *deformed_points, uint32_t cols, uint32_t rows, uint32_t w, uint32_t h,
                       uint32_t y0, uint32_t rows_out, uint8_t *dst_band);
+/* Reach of a band's displacement field, for sizing the halo of pfe_dev_warp_band: minmax_dev[0..1] (DEVICE
+ * memory, int32) = min / max over the band's rows [y0, y0+rows) of floor(clamp(y - dy, -1, h_total)), with
+ * non-finite dy counted as 0. Asynchronous: the result stays on the device so that it can go straight into
+ * the ranks' max-reduction. */
+int pfe_dev_disp_reach(pfe_ctx *ctx, const float *disp_band, uint32_t w, uint32_t rows, uint32_t y0,
+                       uint32_t h_total, int32_t *minmax_dev);
 /* DisplacementField::apply_push / expand / contract / twirl (:1051-1200), in place on a
  * w*h*2 field. a0,a1: push = (delta_x, delta_y); twirl = (clockwise ? 1 : 0, -).
  * bbox_out (may be NULL) = (x0, y0, x1, y1) like the reference's return value. */

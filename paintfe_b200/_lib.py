@@ -156,6 +156,7 @@ SIGNATURES = {
     "pfe_mesh_warp": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_mesh_warp": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_warp_band": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
+    "pfe_dev_disp_reach": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pfe_dev_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pfe_brush_stamps": (C.c_int, [_ctx, _vp, _u32, _u32, C.POINTER(BrushDesc), _vp, _u32, _vp]),

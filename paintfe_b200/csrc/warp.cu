@@ -279,6 +279,44 @@ extern "C" int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t
     return PFE_OK;
 }
 
+// How far a band's displacement field reaches outside the band: min / max over the band of
+// floor(clamp(y - dy, -1, h)), non-finite dy counted as 0 (such taps read nothing, transform.rs:1303-1312).
+// out = {min, max} stays on the device so the caller can fold it into its collective before reading it.
+namespace {
+__global__ void __launch_bounds__(256) disp_reach_kernel(const float2 *disp, uint32_t w, uint32_t rows, uint32_t y0, float h_total,
+                                                         int *out) {
+    int mn = 0x7FFFFFFF, mx = (int)0x80000000;
+    const size_t n = (size_t)w * rows;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float dy = __ldg(&disp[i].y);
+        if (!(fabsf(dy) <= 3.402823466e+38f)) dy = 0.0f;  // NaN / +-inf
+        const float sy = fminf(fmaxf((float)(y0 + (uint32_t)(i / w)) - dy, -1.0f), h_total);
+        const int f = __float2int_rd(sy);
+        mn = min(mn, f);
+        mx = max(mx, f);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out, mn); atomicMax(out + 1, mx); }
+}
+}  // namespace
+extern "C" int pfe_dev_disp_reach(pfe_ctx *ctx, const float *disp_band, uint32_t w, uint32_t rows, uint32_t y0, uint32_t h_total,
+                                  int32_t *minmax_dev) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!disp_band || !minmax_dev || !w || !rows) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "disp_reach: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int init[2] = {0x7FFFFFFF, (int)0x80000000};
+    void *stage;
+    PFE_TRY(pfe_small_upload(ctx, init, sizeof(init), &stage));
+    PFE_CUDA(ctx, cudaMemcpyAsync(minmax_dev, stage, sizeof(init), cudaMemcpyDeviceToDevice, ctx->stream));
+    PFE_KERNEL(ctx, "disp_reach", disp_reach_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(
+        (const float2 *)disp_band, w, rows, y0, (float)h_total, (int *)minmax_dev));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
 extern "C" int pfe_dev_liquify(pfe_ctx *ctx, float *field, uint32_t w, uint32_t h, int kind, float cx, float cy,
                                float radius, float strength, float a0, float a1, int32_t bbox[4]) {
     if (!ctx) return PFE_ERR_INVALID_ARG;

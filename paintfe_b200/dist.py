@@ -226,21 +226,20 @@ def flatten_banded(eng, layer_bands, w: int, band_rows: int, active=None):
     return eng.flatten(layer_bands, w, band_rows, active=active)
 
 
-def _max_over_ranks(v: float, device, group) -> float:
-    rank, world = _world(group)
-    if world == 1:
-        return v
-    t = torch.tensor([v], dtype=torch.float32, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    return float(t[0])
-
-
-def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach_up, reach_down, bounds, group, **warp_kw):
+def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach, bounds, group, uniform=False, **warp_kw):
+    """`reach` = (up, down) halo rows this rank needs: python ints, or a 2-element device tensor. One
+    max-reduction (a single collective and a single host read) sizes the halo identically on every rank
+    (SURVEY 8e); `uniform` = every rank already holds the same numbers (mesh warps), no collective at all."""
     band = _as_tensor(band)
     rank, world = _world(group)
-    # one scalar all-reduce sizes the halo identically on every rank, then one exchange
-    up = int(_max_over_ranks(float(reach_up), band.device, group))
-    down = int(_max_over_ranks(float(reach_down), band.device, group))
+    if world > 1 and not uniform:
+        t = reach if isinstance(reach, torch.Tensor) else torch.tensor(list(reach), dtype=torch.int32, device=band.device)
+        if t.device.type == "cpu" and dist.get_backend(group) == "nccl":
+            t = t.to(band.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        up, down = (int(v) for v in t.tolist())
+    else:
+        up, down = (int(v) for v in (reach.tolist() if isinstance(reach, torch.Tensor) else reach))
     top, bot = exchange_halo(band, up, down, bounds, group)
     window = torch.cat([top, band, bot]) if (len(top) or len(bot)) else band
     src_y0 = bounds[rank][0] - len(top)
@@ -250,20 +249,23 @@ def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach_up, reach_down, bo
 
 def warp_displacement_banded(eng, band, disp_band, h_total: int, group=None, bounds=None):
     """warp_displacement_full (transform.rs:1288-1345) on a row-split canvas (source and output share
-    the split). Reach = how far (y - dy) leaves the band, taken from the band's own field."""
+    the split). Reach = how far (y - dy) leaves the band, taken from the band's own field: on the device in
+    one pass (pfe_dev_disp_reach), folded into the ranks' max-reduction before the host reads it."""
     rank, world = _world(group)
     bounds = bounds or band_bounds(h_total, world)
     y0, y1 = bounds[rank]
     d = _as_tensor(disp_band)
-    if y1 > y0:
+    if y1 > y0 and d.is_cuda and hasattr(eng, "disp_reach"):
+        mm = eng.disp_reach(d, y0, h_total)  # [min, max] of floor(clamp(y - dy, -1, h))
+        reach = torch.stack([(y0 - mm[0]).clamp(min=0), (mm[1] + 2 - y1).clamp(min=0)]).to(torch.int32)
+    elif y1 > y0:
         ys = torch.arange(y0, y1, dtype=torch.float32, device=d.device)[:, None]
         sy = ys - torch.nan_to_num(d[..., 1], nan=0.0, posinf=0.0, neginf=0.0)
         sy = sy.clamp(-1.0, float(h_total))
-        up = max(0.0, y0 - float(torch.floor(sy.min())))
-        down = max(0.0, float(torch.floor(sy.max())) + 2 - y1)
+        reach = (math.ceil(max(0.0, y0 - float(torch.floor(sy.min())))), math.ceil(max(0.0, float(torch.floor(sy.max())) + 2 - y1)))
     else:
-        up = down = 0.0
-    return _warp_band(eng, band, h_total, int(d.shape[1]), y0, y1 - y0, math.ceil(up), math.ceil(down), bounds, group,
+        reach = (0, 0)
+    return _warp_band(eng, band, h_total, int(d.shape[1]), y0, y1 - y0, reach, bounds, group,
                       disp_band=d if d.is_cuda else d.numpy())
 
 
@@ -280,6 +282,6 @@ def mesh_warp_banded(eng, band, original, deformed, cols: int, rows: int, w: int
     rank, world = _world(group)
     bounds = bounds or band_bounds(h_total, world)
     y0, y1 = bounds[rank]
-    reach = mesh_reach(original, deformed)
-    return _warp_band(eng, band, h_total, w, y0, y1 - y0, reach, reach, bounds, group,
+    reach = mesh_reach(original, deformed)  # from the control points alone: identical on every rank
+    return _warp_band(eng, band, h_total, w, y0, y1 - y0, (reach, reach), bounds, group, uniform=True,
                       original=original, deformed=deformed, cols=cols, rows=rows)

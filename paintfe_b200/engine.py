@@ -568,6 +568,14 @@ class Engine:
         self._ck(fn(self.h, _ptr(field), w, h, int(kind), cx, cy, radius, strength, a0, a1, bbox))
         return tuple(bbox)
 
+    def disp_reach(self, disp_band, y0, h_total, out=None):
+        """Device-side reach of a band's field (pfe_dev_disp_reach): int32 tensor [min, max] of floor(y - dy)."""
+        rows, w = int(disp_band.shape[0]), int(disp_band.shape[1])
+        out = out if out is not None else torch.empty(2, dtype=torch.int32, device=disp_band.device)
+        self.use_torch_stream()
+        self._ck(self.lib.pfe_dev_disp_reach(self.h, _ptr(disp_band), w, rows, int(y0), int(h_total), _ptr(out)))
+        return out
+
     # -- brush --------------------------------------------------------------------------------
     @staticmethod
     def brush_desc(size, hardness, anti_aliased, color, flow=1.0, is_eraser=False, mode=0):

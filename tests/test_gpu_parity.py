@@ -835,6 +835,23 @@ def test_gaussian_ring_pipeline_full_8k(eng, monkeypatch):
             assert bad == 0, f"sigma {sigma} rep {rep}: {bad} pixels differ between the ring and the direct V pass"
 
 
+def test_disp_reach_matches_host_formula(eng):
+    """pfe_dev_disp_reach (halo sizing of the banded displacement warp) == the torch formula it replaces."""
+    import torch
+
+    rng = np.random.default_rng(9)
+    for (w, rows, y0, h_total) in [(300, 128, 256, 1000), (67, 45, 0, 45), (1, 1, 5, 9), (1030, 64, 960, 1024)]:
+        d = rng.normal(0, 40, (rows, w, 2)).astype(np.float32)
+        d[0, 0] = (0.0, np.nan); d[-1, -1] = (1.0, np.inf); d[rows // 2, w // 2] = (0.0, -np.inf)
+        if rows > 2:
+            d[1, 0, 1] = 1e9; d[2, 0, 1] = -1e9
+        t = torch.from_numpy(d).cuda()
+        ys = torch.arange(y0, y0 + rows, dtype=torch.float32, device="cuda")[:, None]
+        sy = (ys - torch.nan_to_num(t[..., 1], nan=0.0, posinf=0.0, neginf=0.0)).clamp(-1.0, float(h_total))
+        want = [int(torch.floor(sy.min())), int(torch.floor(sy.max()))]
+        assert eng.disp_reach(t, y0, h_total).tolist() == want, (w, rows, y0, h_total)
+
+
 def test_error_statuses_of_widened_entry_points(eng):
     """Bad enums / unsupported sizes come back as statuses (the ABI never unwinds, never falls back) and the
     context stays usable afterwards."""
