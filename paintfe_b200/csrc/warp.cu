@@ -26,43 +26,64 @@ __device__ __forceinline__ void cr_weights(float t, float w[4]) {  // transform.
     w[3] = 0.5f * t3 - 0.5f * t2;
 }
 
-// catmull_rom_surface, transform.rs:1589-1646
-__device__ __forceinline__ void cr_surface(const float *pts, int cols, int rows, float ug, float vg, float &ox, float &oy) {
-    const int ppr = cols + 1, nrows = rows + 1;
-    float col_f = pfe_clampf(ug, 0.0f, (float)cols - 0.0001f);
-    float row_f = pfe_clampf(vg, 0.0f, (float)rows - 0.0001f);
-    int ci = min(__float2int_rz(col_f), cols - 1), ri = min(__float2int_rz(row_f), rows - 1);
-    ci = max(ci, 0); ri = max(ri, 0);
-    float wu[4], wv[4];
-    cr_weights(row_f - (float)ri, wv);
-    cr_weights(col_f - (float)ci, wu);
+// catmull_rom_surface (transform.rs:1589-1646) and generate_displacement_from_mesh[_fast] (:1670-1739),
+// factored for a thread that walks DOWN a column: everything that depends on x alone
+// (column index, the four column weights and clamped column indices) is computed once, and the four
+// row-wise interpolants rx[j], ry[j] - 8 of the 10 dot products of catmull_rom_surface - depend only on x
+// and on the mesh row `ri`, so they are recomputed only when the walk crosses into the next mesh row.
+// Every product and sum is the one catmull_rom_surface evaluates, in the same order: results are identical.
+constexpr int kMeshRows = 8;  // consecutive output rows per thread
+struct MeshColumn {
+    float ug, px;  // px = x + 0.5
+    float wu[4];
+    int cu[4];
+};
+__device__ __forceinline__ MeshColumn mesh_column(const MeshParams &M, int x, uint32_t w) {
+    MeshColumn C;
+    C.px = (float)x + 0.5f;
+    C.ug = C.px / (float)w * (float)M.cols;
+    const int ppr = M.cols + 1;
+    const float col_f = pfe_clampf(C.ug, 0.0f, (float)M.cols - 0.0001f);
+    int ci = max(min(__float2int_rz(col_f), M.cols - 1), 0);
+    cr_weights(col_f - (float)ci, C.wu);
+    C.cu[0] = ci == 0 ? 0 : ci - 1; C.cu[1] = ci; C.cu[2] = min(ci + 1, ppr - 1); C.cu[3] = min(ci + 2, ppr - 1);
+    return C;
+}
+struct MeshRowCache {
+    int ri;
+    float ax[4], ay[4], bx[4], by[4];  // row interpolants of the deformed (a) and original (b) grids
+};
+__device__ __forceinline__ void mesh_rows(const float *pts, int ppr, int nrows, int ri, const MeshColumn &C, float rx[4], float ry[4]) {
     const int rv[4] = {ri == 0 ? 0 : ri - 1, ri, min(ri + 1, nrows - 1), min(ri + 2, nrows - 1)};
-    const int cu[4] = {ci == 0 ? 0 : ci - 1, ci, min(ci + 1, ppr - 1), min(ci + 2, ppr - 1)};
-    float rx[4], ry[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const float *b = pts + (size_t)rv[j] * ppr * 2;
-        const float *p0 = b + cu[0] * 2, *p1 = b + cu[1] * 2, *p2 = b + cu[2] * 2, *p3 = b + cu[3] * 2;
-        rx[j] = wu[0] * p0[0] + wu[1] * p1[0] + wu[2] * p2[0] + wu[3] * p3[0];
-        ry[j] = wu[0] * p0[1] + wu[1] * p1[1] + wu[2] * p2[1] + wu[3] * p3[1];
+        const float *p0 = b + C.cu[0] * 2, *p1 = b + C.cu[1] * 2, *p2 = b + C.cu[2] * 2, *p3 = b + C.cu[3] * 2;
+        rx[j] = C.wu[0] * p0[0] + C.wu[1] * p1[0] + C.wu[2] * p2[0] + C.wu[3] * p3[0];
+        ry[j] = C.wu[0] * p0[1] + C.wu[1] * p1[1] + C.wu[2] * p2[1] + C.wu[3] * p3[1];
     }
-    ox = wv[0] * rx[0] + wv[1] * rx[1] + wv[2] * rx[2] + wv[3] * rx[3];
-    oy = wv[0] * ry[0] + wv[1] * ry[1] + wv[2] * ry[2] + wv[3] * ry[3];
 }
-
-// generate_displacement_from_mesh[_fast], transform.rs:1670-1739, for one pixel
-__device__ __forceinline__ void mesh_disp(const MeshParams &M, const float *sdef, const float *sorig, int x, int y,
-                                          uint32_t w, uint32_t h, float &dx, float &dy) {
-    float ug = ((float)x + 0.5f) / (float)w * (float)M.cols;
-    float vg = ((float)y + 0.5f) / (float)h * (float)M.rows;
-    float ax, ay;
-    cr_surface(sdef, M.cols, M.rows, ug, vg, ax, ay);
+// generate_displacement_from_mesh[_fast] for pixel (C's x, y), reusing `rc` while the mesh row is unchanged
+__device__ __forceinline__ void mesh_disp_col(const MeshParams &M, const float *sdef, const float *sorig, const MeshColumn &C,
+                                              MeshRowCache &rc, int y, uint32_t h, float &dx, float &dy) {
+    const float vg = ((float)y + 0.5f) / (float)h * (float)M.rows;
+    const float row_f = pfe_clampf(vg, 0.0f, (float)M.rows - 0.0001f);
+    const int ri = max(min(__float2int_rz(row_f), M.rows - 1), 0);
+    float wv[4];
+    cr_weights(row_f - (float)ri, wv);
+    if (ri != rc.ri) {
+        rc.ri = ri;
+        mesh_rows(sdef, M.cols + 1, M.rows + 1, ri, C, rc.ax, rc.ay);
+        if (M.has_orig) mesh_rows(sorig, M.cols + 1, M.rows + 1, ri, C, rc.bx, rc.by);
+    }
+    const float ax = wv[0] * rc.ax[0] + wv[1] * rc.ax[1] + wv[2] * rc.ax[2] + wv[3] * rc.ax[3];
+    const float ay = wv[0] * rc.ay[0] + wv[1] * rc.ay[1] + wv[2] * rc.ay[2] + wv[3] * rc.ay[3];
     if (M.has_orig) {
-        float bx, by;
-        cr_surface(sorig, M.cols, M.rows, ug, vg, bx, by);
+        const float bx = wv[0] * rc.bx[0] + wv[1] * rc.bx[1] + wv[2] * rc.bx[2] + wv[3] * rc.bx[3];
+        const float by = wv[0] * rc.by[0] + wv[1] * rc.by[1] + wv[2] * rc.by[2] + wv[3] * rc.by[3];
         dx = ax - bx; dy = ay - by;
     } else {
-        dx = ax - ((float)x + 0.5f); dy = ay - ((float)y + 0.5f);
+        dx = ax - C.px; dy = ay - ((float)y + 0.5f);
     }
 }
 
@@ -98,13 +119,22 @@ __device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int
     return pfe_pack(o[0], o[1], o[2], o[3]);
 }
 
-__global__ void __launch_bounds__(256) warp_kernel(const uint32_t *src, int sw, int sh, const float2 *disp,
-                                                   uint32_t *dst, int w, int h) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= w || y >= h) return;
-    const size_t o = (size_t)y * w + x;
-    const float2 d = __ldg(disp + o);
-    dst[o] = warp_sample(src, sw, sh, x, y, d.x, d.y);
+// Four rows per thread, all loads of the four pixels (4 field entries, 16 taps) issued before any store: the
+// kernel is a gather, bound by how many loads an SM keeps in flight, not by arithmetic or DRAM.
+constexpr int kWarpRows = 4;
+__global__ void __launch_bounds__(256) warp_kernel(const uint32_t *__restrict__ src, int sw, int sh, const float2 *__restrict__ disp,
+                                                   uint32_t *__restrict__ dst, int w, int h) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), ya = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kWarpRows;
+    if (x >= w || ya >= h) return;
+    float2 d[kWarpRows];
+    uint32_t o[kWarpRows];
+#pragma unroll
+    for (int r = 0; r < kWarpRows; r++) d[r] = (ya + r < h) ? __ldg(disp + (size_t)(ya + r) * w + x) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kWarpRows; r++) o[r] = (ya + r < h) ? warp_sample(src, sw, sh, x, ya + r, d[r].x, d[r].y) : 0u;
+#pragma unroll
+    for (int r = 0; r < kWarpRows; r++)
+        if (ya + r < h) dst[(size_t)(ya + r) * w + x] = o[r];
 }
 
 __global__ void __launch_bounds__(256) mesh_disp_kernel(const __grid_constant__ MeshParams M, float2 *out, uint32_t w,
@@ -113,11 +143,17 @@ __global__ void __launch_bounds__(256) mesh_disp_kernel(const __grid_constant__ 
     const int np = (M.cols + 1) * (M.rows + 1) * 2;
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
     __syncthreads();
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= (int)w || y >= (int)h) return;
-    float dx, dy;
-    mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
-    out[(size_t)y * w + x] = make_float2(dx, dy);
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (x >= (int)w) return;
+    const MeshColumn C = mesh_column(M, x, w);
+    MeshRowCache rc;
+    rc.ri = -1;
+    const int ya = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kMeshRows;
+    for (int y = ya; y < ya + kMeshRows && y < (int)h; y++) {
+        float dx, dy;
+        mesh_disp_col(M, sdef, sorig, C, rc, y, h, dx, dy);
+        out[(size_t)y * w + x] = make_float2(dx, dy);
+    }
 }
 
 // warp_mesh_catmull_rom fused: displacement stays in registers. Rows [y0, y0+rows_out).
@@ -129,12 +165,17 @@ __global__ void __launch_bounds__(256) mesh_warp_kernel(const __grid_constant__ 
     for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
     __syncthreads();
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const uint32_t ry = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= (int)w || ry >= rows_out) return;
-    const int y = (int)(y0 + ry);
-    float dx, dy;
-    mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
-    dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy);
+    if (x >= (int)w) return;
+    const MeshColumn C = mesh_column(M, x, w);
+    MeshRowCache rc;
+    rc.ri = -1;
+    const uint32_t ra = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kMeshRows;
+    for (uint32_t ry = ra; ry < ra + kMeshRows && ry < rows_out; ry++) {
+        const int y = (int)(y0 + ry);
+        float dx, dy;
+        mesh_disp_col(M, sdef, sorig, C, rc, y, h, dx, dy);
+        dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy);
+    }
 }
 
 // Band form shared by the displacement warp and the fused mesh warp: output rows [y0, y0+rows_out)
@@ -149,13 +190,19 @@ __global__ void __launch_bounds__(256) warp_band_kernel(const __grid_constant__ 
         __syncthreads();
     }
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const uint32_t ry = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= (int)w || ry >= rows_out) return;
-    const int y = (int)(y0 + ry);
-    float dx, dy;
-    if (disp) { const float2 d = __ldg(disp + (size_t)ry * w + x); dx = d.x; dy = d.y; }
-    else mesh_disp(M, sdef, sorig, x, y, w, h, dx, dy);
-    dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy, sy0, snr, missing);
+    if (x >= (int)w) return;
+    MeshColumn C;
+    MeshRowCache rc;
+    rc.ri = -1;
+    if (!disp) C = mesh_column(M, x, w);
+    const uint32_t ra = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kMeshRows;
+    for (uint32_t ry = ra; ry < ra + kMeshRows && ry < rows_out; ry++) {
+        const int y = (int)(y0 + ry);
+        float dx, dy;
+        if (disp) { const float2 d = __ldg(disp + (size_t)ry * w + x); dx = d.x; dy = d.y; }
+        else mesh_disp_col(M, sdef, sorig, C, rc, y, h, dx, dy);
+        dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy, sy0, snr, missing);
+    }
 }
 
 // exp() as the reference's libm expf sees it: correctly rounded f32. Evaluated in f64 and rounded
@@ -220,7 +267,7 @@ extern "C" int pfe_dev_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint3
     if (!ctx) return PFE_ERR_INVALID_ARG;
     if (!src || !disp || !dst || !sw || !sh || !w || !h || src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp: bad args");
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
-    PFE_KERNEL(ctx, "warp", warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
+    PFE_KERNEL(ctx, "warp", warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8 * kWarpRows)), 256, 0, ctx->stream>>>(
         (const uint32_t *)src, (int)sw, (int)sh, (const float2 *)disp, (uint32_t *)dst, (int)w, (int)h));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
@@ -233,7 +280,7 @@ extern "C" int pfe_dev_mesh_displacement(pfe_ctx *ctx, const float *orig, const 
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
     MeshParams M;
     PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
-    PFE_KERNEL(ctx, "mesh_disp", mesh_disp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(M, (float2 *)out, w, h));
+    PFE_KERNEL(ctx, "mesh_disp", mesh_disp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8 * kMeshRows)), 256, 0, ctx->stream>>>(M, (float2 *)out, w, h));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
@@ -247,7 +294,7 @@ extern "C" int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, 
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
     MeshParams M;
     PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
-    PFE_KERNEL(ctx, "mesh_warp", mesh_warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8)), 256, 0, ctx->stream>>>(
+    PFE_KERNEL(ctx, "mesh_warp", mesh_warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8 * kMeshRows)), 256, 0, ctx->stream>>>(
         M, (const uint32_t *)src, (int)sw, (int)sh, (uint32_t *)dst, w, h, y0, rows_out));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
@@ -268,7 +315,7 @@ extern "C" int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t
     int zero = 0;
     void *flag;
     PFE_TRY(pfe_small_upload(ctx, &zero, sizeof(zero), &flag));
-    PFE_KERNEL(ctx, "warp_band", warp_band_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8)), 256, 0, ctx->stream>>>(
+    PFE_KERNEL(ctx, "warp_band", warp_band_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8 * kMeshRows)), 256, 0, ctx->stream>>>(
         M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, (const float2 *)disp_band,
         (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
     PFE_LAUNCHED(ctx);
