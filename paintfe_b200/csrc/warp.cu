@@ -180,28 +180,45 @@ __global__ void __launch_bounds__(256) mesh_warp_kernel(const __grid_constant__ 
 
 // Band form shared by the displacement warp and the fused mesh warp: output rows [y0, y0+rows_out)
 // of a w x h result, source given as a row window. disp == nullptr selects the mesh path.
-__global__ void __launch_bounds__(256) warp_band_kernel(const __grid_constant__ MeshParams M, const uint32_t *src, int sw,
-                                                        int sh, int sy0, int snr, const float2 *disp, uint32_t *dst,
-                                                        uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out, int *missing) {
-    __shared__ float sdef[PFE_MESH_MAX_POINTS * 2], sorig[PFE_MESH_MAX_POINTS * 2];
-    if (!disp) {
+template <bool MESH>
+__global__ void __launch_bounds__(256) warp_band_kernel(const __grid_constant__ MeshParams M, const uint32_t *__restrict__ src, int sw,
+                                                        int sh, int sy0, int snr, const float2 *__restrict__ disp,
+                                                        uint32_t *__restrict__ dst, uint32_t w, uint32_t h, uint32_t y0,
+                                                        uint32_t rows_out, int *missing) {
+    __shared__ float sdef[MESH ? PFE_MESH_MAX_POINTS * 2 : 1], sorig[MESH ? PFE_MESH_MAX_POINTS * 2 : 1];
+    if (MESH) {
         const int np = (M.cols + 1) * (M.rows + 1) * 2;
         for (int i = threadIdx.x; i < np; i += blockDim.x) { sdef[i] = M.def[i]; sorig[i] = M.orig[i]; }
         __syncthreads();
     }
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     if (x >= (int)w) return;
-    MeshColumn C;
-    MeshRowCache rc;
-    rc.ri = -1;
-    if (!disp) C = mesh_column(M, x, w);
     const uint32_t ra = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kMeshRows;
-    for (uint32_t ry = ra; ry < ra + kMeshRows && ry < rows_out; ry++) {
-        const int y = (int)(y0 + ry);
-        float dx, dy;
-        if (disp) { const float2 d = __ldg(disp + (size_t)ry * w + x); dx = d.x; dy = d.y; }
-        else mesh_disp_col(M, sdef, sorig, C, rc, y, h, dx, dy);
-        dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy, sy0, snr, missing);
+    if (MESH) {
+        const MeshColumn C = mesh_column(M, x, w);
+        MeshRowCache rc;
+        rc.ri = -1;
+        for (uint32_t ry = ra; ry < ra + kMeshRows && ry < rows_out; ry++) {
+            const int y = (int)(y0 + ry);
+            float dx, dy;
+            mesh_disp_col(M, sdef, sorig, C, rc, y, h, dx, dy);
+            dst[(size_t)ry * w + x] = warp_sample(src, sw, sh, x, y, dx, dy, sy0, snr, missing);
+        }
+    } else {  // field path: loads of kWarpRows pixels batched like warp_kernel
+#pragma unroll
+        for (int half = 0; half < kMeshRows / kWarpRows; half++) {
+            const uint32_t rb = ra + half * kWarpRows;
+            float2 d[kWarpRows];
+            uint32_t o[kWarpRows];
+#pragma unroll
+            for (int r = 0; r < kWarpRows; r++) d[r] = (rb + r < rows_out) ? __ldg(disp + (size_t)(rb + r) * w + x) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < kWarpRows; r++)
+                o[r] = (rb + r < rows_out) ? warp_sample(src, sw, sh, x, (int)(y0 + rb + r), d[r].x, d[r].y, sy0, snr, missing) : 0u;
+#pragma unroll
+            for (int r = 0; r < kWarpRows; r++)
+                if (rb + r < rows_out) dst[(size_t)(rb + r) * w + x] = o[r];
+        }
     }
 }
 
@@ -315,9 +332,15 @@ extern "C" int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t
     int zero = 0;
     void *flag;
     PFE_TRY(pfe_small_upload(ctx, &zero, sizeof(zero), &flag));
-    PFE_KERNEL(ctx, "warp_band", warp_band_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(rows_out, 8 * kMeshRows)), 256, 0, ctx->stream>>>(
-        M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, (const float2 *)disp_band,
-        (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
+    const dim3 grid(pfe_div_up(w, 32), pfe_div_up(rows_out, 8 * kMeshRows));
+    if (disp_band)
+        PFE_KERNEL(ctx, "warp_band", warp_band_kernel<false><<<grid, 256, 0, ctx->stream>>>(
+            M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, (const float2 *)disp_band,
+            (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
+    else
+        PFE_KERNEL(ctx, "warp_band", warp_band_kernel<true><<<grid, 256, 0, ctx->stream>>>(
+            M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, nullptr,
+            (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
     PFE_LAUNCHED(ctx);
     int missing = 0;
     PFE_CUDA(ctx, cudaMemcpyAsync(&missing, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -255,7 +255,9 @@ def warp_displacement_banded(eng, band, disp_band, h_total: int, group=None, bou
     bounds = bounds or band_bounds(h_total, world)
     y0, y1 = bounds[rank]
     d = _as_tensor(disp_band)
-    if y1 > y0 and d.is_cuda and hasattr(eng, "disp_reach"):
+    if world == 1:
+        reach = (0, 0)  # the band is the whole image: nothing to exchange, nothing to size
+    elif y1 > y0 and d.is_cuda and hasattr(eng, "disp_reach"):
         mm = eng.disp_reach(d, y0, h_total)  # [min, max] of floor(clamp(y - dy, -1, h))
         reach = torch.stack([(y0 - mm[0]).clamp(min=0), (mm[1] + 2 - y1).clamp(min=0)]).to(torch.int32)
     elif y1 > y0:
