@@ -221,9 +221,17 @@ struct Layer {
     std::optional<TiledImage> mask;  // alpha = concealment, 0 = reveal (layers.rs:395-397)
     bool mask_enabled = false;
     std::optional<AdjustmentLayerData> adjustment;  // LayerContent::Adjustment
+    std::optional<uint64_t> folder_id;              // layers.rs:392
     Layer(std::string n, uint32_t w, uint32_t h, Rgba fill) : name(std::move(n)), pixels(w, h) {
         if (fill[3] > 0) pixels = TiledImage::from_rgba_image(RgbaImage::from_pixel(w, h, fill));
     }
+};
+
+// src/canvas/layers.rs:378-387
+struct LayerFolder {
+    uint64_t id = 0;
+    std::string name;
+    bool visible = true, collapsed = false;
 };
 
 // src/canvas/canvas_state.rs: the compositing subset of CanvasState
@@ -231,6 +239,15 @@ class CanvasState {
 public:
     uint32_t width, height;
     std::vector<Layer> layers;
+    std::vector<LayerFolder> layer_folders;
+    // canvas_state.rs:216-227: hidden itself, or a member of a hidden folder
+    bool layer_effectively_visible(size_t idx) const {
+        if (idx >= layers.size() || !layers[idx].visible) return false;
+        if (!layers[idx].folder_id) return true;
+        for (const LayerFolder &f : layer_folders)
+            if (f.id == *layers[idx].folder_id) return f.visible;
+        return true;
+    }
     std::optional<GrayImage> selection_mask;
     CanvasState(uint32_t w, uint32_t h) : width(w), height(h) {  // CanvasState::new: one white background layer
         layers.emplace_back("Background", w, h, Rgba{{255, 255, 255, 255}});
@@ -241,11 +258,13 @@ public:
         std::vector<std::vector<const uint8_t *>> tables;
         tables.reserve(layers.size() * 2);
         std::vector<pfe_tile_layer_desc> descs;
-        for (const Layer &L : layers) {
+        for (size_t li = 0; li < layers.size(); li++) {
+            const Layer &L = layers[li];
+            const bool vis = layer_effectively_visible(li);
             pfe_tile_layer_desc d{};
             d.opacity = L.opacity;
             d.blend = to_u8(L.blend_mode);
-            d.visible = L.visible ? 1 : 0;
+            d.visible = vis ? 1 : 0;
             if (L.adjustment) {
                 const auto &a = *L.adjustment;
                 d.kind = (uint8_t)a.kind;
@@ -253,7 +272,7 @@ public:
                 if (a.kind == AdjustmentLayerData::BrightnessContrast) { d.adj[0] = a.brightness; d.adj[1] = a.contrast; }
                 if (a.kind == AdjustmentLayerData::ChannelMixer)
                     for (int i = 0; i < 4; i++) { d.adj[i] = a.red[i]; d.adj[4 + i] = a.green[i]; d.adj[8 + i] = a.blue[i]; d.adj[12 + i] = a.alpha[i]; }
-            } else if (L.visible) {
+            } else if (vis) {
                 tables.push_back(L.pixels.chunk_table());
                 d.chunks = tables.back().data();
                 if (L.mask_enabled && L.mask) {
@@ -281,11 +300,13 @@ public:
         flats.reserve(layers.size());
         masks.reserve(layers.size());
         bool any_adjustment = false;
-        for (const Layer &L : layers) {
+        for (size_t li = 0; li < layers.size(); li++) {
+            const Layer &L = layers[li];
+            const bool vis = layer_effectively_visible(li);
             pfe_layer_desc d{};
             d.opacity = L.opacity;
             d.blend = to_u8(L.blend_mode);
-            d.visible = L.visible ? 1 : 0;
+            d.visible = vis ? 1 : 0;
             if (L.adjustment) {
                 const auto &a = *L.adjustment;
                 d.kind = (uint8_t)a.kind;
@@ -293,8 +314,8 @@ public:
                 if (a.kind == AdjustmentLayerData::BrightnessContrast) { d.adj[0] = a.brightness; d.adj[1] = a.contrast; }
                 if (a.kind == AdjustmentLayerData::ChannelMixer)
                     for (int i = 0; i < 4; i++) { d.adj[i] = a.red[i]; d.adj[4 + i] = a.green[i]; d.adj[8 + i] = a.blue[i]; d.adj[12 + i] = a.alpha[i]; }
-                any_adjustment = any_adjustment || L.visible;
-            } else if (L.visible) {
+                any_adjustment = any_adjustment || vis;
+            } else if (vis) {
                 flats.push_back(L.pixels.to_rgba_image());
                 d.rgba = flats.back().as_raw().data();
                 auto occ = L.pixels.occupancy();

@@ -144,6 +144,62 @@ int main(int argc, char **argv) {
         check(out.get_pixel(40, 5) == Rgba{{255, 255, 0, 255}}, "revealed half: blue inverted");
     });
 
+    // layer_ops.rs:151-316
+    auto solid_layer = [](const char *name, Rgba c) {
+        Layer l(name, 32, 32, Rgba{{0, 0, 0, 0}});
+        l.pixels = TiledImage::from_rgba_image(RgbaImage::from_pixel(32, 32, c));
+        return l;
+    };
+    run("hidden_layer_not_composited", [&] {
+        CanvasState state(32, 32);
+        Layer red = solid_layer("Red", Rgba{{255, 0, 0, 255}});
+        red.visible = false;
+        state.layers.push_back(std::move(red));
+        check(state.composite().get_pixel(16, 16) == Rgba{{255, 255, 255, 255}}, "hidden layer showed");
+    });
+    run("hidden_folder_hides_member_layers", [&] {
+        CanvasState state(32, 32);
+        state.layer_folders.push_back(canvas::LayerFolder{1, "Group", false, false});
+        Layer red = solid_layer("Red", Rgba{{255, 0, 0, 255}});
+        red.folder_id = 1;
+        state.layers.push_back(std::move(red));
+        check(state.composite().get_pixel(16, 16) == Rgba{{255, 255, 255, 255}}, "layer of a hidden folder showed");
+        check(state.composite_dense().get_pixel(16, 16) == Rgba{{255, 255, 255, 255}}, "dense: layer of a hidden folder showed");
+        check(!state.layer_effectively_visible(1), "layer_effectively_visible");
+    });
+    run("layer_opacity_affects_composite", [&] {
+        CanvasState state(32, 32);
+        Layer black = solid_layer("Black50", Rgba{{0, 0, 0, 255}});
+        black.opacity = 0.5f;
+        state.layers.push_back(std::move(black));
+        check(std::abs((int)state.composite().get_pixel(16, 16)[0] - 128) <= 2, "expected ~128 gray");
+    });
+    run("layer_reorder_changes_composite", [&] {
+        CanvasState state(32, 32);
+        state.layers.push_back(solid_layer("Red", Rgba{{255, 0, 0, 255}}));
+        state.layers.push_back(solid_layer("Blue", Rgba{{0, 0, 255, 255}}));
+        check(state.composite().get_pixel(16, 16)[2] == 255, "blue on top");
+        std::swap(state.layers[1], state.layers[2]);
+        check(state.composite().get_pixel(16, 16)[0] == 255, "red on top after swap");
+    });
+    run("flatten_multiple_layers", [&] {
+        CanvasState state(32, 32);
+        state.layers.push_back(solid_layer("Red", Rgba{{255, 0, 0, 128}}));
+        RgbaImage before = state.composite();
+        ops::transform::flatten_image(state);
+        check(state.layers.size() == 1, "flatten should produce one layer");
+        check(state.composite() == before, "composite should be unchanged after flatten");
+    });
+    run("flatten_preserves_hidden_layer_exclusion", [&] {
+        CanvasState state(32, 32);
+        Layer green = solid_layer("Green", Rgba{{0, 255, 0, 255}});
+        green.visible = false;
+        state.layers.push_back(std::move(green));
+        RgbaImage before = state.composite();
+        ops::transform::flatten_image(state);
+        check(state.layers.size() == 1 && state.composite().get_pixel(16, 16) == Rgba{{255, 255, 255, 255}} && state.composite() == before, "hidden layer leaked into flatten");
+    });
+
     // visual_filters.rs
     const RgbaImage img = create_test_gradient(64, 64);
     run("gaussian_blur_s2", [&] { assert_golden("filters", "gaussian_blur_s2", ops::filters::parallel_gaussian_blur_pub(img, 2.0f)); });
