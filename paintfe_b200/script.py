@@ -7,7 +7,10 @@ PaintFE's Rhai host itself is kept as the caller; this runner exi
 benchmark (config 5) and the parity tests can execute the same effect sequences on the device
 without a Rust toolchain.  Each binding maps to the entry point that replaces the reference function
 it calls, with the reference's fixed arguments (e.g. apply_sharpen uses radius 1.0, scripting.rs:847).
-Anything that is not a plain `apply_*(numbers...)` call raises: there is no interpreter here.
+Covered: every `apply_*` effect, the flips / rotations, `resize_image`, `resize_canvas` and the selection API
+(`select_rect`, `select_ellipse`, `clear_selection`, `invert_selection`, `fill_selected`, `delete_selected`).
+Anything that is not a plain `name(literals...)` call - closures (`for_each_pixel`, `map_channels`), variables,
+control flow - raises: there is no interpreter here.
 """
 from __future__ import annotations
 
@@ -129,7 +132,58 @@ def execute_script_sync(eng, source: str, pixels, mask=None, exact: bool = False
     table = bindings(eng, exact)
     img = pixels
     for name, args in parse(source):
+        if name in _SELECTION_API:
+            img, mask = _selection_call(eng, name, args, img, mask)
+            continue
         if name not in table:
             raise ValueError(f"effect {name!r} is outside the B200 hot path (see DESIGN.md, out of scope)")
+        h0, w0 = img.shape[:2]
         img = table[name](img, mask, *args)
+        if mask is not None and tuple(img.shape[:2]) != (h0, w0):
+            mask = None  # the reference keeps a stale w*h mask after a resize / quarter turn; scripts re-select
     return img
+
+
+# Selection API of the script host (scripting.rs:1359-1481): the mask is host state of the script context;
+# fill / delete run on the device as a masked constant fill.
+_SELECTION_API = {"select_rect", "select_ellipse", "clear_selection", "invert_selection", "fill_selected", "delete_selected"}
+
+
+def _selection_call(eng, name, args, img, mask):
+    import torch  # noqa: F401  (only needed for device-tier images)
+
+    h, w = int(img.shape[0]), int(img.shape[1])
+    on_dev = not isinstance(img, np.ndarray)
+
+    def to_side(m):
+        if m is None or not on_dev:
+            return m
+        import torch as _t
+        return _t.from_numpy(np.ascontiguousarray(m)).to(img.device)
+
+    def host(m):
+        return m if (m is None or isinstance(m, np.ndarray)) else m.cpu().numpy()
+
+    if name == "select_rect":  # :1359-1375, half-open [x1, x2) x [y1, y2)
+        x1, y1, x2, y2 = (int(a) for a in args)
+        cl = lambda v, hi: min(max(v, 0), hi)
+        m = np.zeros((h, w), np.uint8)
+        m[cl(y1, h):cl(y2, h), cl(x1, w):cl(x2, w)] = 255
+        return img, to_side(m)
+    if name == "select_ellipse":  # :1380-1399, f64 arithmetic
+        cx, cy, rx, ry = (float(a) for a in args)
+        rx2, ry2 = max(rx * rx, 0.001), max(ry * ry, 0.001)
+        dx = np.arange(w, dtype=np.float64)[None, :] - cx
+        dy = np.arange(h, dtype=np.float64)[:, None] - cy
+        m = np.where((dx * dx) / rx2 + (dy * dy) / ry2 <= 1.0, 255, 0).astype(np.uint8)
+        return img, to_side(m)
+    if name == "clear_selection":
+        return img, None
+    if name == "invert_selection":  # :1418-1431: no selection -> nothing selected
+        m = host(mask)
+        m = np.zeros((h, w), np.uint8) if m is None else (255 - m).astype(np.uint8)
+        return img, to_side(m)
+    # fill_selected(r, g, b, a) / delete_selected(): every selected pixel becomes the colour (:1435-1481).
+    # canvas_border with a border as wide as the canvas is exactly that masked constant fill.
+    color = (0, 0, 0, 0) if name == "delete_selected" else tuple(min(max(int(a), 0), 255) for a in args)
+    return eng.canvas_border(img, 1 << 30, color, mask=mask), mask

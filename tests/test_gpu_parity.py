@@ -910,6 +910,30 @@ def test_script_runner_covers_effect_api(eng, oracle):
         execute_script_sync(eng, "for_each_pixel(3);", img)
 
 
+def test_script_selection_api(eng, oracle):
+    """tests/scripting.rs:266-400: select_rect / select_ellipse / invert / clear / fill / delete drive the
+    mask the effects honour."""
+    import torch
+    from paintfe_b200.script import execute_script_sync
+
+    img = fx.gradient(64, 64)
+    rect = np.zeros((64, 64), np.uint8); rect[10:40, 5:30] = 255
+    exact(execute_script_sync(eng, "select_rect(5, 10, 30, 40); apply_blur(3.0);", img, exact=True), oracle.gaussian_blur(img, 3.0, mask=rect))
+    exact(execute_script_sync(eng, "select_rect(5, 10, 30, 40); invert_selection(); apply_box_blur(2);", img),
+          oracle.box_blur(img, 2.0, mask=255 - rect))
+    exact(execute_script_sync(eng, "select_rect(-5, -5, 500, 500); clear_selection(); apply_median(1);", img), oracle.median(img, 1))
+    yy, xx = np.mgrid[0:64, 0:64].astype(np.float64)
+    ell = np.where(((xx - 32.0) ** 2) / 100.0 + ((yy - 20.0) ** 2) / 400.0 <= 1.0, 255, 0).astype(np.uint8)
+    exact(execute_script_sync(eng, "select_ellipse(32.0, 20.0, 10.0, 20.0); apply_vignette(0.8, 0.5);", img), oracle.vignette(img, 0.8, 0.5, mask=ell))
+    want = img.copy(); want[rect > 0] = (9, 8, 7, 200)
+    exact(execute_script_sync(eng, "select_rect(5, 10, 30, 40); fill_selected(9, 8, 7, 200);", img), want)
+    want = img.copy(); want[rect > 0] = 0
+    dev = execute_script_sync(eng, "select_rect(5, 10, 30, 40); delete_selected();", torch.from_numpy(img).cuda())
+    exact(dev.cpu().numpy(), want)
+    exact(execute_script_sync(eng, "invert_selection(); fill_selected(1, 2, 3, 4);", img), img)  # nothing selected
+    exact(execute_script_sync(eng, "delete_selected();", img), np.zeros_like(img))                 # no mask = everything
+
+
 def test_host_tier_band_pipeline(eng, oracle):
     """pfe_flatten / pfe_flatten_gaussian pipeline uploads, compute and downloads in row bands once the
     image exceeds 8 MB; the result must equal the unpipelined device tier, including a blur radius larger
