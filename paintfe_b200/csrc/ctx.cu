@@ -1,6 +1,7 @@
 // Context, memory helpers and the host-pointer tier of the C ABI.
 // The host tier is plumbing only: copy in, call the pfe_dev_* entry point, copy out.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <algorithm>
@@ -152,6 +153,7 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->dev_small) cudaFree(c->dev_small);
+    if (c->gauss_mem) cudaFree(c->gauss_mem);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < 2; i++) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -165,14 +167,21 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     return PFE_OK;
 }
 
+// the device-resident weight tables are ordered on the stream that filled them: forget them on a switch
+static void drop_stream_ordered_caches(pfe_ctx *c) {
+    for (auto &g : c->gauss_slots) g.valid = false;
+}
+
 int pfe_ctx_set_stream(pfe_ctx *c, void *s) {
     if (!c) return PFE_ERR_INVALID_ARG;
+    if (c->stream != (cudaStream_t)s) drop_stream_ordered_caches(c);
     c->stream = (cudaStream_t)s;
     return PFE_OK;
 }
 
 int pfe_ctx_use_own_stream(pfe_ctx *c) {
     if (!c) return PFE_ERR_INVALID_ARG;
+    if (c->stream != c->own_stream) drop_stream_ordered_caches(c);
     c->stream = c->own_stream;
     return PFE_OK;
 }
@@ -536,7 +545,8 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
     }
     // band height: ~8 bands, 64-row aligned; small images go through in one band
     uint32_t band_h = h;
-    if (n4 >= (size_t)8 << 20) band_h = std::max<uint32_t>(PFE_CHUNK_SIZE, ((h / 8 + PFE_CHUNK_SIZE - 1) / PFE_CHUNK_SIZE) * PFE_CHUNK_SIZE);
+    static const uint32_t want_bands = getenv("PFE_PIPE_BANDS") ? (uint32_t)std::max(1, atoi(getenv("PFE_PIPE_BANDS"))) : 8u;  // tuning aid
+    if (n4 >= (size_t)8 << 20) band_h = std::max<uint32_t>(PFE_CHUNK_SIZE, ((h / want_bands + PFE_CHUNK_SIZE - 1) / PFE_CHUNK_SIZE) * PFE_CHUNK_SIZE);
     const uint32_t nbands = pfe_div_up(h, band_h);
 
     // the upload stream must not overwrite buffers that earlier work on ctx->stream still reads
@@ -553,6 +563,12 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
         return e;
     };
     int rc = PFE_OK;
+    static const bool dbg = getenv("PFE_PIPE_DEBUG") != nullptr;  // tuning aid: where the call's time goes
+    cudaEvent_t t0 = nullptr, t_up = nullptr, t_cmp = nullptr, t_dn = nullptr;
+    if (dbg) {
+        cudaEventCreate(&t0); cudaEventCreate(&t_up); cudaEventCreate(&t_cmp); cudaEventCreate(&t_dn);
+        cudaEventRecord(t0, ctx->copy_stream);
+    }
     uint32_t v_next = 0;  // first band whose V pass (or download) has not been issued yet
     auto download_band = [&](uint32_t k) -> int {
         const uint32_t y0 = k * band_h, rows = std::min(band_h, h - y0);
@@ -597,8 +613,15 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
             v_next++;
         }
     }
+    if (dbg) { cudaEventRecord(t_up, ctx->copy_stream); cudaEventRecord(t_cmp, ctx->stream); cudaEventRecord(t_dn, ctx->d2h_stream); }
     cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream), e2 = cudaStreamSynchronize(ctx->stream),
                 e3 = cudaStreamSynchronize(ctx->d2h_stream);
+    if (dbg) {
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, t0, t_up); cudaEventElapsedTime(&b, t0, t_cmp); cudaEventElapsedTime(&c, t0, t_dn);
+        fprintf(stderr, "[pfe pipe] uploads done %.2f ms, compute done %.2f ms, downloads done %.2f ms (bands %u)\n", a, b, c, nbands);
+        cudaEventDestroy(t0); cudaEventDestroy(t_up); cudaEventDestroy(t_cmp); cudaEventDestroy(t_dn);
+    }
     for (cudaEvent_t e : events) cudaEventDestroy(e);
     if (rc != PFE_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)

@@ -43,6 +43,7 @@ struct GaussParams {
     uint32_t rw, rh;      // region size
     uint32_t v_y0, v_rows; // V pass: produce output rows [v_y0, v_y0 + v_rows) only (band pipelining)
     int radius;
+    float sigma;          // host side only: key of the device-resident weight table
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
 };
@@ -415,21 +416,46 @@ std::vector<float> build_kernel(float sigma, int *radius_out) {
 
 // Padded, duplicated weights for register-block size N: wp[m] = (w, w)[m-(N-1)] inside the support.
 template <int N>
-int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k) {
+int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, float sigma) {
     const int taps = (int)k.size();
     P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
     P.wp_len = P.steps + N - 1;
+    const size_t bytes = (size_t)P.wp_len * sizeof(float2);
+    uint32_t sigma_bits;
+    memcpy(&sigma_bits, &sigma, 4);
+    const bool cacheable = bytes <= pfe_ctx::kGaussSlotBytes;
+    if (cacheable) {
+        if (!ctx->gauss_mem) PFE_CUDA(ctx, cudaMalloc(&ctx->gauss_mem, pfe_ctx::kGaussSlots * pfe_ctx::kGaussSlotBytes));
+        for (int i = 0; i < pfe_ctx::kGaussSlots; i++) {
+            pfe_ctx::GaussSlot &g = ctx->gauss_slots[i];
+            if (g.valid && g.sigma_bits == sigma_bits && g.n == N) {  // the table is already on the device
+                g.stamp = ++ctx->gauss_clock;
+                P.wp = (const float2 *)((char *)ctx->gauss_mem + (size_t)i * pfe_ctx::kGaussSlotBytes);
+                return PFE_OK;
+            }
+        }
+    }
     std::vector<float2> wp((size_t)P.wp_len, make_float2(0.0f, 0.0f));
     for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
     void *wdev;
-    PFE_TRY(pfe_small_upload(ctx, wp.data(), wp.size() * sizeof(float2), &wdev));
+    PFE_TRY(pfe_small_upload(ctx, wp.data(), bytes, &wdev));
     P.wp = (const float2 *)wdev;
+    if (cacheable) {  // keep a copy in the least recently used slot (stream ordered after its last reader)
+        int lru = 0;
+        for (int i = 0; i < pfe_ctx::kGaussSlots; i++) {
+            if (!ctx->gauss_slots[i].valid) { lru = i; break; }
+            if (ctx->gauss_slots[i].stamp < ctx->gauss_slots[lru].stamp) lru = i;
+        }
+        void *slot = (char *)ctx->gauss_mem + (size_t)lru * pfe_ctx::kGaussSlotBytes;
+        PFE_CUDA(ctx, cudaMemcpyAsync(slot, wdev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->gauss_slots[lru] = pfe_ctx::GaussSlot{sigma_bits, N, ++ctx->gauss_clock, true};
+    }
     return PFE_OK;
 }
 
 template <int N, bool EXACT>
 int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
-    PFE_TRY(upload_weights<N>(ctx, P, k));
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
     const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     int warps = 4;
@@ -453,7 +479,7 @@ int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
 // V pass: tile variant when its shared-memory footprint fits, else the direct variant
 template <int N, bool EXACT>
 int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
-    PFE_TRY(upload_weights<N>(ctx, P, k));
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
     const int wp_pad = (P.wp_len + 1) & ~1;
     const size_t extra = (size_t)wp_pad * 8 + 16 * kChunks + 64;
     auto tile_smem = [&](int warps) {
@@ -537,7 +563,7 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     P.src = src; P.mid = (float *)mid; P.dst = dst;
     P.orig = orig; P.mask = mask; P.amount = amount; P.epilogue = orig ? epilogue : 0;
     P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
-    P.rw = rw; P.rh = rh; P.radius = radius;
+    P.rw = rw; P.rh = rh; P.radius = radius; P.sigma = sigma;
     P.v_y0 = 0; P.v_rows = rh;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_n<true>(ctx, P, k) : dispatch_n<false>(ctx, P, k);
 }
@@ -555,7 +581,7 @@ int pfe_gauss_h_rows(pfe_ctx *ctx, const uint8_t *src, float *mid, uint32_t w, u
     GaussParams P;
     memset(&P, 0, sizeof(P));
     P.src = src + (size_t)y0 * w * 4; P.mid = mid + (size_t)y0 * w * 4;
-    P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = rows; P.radius = radius;
+    P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = rows; P.radius = radius; P.sigma = sigma;
     (void)h;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_h<true>(ctx, P, k) : dispatch_h<false>(ctx, P, k);
 }
@@ -565,7 +591,7 @@ int pfe_gauss_v_rows(pfe_ctx *ctx, float *mid, uint8_t *dst, uint32_t w, uint32_
     std::vector<float> k = build_kernel(sigma, &radius);
     GaussParams P;
     memset(&P, 0, sizeof(P));
-    P.mid = mid; P.dst = dst; P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius;
+    P.mid = mid; P.dst = dst; P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius; P.sigma = sigma;
     P.v_y0 = y0; P.v_rows = rows;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_v<true>(ctx, P, k) : dispatch_v<false>(ctx, P, k);
 }
