@@ -547,7 +547,18 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
     uint32_t band_h = h;
     static const uint32_t want_bands = getenv("PFE_PIPE_BANDS") ? (uint32_t)std::max(1, atoi(getenv("PFE_PIPE_BANDS"))) : 8u;  // tuning aid
     if (n4 >= (size_t)8 << 20) band_h = std::max<uint32_t>(PFE_CHUNK_SIZE, ((h / want_bands + PFE_CHUNK_SIZE - 1) / PFE_CHUNK_SIZE) * PFE_CHUNK_SIZE);
-    const uint32_t nbands = pfe_div_up(h, band_h);
+    // Band list: regular bands, then the last stretch in shrinking pieces (down to one chunk row), because
+    // what remains exposed after the last upload is the compute and download of the final band(s) only.
+    std::vector<uint32_t> band_y0, band_rows;
+    for (uint32_t y = 0; y < h;) {
+        uint32_t rows = std::min(band_h, h - y);
+        if (band_h < h && h - y <= band_h && rows > PFE_CHUNK_SIZE)
+            rows = std::max<uint32_t>(PFE_CHUNK_SIZE, ((rows / 2 + PFE_CHUNK_SIZE - 1) / PFE_CHUNK_SIZE) * PFE_CHUNK_SIZE);
+        band_y0.push_back(y);
+        band_rows.push_back(rows);
+        y += rows;
+    }
+    const uint32_t nbands = (uint32_t)band_y0.size();
 
     // the upload stream must not overwrite buffers that earlier work on ctx->stream still reads
     PFE_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->stream));
@@ -555,6 +566,16 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
     PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_copy, 0));
     if (active) PFE_CUDA(ctx, cudaMemcpyAsync(active_dev, active, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
 
+    // are all layer (and mask) buffers page-locked?
+    bool all_pinned = getenv("PFE_PIPE_NO_BATCH") == nullptr;
+    for (uint32_t i = 0; i < n && all_pinned; i++) {
+        if (!dl[i].rgba) continue;
+        for (const void *hp : {(const void *)layers[i].rgba, (const void *)layers[i].mask}) {
+            if (!hp) continue;
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, hp) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); all_pinned = false; }
+        }
+    }
     std::vector<cudaEvent_t> events;
     auto new_event = [&]() -> cudaEvent_t {
         cudaEvent_t e = nullptr;
@@ -571,7 +592,7 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
     }
     uint32_t v_next = 0;  // first band whose V pass (or download) has not been issued yet
     auto download_band = [&](uint32_t k) -> int {
-        const uint32_t y0 = k * band_h, rows = std::min(band_h, h - y0);
+        const uint32_t y0 = band_y0[k], rows = band_rows[k];
         cudaEvent_t e = new_event();
         if (!e) return pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate");
         PFE_CUDA(ctx, cudaEventRecord(e, ctx->stream));
@@ -581,20 +602,38 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
         return PFE_OK;
     };
     for (uint32_t b = 0; b < nbands && rc == PFE_OK; b++) {
-        const uint32_t y0 = b * band_h, rows = std::min(band_h, h - y0);
+        const uint32_t y0 = band_y0[b], rows = band_rows[b];
         const size_t off4 = (size_t)y0 * w * 4, off1 = (size_t)y0 * w;
         std::vector<pfe_layer_desc> bl(dl);
+        std::vector<void *> cp_dst, cp_src;
+        std::vector<size_t> cp_len;
         for (uint32_t i = 0; i < n; i++) {
             if (!dl[i].rgba) continue;
-            PFE_CUDA(ctx, cudaMemcpyAsync((void *)(dl[i].rgba + off4), layers[i].rgba + off4, (size_t)rows * w * 4,
-                                          cudaMemcpyHostToDevice, ctx->copy_stream));
+            cp_dst.push_back((void *)(dl[i].rgba + off4)); cp_src.push_back((void *)(layers[i].rgba + off4)); cp_len.push_back((size_t)rows * w * 4);
             bl[i].rgba = dl[i].rgba + off4;
             if (dl[i].mask) {
-                PFE_CUDA(ctx, cudaMemcpyAsync((void *)(dl[i].mask + off1), layers[i].mask + off1, (size_t)rows * w,
-                                              cudaMemcpyHostToDevice, ctx->copy_stream));
+                cp_dst.push_back((void *)(dl[i].mask + off1)); cp_src.push_back((void *)(layers[i].mask + off1)); cp_len.push_back((size_t)rows * w);
                 bl[i].mask = dl[i].mask + off1;
             }
         }
+        // One batched submission per band when every source is pinned (the copy engine then runs the band's
+        // copies back to back instead of paying a gap per cudaMemcpyAsync); individual copies otherwise.
+        bool batched = false;
+        if (all_pinned && cp_dst.size() > 1) {
+            cudaMemcpyAttributes attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+            size_t attr_idx = 0, fail = 0;
+            if (cudaMemcpyBatchAsync(cp_dst.data(), cp_src.data(), cp_len.data(), cp_dst.size(), &attr, &attr_idx, 1, &fail, ctx->copy_stream) == cudaSuccess)
+                batched = true;
+            else {
+                cudaGetLastError();
+                all_pinned = false;  // not supported here: stay with plain copies for the rest of the call
+            }
+        }
+        if (!batched)
+            for (size_t c = 0; c < cp_dst.size(); c++)
+                PFE_CUDA(ctx, cudaMemcpyAsync(cp_dst[c], cp_src[c], cp_len[c], cudaMemcpyHostToDevice, ctx->copy_stream));
         cudaEvent_t up = new_event();
         if (!up) { rc = pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate"); break; }
         PFE_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
@@ -606,7 +645,7 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
         rc = pfe_gauss_h_rows(ctx, flat, mid, w, h, y0, rows, sigma, flags);
         const uint32_t h_done = y0 + rows;
         while (rc == PFE_OK && v_next < nbands) {
-            const uint32_t vy0 = v_next * band_h, vrows = std::min(band_h, h - vy0);
+            const uint32_t vy0 = band_y0[v_next], vrows = band_rows[v_next];
             if (h_done < h && vy0 + vrows + (uint32_t)radius > h_done) break;  // its lower halo is not blurred yet
             rc = pfe_gauss_v_rows(ctx, mid, out, w, h, vy0, vrows, sigma, flags);
             if (rc == PFE_OK) rc = download_band(v_next);
