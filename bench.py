@@ -161,6 +161,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    _real_stdout = None
     if args.gpus > 1 and world == 1:
         port = 29500 + (os.getpid() % 2000)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
@@ -173,9 +174,12 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; rank 0's stdout must be ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner straight to fd 1 at communicator creation (whatever NCCL_DEBUG says on
+        # this image), and rank 0's stdout must be ONE JSON line: from here on everything any library writes to
+        # stdout goes to stderr, and the result line is written to the saved descriptor at the end.
+        sys.stdout.flush()
+        _real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     from paintfe_b200.engine import Engine, make_layer
@@ -335,7 +339,11 @@ def run_b200(args):
             "kernel_spans_share_of_step": span_share,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        if _real_stdout is not None:
+            sys.stdout.flush()
+            os.write(_real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
