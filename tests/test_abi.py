@@ -149,3 +149,42 @@ def test_no_cpu_fallback_without_gpu(lib):
     assert lib.pfe_ctx_create(0, C.byref(h)) == -4  # PFE_ERR_NO_DEVICE
     with pytest.raises(_lib.PfeError):
         engine.Engine(0)
+
+
+def _build_c_smoke(tmp_path):
+    from paintfe_b200 import build
+
+    build.build()
+    out = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(ROOT, "paintfe_b200")
+    r = subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-std=c99", "-Wall", "-Wextra", "-Werror",
+                        "-pedantic", "-o", out, os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-L" + libdir, "-lpfe_b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return out
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/pfe_b200.h is the drop-in boundary: it must be usable from C (cgo, Rust bindgen, ctypes all
+    assume exactly that), not only from C++."""
+    import torch
+
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ("ok: launches" in r.stdout) if torch.cuda.is_available() else ("no device" in r.stdout)
+
+
+@pytest.mark.gpu
+def test_c_caller_matches_oracle(tmp_path, oracle):
+    """The C program's flatten + blur through the host-pointer tier equals the oracle on the same inputs."""
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok: launches" in r.stdout, r.stdout + r.stderr
+    w, h = 96, 80
+    i = np.arange(w * h, dtype=np.uint32)
+    a = np.stack([(i * 7) & 255, (i * 3) & 255, np.full_like(i, 40), np.full_like(i, 255)], 1).astype(np.uint8).reshape(h, w, 4)
+    b = np.stack([np.full_like(i, 200), (i * 5) & 255, i & 255, i % 256], 1).astype(np.uint8).reshape(h, w, 4)
+    flat = oracle.flatten([oracle.make_layer(a), oracle.make_layer(b, opacity=0.5, blend=8)], w, h)
+    want = int(oracle.gaussian_blur(flat, 2.0).astype(np.uint64).sum())
+    assert f"checksum {want}" in r.stdout, (r.stdout, want)
