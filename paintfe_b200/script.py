@@ -150,8 +150,6 @@ _SELECTION_API = {"select_rect", "select_ellipse", "clear_selection", "invert_se
 
 
 def _selection_call(eng, name, args, img, mask):
-    import torch  # noqa: F401  (only needed for device-tier images)
-
     h, w = int(img.shape[0]), int(img.shape[1])
     on_dev = not isinstance(img, np.ndarray)
 
