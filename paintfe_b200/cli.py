@@ -55,7 +55,19 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
     from PIL import Image
 
     from .engine import make_layer
-    from .script import execute_script_sync
+    from .rhai_host import Interpreter, ScriptError
+    from .script import apply_canvas_ops
+
+    def run_script(pixels):  # cli.rs:247-254
+        it = Interpreter(eng, pixels, exact=exact)
+        try:
+            res = it.run(script)
+        except ScriptError as e:
+            raise RuntimeError(f"script error: {e}") from None
+        if verbose:
+            for line in it.console:
+                print(f"  [script] {line}")
+        return res, it.canvas_ops
 
     if inp.lower().endswith(".pfe"):  # io::load_image_sync -> load_pfe (io.rs:693, :469)
         from . import pfe_io
@@ -74,9 +86,17 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
 
         tables = [table(L) for L in proj.layers]
         if script:  # the script sees the active layer as a flat image and commits it back as tiles (cli.rs:239-260)
-            res = np.asarray(execute_script_sync(eng, script, proj.layers[ai].to_flat(w, h), exact=exact))
-            occ, tiles = eng.flat_to_tiles(res)
-            tables[ai] = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
+            res, canvas_ops = run_script(proj.layers[ai].to_flat(w, h))
+            flats = [np.asarray(res) if i == ai else None for i in range(len(tables))]
+            if canvas_ops:  # canvas-wide calls (resize, quarter turns, ...) are replayed on the other layers (cli.rs:262-266)
+                flats = [f if i == ai else (None if L.adjustment is not None else L.to_flat(w, h))
+                         for i, (f, L) in enumerate(zip(flats, proj.layers))]
+                flats = [None if f is None else np.asarray(f) for f in apply_canvas_ops(eng, flats, ai, canvas_ops)]
+            h, w = flats[ai].shape[:2]
+            for i, f in enumerate(flats):
+                if f is not None:
+                    occ, tiles = eng.flat_to_tiles(f)
+                    tables[i] = [tiles[k] if occ.reshape(-1)[k] else None for k in range(occ.size)]
         if flatten and len(tables) > 1:  # cli.rs:282-285 state.composite(): straight from the chunk tables
             descs = []
             for i, (t, L) in enumerate(zip(tables, proj.layers)):
@@ -93,7 +113,7 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
     else:
         img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
         if script:
-            img = execute_script_sync(eng, script, img, exact=exact)
+            img = run_script(img)[0]
     os.makedirs(os.path.dirname(os.path.abspath(outp)), exist_ok=True)
     Image.fromarray(np.asarray(img), "RGBA").save(outp)
 

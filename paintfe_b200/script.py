@@ -9,8 +9,9 @@ without a Rust toolchain.  Each binding maps to the entry point that replaces th
 it calls, with the reference's fixed arguments (e.g. apply_sharpen uses radius 1.0, scripting.rs:847).
 Covered: every `apply_*` effect, the flips / rotations, `resize_image`, `resize_canvas` and the selection API
 (`select_rect`, `select_ellipse`, `clear_selection`, `invert_selection`, `fill_selected`, `delete_selected`).
-Anything that is not a plain `name(literals...)` call - closures (`for_each_pixel`, `map_channels`), variables,
-control flow - raises: there is no interpreter here.
+`execute_script_sync` runs a script through paintfe_b200.rhai_host, the interpreter for the host language around
+these calls (variables, control flow, closures, the pixel / utility API); `parse` remains as the splitter for
+straight-line scripts.
 """
 from __future__ import annotations
 
@@ -129,19 +130,26 @@ def execute_script_sync(eng, source: str, pixels, mask=None, exact: bool = False
     `pixels` may be a numpy array (host tier) or a CUDA tensor (device tier: the whole script runs
     without leaving the device). `exact` selects the bit-exact Gaussian (PFE_GAUSS_EXACT) over the
     default FMA path (<= 1 level)."""
-    table = bindings(eng, exact)
-    img = pixels
-    for name, args in parse(source):
-        if name in _SELECTION_API:
-            img, mask = _selection_call(eng, name, args, img, mask)
-            continue
-        if name not in table:
-            raise ValueError(f"effect {name!r} is outside the B200 hot path (see DESIGN.md, out of scope)")
-        h0, w0 = img.shape[:2]
-        img = table[name](img, mask, *args)
-        if mask is not None and tuple(img.shape[:2]) != (h0, w0):
-            mask = None  # the reference keeps a stale w*h mask after a resize / quarter turn; scripts re-select
-    return img
+    from .rhai_host import run_script
+    return run_script(eng, source, pixels, mask, exact)[0]
+
+
+# Calls that log a CanvasOpRequest (scripting.rs:687-813): the caller replays them on every other layer.
+CANVAS_OPS = {"flip_canvas_horizontal", "flip_canvas_vertical", "rotate_canvas_90cw", "rotate_canvas_90ccw", "rotate_canvas_180",
+              "resize_image", "resize_canvas"}
+
+
+def apply_canvas_ops(eng, layers, active_index: int, canvas_ops):
+    """scripting::apply_canvas_ops (scripting.rs:1640): replay the logged canvas-wide calls, in order, on every layer
+    image except the active one (which the script already transformed).  `layers` are flat RGBA images (host arrays or
+    device tensors) of the pre-script canvas size; returns the new list."""
+    table = bindings(eng)
+    out = list(layers)
+    for name, args in canvas_ops:
+        for i, img in enumerate(out):
+            if i != active_index and img is not None:
+                out[i] = table[name](img, None, *args)
+    return out
 
 
 # Selection API of the script host (scripting.rs:1359-1481): the mask is host state of the script context;

@@ -879,6 +879,72 @@ def test_error_statuses_of_widened_entry_points(eng):
     exact(eng.orient(eng.orient(img, 0), 0), img, "context still usable")
 
 
+def test_script_host_on_device(eng, oracle):
+    """paintfe_b200/rhai_host.py against the CUDA path: control flow around effect calls, pixel access between them and
+    closures, on host arrays (host tier) and on a CUDA tensor (device tier, pending set_pixel writes carried over)."""
+    import torch
+
+    from paintfe_b200.rhai_host import run_script
+    from test_rhai_host import OracleEngine
+
+    class Ref(OracleEngine):
+        def box_blur(self, img, radius, mask=None):
+            return self.o.box_blur(img, radius, mask=mask)
+
+        def median(self, img, radius, mask=None):
+            return self.o.median(img, radius, mask=mask)
+
+    source = """
+        fn passes(n) { if n > 2 { 2 } else { n } }
+        set_pixel(3, 2, 250, 10, 20, 255);
+        for i in 0..passes(5) { apply_box_blur(i + 1); }
+        let p = get_pixel(3, 2); print(`${p}`);
+        select_ellipse(40.0, 30.0, 25.0, 18.0);
+        if has_selection() && p[3] == 255 { apply_median(1); apply_invert(); }
+        for_each_pixel(|x, y, r, g, b, a| { if is_selected(x, y) { [r, b, g, a] } else { [r / 2, g, b, a] } });
+        set_pixel(0, 0, 1, 2, 3, 4);
+        invert_selection(); fill_selected(9, 8, 7, 255);
+        rotate_canvas_90cw();
+        print(`${width()}x${height()} ${get_pixel(width() - 1, 0)}`);
+        apply_pixelate(3);
+    """
+    img = fx.random_rgba(np.random.default_rng(12), 96, 64, alpha="opaque")
+    want, console = run_script(Ref(oracle), source, img)
+    got, con_host = run_script(eng, source, img)
+    exact(got, want, "script host, host tier")
+    dev, con_dev = run_script(eng, source, torch.from_numpy(img).cuda())
+    assert dev.is_cuda
+    exact(dev.cpu().numpy(), want, "script host, device tier")
+    assert console == con_host == con_dev and console[1].startswith("64x96 ")
+    exact(run_script(eng, "for_each_pixel(|x, y, r, g, b, a| { [255 - r, 255 - g, 255 - b, a] });", fx.gradient(64, 64))[0],
+          fx.golden("scripting", "for_each_pixel_invert"))
+
+
+def test_cli_script_canvas_ops_replayed_on_other_layers(eng, oracle, tmp_path, capsys):
+    """cli.rs:247-266: console lines under --verbose, canvas-wide calls replayed on the non-active layers."""
+    from PIL import Image
+
+    from paintfe_b200 import cli, pfe_io
+
+    rng = np.random.default_rng(21)
+    w, h = 150, 90
+    bg, top = fx.random_rgba(rng, w, h, alpha="opaque"), fx.random_rgba(rng, w, h)
+    proj = pfe_io.PfeProject(w, h, 1, [pfe_io.layer_from_flat("bg", bg), pfe_io.layer_from_flat("top", top, opacity=0.7, blend_mode=3)])
+    (tmp_path / "p.pfe").write_bytes(pfe_io.save_pfe_v3(proj))
+    script = tmp_path / "s.rhai"
+    script.write_text('let w = width();\nif w > 100 { rotate_canvas_90ccw(); resize_image(60, 100, "bicubic"); }\n'
+                      'apply_invert(); print_line(`now ${width()}x${height()}`);\n')
+    assert cli.main(["-i", str(tmp_path / "p.pfe"), "-s", str(script), "-o", str(tmp_path / "o.png"), "-v"]) == 0
+    assert "  [script] now 60x100" in capsys.readouterr().out
+    tf = lambda im: oracle.resize(oracle.orient(im, oracle.ROT90CCW), 60, 100, 2)
+    top2 = oracle.adjust(tf(top), 32)
+    exp = oracle.flatten([oracle.make_layer(tf(bg)), oracle.make_layer(top2, opacity=0.7, blend=3)], 60, 100)
+    exact(np.array(Image.open(tmp_path / "o.png").convert("RGBA")), exp, "cli script with canvas ops")
+    script.write_text("let x = 1 / 0;\n")
+    assert cli.main(["-i", str(tmp_path / "p.pfe"), "-s", str(script), "-o", str(tmp_path / "o2.png")]) == 1
+    assert "script error" in capsys.readouterr().err
+
+
 def test_script_runner_covers_effect_api(eng, oracle):
     """The Rhai bindings' fixed arguments (scripting.rs:822-1165) through the script runner."""
     from paintfe_b200.script import execute_script_sync
