@@ -29,7 +29,7 @@ from typing import Any, Callable, Dict, List, Optional
 import numpy as np
 
 
-class ScriptError(Exception):
+class ScriptError(ValueError):
     """ScriptError of scripting.rs:90: message plus the source line when it is known."""
 
     def __init__(self, message: str, line: Optional[int] = None):
