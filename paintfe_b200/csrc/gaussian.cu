@@ -46,6 +46,7 @@ struct GaussParams {
     float sigma;          // host side only: key of the device-resident weight table
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
+    int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
 };
 
 // One RGBA accumulator as two packed f32x2 halves: sm_100's FFMA2 / FMUL2 / FADD2 retire two IEEE
@@ -83,6 +84,14 @@ __device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2
 
 __host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
+// u8 -> f32 uses PRMT + FADD against 2^23 (ALU/FMA pipes) instead of the quarter-rate I2F:
+// 0x4B0000xx is 2^23 + xx as a float, so one PRMT per channel and an exact subtract.
+__device__ __forceinline__ float4 to_f4(uint32_t v) {
+    const float m = 8388608.0f;
+    return make_float4(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - m,
+                       __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - m);
+}
+
 // ---- H pass: u8 -> f32 ----------------------------------------------------------------------
 // A warp owns one row segment of 32*N pixels. The u8 pixels are converted to f32 once while being
 // staged into a skewed shared-memory tile (one pad float4 every N, so lane stride N+1 keeps
@@ -105,13 +114,6 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     const uint64_t ntask = (uint64_t)nseg * P.rh;
     const int rw = (int)P.rw;
 
-    // u8 -> f32 uses PRMT + FADD against 2^23 (ALU/FMA pipes) instead of the quarter-rate I2F:
-    // 0x4B0000xx is 2^23 + xx as a float, so one PRMT per channel and an exact subtract.
-    auto to_f4 = [](uint32_t v) {
-        const float m = 8388608.0f;
-        return make_float4(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - m,
-                           __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - m, __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - m);
-    };
     for (uint64_t task = (uint64_t)blockIdx.x * WARPS + warp; task < ntask; task += (uint64_t)gridDim.x * WARPS) {
         const uint32_t y = (uint32_t)(task / nseg);
         const int x0 = (int)(task % nseg) * SEG;
@@ -361,6 +363,129 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     }
 }
 
+// ---- Fused H+V for small radii ------------------------------------------------------------------
+// For small radii (use_fused below) the f32 intermediate never leaves the SM.  A CTA walks down a 128-pixel-wide
+// strip segment in batches of 8 rows.  Per batch:
+//   H phase: warp w turns source row (batch row w) into one row of the intermediate, exactly as gauss_h_kernel
+//            does (u8 -> f32 once into a skewed per-warp tile, lane owns 4 consecutive outputs), but the result
+//            goes into a shared-memory ring of (lag+1) batches instead of HBM;
+//   V phase: 256 threads = 128 columns x 2 half-batches; a thread streams 4 + 2r ring rows past its 4 outputs
+//            (conflict-free LDS.128, lanes run along x) and stores u8 - with the sharpen / glow epilogue if set.
+// The V phase runs `lag` = ceil(2r/8) batches behind the H phase, so every input row is filtered horizontally
+// once per segment (plus 2r warm-up rows at the head of a segment) and the image crosses HBM once in, once out:
+// 8 B per pixel instead of the two-pass 40 B.  Tap order and arithmetic are those of the two-pass kernels, so
+// the results are identical to theirs in both modes.
+constexpr int kFusedMaxRadius = 16;
+constexpr int kFusedTW = 128;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_constant__ GaussParams P) {
+    constexpr int N = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
+    const int wp_pad = (P.wp_len + 1) & ~1;
+    const int tile_px = 31 * N + P.steps;
+    const int tile_len = skew(tile_px, N) + 1;
+    float4 *tiles = reinterpret_cast<float4 *>(wsm + wp_pad);
+    float4 *ring = tiles + (size_t)8 * tile_len;  // ring_rows x 128 float4
+    const int ring_rows = (P.lag + 1) * 8;
+    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *tile = tiles + (size_t)warp * tile_len;
+    const int rw = (int)P.rw, rh = (int)P.rh, r = P.radius;
+    const int nstrips = (rw + kFusedTW - 1) / kFusedTW;
+    const int ntask = nstrips * P.nseg;
+    const int vc = threadIdx.x & 127, vhalf = threadIdx.x >> 7;
+
+    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+        // consecutive CTAs take neighbouring strips of one segment: their halo columns are L2-hot
+        const int x0 = (task % nstrips) * kFusedTW;
+        const int ys = (task / nstrips) * P.seg_rows, ye = min(ys + P.seg_rows, rh);
+        const int nb = (ye - ys + 7) / 8 + P.lag;
+        int hslot = 0;  // ring batch the H phase writes: b mod (lag+1)
+        int vslot = 0;  // ring batch holding the first row the V phase reads: (b - lag) mod (lag+1)
+        // source pixels of the NEXT batch travel in registers while this batch is being filtered
+        // (tile_px <= 31*4 + 36 = 160 = 5 per lane)
+        uint32_t pre[5];
+        auto fetch = [&](int b) {
+            const int yy = min(max(ys - r + 8 * b + warp, 0), rh - 1);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)yy * P.src_pitch;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                const int p = lane + 32 * i;
+                pre[i] = p < tile_px ? __ldg(row + min(max(x0 - r + p, 0), rw - 1)) : 0u;
+            }
+        };
+        fetch(0);
+        for (int b = 0; b < nb; b++) {
+            {   // ===== H phase: intermediate row ys - r + 8b + warp (clamp-to-edge is a clamped source row) =====
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                    const int p = lane + 32 * i;
+                    if (p < tile_px) tile[skew(p, N)] = to_f4(pre[i]);
+                }
+                if (b + 1 < nb) fetch(b + 1);
+                __syncwarp();
+                Acc4 acc[N];
+                float2 R[N];
+#pragma unroll
+                for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+                const float4 *tl = tile + lane * (N + 1);
+                for (int g = 0; g < P.steps; g += N) {
+                    const float4 *tg = tl + g + g / N;
+#define F_HLOAD(s) tg[s]
+                    PFE_GAUSS_GROUP(F_HLOAD)
+#undef F_HLOAD
+                }
+                float4 *mrow = ring + (size_t)(hslot * 8 + warp) * kFusedTW + lane * N;
+#pragma unroll
+                for (int j = 0; j < N; j++) mrow[j] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
+                if (++hslot > P.lag) hslot = 0;
+            }
+            __syncthreads();  // batch b of the intermediate is complete
+            if (b >= P.lag) {
+                // ===== V phase: output rows ys + 8(b-lag) + 4*vhalf + [0,4); first ring row = that minus r =====
+                const int yo = ys + 8 * (b - P.lag) + 4 * vhalf;
+                int slot = vslot * 8 + 4 * vhalf;  // a multiple of 4: a group of 4 rows never straddles the wrap
+                Acc4 acc[N];
+                float2 R[N];
+#pragma unroll
+                for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+                for (int g = 0; g < P.steps; g += N) {
+                    const float4 *cg = ring + (size_t)slot * kFusedTW + vc;
+#define F_VLOAD(s) cg[(s) * kFusedTW]
+                    PFE_GAUSS_GROUP(F_VLOAD)
+#undef F_VLOAD
+                    slot += N;
+                    if (slot >= ring_rows) slot -= ring_rows;
+                }
+                const int x = x0 + vc;
+                if (x < rw) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        if (yo + j >= ye) break;
+                        if (P.orig) {
+                            v_store(P, acc[j], x, yo + j);
+                        } else {
+                            reinterpret_cast<uint32_t *>(P.dst)[(size_t)(yo + j) * P.dst_pitch + x] =
+                                pfe_pack(round_u8_nonneg(acc[j].lo.x), round_u8_nonneg(acc[j].lo.y), round_u8_nonneg(acc[j].hi.x),
+                                         round_u8_nonneg(acc[j].hi.y));
+                        }
+                    }
+                }
+                if (++vslot > P.lag) vslot = 0;
+            }
+            __syncthreads();  // the V phase is done with the batch the next H phase overwrites
+        }
+    }
+}
+
 // blur_with_selection's copy-back (filters.rs:183-200): dst = mask > 0 ? blurred : src
 __global__ void select_kernel(const uint32_t *src, const uint32_t *blur, const uint8_t *mask, uint32_t *dst,
                               size_t n) {
@@ -544,8 +669,51 @@ int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
     }
 }
 
+// Fused H+V launch: segments are sized so that one wave of resident CTAs covers the image, but never so short that
+// the 2r warm-up rows at the head of a segment dominate.
+template <bool EXACT>
+int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+    constexpr int N = 4;
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    P.lag = (2 * P.radius + 7) / 8;
+    const int wp_pad = (P.wp_len + 1) & ~1;
+    const int tile_len = skew(31 * N + P.steps, N) + 1;
+    const size_t smem = (size_t)wp_pad * 8 + (size_t)8 * tile_len * 16 + (size_t)(P.lag + 1) * 8 * kFusedTW * 16;
+    PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned nstrips = pfe_div_up(P.rw, kFusedTW);
+    const unsigned resident = pfe_persistent_grid(ctx, gauss_fused_kernel<EXACT>, 256, smem, 0xFFFFFFFFu);
+    // segments per strip: fill whole waves of resident CTAs without letting the 2r warm-up rows of a segment dominate
+    const unsigned max_seg = std::max(1u, P.rh / (unsigned)std::max(64, 48 * P.lag));
+    unsigned nseg = 1;
+    double best = 0.0;
+    for (unsigned n = 1; n <= max_seg; n++) {
+        const double tasks = (double)nstrips * n, seg = (double)P.rh / n;
+        const double eff = tasks / (std::ceil(tasks / resident) * resident) * seg / (seg + P.radius);
+        if (eff > best + 1e-9) { best = eff; nseg = n; }
+    }
+    if (const char *force = getenv("PFE_GAUSS_FUSED_SEGS")) nseg = std::max(1, atoi(force));  // tuning aid
+    P.seg_rows = (int)(pfe_div_up(pfe_div_up(P.rh, nseg), 8) * 8);
+    P.nseg = (int)pfe_div_up(P.rh, (unsigned)P.seg_rows);
+    const unsigned blocks = std::min(resident, nstrips * (unsigned)P.nseg);
+    PFE_KERNEL(ctx, "gauss_fused", gauss_fused_kernel<EXACT><<<blocks, 256, smem, ctx->stream>>>(P));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+// The fused kernel wins where the two-pass pair is bound by the f32 intermediate's HBM round trip: small radii on
+// images with enough strip segments to occupy every SM (measured on B200, profiles/r01_gauss_fused.jsonl: 10-20%
+// faster up to radius 6, level at radius 12, slower beyond and on small images).  PFE_GAUSS_FUSED=1 / =0 force it.
+static bool use_fused(const pfe_ctx *ctx, int radius, uint32_t rw, uint32_t rh) {
+    if (radius < 1 || radius > kFusedMaxRadius) return false;
+    if (const char *force = getenv("PFE_GAUSS_FUSED")) return atoi(force) != 0;
+    const int lag = (2 * radius + 7) / 8;
+    const uint64_t tasks = (uint64_t)pfe_div_up(rw, kFusedTW) * std::max(1u, rh / (unsigned)std::max(64, 48 * lag));
+    return radius <= 12 && tasks >= (uint64_t)ctx->sm_count;
+}
+
 template <bool EXACT>
 int dispatch_n(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
+    if (use_fused(ctx, P.radius, P.rw, P.rh)) return run_fused<EXACT>(ctx, P, k);
     PFE_TRY(dispatch_h<EXACT>(ctx, P, k));
     return dispatch_v<EXACT>(ctx, P, k);
 }
@@ -556,8 +724,8 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     int radius;
     std::vector<float> k = build_kernel(sigma, &radius);
     if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
-    void *mid;
-    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)rw * rh * 16, &mid));
+    void *mid = nullptr;  // the fused kernel keeps the intermediate in shared memory
+    if (!use_fused(ctx, radius, rw, rh)) PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)rw * rh * 16, &mid));
     GaussParams P;
     memset(&P, 0, sizeof(P));
     P.src = src; P.mid = (float *)mid; P.dst = dst;

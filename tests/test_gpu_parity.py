@@ -278,6 +278,40 @@ def test_gaussian_random(eng, oracle, w, h, sigma):
     within1(eng.gaussian_blur(img, sigma), exp, f"fast {w}x{h} s={sigma}")
 
 
+@pytest.mark.parametrize("w,h", [(300, 200), (129, 77), (1, 50), (50, 1), (640, 481)])
+@pytest.mark.parametrize("sigma", [0.2, 1.0, 2.5, 4.0, 5.3])
+def test_gaussian_fused_small_radius(eng, oracle, monkeypatch, w, h, sigma):
+    """The fused H+V kernel (radius <= 16; normally picked for large images only) forced on small ones: bit-exact
+    with the oracle in exact mode, identical to the two-pass kernels in FMA mode, epilogues and selection included."""
+    rng = np.random.default_rng(int(sigma * 10) + 7 * w)
+    img = fx.random_rgba(rng, w, h)
+    mask = (rng.random((h, w)) < 0.5).astype(np.uint8) * 255
+    monkeypatch.setenv("PFE_GAUSS_FUSED", "0")
+    two_pass = [eng.gaussian_blur(img, sigma), eng.sharpen(img, 1.5, sigma), eng.glow(img, sigma, 0.7, mask=mask)]
+    monkeypatch.setenv("PFE_GAUSS_FUSED", "1")
+    exact(eng.gaussian_blur(img, sigma, exact=True), oracle.gaussian_blur(img, sigma), f"fused exact {w}x{h} s={sigma}")
+    exact(eng.gaussian_blur(img, sigma, mask=mask, exact=True), oracle.gaussian_blur(img, sigma, mask=mask), "fused, selection crop")
+    exact(eng.sharpen(img, 1.5, sigma, mask=mask, exact=True), oracle.sharpen(img, 1.5, sigma, mask=mask), "fused sharpen")
+    exact(eng.glow(img, sigma, 0.7, exact=True), oracle.glow(img, sigma, 0.7), "fused glow")
+    for got, ref, what in zip([eng.gaussian_blur(img, sigma), eng.sharpen(img, 1.5, sigma), eng.glow(img, sigma, 0.7, mask=mask)],
+                              two_pass, ("blur", "sharpen", "glow")):
+        exact(got, ref, f"fused FMA {what} == two-pass FMA {what}")
+
+
+def test_gaussian_fused_is_picked_for_large_images(eng, oracle):
+    """4K, sigma 2: the dispatcher takes the fused kernel by itself (launch counter: 1 kernel instead of 2)."""
+    import torch
+
+    img = torch.randint(0, 256, (2160, 3840, 4), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    n0 = eng.launches
+    blurred = eng.gaussian_blur(img, 2.0, exact=True)
+    assert eng.launches - n0 == 1
+    y0, x0 = 1000, 1800  # interior window against the oracle on a crop with a radius-6 apron
+    crop = img[y0 - 6:y0 + 70, x0 - 6:x0 + 134].cpu().numpy()
+    exact(blurred[y0:y0 + 64, x0:x0 + 128].cpu().numpy(), oracle.gaussian_blur(crop, 2.0)[6:70, 6:134], "4K fused window")
+    exact(blurred[:40, :200].cpu().numpy(), oracle.gaussian_blur(img[:46, :206].cpu().numpy(), 2.0)[:40, :200], "4K fused corner")
+
+
 def test_gaussian_selection_mask(eng, oracle):
     rng = np.random.default_rng(2)
     w, h = 300, 200

@@ -34,6 +34,12 @@ check("flatten", eng.flatten([make_layer(im, **m) for im, m in zip(layers, meta)
 for s in (2.0, 20.0):
     check(f"gaussian exact s={s}", eng.gaussian_blur(img, s, exact=True), pfo.gaussian_blur(img, s))
     check(f"gaussian fast s={s}", eng.gaussian_blur(img, s), pfo.gaussian_blur(img, s), 1)
+os.environ["PFE_GAUSS_FUSED"] = "1"  # the fused small-radius kernel, which the dispatcher keeps for large images
+for s in (0.3, 1.0, 5.3):
+    check(f"gaussian fused exact s={s}", eng.gaussian_blur(img, s, exact=True), pfo.gaussian_blur(img, s))
+    check(f"gaussian fused fast s={s}", eng.gaussian_blur(img, s), pfo.gaussian_blur(img, s), 1)
+check("sharpen fused", eng.sharpen(img, 1.0, 2.0, mask=mask, exact=True), pfo.sharpen(img, 1.0, 2.0, mask=mask))
+del os.environ["PFE_GAUSS_FUSED"]
 check("gaussian masked", eng.gaussian_blur(img, 3.0, mask=mask, exact=True), pfo.gaussian_blur(img, 3.0, mask=mask))
 check("sharpen", eng.sharpen(img, 1.0, 2.0, exact=True), pfo.sharpen(img, 1.0, 2.0))
 check("glow", eng.glow(img, 3.0, 0.5, exact=True), pfo.glow(img, 3.0, 0.5))
