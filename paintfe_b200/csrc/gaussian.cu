@@ -365,18 +365,24 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 
 // ---- Fused H+V for small radii ------------------------------------------------------------------
 // For small radii (use_fused below) the f32 intermediate never leaves the SM.  A CTA walks down a 128-pixel-wide
-// strip segment in batches of 8 rows.  Per batch:
-//   H phase: warp w turns source row (batch row w) into one row of the intermediate, exactly as gauss_h_kernel
-//            does (u8 -> f32 once into a skewed per-warp tile, lane owns 4 consecutive outputs), but the result
-//            goes into a shared-memory ring of (lag+1) batches instead of HBM;
-//   V phase: 256 threads = 128 columns x 2 half-batches; a thread streams 4 + 2r ring rows past its 4 outputs
-//            (conflict-free LDS.128, lanes run along x) and stores u8 - with the sharpen / glow epilogue if set.
-// The V phase runs `lag` = ceil(2r/8) batches behind the H phase, so every input row is filtered horizontally
-// once per segment (plus 2r warm-up rows at the head of a segment) and the image crosses HBM once in, once out:
-// 8 B per pixel instead of the two-pass 40 B.  Tap order and arithmetic are those of the two-pass kernels, so
-// the results are identical to theirs in both modes.
+// strip segment in batches of 8 rows, its warps split into two roles that meet in a shared-memory ring of
+// lag+2 batches of the intermediate (lag = ceil(2r/8)), each batch guarded by a full/empty mbarrier pair:
+//   * 4 H warps: warp w turns source rows w and w+4 of the batch into intermediate rows exactly as gauss_h_kernel does
+//     (u8 -> f32 once into a skewed per-warp tile, a lane owns 4 consecutive outputs; the next row's pixels are
+//     already in registers while this one is filtered), waits for the ring slot to be free, and arrives on `full`;
+//   * 4 V warps: 128 lanes = 128 columns.  Once batch b is full, outputs of batch b-lag have all their 8+2r rows in
+//     the ring: a lane streams them past 4 outputs at a time (conflict-free LDS.128, lanes run along x), stores u8
+//     - with the sharpen / glow epilogue if set - and arrives on `empty` of the batch it no longer needs.
+// Both roles carry the same FMA count per batch, one warp of each role lands on each SM sub-partition, and no
+// CTA-wide barrier is left: the FMA pipe stays fed while either role waits on memory.
+// Protocol safety (same argument as the V ring above): `full[s]` of lap L+1 needs `empty[s]` of lap L, which needs
+// every V warp to have waited `full[s]` of lap L first, and vice versa - no waiter can fall two phases behind.
+// Every input row is filtered horizontally once per segment (plus 2r warm-up rows at the head of a segment) and
+// the image crosses HBM once in, once out: 8 B per pixel instead of the two-pass 40 B.  Tap order and arithmetic
+// are those of the two-pass kernels, so the results are identical to theirs in both modes.
 constexpr int kFusedMaxRadius = 16;
 constexpr int kFusedTW = 128;
+constexpr int kFusedMaxRing = 8;  // batches; lag + 2 <= 6 for radius <= 16
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_constant__ GaussParams P) {
@@ -384,73 +390,107 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
     const int wp_pad = (P.wp_len + 1) & ~1;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + wp_pad);  // full[kFusedMaxRing], empty[kFusedMaxRing]
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
-    float4 *tiles = reinterpret_cast<float4 *>(wsm + wp_pad);
-    float4 *ring = tiles + (size_t)8 * tile_len;  // ring_rows x 128 float4
-    const int ring_rows = (P.lag + 1) * 8;
+    float4 *tiles = reinterpret_cast<float4 *>(bars + 2 * kFusedMaxRing);
+    float4 *ring = tiles + (size_t)4 * tile_len;  // RB batches x 8 rows x 128 float4
+    const int RB = P.lag + 2;
+    const int ring_rows = RB * 8;
+    const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kFusedMaxRing);
     for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < RB; c++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * c), "r"(4));   // one arrival per H warp
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8u * c), "r"(4));  // one arrival per V warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *tile = tiles + (size_t)warp * tile_len;
     const int rw = (int)P.rw, rh = (int)P.rh, r = P.radius;
     const int nstrips = (rw + kFusedTW - 1) / kFusedTW;
     const int ntask = nstrips * P.nseg;
-    const int vc = threadIdx.x & 127, vhalf = threadIdx.x >> 7;
 
-    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
-        // consecutive CTAs take neighbouring strips of one segment: their halo columns are L2-hot
-        const int x0 = (task % nstrips) * kFusedTW;
-        const int ys = (task / nstrips) * P.seg_rows, ye = min(ys + P.seg_rows, rh);
-        const int nb = (ye - ys + 7) / 8 + P.lag;
-        int hslot = 0;  // ring batch the H phase writes: b mod (lag+1)
-        int vslot = 0;  // ring batch holding the first row the V phase reads: (b - lag) mod (lag+1)
-        // source pixels of the NEXT batch travel in registers while this batch is being filtered
-        // (tile_px <= 31*4 + 36 = 160 = 5 per lane)
-        uint32_t pre[5];
-        auto fetch = [&](int b) {
-            const int yy = min(max(ys - r + 8 * b + warp, 0), rh - 1);
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)yy * P.src_pitch;
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                const int p = lane + 32 * i;
-                pre[i] = p < tile_px ? __ldg(row + min(max(x0 - r + p, 0), rw - 1)) : 0u;
-            }
-        };
-        fetch(0);
-        for (int b = 0; b < nb; b++) {
-            {   // ===== H phase: intermediate row ys - r + 8b + warp (clamp-to-edge is a clamped source row) =====
+    if (warp < 4) {
+        // ===== H warps =====
+        float4 *tile = tiles + (size_t)warp * tile_len;
+        int slot = 0;        // ring slot of the batch being produced
+        uint32_t lap = 0;    // how many times the ring has wrapped
+        for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+            // consecutive CTAs take neighbouring strips of one segment: their halo columns are L2-hot
+            const int x0 = (task % nstrips) * kFusedTW;
+            const int ys = (task / nstrips) * P.seg_rows, ye = min(ys + P.seg_rows, rh);
+            const int nb = (ye - ys + 7) / 8 + P.lag;
+            // this warp's k-th row is batch k/2, row warp + 4*(k&1); its source pixels travel in registers one row
+            // ahead (tile_px <= 31*4 + 36 = 160 = 5 per lane)
+            uint32_t pre[5];
+            auto fetch = [&](int k) {
+                const int yy = min(max(ys - r + 8 * (k >> 1) + warp + 4 * (k & 1), 0), rh - 1);  // clamp-to-edge
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)yy * P.src_pitch;
 #pragma unroll
                 for (int i = 0; i < 5; i++) {
                     const int p = lane + 32 * i;
-                    if (p < tile_px) tile[skew(p, N)] = to_f4(pre[i]);
+                    pre[i] = p < tile_px ? __ldg(row + min(max(x0 - r + p, 0), rw - 1)) : 0u;
                 }
-                if (b + 1 < nb) fetch(b + 1);
-                __syncwarp();
-                Acc4 acc[N];
-                float2 R[N];
+            };
+            fetch(0);
+            for (int b = 0; b < nb; b++) {
+                if (lap > 0) mbar_wait(empty0 + 8u * (uint32_t)slot, (lap - 1) & 1u);  // the V warps are done with this slot's previous batch
+#pragma unroll 1
+                for (int half = 0; half < 2; half++) {
 #pragma unroll
-                for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
+                    for (int i = 0; i < 5; i++) {
+                        const int p = lane + 32 * i;
+                        if (p < tile_px) tile[skew(p, N)] = to_f4(pre[i]);
+                    }
+                    if (2 * b + half + 1 < 2 * nb) fetch(2 * b + half + 1);
+                    __syncwarp();
+                    Acc4 acc[N];
+                    float2 R[N];
 #pragma unroll
-                for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
-                const float4 *tl = tile + lane * (N + 1);
-                for (int g = 0; g < P.steps; g += N) {
-                    const float4 *tg = tl + g + g / N;
+                    for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
+                    const float4 *tl = tile + lane * (N + 1);
+                    for (int g = 0; g < P.steps; g += N) {
+                        const float4 *tg = tl + g + g / N;
 #define F_HLOAD(s) tg[s]
-                    PFE_GAUSS_GROUP(F_HLOAD)
+                        PFE_GAUSS_GROUP(F_HLOAD)
 #undef F_HLOAD
-                }
-                float4 *mrow = ring + (size_t)(hslot * 8 + warp) * kFusedTW + lane * N;
+                    }
+                    float4 *mrow = ring + (size_t)(slot * 8 + warp + 4 * half) * kFusedTW + lane * N;
 #pragma unroll
-                for (int j = 0; j < N; j++) mrow[j] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
-                if (++hslot > P.lag) hslot = 0;
+                    for (int j = 0; j < N; j++) mrow[j] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
+                    __syncwarp();  // every lane is done with the tile (and has written its part of the row)
+                }
+                if (lane == 0) mbar_arrive(full0 + 8u * (uint32_t)slot);
+                if (++slot == RB) { slot = 0; lap++; }
             }
-            __syncthreads();  // batch b of the intermediate is complete
-            if (b >= P.lag) {
-                // ===== V phase: output rows ys + 8(b-lag) + 4*vhalf + [0,4); first ring row = that minus r =====
-                const int yo = ys + 8 * (b - P.lag) + 4 * vhalf;
-                int slot = vslot * 8 + 4 * vhalf;  // a multiple of 4: a group of 4 rows never straddles the wrap
+        }
+        return;
+    }
+
+    // ===== V warps =====
+    const int vc = (warp - 4) * 32 + lane;  // column inside the strip
+    int wslot = 0;       // ring slot of the next batch to wait for
+    uint32_t wlap = 0;
+    int rslot = 0;       // ring slot of the next batch to filter and release
+    for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+        const int x0 = (task % nstrips) * kFusedTW;
+        const int ys = (task / nstrips) * P.seg_rows, ye = min(ys + P.seg_rows, rh);
+        const int nb = (ye - ys + 7) / 8 + P.lag;
+        const int x = x0 + vc;
+        for (int b = 0; b < nb; b++) {
+            mbar_wait(full0 + 8u * (uint32_t)wslot, wlap & 1u);
+            if (++wslot == RB) { wslot = 0; wlap++; }
+            if (b < P.lag) continue;
+            // output rows ys + 8(b-lag) + [0,8): their first ring row is row 0 of batch b-lag (= slot rslot)
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const int yo = ys + 8 * (b - P.lag) + 4 * half;
+                int row = rslot * 8 + 4 * half;  // a multiple of 4: a group of 4 rows never straddles the wrap
                 Acc4 acc[N];
                 float2 R[N];
 #pragma unroll
@@ -458,14 +498,13 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
 #pragma unroll
                 for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
                 for (int g = 0; g < P.steps; g += N) {
-                    const float4 *cg = ring + (size_t)slot * kFusedTW + vc;
+                    const float4 *cg = ring + (size_t)row * kFusedTW + vc;
 #define F_VLOAD(s) cg[(s) * kFusedTW]
                     PFE_GAUSS_GROUP(F_VLOAD)
 #undef F_VLOAD
-                    slot += N;
-                    if (slot >= ring_rows) slot -= ring_rows;
+                    row += N;
+                    if (row >= ring_rows) row -= ring_rows;
                 }
-                const int x = x0 + vc;
                 if (x < rw) {
 #pragma unroll
                     for (int j = 0; j < N; j++) {
@@ -479,9 +518,16 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
                         }
                     }
                 }
-                if (++vslot > P.lag) vslot = 0;
             }
-            __syncthreads();  // the V phase is done with the batch the next H phase overwrites
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)rslot);
+            if (++rslot == RB) rslot = 0;
+        }
+        // the last `lag` batches of the segment were only ever read as the tail of earlier outputs
+        __syncwarp();
+        for (int i = 0; i < P.lag; i++) {
+            if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)rslot);
+            if (++rslot == RB) rslot = 0;
         }
     }
 }
@@ -678,7 +724,7 @@ int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     P.lag = (2 * P.radius + 7) / 8;
     const int wp_pad = (P.wp_len + 1) & ~1;
     const int tile_len = skew(31 * N + P.steps, N) + 1;
-    const size_t smem = (size_t)wp_pad * 8 + (size_t)8 * tile_len * 16 + (size_t)(P.lag + 1) * 8 * kFusedTW * 16;
+    const size_t smem = (size_t)wp_pad * 8 + 2 * kFusedMaxRing * 8 + (size_t)4 * tile_len * 16 + (size_t)(P.lag + 2) * 8 * kFusedTW * 16;
     PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned nstrips = pfe_div_up(P.rw, kFusedTW);
     const unsigned resident = pfe_persistent_grid(ctx, gauss_fused_kernel<EXACT>, 256, smem, 0xFFFFFFFFu);
