@@ -235,13 +235,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 constexpr int kChunks = 8;
 
-// Round-half-away + clamp for a NON-NEGATIVE value (blur outputs: weights and inputs are >= 0):
-// t = trunc(x) via FADD.RZ against 2^23, x - t is exact, add one when the fraction is >= 0.5.
+// Round-half-away + clamp for a NON-NEGATIVE value below 1023.5 (blur outputs: weights and inputs are >= 0), i.e.
+// floor(x + 0.5) without a float-to-int conversion: the round-toward-zero add of 0.5 can never step over an integer
+// (integers are representable, so RZ(x + 0.5) >= n whenever x + 0.5 >= n), and a second RZ add against 2^23 leaves
+// floor() of that in the low mantissa bits.
 __device__ __forceinline__ uint32_t round_u8_nonneg(float x) {
-    const uint32_t tb = __float_as_uint(__fadd_rz(x, 8388608.0f));
-    const float t = __uint_as_float(tb) - 8388608.0f;
-    const uint32_t v = (tb & 0x3FFu) + ((x - t) >= 0.5f ? 1u : 0u);
-    return min(v, 255u);
+    const uint32_t tb = __float_as_uint(__fadd_rz(__fadd_rz(x, 0.5f), 8388608.0f));
+    return min(tb & 0x3FFu, 255u);
 }
 
 template <int N, bool EXACT, int WARPS>
