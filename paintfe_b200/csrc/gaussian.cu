@@ -383,14 +383,26 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 constexpr int kFusedMaxRadius = 16;
 constexpr int kFusedTW = 128;
 constexpr int kFusedMaxRing = 8;  // batches; lag + 2 <= 6 for radius <= 16
+constexpr int kFusedMaxWp = 40;   // padded weights for N = 4: steps + 3 <= 36 + 3
+
+// The padded weight table travels in the kernel parameters: the per-step weight is a uniform constant-bank read
+// (no shared-memory wavefront, no staging), which matters because at N = 4 this kernel is bound by the
+// shared-memory pipe, not by the FMA pipe.
+struct FusedWeights {
+    float2 wk[kFusedMaxWp];
+};
+
+// Ring column swizzle: pixel x of a ring row lives in 16-byte slot x ^ ((x >> 3) & 7).  The H warps write 4
+// consecutive pixels per lane (a quarter-warp would hit only 2 of the 8 bank groups: 4-way conflicts), the V warps
+// read consecutive pixels across lanes; with the swizzle both are conflict free.
+__device__ __forceinline__ int fused_swz(int x) { return x ^ ((x >> 3) & 7); }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_constant__ GaussParams P) {
+__global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ FusedWeights W) {
     constexpr int N = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
-    const int wp_pad = (P.wp_len + 1) & ~1;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + wp_pad);  // full[kFusedMaxRing], empty[kFusedMaxRing]
+    const float2 *wsm = W.wk;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);  // full[kFusedMaxRing], empty[kFusedMaxRing]
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
     float4 *tiles = reinterpret_cast<float4 *>(bars + 2 * kFusedMaxRing);
@@ -398,7 +410,6 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
     const int RB = P.lag + 2;
     const int ring_rows = RB * 8;
     const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kFusedMaxRing);
-    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
     if (threadIdx.x == 0) {
         for (int c = 0; c < RB; c++) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8u * c), "r"(4));   // one arrival per H warp
@@ -460,9 +471,9 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
                         PFE_GAUSS_GROUP(F_HLOAD)
 #undef F_HLOAD
                     }
-                    float4 *mrow = ring + (size_t)(slot * 8 + warp + 4 * half) * kFusedTW + lane * N;
+                    float4 *mrow = ring + (size_t)(slot * 8 + warp + 4 * half) * kFusedTW;
 #pragma unroll
-                    for (int j = 0; j < N; j++) mrow[j] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
+                    for (int j = 0; j < N; j++) mrow[fused_swz(lane * N + j)] = make_float4(acc[j].lo.x, acc[j].lo.y, acc[j].hi.x, acc[j].hi.y);
                     __syncwarp();  // every lane is done with the tile (and has written its part of the row)
                 }
                 if (lane == 0) mbar_arrive(full0 + 8u * (uint32_t)slot);
@@ -474,6 +485,7 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
 
     // ===== V warps =====
     const int vc = (warp - 4) * 32 + lane;  // column inside the strip
+    const int vcs = fused_swz(vc);          // ... and where it lives in a ring row
     int wslot = 0;       // ring slot of the next batch to wait for
     uint32_t wlap = 0;
     int rslot = 0;       // ring slot of the next batch to filter and release
@@ -498,7 +510,7 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
 #pragma unroll
                 for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
                 for (int g = 0; g < P.steps; g += N) {
-                    const float4 *cg = ring + (size_t)row * kFusedTW + vc;
+                    const float4 *cg = ring + (size_t)row * kFusedTW + vcs;
 #define F_VLOAD(s) cg[(s) * kFusedTW]
                     PFE_GAUSS_GROUP(F_VLOAD)
 #undef F_VLOAD
@@ -720,11 +732,15 @@ int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
 template <bool EXACT>
 int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     constexpr int N = 4;
-    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    const int taps = (int)k.size();
+    P.steps = ((N + taps - 1 + N - 1) / N) * N;
+    P.wp_len = P.steps + N - 1;
+    FusedWeights W;
+    memset(&W, 0, sizeof(W));
+    for (int t = 0; t < taps; t++) W.wk[t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
     P.lag = (2 * P.radius + 7) / 8;
-    const int wp_pad = (P.wp_len + 1) & ~1;
     const int tile_len = skew(31 * N + P.steps, N) + 1;
-    const size_t smem = (size_t)wp_pad * 8 + 2 * kFusedMaxRing * 8 + (size_t)4 * tile_len * 16 + (size_t)(P.lag + 2) * 8 * kFusedTW * 16;
+    const size_t smem = 2 * kFusedMaxRing * 8 + (size_t)4 * tile_len * 16 + (size_t)(P.lag + 2) * 8 * kFusedTW * 16;
     PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_fused_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned nstrips = pfe_div_up(P.rw, kFusedTW);
     const unsigned resident = pfe_persistent_grid(ctx, gauss_fused_kernel<EXACT>, 256, smem, 0xFFFFFFFFu);
@@ -741,20 +757,20 @@ int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     P.seg_rows = (int)(pfe_div_up(pfe_div_up(P.rh, nseg), 8) * 8);
     P.nseg = (int)pfe_div_up(P.rh, (unsigned)P.seg_rows);
     const unsigned blocks = std::min(resident, nstrips * (unsigned)P.nseg);
-    PFE_KERNEL(ctx, "gauss_fused", gauss_fused_kernel<EXACT><<<blocks, 256, smem, ctx->stream>>>(P));
+    PFE_KERNEL(ctx, "gauss_fused", gauss_fused_kernel<EXACT><<<blocks, 256, smem, ctx->stream>>>(P, W));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
 
-// The fused kernel wins where the two-pass pair is bound by the f32 intermediate's HBM round trip: small radii on
-// images with enough strip segments to occupy every SM (measured on B200, profiles/r01_gauss_fused.jsonl: 10-20%
-// faster up to radius 6, level at radius 12, slower beyond and on small images).  PFE_GAUSS_FUSED=1 / =0 force it.
+// The fused kernel wins wherever it applies (radius <= 16) provided the image has enough strip segments to occupy
+// every SM (measured on B200, profiles/r01_gauss_fused.jsonl: 1.5x at radius 2 down to 1.03x at radius 16 on 4K / 8K
+// images, but 2-4x slower on a 0.7 Mpx image).  PFE_GAUSS_FUSED=1 / =0 force it.
 static bool use_fused(const pfe_ctx *ctx, int radius, uint32_t rw, uint32_t rh) {
     if (radius < 1 || radius > kFusedMaxRadius) return false;
     if (const char *force = getenv("PFE_GAUSS_FUSED")) return atoi(force) != 0;
     const int lag = (2 * radius + 7) / 8;
     const uint64_t tasks = (uint64_t)pfe_div_up(rw, kFusedTW) * std::max(1u, rh / (unsigned)std::max(64, 48 * lag));
-    return radius <= 12 && tasks >= (uint64_t)ctx->sm_count;
+    return tasks >= (uint64_t)ctx->sm_count;
 }
 
 template <bool EXACT>
