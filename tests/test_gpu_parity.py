@@ -298,6 +298,16 @@ def test_gaussian_fused_small_radius(eng, oracle, monkeypatch, w, h, sigma):
         exact(got, ref, f"fused FMA {what} == two-pass FMA {what}")
 
 
+def test_gaussian_fused_several_tasks_per_cta(eng, oracle, monkeypatch):
+    """More strip segments than resident CTAs: a CTA walks several segments in a row and the ring's barrier phases run
+    on across them (what happens by itself on an 8K image)."""
+    monkeypatch.setenv("PFE_GAUSS_FUSED", "1")
+    monkeypatch.setenv("PFE_GAUSS_FUSED_SEGS", "40")  # 11 strips x 40 segments = 440 tasks > 2 CTAs x 148 SMs
+    img = fx.random_rgba(np.random.default_rng(77), 1300, 1900)
+    for sigma in (0.8, 3.0):
+        exact(eng.gaussian_blur(img, sigma, exact=True), oracle.gaussian_blur(img, sigma), f"fused, many segments, s={sigma}")
+
+
 def test_gaussian_fused_is_picked_for_large_images(eng, oracle):
     """4K, sigma 2: the dispatcher takes the fused kernel by itself (launch counter: 1 kernel instead of 2)."""
     import torch
