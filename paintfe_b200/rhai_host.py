@@ -588,6 +588,7 @@ class Interpreter:
         self.scopes: List[Dict[str, Any]] = [{}]
         self.vector_mode = False
         self.ops = 0
+        self.bulk_evaluations = {"whole_image": 0, "per_pixel": 0}  # how closures of the bulk calls were evaluated
         self._host: Optional[np.ndarray] = None  # host copy of a device image while pixel access is in use
         self._host_dirty = False
 
@@ -1106,6 +1107,7 @@ class Interpreter:
             self.ops = saved_ops
         finally:
             self.vector_mode = False
+        self.bulk_evaluations["whole_image" if out is not None else "per_pixel"] += 1
         if out is None:
             out = self._bulk_scalar(fn, region, x0, y0, with_xy)
         self.touch_host()

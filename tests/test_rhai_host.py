@@ -275,3 +275,55 @@ def test_canvas_ops_are_logged_and_replayed(oracle):
     flats = apply_canvas_ops(eng, [other, out, None], 1, it.canvas_ops)
     exp = oracle.orient(oracle.resize_canvas(oracle.resize(oracle.orient(other, oracle.ROT90CW), 16, 24, 3), 20, 30, (1, 1), (0, 0, 0, 0)), oracle.FLIP_V)
     assert flats[1] is out and flats[2] is None and (flats[0] == exp).all() and out.shape == exp.shape
+
+
+# ---- Property: evaluating a closure once over whole-image arrays == evaluating it per pixel
+def _random_body(rng, depth=0):
+    """A random closure body over r, g, b, a, x, y: integer / float arithmetic, comparisons, data-dependent ifs."""
+    ints = ["r", "g", "b", "a", "x", "y", "7", "255", "3", "(r + g)", "(b - a)", "(x * 2 + y)"]
+
+    def int_expr(d):
+        if d > 2 or rng.random() < 0.3:
+            return ints[rng.integers(len(ints))]
+        op = ["+", "-", "*", "/", "%", "&", "|", "^"][rng.integers(8)]
+        rhs = int_expr(d + 1)
+        if op in "/%":
+            rhs = f"({rhs} | 1)"  # never zero
+        kind = rng.integers(6)
+        if kind == 0:
+            return f"max({int_expr(d + 1)}, {rhs})"
+        if kind == 1:
+            return f"clamp({int_expr(d + 1)}, 0, 255)"
+        if kind == 2:
+            return f"to_int(floor({int_expr(d + 1)} / 2.5))"
+        if kind == 3:
+            return f"abs({int_expr(d + 1)} - {rhs})"
+        return f"({int_expr(d + 1)} {op} {rhs})"
+
+    def cond(d):
+        c = f"{int_expr(d)} {['<', '<=', '>', '>=', '==', '!='][rng.integers(6)]} {int_expr(d)}"
+        if rng.random() < 0.3:
+            c = f"({c}) {['&&', '||'][rng.integers(2)]} is_selected(x, y)"
+        return c
+
+    lines = [f"let u = {int_expr(0)};", f"let v = {int_expr(0)};"]
+    for _ in range(rng.integers(1, 4)):
+        if rng.random() < 0.5:
+            lines.append(f"if {cond(0)} {{ u = {int_expr(1)}; }} else if {cond(1)} {{ v += {int_expr(1)}; }} else {{ u -= 1; v = u; }}")
+        else:
+            lines.append(f"let w = if {cond(0)} {{ {int_expr(1)} }} else {{ {int_expr(1)} }}; u = u + w % 17;")
+    lines.append(f"[u, v, if {cond(0)} {{ b }} else {{ 255 - b }}, {['a', '255', 'a / 2.0'][rng.integers(3)]}]")
+    return "{ " + " ".join(lines) + " }"
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_random_closures_whole_image_vs_per_pixel(oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    body = _random_body(rng)
+    src = rng.integers(0, 256, (9, 13, 4), dtype=np.uint8)
+    script = "select_rect(2, 1, 11, 7); for_each_pixel(|x, y, r, g, b, a| %s);"
+    fast, slow = Interpreter(OracleEngine(oracle), src), Interpreter(OracleEngine(oracle), src)
+    a, b = fast.run(script % body), slow.run(script % _per_pixel_only(body))
+    assert fast.bulk_evaluations == {"whole_image": 1, "per_pixel": 0}, body
+    assert slow.bulk_evaluations == {"whole_image": 0, "per_pixel": 1}
+    assert (a == b).all(), body
