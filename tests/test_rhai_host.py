@@ -39,6 +39,9 @@ class OracleEngine:
     def resize_canvas(self, img, w, h, anchor, fill):
         return self.o.resize_canvas(img, w, h, anchor, fill)
 
+    def vignette(self, img, amount, softness, mask=None):
+        return self.o.vignette(img, amount, softness, mask=mask)
+
 
 @pytest.fixture()
 def run(oracle):
@@ -327,3 +330,22 @@ def test_random_closures_whole_image_vs_per_pixel(oracle, seed):
     assert fast.bulk_evaluations == {"whole_image": 1, "per_pixel": 0}, body
     assert slow.bulk_evaluations == {"whole_image": 0, "per_pixel": 1}
     assert (a == b).all(), body
+
+
+def test_reference_readme_script(run, oracle):
+    """The example of the reference's README (Scripting section), statement for statement."""
+    out, _ = run("""
+        apply_desaturate();
+        apply_brightness_contrast(10.0, 40.0);
+        apply_vignette(0.5, 0.3);
+
+        map_channels(|r, g, b, a| {
+            [clamp(r + 15, 0, 255), g, clamp(b - 8, 0, 255), a]
+        });
+    """)
+    exp = oracle.adjust(fx.gradient(64, 64), 33)                       # PFE_ADJ_S_DESATURATE
+    exp = oracle.adjust(exp, 36, (10.0, 40.0))                         # PFE_ADJ_S_BRIGHTNESS_CONTRAST
+    exp = oracle.vignette(exp, 0.5, 0.3).astype(np.int64)
+    exp[..., 0] = np.clip(exp[..., 0] + 15, 0, 255)
+    exp[..., 2] = np.clip(exp[..., 2] - 8, 0, 255)
+    assert (out == exp.astype(np.uint8)).all()
