@@ -96,16 +96,28 @@ __device__ __forceinline__ float4 to_f4(uint32_t v) {
 // A warp owns one row segment of 32*N pixels. The u8 pixels are converted to f32 once while being
 // staged into a skewed shared-memory tile (one pad float4 every N, so lane stride N+1 keeps
 // LDS.128 conflict free); results return through the same tile for fully coalesced stores.
-template <int N, bool EXACT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P) {
+// EXPERIMENT (branch next/gauss-uniform-weights): the padded weight table as a kernel parameter.  With UW = true the
+// per-step weight is an `LDCU.64` into a uniform register pair and every tap becomes `FFMA2 acc, in.reuse, UR, acc`:
+// one fresh 64-bit register operand per instruction instead of two, no weight LDS, N fewer live register pairs.
+// Same table, same arithmetic, same results.  Not yet timed on a GPU.
+constexpr int kWeightTableLen = 400;  // float2 entries: 3.2 KB of the 4 KB parameter space; wp_len <= 400 covers sigma <= ~60
+struct WeightTable {
+    float2 wk[kWeightTableLen];
+};
+
+template <int N, bool EXACT, int WARPS, bool UW>
+__global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ WeightTable W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
+    float2 *wshared = reinterpret_cast<float2 *>(smem_raw);
+    const float2 *wsm = UW ? W.wk : wshared;
     const int wp_pad = (P.wp_len + 1) & ~1;
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
-    float4 *tiles = reinterpret_cast<float4 *>(wsm + wp_pad);
-    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
-    __syncthreads();
+    float4 *tiles = reinterpret_cast<float4 *>(wshared + wp_pad);
+    if (!UW) {
+        for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wshared[i] = P.wp[i];
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *tile = tiles + (size_t)warp * tile_len;
@@ -238,17 +250,19 @@ constexpr int kChunks = 8;
 // Blur outputs are non-negative (weights and inputs are >= 0): the clamp-free rounding applies directly.
 __device__ __forceinline__ uint32_t round_u8_nonneg(float x) { return pfe_round_u8_nonneg(x); }
 
-template <int N, bool EXACT, int WARPS>
-__global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P) {
+template <int N, bool EXACT, int WARPS, bool UW>
+__global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ WeightTable W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TH = WARPS * N;
     const int rows = TH + P.steps - N;
     const int chunk_rows = (rows + kChunks - 1) / kChunks;
     const int ring_rows = chunk_rows * kChunks;
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // ring_rows x 32 float4
-    float2 *wsm = reinterpret_cast<float2 *>(smem_raw + (size_t)ring_rows * 512);
+    float2 *wshared = reinterpret_cast<float2 *>(smem_raw + (size_t)ring_rows * 512);
+    const float2 *wsm = UW ? W.wk : wshared;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ring_rows * 512 + (size_t)((P.wp_len + 1) & ~1) * 8);
-    for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
+    if (!UW)
+        for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wshared[i] = P.wp[i];
     const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kChunks);
     if (threadIdx.x == 0) {
         for (int c = 0; c < kChunks; c++) {
@@ -266,7 +280,9 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // the shuffle tells the compiler that `warp` is warp-uniform: the role branch below is then uniform control flow and
+    // the consumer loop may use the uniform datapath (weights in uniform registers)
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int rw = (int)P.rw, rh = (int)P.rh;
     const int y_end = (int)(P.v_y0 + P.v_rows);
     const int tx = (rw + 31) / 32, ty = ((int)P.v_rows + TH - 1) / TH;
@@ -415,7 +431,7 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform role
     const int rw = (int)P.rw, rh = (int)P.rh, r = P.radius;
     const int nstrips = (rw + kFusedTW - 1) / kFusedTW;
     const int ntask = nstrips * P.nseg;
@@ -630,9 +646,21 @@ int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, fl
     return PFE_OK;
 }
 
-template <int N, bool EXACT>
-int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
-    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+// Uniform-weight variants apply when the padded table fits the parameter block; PFE_GAUSS_UW=0 selects the
+// shared-memory table for A/B runs.
+static bool use_uniform_weights(int wp_len) {
+    if (wp_len > kWeightTableLen) return false;
+    const char *e = getenv("PFE_GAUSS_UW");
+    return !e || atoi(e) != 0;
+}
+template <int N>
+static void fill_weight_table(WeightTable &W, const std::vector<float> &k) {
+    memset(&W, 0, sizeof(W));
+    for (size_t t = 0; t < k.size() && t + N - 1 < (size_t)kWeightTableLen; t++) W.wk[t + N - 1] = make_float2(k[t], k[t]);
+}
+
+template <int N, bool EXACT, bool UW>
+int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
     const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     int warps = 4;
@@ -641,22 +669,29 @@ int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
     const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
     if (warps == 4) {
-        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = (unsigned)std::min<uint64_t>((ntask + 3) / 4, (uint64_t)ctx->sm_count * 8);
-        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4><<<blocks, 128, smem, ctx->stream>>>(P));
+        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4, UW><<<blocks, 128, smem, ctx->stream>>>(P, W));
     } else {
-        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = (unsigned)std::min<uint64_t>(ntask, (uint64_t)ctx->sm_count * 8);
-        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1><<<blocks, 32, smem, ctx->stream>>>(P));
+        PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1, UW><<<blocks, 32, smem, ctx->stream>>>(P, W));
     }
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
 
-// V pass: tile variant when its shared-memory footprint fits, else the direct variant
 template <int N, bool EXACT>
-int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    WeightTable W;
+    fill_weight_table<N>(W, k);
+    return use_uniform_weights(P.wp_len) ? launch_h<N, EXACT, true>(ctx, P, W) : launch_h<N, EXACT, false>(ctx, P, W);
+}
+
+// V pass: tile variant when its shared-memory footprint fits, else the direct variant
+template <int N, bool EXACT, bool UW>
+int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
     const int wp_pad = (P.wp_len + 1) & ~1;
     const size_t extra = (size_t)wp_pad * 8 + 16 * kChunks + 64;
     auto tile_smem = [&](int warps) {
@@ -667,9 +702,9 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 8 * N);
     if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
         const size_t smem = tile_smem(8);
-        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8>, 288, smem, tiles8);
-        PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8><<<blocks, 288, smem, ctx->stream>>>(P));
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8, UW>, 288, smem, tiles8);
+        PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8, UW><<<blocks, 288, smem, ctx->stream>>>(P, W));
     } else {
         size_t smem = (size_t)wp_pad * 8;
         if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
@@ -680,6 +715,15 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     }
     PFE_LAUNCHED(ctx);
     return PFE_OK;
+}
+
+// V pass: tile variant when its shared-memory footprint fits, else the direct variant
+template <int N, bool EXACT>
+int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    WeightTable W;
+    fill_weight_table<N>(W, k);
+    return use_uniform_weights(P.wp_len) ? launch_v<N, EXACT, true>(ctx, P, W) : launch_v<N, EXACT, false>(ctx, P, W);
 }
 
 // Register-block size per pass: the one that wastes the fewest issue slots on zero-padded steps plus
