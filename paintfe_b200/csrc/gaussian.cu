@@ -700,7 +700,16 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
     };
     const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
     const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 8 * N);
-    if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
+    // EXPERIMENT: 12 consumer warps (a taller tile: less halo per output row, 13 warps per SM) now that the uniform-weight
+    // kernel needs 90 registers; PFE_GAUSS_V_WARPS=12 selects it when its ring fits.
+    const char *vw = getenv("PFE_GAUSS_V_WARPS");
+    if (!force_direct && UW && N >= 4 && vw && atoi(vw) == 12 && tile_smem(12) <= 225 * 1024) {
+        const size_t smem = tile_smem(12);
+        const unsigned tiles12 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 12 * N);
+        PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 12, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 12, UW>, 416, smem, tiles12);
+        PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 12, UW><<<blocks, 416, smem, ctx->stream>>>(P, W));
+    } else if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
         const size_t smem = tile_smem(8);
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8, UW>, 288, smem, tiles8);
