@@ -738,7 +738,7 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
 // Register-block size per pass: the one that wastes the fewest issue slots on zero-padded steps plus
 // per-step overhead. The V pass pays more per step (ring bookkeeping), so it prefers a larger block:
 // measured at sigma=20, H is fastest with N=8 and V with N=16.
-static int pick_n(int taps, double per_step_overhead) {
+static int pick_n(int taps, double per_step_overhead, const char *pass_knob) {
     auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + per_step_overhead) / n; };
     int best = 1;
     if (taps >= 3) {
@@ -746,7 +746,9 @@ static int pick_n(int taps, double per_step_overhead) {
         if (taps >= 9 && cost(8) < cost(best)) best = 8;
         if (taps >= 17 && cost(16) < cost(best)) best = 16;
     }
-    if (const char *force = getenv("PFE_GAUSS_N")) {  // tuning aid
+    for (const char *knob : {"PFE_GAUSS_N", pass_knob}) {  // tuning aids: both passes / this pass only
+        const char *force = getenv(knob);
+        if (!force) continue;
         const int n = atoi(force);
         if ((n == 4 || n == 8 || n == 16) && taps >= n + 1) best = n;
     }
@@ -755,7 +757,7 @@ static int pick_n(int taps, double per_step_overhead) {
 
 template <bool EXACT>
 int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
-    switch (pick_n((int)k.size(), 6.0)) {
+    switch (pick_n((int)k.size(), 6.0, "PFE_GAUSS_NH")) {
         case 16: return run_h<16, EXACT>(ctx, P, k);
         case 8: return run_h<8, EXACT>(ctx, P, k);
         case 4: return run_h<4, EXACT>(ctx, P, k);
@@ -766,7 +768,7 @@ int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
 template <bool EXACT>
 int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
     const int taps = (int)k.size();
-    switch (pick_n(taps, 12.0)) {
+    switch (pick_n(taps, 12.0, "PFE_GAUSS_NV")) {
         case 16: return run_v<16, EXACT>(ctx, P, k);
         case 8: return run_v<8, EXACT>(ctx, P, k);
         case 4: return run_v<4, EXACT>(ctx, P, k);
