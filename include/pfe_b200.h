@@ -55,6 +55,12 @@ int pfe_ctx_destroy(pfe_ctx *ctx);
 int pfe_ctx_set_stream(pfe_ctx *ctx, void *cuda_stream);
 int pfe_ctx_use_own_stream(pfe_ctx *ctx);
 int pfe_ctx_sync(pfe_ctx *ctx);
+/* Stream-asynchronous device-tier calls that can only detect a caller error on the device (today:
+ * pfe_dev_warp_band, whose source-row window may turn out not to cover the warp's reach) record it in a
+ * sticky flag instead of synchronising.  This call synchronises the context's stream, returns
+ * PFE_ERR_INVALID_ARG (message in pfe_last_error) if any such error was recorded since the last call, PFE_OK
+ * otherwise, and clears the flag. */
+int pfe_ctx_check_async(pfe_ctx *ctx);
 const char *pfe_last_error(const pfe_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t pfe_ctx_launch_count(const pfe_ctx *ctx);
@@ -446,12 +452,29 @@ int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t
 /* Row-band form of both warps for a canvas split across GPUs: produce output rows
  * [y0, y0+rows_out) of the w x h result from a WINDOW of source rows [src_y0, src_y0+src_nrows) of
  * the src_w x src_h source (own band + halo). disp_band != NULL: displacement warp with the band's
- * rows_out*w*2 field; disp_band == NULL: fused mesh warp (points are HOST pointers). Synchronises,
- * and fails with PFE_ERR_INVALID_ARG if any bilinear tap inside the image fell outside the window. */
+ * rows_out*w*2 field; disp_band == NULL: fused mesh warp (points are HOST pointers). Asynchronous on the
+ * context's stream. A bilinear tap inside the image that fell outside the window reads as transparent and
+ * sets the context's sticky error flag: pfe_ctx_check_async reports it (PFE_ERR_INVALID_ARG). */
 int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t src_w, uint32_t src_h, uint32_t src_y0,
                       uint32_t src_nrows, const float *disp_band, const float *original_points,
                       const float *deformed_points, uint32_t cols, uint32_t rows, uint32_t w, uint32_t h,
                       uint32_t y0, uint32_t rows_out, uint8_t *dst_band);
+/* Row-band form of parallel_gaussian_blur (src/ops/filters.rs:242-316) for a canvas split across GPUs
+ * (SURVEY §8e).  `ext` is this GPU's band EXTENDED by the halo rows its neighbours sent: ext_rows rows of w
+ * pixels, band rows preceded by up to ceil(3 sigma) rows from above and followed by as many from below (fewer
+ * only where the band is that close to the true image border, so that clamp-to-edge at ext's first / last row
+ * IS the image's).  The f32 intermediate of the extended band lives in the context's scratch:
+ *   pfe_dev_gaussian_band_h  filters rows [y0, y0+rows) of ext horizontally into it - call it for the band's own
+ *                            rows while the halo is still in flight, then for the halo rows once they have landed;
+ *   pfe_dev_gaussian_band_v  filters vertically and writes output rows [y0, y0+rows) of ext (normally the band's
+ *                            own rows) to dst_rows (rows*w*4 bytes, row 0 = ext row y0).
+ * Both are asynchronous on the context's stream; the scratch is only valid between one sequence of _h calls
+ * and the _v call that follows them (any other Gaussian-family call on the context overwrites it).  The
+ * result is bit-identical to the band's rows of the unsplit blur in both modes. */
+int pfe_dev_gaussian_band_h(pfe_ctx *ctx, const uint8_t *ext, uint32_t w, uint32_t ext_rows, uint32_t y0,
+                            uint32_t rows, float sigma, uint32_t flags);
+int pfe_dev_gaussian_band_v(pfe_ctx *ctx, uint32_t w, uint32_t ext_rows, uint32_t y0, uint32_t rows, float sigma,
+                            uint8_t *dst_rows, uint32_t flags);
 /* Reach of a band's displacement field, for sizing the halo of pfe_dev_warp_band: minmax_dev[0..1] (DEVICE
  * memory, int32) = min / max over the band's rows [y0, y0+rows) of floor(clamp(y - dy, -1, h_total)), with
  * non-finite dy counted as 0. Asynchronous: the result stays on the device so that it can go straight into

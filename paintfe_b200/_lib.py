@@ -56,6 +56,7 @@ SIGNATURES = {
     "pfe_ctx_set_stream": (C.c_int, [_ctx, _vp]),
     "pfe_ctx_use_own_stream": (C.c_int, [_ctx]),
     "pfe_ctx_sync": (C.c_int, [_ctx]),
+    "pfe_ctx_check_async": (C.c_int, [_ctx]),
     "pfe_last_error": (C.c_char_p, [_ctx]),
     "pfe_ctx_launch_count": (C.c_uint64, [_ctx]),
     "pfe_ctx_profile": (C.c_int, [_ctx, C.c_int]),
@@ -156,6 +157,8 @@ SIGNATURES = {
     "pfe_mesh_warp": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_mesh_warp": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_warp_band": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
+    "pfe_dev_gaussian_band_h": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _f32, _u32]),
+    "pfe_dev_gaussian_band_v": (C.c_int, [_ctx, _u32, _u32, _u32, _u32, _f32, _vp, _u32]),
     "pfe_dev_disp_reach": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pfe_dev_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),

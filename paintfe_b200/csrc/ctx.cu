@@ -137,7 +137,8 @@ int pfe_ctx_create(int device, pfe_ctx **out) {
               cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&c->pinned, PFE_SMALL_BYTES) == cudaSuccess &&
-              cudaMalloc(&c->dev_small, PFE_SMALL_BYTES) == cudaSuccess;
+              cudaMalloc(&c->dev_small, PFE_SMALL_BYTES) == cudaSuccess &&
+              cudaMalloc((void **)&c->async_err, 64) == cudaSuccess && cudaMemset(c->async_err, 0, 64) == cudaSuccess;
     if (!ok) { pfe_ctx_destroy(c); return PFE_ERR_CUDA; }
     c->pinned_bytes = PFE_SMALL_BYTES;
     c->stream = c->own_stream;
@@ -153,6 +154,7 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->dev_small) cudaFree(c->dev_small);
+    if (c->async_err) cudaFree(c->async_err);
     if (c->gauss_mem) cudaFree(c->gauss_mem);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < 2; i++) {
@@ -191,6 +193,17 @@ int pfe_ctx_sync(pfe_ctx *c) {
     PFE_CUDA(c, cudaSetDevice(c->device));
     PFE_CUDA(c, cudaStreamSynchronize(c->stream));
     return PFE_OK;
+}
+
+int pfe_ctx_check_async(pfe_ctx *c) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    int flag = 0;
+    PFE_CUDA(c, cudaMemcpyAsync(&flag, c->async_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PFE_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!flag) return PFE_OK;
+    PFE_CUDA(c, cudaMemsetAsync(c->async_err, 0, sizeof(int), c->stream));
+    return pfe_fail(c, PFE_ERR_INVALID_ARG, "warp_band: the source row window does not cover the warp's reach");
 }
 
 const char *pfe_last_error(const pfe_ctx *c) { return c ? c->err.c_str() : "null context"; }

@@ -46,7 +46,11 @@ struct GaussParams {
     float sigma;          // host side only: key of the device-resident weight table
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
+    int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
+    // (1, 1) and (-0, -0) for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
+    // stage can see their values (see tap<true> below and blend.cuh).
+    float2 one, nzero;
 };
 
 // One RGBA accumulator as two packed f32x2 halves: sm_100's FFMA2 / FMUL2 / FADD2 retire two IEEE
@@ -57,14 +61,16 @@ struct GaussParams {
 struct Acc4 {
     float2 lo, hi;  // (r,g) (b,a)
 };
+// EXACT: the reference's separately rounded multiply and add, two lanes per instruction.  a*b == fma(a, b, -0) and
+// t + c == fma(t, 1, c) exactly, and with the constants hidden in kernel parameters neither NVVM nor ptxas can turn
+// the pair back into a contractable mul + add (ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even
+// under --fmad=false).  Same FMA-pipe time as four scalar FMUL + four FADD, half the issue slots and half the code.
 template <bool EXACT>
-__device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2) {
+__device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2, const float2 one, const float2 nzero) {
     const float2 ilo = make_float2(in.x, in.y), ihi = make_float2(in.z, in.w);
     if (EXACT) {
-        acc.lo.x = __fadd_rn(acc.lo.x, __fmul_rn(in.x, w2.x));
-        acc.lo.y = __fadd_rn(acc.lo.y, __fmul_rn(in.y, w2.x));
-        acc.hi.x = __fadd_rn(acc.hi.x, __fmul_rn(in.z, w2.x));
-        acc.hi.y = __fadd_rn(acc.hi.y, __fmul_rn(in.w, w2.x));
+        acc.lo = __ffma2_rn(__ffma2_rn(ilo, w2, nzero), one, acc.lo);
+        acc.hi = __ffma2_rn(__ffma2_rn(ihi, w2, nzero), one, acc.hi);
     } else {
         acc.lo = __ffma2_rn(ilo, w2, acc.lo);
         acc.hi = __ffma2_rn(ihi, w2, acc.hi);
@@ -73,14 +79,23 @@ __device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2
 
 // wp[m] = w[m-(N-1)] inside the kernel support, 0 outside: every output uses the same unrolled
 // N-step body; zero-weight taps are exact no-ops in both modes (x*0 + acc == acc).  The N live
-// weights sit in a rotating register window R[] (one uniform 8-byte smem read per step).
-// LOAD(s) yields the input for step g+s.
-#define PFE_GAUSS_GROUP(LOAD)                                                                   \
+// weights sit in a rotating register window R[] (one uniform 8-byte read per step).
+// LOAD(s) yields the input for step g+s.  Output j meets weight w[g+s-j] at step s of group g.
+#define PFE_GAUSS_GROUP_C(LOAD, COND)                                                           \
     _Pragma("unroll") for (int s = 0; s < N; s++) {                                             \
         R[(s + N - 1) % N] = wsm[g + s + N - 1];                                                \
         const float4 in = LOAD(s);                                                              \
-        _Pragma("unroll") for (int j = 0; j < N; j++) tap<EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N]); \
+        _Pragma("unroll") for (int j = 0; j < N; j++)                                           \
+            if (COND) tap<EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N], P.one, P.nzero);       \
     }
+// When the padded step count is exactly N + taps - 1 (P.tri: 2*radius divisible by N - sigma 20 with N = 8 is), the
+// zero-weight taps are the upper triangle of the first group (w[s-j] with j > s) and the lower triangle of the last
+// one (j < s): those groups run triangular bodies that skip them - N-1 of the N+taps-1 FMAs per output (5.5 % at
+// sigma 20, 10 % in the fused small-radius kernel).  Skipping an exact no-op changes no result.
+#define PFE_GAUSS_GROUP(LOAD)                                                                   \
+    if (P.tri && g == 0) { PFE_GAUSS_GROUP_C(LOAD, j <= s) }                                    \
+    else if (P.tri && g == P.steps - N) { PFE_GAUSS_GROUP_C(LOAD, j >= s) }                     \
+    else { PFE_GAUSS_GROUP_C(LOAD, true) }
 
 __host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
@@ -110,7 +125,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float2 *wshared = reinterpret_cast<float2 *>(smem_raw);
     const float2 *wsm = UW ? W.wk : wshared;
-    const int wp_pad = (P.wp_len + 1) & ~1;
+    const int wp_pad = UW ? 0 : (P.wp_len + 1) & ~1;
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
     float4 *tiles = reinterpret_cast<float4 *>(wshared + wp_pad);
@@ -609,10 +624,16 @@ std::vector<float> build_kernel(float sigma, int *radius_out) {
 
 // Padded, duplicated weights for register-block size N: wp[m] = (w, w)[m-(N-1)] inside the support.
 template <int N>
-int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, float sigma) {
+void set_steps(GaussParams &P, const std::vector<float> &k) {
     const int taps = (int)k.size();
     P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
     P.wp_len = P.steps + N - 1;
+    P.tri = (N > 1 && P.steps == N + taps - 1 && getenv("PFE_GAUSS_NO_TRI") == nullptr) ? 1 : 0;
+}
+template <int N>
+int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, float sigma) {
+    const int taps = (int)k.size();
+    set_steps<N>(P, k);
     const size_t bytes = (size_t)P.wp_len * sizeof(float2);
     uint32_t sigma_bits;
     memcpy(&sigma_bits, &sigma, 4);
@@ -661,20 +682,23 @@ static void fill_weight_table(WeightTable &W, const std::vector<float> &k) {
 
 template <int N, bool EXACT, bool UW>
 int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
-    const int wp_pad = (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
+    const int wp_pad = UW ? 0 : (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     int warps = 4;
     size_t smem = (size_t)wp_pad * 8 + (size_t)warps * tile_len * 16;
     if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 8 + (size_t)tile_len * 16; }
     if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
     const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
+    // Exactly one resident wave of grid-stride CTAs: the task loop strides by the grid, so a CTA that does not fit
+    // next to the others would run its share alone after they finish (the r01 grid of 8 per SM did exactly that
+    // where 7 fit: 30 % warps-active average and a second wave at 1/7 occupancy).
     if (warps == 4) {
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned blocks = (unsigned)std::min<uint64_t>((ntask + 3) / 4, (uint64_t)ctx->sm_count * 8);
+        const unsigned blocks = pfe_persistent_grid(ctx, gauss_h_kernel<N, EXACT, 4, UW>, 128, smem, (ntask + 3) / 4);
         PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4, UW><<<blocks, 128, smem, ctx->stream>>>(P, W));
     } else {
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 1, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const unsigned blocks = (unsigned)std::min<uint64_t>(ntask, (uint64_t)ctx->sm_count * 8);
+        const unsigned blocks = pfe_persistent_grid(ctx, gauss_h_kernel<N, EXACT, 1, UW>, 32, smem, ntask);
         PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 1, UW><<<blocks, 32, smem, ctx->stream>>>(P, W));
     }
     PFE_LAUNCHED(ctx);
@@ -683,10 +707,29 @@ int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
 
 template <int N, bool EXACT>
 int run_h(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
-    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
     WeightTable W;
     fill_weight_table<N>(W, k);
-    return use_uniform_weights(P.wp_len) ? launch_h<N, EXACT, true>(ctx, P, W) : launch_h<N, EXACT, false>(ctx, P, W);
+    set_steps<N>(P, k);
+    if (use_uniform_weights(P.wp_len)) return launch_h<N, EXACT, true>(ctx, P, W);  // the table travels in the parameters
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    return launch_h<N, EXACT, false>(ctx, P, W);
+}
+
+// Consumer warps of the V tile kernel for this radius: 12 when that ring fits (measured at sigma 20, 8K: N = 8 with
+// 12 warps 0.64 ms, N = 8 or 16 with 8 warps 0.67 ms), else 8, else 0 = the direct-from-global kernel.
+// PFE_GAUSS_V_WARPS=8|12 and PFE_GAUSS_V_DIRECT=1 force a variant.
+template <int N>
+int v_tile_warps(const GaussParams &P) {
+    if (N < 4 || getenv("PFE_GAUSS_V_DIRECT") != nullptr) return 0;
+    const size_t extra = (size_t)((P.wp_len + 1) & ~1) * 8 + 16 * kChunks + 64;
+    auto fits = [&](int warps) {
+        const int rows = warps * N + P.steps - N;
+        return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra <= 225 * 1024;
+    };
+    const char *force = getenv("PFE_GAUSS_V_WARPS");
+    const int want = force ? atoi(force) : 12;
+    if (want == 12 && fits(12)) return 12;
+    return fits(8) ? 8 : 0;
 }
 
 // V pass: tile variant when its shared-memory footprint fits, else the direct variant
@@ -698,24 +741,22 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
         const int rows = warps * N + P.steps - N;
         return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra;
     };
-    const bool force_direct = getenv("PFE_GAUSS_V_DIRECT") != nullptr;
-    const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 8 * N);
-    // EXPERIMENT: 12 consumer warps (a taller tile: less halo per output row, 13 warps per SM) now that the uniform-weight
-    // kernel needs 90 registers; PFE_GAUSS_V_WARPS=12 selects it when its ring fits.
-    const char *vw = getenv("PFE_GAUSS_V_WARPS");
-    if (!force_direct && UW && N >= 4 && vw && atoi(vw) == 12 && tile_smem(12) <= 225 * 1024) {
+    const int vw = v_tile_warps<N>(P);
+    if (vw == 12) {
+        // 12 consumer warps: a taller tile (less halo per output row) and, with N = 8, two CTAs per SM
         const size_t smem = tile_smem(12);
         const unsigned tiles12 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 12 * N);
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 12, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 12, UW>, 416, smem, tiles12);
         PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 12, UW><<<blocks, 416, smem, ctx->stream>>>(P, W));
-    } else if (!force_direct && N >= 4 && tile_smem(8) <= 225 * 1024) {
+    } else if (vw == 8) {
         const size_t smem = tile_smem(8);
+        const unsigned tiles8 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 8 * N);
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 8, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8, UW>, 288, smem, tiles8);
         PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8, UW><<<blocks, 288, smem, ctx->stream>>>(P, W));
     } else {
-        size_t smem = (size_t)wp_pad * 8;
+        size_t smem = (size_t)wp_pad * 8;  // the direct variant reads its weights from P.wp (run_v uploads them)
         if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
         if (smem > 48 * 1024)
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -729,15 +770,18 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
 // V pass: tile variant when its shared-memory footprint fits, else the direct variant
 template <int N, bool EXACT>
 int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
-    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
     WeightTable W;
     fill_weight_table<N>(W, k);
-    return use_uniform_weights(P.wp_len) ? launch_v<N, EXACT, true>(ctx, P, W) : launch_v<N, EXACT, false>(ctx, P, W);
+    set_steps<N>(P, k);
+    if (use_uniform_weights(P.wp_len) && v_tile_warps<N>(P) != 0) return launch_v<N, EXACT, true>(ctx, P, W);
+    PFE_TRY(upload_weights<N>(ctx, P, k, P.sigma));
+    return launch_v<N, EXACT, false>(ctx, P, W);
 }
 
-// Register-block size per pass: the one that wastes the fewest issue slots on zero-padded steps plus
-// per-step overhead. The V pass pays more per step (ring bookkeeping), so it prefers a larger block:
-// measured at sigma=20, H is fastest with N=8 and V with N=16.
+// Register-block size per pass: the one that wastes the fewest FMA-pipe slots on zero-padded steps plus per-step
+// overhead (input load, weight fetch, ring bookkeeping: worth about 6 FFMA2 slots per step with the weights in
+// uniform registers, half that relative to the doubled arithmetic of the EXACT path).  Measured at sigma 20 on
+// 8K (profiles/r02_ops_a.jsonl): N = 8 for both passes (128 steps for 121 taps; N = 16 pads to 144).
 static int pick_n(int taps, double per_step_overhead, const char *pass_knob) {
     auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + per_step_overhead) / n; };
     int best = 1;
@@ -757,7 +801,7 @@ static int pick_n(int taps, double per_step_overhead, const char *pass_knob) {
 
 template <bool EXACT>
 int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
-    switch (pick_n((int)k.size(), 6.0, "PFE_GAUSS_NH")) {
+    switch (pick_n((int)k.size(), EXACT ? 3.0 : 6.0, "PFE_GAUSS_NH")) {
         case 16: return run_h<16, EXACT>(ctx, P, k);
         case 8: return run_h<8, EXACT>(ctx, P, k);
         case 4: return run_h<4, EXACT>(ctx, P, k);
@@ -768,7 +812,7 @@ int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
 template <bool EXACT>
 int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
     const int taps = (int)k.size();
-    switch (pick_n(taps, 12.0, "PFE_GAUSS_NV")) {
+    switch (pick_n(taps, EXACT ? 3.0 : 6.0, "PFE_GAUSS_NV")) {
         case 16: return run_v<16, EXACT>(ctx, P, k);
         case 8: return run_v<8, EXACT>(ctx, P, k);
         case 4: return run_v<4, EXACT>(ctx, P, k);
@@ -784,6 +828,7 @@ int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     const int taps = (int)k.size();
     P.steps = ((N + taps - 1 + N - 1) / N) * N;
     P.wp_len = P.steps + N - 1;
+    P.tri = (P.steps == N + taps - 1 && getenv("PFE_GAUSS_NO_TRI") == nullptr) ? 1 : 0;
     FusedWeights W;
     memset(&W, 0, sizeof(W));
     for (int t = 0; t < taps; t++) W.wk[t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
@@ -839,6 +884,7 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     if (!use_fused(ctx, radius, rw, rh)) PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)rw * rh * 16, &mid));
     GaussParams P;
     memset(&P, 0, sizeof(P));
+    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
     P.src = src; P.mid = (float *)mid; P.dst = dst;
     P.orig = orig; P.mask = mask; P.amount = amount; P.epilogue = orig ? epilogue : 0;
     P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
@@ -859,6 +905,7 @@ int pfe_gauss_h_rows(pfe_ctx *ctx, const uint8_t *src, float *mid, uint32_t w, u
     if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
     GaussParams P;
     memset(&P, 0, sizeof(P));
+    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
     P.src = src + (size_t)y0 * w * 4; P.mid = mid + (size_t)y0 * w * 4;
     P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = rows; P.radius = radius; P.sigma = sigma;
     (void)h;
@@ -870,6 +917,7 @@ int pfe_gauss_v_rows(pfe_ctx *ctx, float *mid, uint8_t *dst, uint32_t w, uint32_
     std::vector<float> k = build_kernel(sigma, &radius);
     GaussParams P;
     memset(&P, 0, sizeof(P));
+    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
     P.mid = mid; P.dst = dst; P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius; P.sigma = sigma;
     P.v_y0 = y0; P.v_rows = rows;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_v<true>(ctx, P, k) : dispatch_v<false>(ctx, P, k);
@@ -920,6 +968,32 @@ extern "C" int pfe_dev_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t 
                                                               (uint32_t *)dst, n));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
+}
+
+// Row-band form for a canvas split across GPUs: the caller's extended band (own rows + halo rows
+// received from the neighbours) is filtered with the ordinary kernels; the H pass can be issued per row range so
+// that the band's own rows are filtered while the halo is still in flight.
+extern "C" int pfe_dev_gaussian_band_h(pfe_ctx *ctx, const uint8_t *ext, uint32_t w, uint32_t ext_rows, uint32_t y0,
+                                       uint32_t rows, float sigma, uint32_t flags) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!ext || !w || !ext_rows || (uint64_t)y0 + rows > ext_rows) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "gaussian_band_h: bad args");
+    if (!rows) return PFE_OK;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *mid;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)w * ext_rows * 16, &mid));
+    return pfe_gauss_h_rows(ctx, ext, (float *)mid, w, ext_rows, y0, rows, sigma, flags);
+}
+extern "C" int pfe_dev_gaussian_band_v(pfe_ctx *ctx, uint32_t w, uint32_t ext_rows, uint32_t y0, uint32_t rows, float sigma,
+                                       uint8_t *dst_rows, uint32_t flags) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!dst_rows || !w || !ext_rows || (uint64_t)y0 + rows > ext_rows) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "gaussian_band_v: bad args");
+    if (!rows) return PFE_OK;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)w * ext_rows * 16 > ctx->scratch_bytes[PFE_SCRATCH_F32])
+        return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "gaussian_band_v: no H pass of this band precedes it");
+    // the V kernels address dst by absolute ext row: hand them the address row 0 would have
+    uint8_t *base = dst_rows - (size_t)y0 * w * 4;
+    return pfe_gauss_v_rows(ctx, (float *)ctx->scratch[PFE_SCRATCH_F32], base, w, ext_rows, y0, rows, sigma, flags);
 }
 
 extern "C" int pfe_dev_sharpen(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float amount, float radius,

@@ -329,23 +329,17 @@ extern "C" int pfe_dev_warp_band(pfe_ctx *ctx, const uint8_t *src_rows, uint32_t
     MeshParams M;
     memset(&M, 0, sizeof(M));
     if (!disp_band) PFE_TRY(fill_mesh(ctx, &M, orig, def, cols, rows));
-    int zero = 0;
-    void *flag;
-    PFE_TRY(pfe_small_upload(ctx, &zero, sizeof(zero), &flag));
+    int *flag = ctx->async_err;  // sticky: read (and cleared) by pfe_ctx_check_async, so this call stays asynchronous
     const dim3 grid(pfe_div_up(w, 32), pfe_div_up(rows_out, 8 * kMeshRows));
     if (disp_band)
         PFE_KERNEL(ctx, "warp_band", warp_band_kernel<false><<<grid, 256, 0, ctx->stream>>>(
             M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, (const float2 *)disp_band,
-            (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
+            (uint32_t *)dst_band, w, h, y0, rows_out, flag));
     else
         PFE_KERNEL(ctx, "warp_band", warp_band_kernel<true><<<grid, 256, 0, ctx->stream>>>(
             M, (const uint32_t *)src_rows, (int)sw, (int)sh, (int)src_y0, (int)src_nrows, nullptr,
-            (uint32_t *)dst_band, w, h, y0, rows_out, (int *)flag));
+            (uint32_t *)dst_band, w, h, y0, rows_out, flag));
     PFE_LAUNCHED(ctx);
-    int missing = 0;
-    PFE_CUDA(ctx, cudaMemcpyAsync(&missing, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (missing) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp_band: the source row window does not cover the warp's reach");
     return PFE_OK;
 }
 

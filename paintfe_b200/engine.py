@@ -301,6 +301,25 @@ class Engine:
         return self._img_op(self.lib.pfe_gaussian_blur, self.lib.pfe_dev_gaussian_blur, src, mask, out,
                             C.c_float(sigma), tail=(L.GAUSS_EXACT if exact else 0,))
 
+    def gaussian_band_h(self, ext, y0, rows, sigma, exact=False):
+        """Device tier: H pass of rows [y0, y0+rows) of an extended band (pfe_dev_gaussian_band_h)."""
+        self._dev(ext)
+        self._ck(self.lib.pfe_dev_gaussian_band_h(self.h, _ptr(ext), int(ext.shape[1]), int(ext.shape[0]), int(y0), int(rows),
+                                                  C.c_float(sigma), L.GAUSS_EXACT if exact else 0))
+
+    def gaussian_band_v(self, ext, y0, rows, sigma, exact=False, out=None):
+        """Device tier: V pass producing rows [y0, y0+rows) of the extended band `ext` (only its shape is used)."""
+        w, ext_rows = int(ext.shape[1]), int(ext.shape[0])
+        dst = out if out is not None else torch.empty((rows, w, 4), dtype=torch.uint8, device=ext.device)
+        self._dev(ext, dst)
+        self._ck(self.lib.pfe_dev_gaussian_band_v(self.h, w, ext_rows, int(y0), int(rows), C.c_float(sigma), _ptr(dst),
+                                                  L.GAUSS_EXACT if exact else 0))
+        return dst
+
+    def check_async(self):
+        """Synchronise and raise if a stream-asynchronous call recorded an error on the device (pfe_ctx_check_async)."""
+        self._ck(self.lib.pfe_ctx_check_async(self.h))
+
     def box_blur(self, src, radius, mask=None, out=None):
         return self._img_op(self.lib.pfe_box_blur, self.lib.pfe_dev_box_blur, src, mask, out, C.c_float(radius))
 
