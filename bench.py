@@ -4,12 +4,26 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 One process per GPU (torchrun for N > 1; `python bench.py --gpus N` re-launches itself under
-torch.distributed.run). Each rank owns its own 8K canvas (whole-image sharding, no data-path
-collective: "weak" scaling).  A step = flatten(16 layers, all 25 modes cycled) followed
-by Gaussian(sigma=20) with inputs resident in HBM.  Rank 0 prints ONE JSON line.
+torch.distributed.run).  A step = flatten(16 layers, all 25 modes cycled) followed by Gaussian(sigma=20) with inputs
+resident in HBM.  Rank 0 prints ONE JSON line.  What the line carries:
 
-`--impl reference` times the CPU restatement of PaintFE's rayon path (oracle/, kind "port": the Rust
-reference cannot be built in this image) on the host cores, on a bounded sample of the same workload.
+  value / ms_per_step   "weak": every rank owns its own 8K canvas (whole-image sharding, the CLI batch axis; no
+                        data-path collective).  value = all ranks' pixels / max-over-ranks time.
+  e2e                   the same step through the host-pointer C ABI call pfe_flatten_gaussian from pinned host
+                        buffers (H2D + D2H inside the timed region), plus `bare_copy_ms`: the same bytes copied
+                        with nothing else running, so the record itself shows how much of e2e is the PCIe fabric.
+  strong (N > 1)        ONE 8K canvas split into N row bands: flatten is band-local, the Gaussian exchanges
+                        ceil(3 sigma) rows of u8 input with the neighbours over NCCL (paintfe_b200.dist) on a side
+                        stream while the band's own rows go through the H pass.  Every rank checks its band against
+                        the single-GPU result of the whole canvas (parity) outside the timed region.
+  config4               BASELINE config 4: 16384^2 mesh warp 6x6 + liquify warp, one canvas in N row bands with a
+                        halo exchange sized by the warp's reach, parity-checked the same way.
+  kernels / roofline    per-kernel CUDA-event times from inside the timed region; `extra` times the EXACT-mode
+                        Gaussian (what INTEGRATION.md's drop-in wrapper binds) and the other two config-2 stacks.
+
+`--impl reference` times the CPU restatement of PaintFE's rayon path (oracle/, kind "port": the Rust reference
+cannot be built in this image) on ALL host cores (the thread count is set explicitly; an inherited OMP_NUM_THREADS
+is ignored), on the same workload.
 """
 from __future__ import annotations
 
@@ -28,11 +42,12 @@ sys.path.insert(0, ROOT)
 W8K, H8K, NLAYERS, SIGMA = 7680, 4320, 16, 20.0
 METRIC = "Mpixels/sec: 16-layer 8K flatten + Gaussian sigma=20"
 WORKLOAD = "8K (7680x4320) 16-layer synthetic stack cycling all 25 blend modes, flatten + Gaussian sigma=20"
+MIN_WARMUP = 3
 
 
-def layer_meta():
-    # mode = i mod 25, opacity = 0.25 + 0.05 i
-    return [dict(blend=i % 25, opacity=0.25 + 0.05 * i) for i in range(NLAYERS)]
+def layer_meta(offset=0):
+    # mode = i mod 25, opacity = 0.25 + 0.05 i; the second stack starts at mode 16
+    return [dict(blend=(i + offset) % 25, opacity=0.25 + 0.05 * i) for i in range(NLAYERS)]
 
 
 def measured_peak():
@@ -93,8 +108,15 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm (oracle port)
+# CPU arm (oracle port).  ONE procedure for both `--impl reference` and the GPU line's cpu_baseline.
 # ---------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_pass(pfo, layers_np, meta, w, h):
     t0 = time.perf_counter()
     flat = pfo.flatten([pfo.make_layer(im, **m) for im, m in zip(layers_np, meta)], w, h)
@@ -109,43 +131,57 @@ def cpu_sample_layers(w, h):
     return [rng.integers(0, 256, (h, w, 4), dtype=np.uint8) for _ in range(NLAYERS)]
 
 
+def cpu_measure(steps, warmup, budget_s, layers_8k=None):
+    """Mean seconds per step of flatten + Gaussian on the CPU port with every host core.  The sample is the full 8K
+    canvas unless (steps + warmup) passes of it would exceed `budget_s`; then the largest of 4K / 1080p that fits,
+    and the returned description says so (the caller puts the real size into the line)."""
+    from oracle import pfo
+
+    pfo.build()
+    threads = pfo.set_num_threads(cpu_threads())
+    meta = layer_meta()
+    cal = cpu_sample_layers(960, 540) if layers_8k is None else [l[:540, :960].copy() for l in layers_8k]
+    cpu_pass(pfo, cal, meta, 960, 540)
+    per_px = min(cpu_pass(pfo, cal, meta, 960, 540) for _ in range(2)) / (960 * 540)
+    w, h = 1920, 1080
+    for cw, ch in ((W8K, H8K), (3840, 2160), (1920, 1080)):
+        if per_px * cw * ch * (steps + warmup) <= budget_s:
+            w, h = cw, ch
+            break
+    if layers_8k is not None:
+        import numpy as np
+
+        layers = layers_8k if (w, h) == (W8K, H8K) else [np.ascontiguousarray(l[:h, :w]) for l in layers_8k]
+    else:
+        layers = cpu_sample_layers(w, h)
+    for _ in range(warmup):
+        cpu_pass(pfo, layers, meta, w, h)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(pfo, layers, meta, w, h)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    full = (w, h) == (W8K, H8K)
+    sample = (f"{'the full' if full else 'top-left crop of the'} {w}x{h} canvas, {NLAYERS} layers, same modes / opacities / sigma; "
+              f"mean of {steps} steps after {warmup} warm-up; {threads} OpenMP threads")
+    return {"seconds": dt, "w": w, "h": h, "full": full, "threads": threads, "sample": sample, "mpx_s": w * h / dt / 1e6}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import pfo
-
-    pfo.build()
-    meta = layer_meta()
-    # calibrate on 960x540, then pick the largest sample that keeps the whole run to ~2 minutes
-    cal = cpu_sample_layers(960, 540)
-    cpu_pass(pfo, cal, meta, 960, 540)
-    t_cal = cpu_pass(pfo, cal, meta, 960, 540)
-    per_px = t_cal / (960 * 540)
-    total = args.steps + args.warmup
-    w, h = 960, 540
-    for cw, ch in ((7680, 4320), (3840, 2160), (1920, 1080)):
-        if per_px * cw * ch * total <= 120.0:
-            w, h = cw, ch
-            break
-    layers = cal if (w, h) == (960, 540) else cpu_sample_layers(w, h)
-    for _ in range(args.warmup):
-        cpu_pass(pfo, layers, meta, w, h)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_pass(pfo, layers, meta, w, h)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    value = (w * h) / dt / 1e6
-    sample = f"{w}x{h} crop-sized canvas, {NLAYERS} layers, same modes/opacities/sigma; {args.steps} steps"
+    warmup = max(args.warmup, MIN_WARMUP)
+    m = cpu_measure(args.steps, warmup, budget_s=300.0)
+    workload = WORKLOAD if m["full"] else f"{m['w']}x{m['h']} crop of: {WORKLOAD}"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": m["mpx_s"], "unit": "Mpixels/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": m["seconds"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample,
+        "config": {"workload": workload, "sample": m["sample"],
                    "note": "CPU restatement of PaintFE's rayon path (OpenMP over chunks / rows); the Rust reference "
-                           "cannot be built in this image (no cargo, ~400 crates)"},
-        "cpu_baseline": {"value": value, "unit": "Mpixels/s", "cores": pfo.num_threads(), "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                           "cannot be built in this image (no cargo, ~400 crates). One CPU run serves every N."},
+        "cpu_baseline": {"value": m["mpx_s"], "unit": "Mpixels/s", "cores": m["threads"], "kind": "port", "sample": m["sample"]},
+        "e2e": {"value": m["mpx_s"], "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -182,6 +218,7 @@ def run_b200(args):
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
+    from paintfe_b200 import dist as pd
     from paintfe_b200.engine import Engine, make_layer
 
     eng = Engine(local)
@@ -189,6 +226,7 @@ def run_b200(args):
     w, h = W8K, H8K
     px = w * h
     meta = layer_meta()
+    warmup = max(args.warmup, MIN_WARMUP)
     gen = torch.Generator(device=dev).manual_seed(0x5EED + rank)
     layers = [torch.randint(0, 256, (h, w, 4), dtype=torch.uint8, device=dev, generator=gen) for _ in range(NLAYERS)]
     dl = [make_layer(t, **m) for t, m in zip(layers, meta)]
@@ -204,7 +242,26 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def timed(fn, steps, warm=MIN_WARMUP):
+        """CUDA-event ms per step of fn on the current stream, barrier + synchronize on both sides, max over ranks."""
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / steps)[0]
+
+    for _ in range(warmup):
         step()
     barrier()
 
@@ -227,10 +284,24 @@ def run_b200(args):
     eng.profile(False)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- end to end through the host-pointer C ABI call (pinned host buffers) -----------------
-    from paintfe_b200.dist import bind_to_gpu_numa
+    # ---- the rest of config 2 and the bit-exact Gaussian, device-resident, rank 0's numbers ------------------
+    few = max(3, min(args.steps, 10))
+    extra = {}
+    extra["gaussian_exact_ms"] = timed(lambda: eng.gaussian_blur(flat, SIGMA, exact=True, out=out), few)
+    dl2 = [make_layer(t, **m) for t, m in zip(layers, layer_meta(16))]
+    extra["flatten_stack2_ms"] = timed(lambda: eng.flatten(dl2, w, h, out=out), few)
+    for t in layers:  # alpha in {0, 255}: the fast-path regime of config 2
+        t[..., 3] = torch.where(t[..., 3] > 127, 255, 0).to(torch.uint8)
+    extra["flatten_binary_alpha_ms"] = timed(lambda: eng.flatten(dl, w, h, out=out), few)
+    extra["note"] = ("gaussian_exact_ms: PFE_GAUSS_EXACT (bit-exact) on the same 8K image; flatten_stack2_ms: modes 16-24 then 0-6; "
+                     "flatten_binary_alpha_ms: modes 0-15 with alpha in {0,255}")
+    gen.manual_seed(0x5EED + rank)
+    for t in layers:
+        t.random_(0, 256, generator=gen)
+    step()  # `out` is again the weak step's result (compared with the host tier below)
 
-    numa = bind_to_gpu_numa(local)  # pinned buffers next to this GPU's root port (matters for N > 1)
+    # ---- end to end through the host-pointer C ABI call (pinned host buffers) -----------------
+    numa = pd.bind_to_gpu_numa(local)  # pinned buffers next to this GPU's root port (matters for N > 1)
     host_layers = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(NLAYERS)]
     for hl, t in zip(host_layers, layers):
         hl.copy_(t)
@@ -251,13 +322,67 @@ def run_b200(args):
     # the host-tier result must equal the device-tier result (same inputs)
     same = bool(torch.equal(host_out.to(dev), out))
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    # the same bytes with nothing else running: 16 layer uploads, then one result download
+    def bare_copy():
+        for hl, t in zip(host_layers, layers):
+            t.copy_(hl, non_blocking=True)
+        host_out.copy_(out, non_blocking=True)
+
+    bare_ms = timed(bare_copy, e2e_steps, warm=1)
+
+    ms_total, e2e_ms = max_over_ranks(ms_total, e2e_ms)
     ms_step = ms_total / args.steps
     value = world * px / (ms_step * 1e-3) / 1e6
     e2e_value = world * px / (e2e_ms / e2e_steps * 1e-3) / 1e6
+
+    # ---- strong scaling: ONE 8K canvas in row bands, NCCL halo exchange for the Gaussian ----------------
+    strong = None
+    if world > 1:
+        del host_layers, hl_np
+        g2 = torch.Generator(device=dev).manual_seed(0x5EED)  # every rank generates the SAME canvas
+        for t in layers:
+            t.random_(0, 256, generator=g2)
+        eng.flatten(dl, w, h, out=flat)
+        whole = eng.gaussian_blur(flat, SIGMA)  # single-GPU result of the whole canvas (outside the timed region)
+        bounds = pd.band_bounds(h, world)
+        y0, y1 = bounds[rank]
+        rows = y1 - y0
+        radius = pd.gaussian_radius(SIGMA)
+        band_layers = [make_layer(t[y0:y1], **m) for t, m in zip(layers, meta)]
+        plan = pd.halo_plan(flat[y0:y1], radius, radius, bounds)
+        out_band = torch.empty((rows, w, 4), dtype=torch.uint8, device=dev)
+
+        def strong_step():
+            eng.flatten(band_layers, w, rows, out=plan.core)  # band-local, written where the blur wants it
+            pd.gaussian_blur_banded(eng, plan.core, h, SIGMA, bounds=bounds, out=out_band)
+
+        strong_ms = timed(strong_step, args.steps, warm=warmup)
+        ok = torch.tensor([1.0 if torch.equal(out_band, whole[y0:y1]) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        exch_ms = timed(plan.exchange, max(args.steps, 10), warm=3)
+        # the same band-local kernels without any exchange (halo rows left as they are): what the exchange costs on top
+        def no_exchange_step():
+            eng.flatten(band_layers, w, rows, out=plan.core)
+            eng.gaussian_band_h(plan.ext, 0, plan.ext.shape[0], SIGMA)
+            eng.gaussian_band_v(plan.ext, plan.top, rows, SIGMA, out=out_band)
+
+        noex_ms = timed(no_exchange_step, args.steps, warm=2)
+        halo = max_over_ranks(float(plan.halo_bytes))[0]
+        strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20 with an NCCL halo exchange of %d u8 rows per side" % (world, radius),
+                  "ms_per_step": strong_ms, "mpx_s": px / strong_ms / 1e3, "band_rows": [b - a for a, b in bounds],
+                  "halo_bytes": int(halo), "exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
+                  "parity": bool(ok.item() == 1.0), "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
+                  "speedup_vs_one_gpu_step": ms_step / strong_ms,
+                  "note": "exchange on a side stream under the band's own H pass; halo rows recompute the H pass; "
+                          "exchange_ms = the exchange alone, back to back; ms_per_step_no_exchange = same kernels, no transfer"}
+        del whole, plan, out_band, band_layers
+
+    # ---- BASELINE config 4: 16384^2 mesh warp + liquify warp on one canvas in row bands ----------------
+    config4 = None
+    if not args.no_config4:
+        del layers, dl, dl2, flat, out
+        torch.cuda.empty_cache()
+        config4 = run_config4(eng, pd, dev, rank, world, timed, max(3, args.steps // 4))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -275,25 +400,23 @@ def run_b200(args):
         # the per-kernel event spans must add up to (just under) the step time measured around the whole loop
         span_share = sum(v["share_of_step"] for v in per_kernel.values())
         dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
-        traffic = None
+        tj = {}
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(dom)
+                tj = json.load(f)
         except Exception:
             pass
         roofline = None
         if dom in alg:
             ach = per_kernel[dom]["achieved_gbs"]
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "traffic": traffic, "peak_source": peak_src,
+                        "traffic": tj.get(dom), "peak_source": peak_src,
                         "note": "algorithmic bytes / CUDA-event kernel time; the kernel is FP32-issue bound when "
                                 "bit-exact (DESIGN.md §4), so frac << 1 is expected"}
         # what actually bounds each kernel: warp-instruction issue for the flatten, FP32 FMA lanes
         # for the Gaussian passes. Static counts from the committed ncu capture, live kernel times.
         compute = {}
         try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)
             sm_clock_hz = (clocks or {}).get("sm_mhz", 1965.0) * 1e6
             issue_peak = 148 * 4 * sm_clock_hz  # one warp instruction per scheduler per clock
             for k, n_inst in tj.get("warp_instructions", {}).items():
@@ -304,39 +427,35 @@ def run_b200(args):
             for k, lanes in tj.get("fma_lanes", {}).items():
                 if k in per_kernel:
                     ach = lanes / (per_kernel[k]["avg_ms"] * 1e-3)
-                    compute[k].update({"fma_bound": "fp32 FMA lanes", "achieved_tfma_s": ach / 1e12,
-                                       "peak_tfma_s": tj["fp32_fma_lanes_per_s_peak"] / 1e12, "fma_frac": ach / tj["fp32_fma_lanes_per_s_peak"]})
+                    compute.setdefault(k, {}).update({"fma_bound": "fp32 FMA lanes", "achieved_tfma_s": ach / 1e12,
+                                                      "peak_tfma_s": tj["fp32_fma_lanes_per_s_peak"] / 1e12,
+                                                      "fma_frac": ach / tj["fp32_fma_lanes_per_s_peak"]})
         except Exception:
             pass
-        whole = {"achieved": 76 * px / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_px": 76}
-        whole["frac"] = whole["achieved"] / peak
+        whole_step = {"achieved": 76 * px / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "bytes_per_px": 76}
+        whole_step["frac"] = whole_step["achieved"] / peak
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import pfo
-
-            pfo.build()
-            cw, ch = 3840, 2160
-            crop = [np.ascontiguousarray(t.numpy()[:ch, :cw]) for t in host_layers]
-            cpu_pass(pfo, [c[:270, :480].copy() for c in crop], meta, 480, 270)
-            best = min(cpu_pass(pfo, crop, meta, cw, ch) for _ in range(2))
-            cpu = {"value": cw * ch / best / 1e6, "unit": "Mpixels/s", "cores": pfo.num_threads(), "kind": "port",
-                   "sample": f"top-left {cw}x{ch} crop of the same 16 layers, flatten + Gaussian sigma=20, best of 2"}
+            m = cpu_measure(3, 1, budget_s=30.0, layers_8k=[t.numpy() for t in host_layers])
+            cpu = {"value": m["mpx_s"], "unit": "Mpixels/s", "cores": m["threads"], "kind": "port", "sample": m["sample"]}
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu": "one 8K canvas per rank, no collective",
-                       "l2": "inputs 2.12 GB per step > 126 MB L2 (no flush needed)", "gaussian": "fast (FMA) path",
+            "config": {"workload": WORKLOAD, "per_gpu": "one 8K canvas per rank, no collective (the `strong` block splits ONE canvas)",
+                       "l2": "inputs 2.12 GB per step > 126 MB L2 (no flush needed)", "gaussian": "fast (FMA) path; EXACT timed in `extra`",
                        "timing": "CUDA events on the launching stream incl. per-kernel event pairs"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": NLAYERS * px * 4,
                     "d2h_bytes_per_step": px * 4, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "bare_copy_ms": bare_ms, "bare_copy_gbs_per_rank": (NLAYERS + 1) * px * 4 / (bare_ms * 1e-3) / 1e9,
                     "api": "pfe_flatten_gaussian (host pointers, pinned)", "matches_device_tier": same,
                     "numa_rank0": numa},
             "gpu_launches": launches,
-            "roofline": roofline, "roofline_whole_step": whole, "roofline_compute": compute, "kernels": per_kernel,
-            "kernel_spans_share_of_step": span_share,
+            "roofline": roofline, "roofline_whole_step": whole_step, "roofline_compute": compute, "kernels": per_kernel,
+            "kernel_spans_share_of_step": span_share, "extra": extra,
+            "strong": strong, "config4": config4,
             "cpu_baseline": cpu,
         }
         if _real_stdout is not None:
@@ -349,6 +468,63 @@ def run_b200(args):
     return 0
 
 
+def run_config4(eng, pd, dev, rank, world, timed, steps, S=16384):
+    """16384^2 single layer: fused mesh warp (6x6 Catmull-Rom) then the liquify displacement warp (64 pushes,
+    r = 200, strength 0.8), SURVEY 8d config 4.  N = 1: the two whole-image kernels.  N > 1: row bands, the source
+    rows each warp reaches exchanged over NCCL, each rank's band compared with the whole-image result."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    g = torch.Generator(device=dev).manual_seed(0xC4)
+    img = torch.randint(0, 256, (S, S, 4), dtype=torch.uint8, device=dev, generator=g)
+    orig = np.zeros((49, 2), np.float32)
+    for r in range(7):
+        for c in range(7):
+            orig[r * 7 + c] = (np.float32(c) / np.float32(6) * S, np.float32(r) / np.float32(6) * S)
+    deformed = orig.copy()
+    for i in range(7):
+        for j in range(7):
+            deformed[i * 7 + j] += np.float32(8.0 * np.sin(i) * np.cos(j))
+    field = torch.zeros((S, S, 2), dtype=torch.float32, device=dev)
+    prng = np.random.default_rng(0x5EED)
+    for _ in range(64):
+        cx, cy, dx, dy = (float(prng.uniform(0, S)), float(prng.uniform(0, S)), float(prng.uniform(-20, 20)), float(prng.uniform(-20, 20)))
+        eng.liquify(field, 0, cx, cy, 200.0, 0.8, dx, dy)
+    a, b = torch.empty_like(img), torch.empty_like(img)
+
+    def whole():
+        eng.mesh_warp(img, orig, deformed, 6, 6, S, S, out=a)
+        eng.warp_displacement(a, field, out=b)
+
+    res = {"workload": f"{S}x{S} mesh warp 6x6 (fused Catmull-Rom) then liquify displacement warp (64 pushes r=200)"}
+    if world == 1:
+        res.update({"ms_per_step": timed(whole, steps), "n_gpus": 1})
+        res["mpx_s"] = S * S / res["ms_per_step"] / 1e3
+        return res
+    whole()
+    bounds = pd.band_bounds(S, world)
+    y0, y1 = bounds[rank]
+    band = img[y0:y1]
+    fband = field[y0:y1]
+    reach = pd.displacement_reach(eng, fband, S, bounds=bounds)  # a property of the field: sized once, outside the loop
+    mreach = pd.mesh_reach(orig, deformed)
+    state = {}
+
+    def banded():
+        m = pd.mesh_warp_banded(eng, band, orig, deformed, 6, 6, S, S, bounds=bounds)
+        state["out"] = pd.warp_displacement_banded(eng, m, fband, S, bounds=bounds, reach=reach)
+
+    ms = timed(banded, steps)
+    eng.check_async()  # no warp tap fell outside the exchanged rows
+    ok = torch.tensor([1.0 if torch.equal(state["out"], b[y0:y1]) else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    res.update({"ms_per_step": ms, "mpx_s": S * S / ms / 1e3, "n_gpus": world, "band_rows": [q - p for p, q in bounds],
+                "halo_rows": {"mesh": mreach, "liquify_up_down": list(reach)}, "parity": bool(ok.item() == 1.0),
+                "parity_against": "single-GPU whole-canvas result, bit for bit"})
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -356,6 +532,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -1171,6 +1171,17 @@ void pfo_tiled_roundtrip(const uint8_t *src, uint32_t w, uint32_t h, uint8_t *oc
         }
 }
 
+/* bench.py's CPU arm sets the thread count explicitly: a launcher (torchrun) exports OMP_NUM_THREADS=1, which
+ * would otherwise turn the "all host cores" baseline into a single-thread run. */
+void pfo_set_num_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int pfo_num_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

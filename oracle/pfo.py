@@ -80,6 +80,12 @@ def num_threads() -> int:
     return int(lib().pfo_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads for every later call (overrides an inherited OMP_NUM_THREADS). Returns the count in effect."""
+    lib().pfo_set_num_threads(int(n))
+    return num_threads()
+
+
 # -- flatten ----------------------------------------------------------------------------
 def make_layer(rgba=None, opacity=1.0, blend=0, visible=True, mask=None, kind=0, adj=()):
     return dict(rgba=_u8(rgba), opacity=float(opacity), blend=int(blend), visible=bool(visible),

@@ -32,7 +32,7 @@ struct GaussParams {
     const uint8_t *src;   // H: region origin inside the source image
     float *mid;           // rw*rh*4 f32 intermediate
     uint8_t *dst;         // V: region origin inside the destination image
-    const float2 *wp;     // padded weights, each duplicated into both halves of a float2, device
+    const float *wp;      // padded weights (scalars), device
     const uint8_t *orig;  // sharpen: original pixels (same geometry as dst), else null
     const uint8_t *mask;  // sharpen: selection mask plane (w*h) at region origin, or null
     float amount;         // sharpen amount / glow intensity
@@ -48,9 +48,9 @@ struct GaussParams {
     int wp_len;           // steps + N - 1
     int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
-    // (1, 1) and (-0, -0) for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
+    // 1 and -0 for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
     // stage can see their values (see tap<true> below and blend.cuh).
-    float2 one, nzero;
+    float one, nzero;
 };
 
 // One RGBA accumulator as two packed f32x2 halves: sm_100's FFMA2 / FMUL2 / FADD2 retire two IEEE
@@ -66,8 +66,12 @@ struct Acc4 {
 // the pair back into a contractable mul + add (ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even
 // under --fmad=false).  Same FMA-pipe time as four scalar FMUL + four FADD, half the issue slots and half the code.
 template <bool EXACT>
-__device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float2 w2, const float2 one, const float2 nzero) {
-    const float2 ilo = make_float2(in.x, in.y), ihi = make_float2(in.z, in.w);
+__device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float w, const float one1, const float nzero1) {
+    // the weight is ONE 32-bit operand broadcast to both lanes (SASS `FFMA2 R, R, UR.F32, R`): measured with
+    // tools/ubench_ffma2.cu, that form issues at the FMA pipe's rate (2.02 cycles per FFMA2 per sub-partition),
+    // a 64-bit (w, w) pair operand at 2.34 from uniform registers and 2.30 from ordinary ones
+    const float2 ilo = make_float2(in.x, in.y), ihi = make_float2(in.z, in.w), w2 = make_float2(w, w);
+    const float2 one = make_float2(one1, one1), nzero = make_float2(nzero1, nzero1);
     if (EXACT) {
         acc.lo = __ffma2_rn(__ffma2_rn(ilo, w2, nzero), one, acc.lo);
         acc.hi = __ffma2_rn(__ffma2_rn(ihi, w2, nzero), one, acc.hi);
@@ -115,17 +119,17 @@ __device__ __forceinline__ float4 to_f4(uint32_t v) {
 // per-step weight is an `LDCU.64` into a uniform register pair and every tap becomes `FFMA2 acc, in.reuse, UR, acc`:
 // one fresh 64-bit register operand per instruction instead of two, no weight LDS, N fewer live register pairs.
 // Same table, same arithmetic, same results.  Not yet timed on a GPU.
-constexpr int kWeightTableLen = 400;  // float2 entries: 3.2 KB of the 4 KB parameter space; wp_len <= 400 covers sigma <= ~60
+constexpr int kWeightTableLen = 800;  // floats: 3.2 KB of the 4 KB parameter space; wp_len <= 800 covers sigma <= ~128
 struct WeightTable {
-    float2 wk[kWeightTableLen];
+    float wk[kWeightTableLen];
 };
 
 template <int N, bool EXACT, int WARPS, bool UW>
 __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ WeightTable W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2 *wshared = reinterpret_cast<float2 *>(smem_raw);
-    const float2 *wsm = UW ? W.wk : wshared;
-    const int wp_pad = UW ? 0 : (P.wp_len + 1) & ~1;
+    float *wshared = reinterpret_cast<float *>(smem_raw);
+    const float *wsm = UW ? W.wk : wshared;
+    const int wp_pad = UW ? 0 : (P.wp_len + 3) & ~3;
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
     float4 *tiles = reinterpret_cast<float4 *>(wshared + wp_pad);
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         for (int p = lane; p < tile_px; p += 32) tile[skew(p, N)] = to_f4(__ldg(row + min(max(x0 - P.radius + p, 0), rw - 1)));
         __syncwarp();
         Acc4 acc[N];
-        float2 R[N];
+        float R[N];
 #pragma unroll
         for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
@@ -211,7 +215,7 @@ __device__ __forceinline__ void v_store(const GaussParams &P, const Acc4 &acc, i
 template <int N, bool EXACT>
 __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ GaussParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2 *wsm = reinterpret_cast<float2 *>(smem_raw);
+    float *wsm = reinterpret_cast<float *>(smem_raw);
     for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wsm[i] = P.wp[i];
     __syncthreads();
     const int x = blockIdx.x * 128 + threadIdx.x;
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
     const int y_end = (int)(P.v_y0 + P.v_rows);
     for (int y0 = (int)P.v_y0 + blockIdx.y * N; y0 < y_end; y0 += gridDim.y * N) {
         Acc4 acc[N];
-        float2 R[N];
+        float R[N];
 #pragma unroll
         for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
@@ -273,8 +277,8 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     const int chunk_rows = (rows + kChunks - 1) / kChunks;
     const int ring_rows = chunk_rows * kChunks;
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // ring_rows x 32 float4
-    float2 *wshared = reinterpret_cast<float2 *>(smem_raw + (size_t)ring_rows * 512);
-    const float2 *wsm = UW ? W.wk : wshared;
+    float *wshared = reinterpret_cast<float *>(smem_raw + (size_t)ring_rows * 512);
+    const float *wsm = UW ? W.wk : wshared;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ring_rows * 512 + (size_t)((P.wp_len + 1) & ~1) * 8);
     if (!UW)
         for (int i = threadIdx.x; i < P.wp_len; i += blockDim.x) wshared[i] = P.wp[i];
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
         const uint32_t parity = it & 1u;
         Acc4 acc[N];
-        float2 R[N];
+        float R[N];
 #pragma unroll
         for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
@@ -414,7 +418,7 @@ constexpr int kFusedMaxWp = 40;   // padded weights for N = 4: steps + 3 <= 36 +
 // (no shared-memory wavefront, no staging), which matters because at N = 4 this kernel is bound by the
 // shared-memory pipe, not by the FMA pipe.
 struct FusedWeights {
-    float2 wk[kFusedMaxWp];
+    float wk[kFusedMaxWp];
 };
 
 // Ring column swizzle: pixel x of a ring row lives in 16-byte slot x ^ ((x >> 3) & 7).  The H warps write 4
@@ -426,7 +430,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ FusedWeights W) {
     constexpr int N = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const float2 *wsm = W.wk;
+    const float *wsm = W.wk;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);  // full[kFusedMaxRing], empty[kFusedMaxRing]
     const int tile_px = 31 * N + P.steps;
     const int tile_len = skew(tile_px, N) + 1;
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
                     if (2 * b + half + 1 < 2 * nb) fetch(2 * b + half + 1);
                     __syncwarp();
                     Acc4 acc[N];
-                    float2 R[N];
+                    float R[N];
 #pragma unroll
                     for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(256, 2) gauss_fused_kernel(const __grid_consta
                 const int yo = ys + 8 * (b - P.lag) + 4 * half;
                 int row = rslot * 8 + 4 * half;  // a multiple of 4: a group of 4 rows never straddles the wrap
                 Acc4 acc[N];
-                float2 R[N];
+                float R[N];
 #pragma unroll
                 for (int j = 0; j < N; j++) acc[j].lo = acc[j].hi = make_float2(0.f, 0.f);
 #pragma unroll
@@ -634,7 +638,7 @@ template <int N>
 int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, float sigma) {
     const int taps = (int)k.size();
     set_steps<N>(P, k);
-    const size_t bytes = (size_t)P.wp_len * sizeof(float2);
+    const size_t bytes = (size_t)P.wp_len * sizeof(float);
     uint32_t sigma_bits;
     memcpy(&sigma_bits, &sigma, 4);
     const bool cacheable = bytes <= pfe_ctx::kGaussSlotBytes;
@@ -644,16 +648,16 @@ int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, fl
             pfe_ctx::GaussSlot &g = ctx->gauss_slots[i];
             if (g.valid && g.sigma_bits == sigma_bits && g.n == N) {  // the table is already on the device
                 g.stamp = ++ctx->gauss_clock;
-                P.wp = (const float2 *)((char *)ctx->gauss_mem + (size_t)i * pfe_ctx::kGaussSlotBytes);
+                P.wp = (const float *)((char *)ctx->gauss_mem + (size_t)i * pfe_ctx::kGaussSlotBytes);
                 return PFE_OK;
             }
         }
     }
-    std::vector<float2> wp((size_t)P.wp_len, make_float2(0.0f, 0.0f));
-    for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
+    std::vector<float> wp((size_t)P.wp_len, 0.0f);
+    for (int t = 0; t < taps; t++) wp[(size_t)t + N - 1] = k[(size_t)t];
     void *wdev;
     PFE_TRY(pfe_small_upload(ctx, wp.data(), bytes, &wdev));
-    P.wp = (const float2 *)wdev;
+    P.wp = (const float *)wdev;
     if (cacheable) {  // keep a copy in the least recently used slot (stream ordered after its last reader)
         int lru = 0;
         for (int i = 0; i < pfe_ctx::kGaussSlots; i++) {
@@ -677,16 +681,16 @@ static bool use_uniform_weights(int wp_len) {
 template <int N>
 static void fill_weight_table(WeightTable &W, const std::vector<float> &k) {
     memset(&W, 0, sizeof(W));
-    for (size_t t = 0; t < k.size() && t + N - 1 < (size_t)kWeightTableLen; t++) W.wk[t + N - 1] = make_float2(k[t], k[t]);
+    for (size_t t = 0; t < k.size() && t + N - 1 < (size_t)kWeightTableLen; t++) W.wk[t + N - 1] = k[t];
 }
 
 template <int N, bool EXACT, bool UW>
 int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
-    const int wp_pad = UW ? 0 : (P.wp_len + 1) & ~1;  // float2 entries, keeps the tiles 16-byte aligned
+    const int wp_pad = UW ? 0 : (P.wp_len + 3) & ~3;  // float entries, keeps the tiles 16-byte aligned
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     int warps = 4;
-    size_t smem = (size_t)wp_pad * 8 + (size_t)warps * tile_len * 16;
-    if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 8 + (size_t)tile_len * 16; }
+    size_t smem = (size_t)wp_pad * 4 + (size_t)warps * tile_len * 16;
+    if (smem > 200 * 1024) { warps = 1; smem = (size_t)wp_pad * 4 + (size_t)tile_len * 16; }
     if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large for the H-pass tile");
     const uint64_t ntask = (uint64_t)pfe_div_up(P.rw, 32 * N) * P.rh;
     // Exactly one resident wave of grid-stride CTAs: the task loop strides by the grid, so a CTA that does not fit
@@ -756,7 +760,7 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
         const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 8, UW>, 288, smem, tiles8);
         PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 8, UW><<<blocks, 288, smem, ctx->stream>>>(P, W));
     } else {
-        size_t smem = (size_t)wp_pad * 8;  // the direct variant reads its weights from P.wp (run_v uploads them)
+        size_t smem = (size_t)wp_pad * 4;  // the direct variant reads its weights from P.wp (run_v uploads them)
         if (smem > 200 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
         if (smem > 48 * 1024)
             PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_kernel<N, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -831,7 +835,7 @@ int run_fused(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
     P.tri = (P.steps == N + taps - 1 && getenv("PFE_GAUSS_NO_TRI") == nullptr) ? 1 : 0;
     FusedWeights W;
     memset(&W, 0, sizeof(W));
-    for (int t = 0; t < taps; t++) W.wk[t + N - 1] = make_float2(k[(size_t)t], k[(size_t)t]);
+    for (int t = 0; t < taps; t++) W.wk[t + N - 1] = k[(size_t)t];
     P.lag = (2 * P.radius + 7) / 8;
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     const size_t smem = 2 * kFusedMaxRing * 8 + (size_t)4 * tile_len * 16 + (size_t)(P.lag + 2) * 8 * kFusedTW * 16;
@@ -884,7 +888,7 @@ int gauss_common(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t src_pi
     if (!use_fused(ctx, radius, rw, rh)) PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, (size_t)rw * rh * 16, &mid));
     GaussParams P;
     memset(&P, 0, sizeof(P));
-    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
+    P.one = 1.0f; P.nzero = -0.0f;
     P.src = src; P.mid = (float *)mid; P.dst = dst;
     P.orig = orig; P.mask = mask; P.amount = amount; P.epilogue = orig ? epilogue : 0;
     P.src_pitch = src_pitch; P.dst_pitch = dst_pitch; P.mask_pitch = mask_pitch;
@@ -905,7 +909,7 @@ int pfe_gauss_h_rows(pfe_ctx *ctx, const uint8_t *src, float *mid, uint32_t w, u
     if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
     GaussParams P;
     memset(&P, 0, sizeof(P));
-    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
+    P.one = 1.0f; P.nzero = -0.0f;
     P.src = src + (size_t)y0 * w * 4; P.mid = mid + (size_t)y0 * w * 4;
     P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = rows; P.radius = radius; P.sigma = sigma;
     (void)h;
@@ -917,7 +921,7 @@ int pfe_gauss_v_rows(pfe_ctx *ctx, float *mid, uint8_t *dst, uint32_t w, uint32_
     std::vector<float> k = build_kernel(sigma, &radius);
     GaussParams P;
     memset(&P, 0, sizeof(P));
-    P.one = make_float2(1.0f, 1.0f); P.nzero = make_float2(-0.0f, -0.0f);
+    P.one = 1.0f; P.nzero = -0.0f;
     P.mid = mid; P.dst = dst; P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius; P.sigma = sigma;
     P.v_y0 = y0; P.v_rows = rows;
     return (flags & PFE_GAUSS_EXACT) ? dispatch_v<true>(ctx, P, k) : dispatch_v<false>(ctx, P, k);

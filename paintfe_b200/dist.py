@@ -83,50 +83,122 @@ def _world(group=None) -> Tuple[int, int]:
     return 0, 1
 
 
-def exchange_halo(band: torch.Tensor, halo_up: int, halo_down: int, bounds: Sequence[Tuple[int, int]], group=None):
-    """Point-to-point halo exchange of whole rows between row-band neighbours.
+class HaloPlan:
+    """A band extended by its halo rows, allocated once, plus the point-to-point transfers that fill it.
 
-    `band` is this rank's rows (rows, ...) of an image split by `bounds`; returns (top, bottom):
-    up to `halo_up` rows that sit directly above the band and up to `halo_down` rows directly
-    below it (fewer at the image edges).  A halo may span several neighbours when bands are
-    thinner than the halo; every transfer is one isend/irecv pair, batched in one group so NCCL
-    issues them as a single ncclGroupStart/End.
+    `ext` holds [top halo | band | bottom halo] rows; `core` is the view of the band's own rows - producers write
+    into it directly (e.g. `eng.flatten(..., out=plan.core)`), so no band is ever concatenated or copied to make
+    room for its halo.  The halo may span several neighbours when bands are thinner than it; every transfer is one
+    isend / irecv of a contiguous row range of `ext`, all batched in one group (one ncclGroupStart/End).
+
+    On CUDA `exchange_async()` runs the group on a side stream: the caller keeps enqueueing band-local work (the
+    interior H pass of a blur) on its own stream and calls `wait()` right before the first kernel that reads halo
+    rows.  `wait()` also orders the sends' reads of `core` before whatever overwrites `core` next.
     """
-    rank, world = _world(group)
-    y0, y1 = bounds[rank]
-    h = bounds[-1][1]
-    want_top = (max(y0 - halo_up, 0), y0)
-    want_bot = (y1, min(y1 + halo_down, h))
-    row_shape = tuple(band.shape[1:])
 
-    def overlap(a, b):
-        lo, hi = max(a[0], b[0]), min(a[1], b[1])
-        return (lo, hi) if hi > lo else None
+    def __init__(self, row_shape, dtype, device, halo_up: int, halo_down: int, bounds: Sequence[Tuple[int, int]], group=None):
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.bounds = list(bounds)
+        y0, y1 = self.bounds[self.rank]
+        h = self.bounds[-1][1]
+        self.y0, self.rows = y0, y1 - y0
+        want_top = (max(y0 - halo_up, 0), y0)
+        want_bot = (y1, min(y1 + halo_down, h))
+        self.top, self.bot = want_top[1] - want_top[0], want_bot[1] - want_bot[0]
+        self.ext = torch.empty((self.top + self.rows + self.bot,) + tuple(row_shape), dtype=dtype, device=device)
+        self.core = self.ext[self.top:self.top + self.rows]
+        ext_y0 = y0 - self.top  # image row of ext row 0
 
-    ops, recvs = [], []
-    for peer in range(world):
-        if peer == rank:
-            continue
-        py0, py1 = bounds[peer]
-        # rows the peer wants from me (same halo sizes everywhere)
-        for want in ((max(py0 - halo_up, 0), py0), (py1, min(py1 + halo_down, h))):
-            ov = overlap(want, (y0, y1))
-            if ov:
-                ops.append(dist.P2POp(dist.isend, band[ov[0] - y0:ov[1] - y0].contiguous(), peer, group))
-        # rows I want from the peer
-        for which, want in (("top", want_top), ("bot", want_bot)):
-            ov = overlap(want, (py0, py1))
-            if ov:
-                buf = torch.empty((ov[1] - ov[0],) + row_shape, dtype=band.dtype, device=band.device)
-                ops.append(dist.P2POp(dist.irecv, buf, peer, group))
-                recvs.append((which, ov[0], buf))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    top = [b for w, _, b in sorted((r for r in recvs if r[0] == "top"), key=lambda r: r[1])]
-    bot = [b for w, _, b in sorted((r for r in recvs if r[0] == "bot"), key=lambda r: r[1])]
-    empty = band[:0]
-    return (torch.cat(top) if top else empty), (torch.cat(bot) if bot else empty)
+        def overlap(a, b):
+            lo, hi = max(a[0], b[0]), min(a[1], b[1])
+            return (lo, hi) if hi > lo else None
+
+        self.sends, self.recvs = [], []  # (peer, ext row lo, ext row hi)
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            py0, py1 = self.bounds[peer]
+            for want in ((max(py0 - halo_up, 0), py0), (py1, min(py1 + halo_down, h))):  # rows the peer wants from me
+                ov = overlap(want, (y0, y1))
+                if ov:
+                    self.sends.append((peer, ov[0] - ext_y0, ov[1] - ext_y0))
+            for want in (want_top, want_bot):  # rows I want from the peer
+                ov = overlap(want, (py0, py1))
+                if ov:
+                    self.recvs.append((peer, ov[0] - ext_y0, ov[1] - ext_y0))
+        self.halo_bytes = sum((b - a) for _, a, b in self.recvs) * int(np.prod(row_shape)) * self.ext.element_size()
+        self._side = self._ready = self._done = None
+        if self.ext.is_cuda:
+            self._side = torch.cuda.Stream(device=device)
+            self._ready = torch.cuda.Event()
+            self._done = torch.cuda.Event()
+
+    def _ops(self):
+        ops = [dist.P2POp(dist.isend, self.ext[a:b], peer, self.group) for peer, a, b in self.sends]
+        ops += [dist.P2POp(dist.irecv, self.ext[a:b], peer, self.group) for peer, a, b in self.recvs]
+        return ops
+
+    def exchange(self):
+        """Fill the halo rows; on return (CPU) / in stream order (CUDA) `ext` is complete."""
+        self.exchange_async()
+        self.wait()
+
+    def exchange_async(self):
+        ops = self._ops()
+        if not ops:
+            self._pending = False
+            return
+        self._pending = True
+        if self._side is None:  # CPU (gloo): nothing to overlap with
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self._pending = False
+            return
+        cur = torch.cuda.current_stream(self.ext.device)
+        self._ready.record(cur)  # core is written, earlier readers of the halo rows are done
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(self._ready)
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()  # NCCL: orders the side stream after the transfers, the host does not block
+            self._done.record(self._side)
+
+    def wait(self):
+        if getattr(self, "_pending", False) and self._side is not None:
+            torch.cuda.current_stream(self.ext.device).wait_event(self._done)
+        self._pending = False
+
+    def load(self, band: torch.Tensor):
+        """Put the band's rows into `core` (a no-op when the caller produced them there)."""
+        if band.data_ptr() != self.core.data_ptr():
+            self.core.copy_(band)
+        return self
+
+
+_plans = {}
+
+
+def halo_plan(band: torch.Tensor, halo_up: int, halo_down: int, bounds, group=None, cache: bool = True) -> HaloPlan:
+    """The (cached) HaloPlan for bands shaped like `band`. A cached plan's buffers are reused by the next call with
+    the same geometry: results that alias `plan.ext` must be consumed (or copied) before then."""
+    key = (tuple(band.shape[1:]), band.dtype, str(band.device), int(halo_up), int(halo_down), tuple(bounds), id(group))
+    plan = _plans.get(key) if cache else None
+    if plan is None:
+        plan = HaloPlan(tuple(band.shape[1:]), band.dtype, band.device, halo_up, halo_down, bounds, group)
+        if cache:
+            if len(_plans) > 16:
+                _plans.clear()
+            _plans[key] = plan
+    return plan
+
+
+def exchange_halo(band: torch.Tensor, halo_up: int, halo_down: int, bounds: Sequence[Tuple[int, int]], group=None):
+    """Point-to-point halo exchange of whole rows between row-band neighbours: returns (top, bottom), up to
+    `halo_up` rows that sit directly above the band and up to `halo_down` rows directly below it (fewer at the
+    image edges)."""
+    plan = halo_plan(band, halo_up, halo_down, bounds, group, cache=False).load(band)
+    plan.exchange()
+    return plan.ext[:plan.top], plan.ext[plan.top + plan.rows:]
 
 
 def _as_tensor(x):
@@ -140,25 +212,47 @@ def gaussian_radius(sigma: float) -> int:
 
 
 def _windowed(eng, op, band, halo, bounds, group):
-    """Run a windowed filter on a band: exchange `halo` rows, filter the extended band, keep the core."""
+    """Run a windowed filter on a band: exchange `halo` rows straight into the pre-allocated extended band, filter
+    it, keep the core rows."""
     band = _as_tensor(band)
-    top, bot = exchange_halo(band, halo, halo, bounds, group)
-    ext = torch.cat([top, band, bot]) if (len(top) or len(bot)) else band
-    if ext.shape[0] == 0:
+    plan = halo_plan(band, halo, halo, bounds, group).load(band)
+    plan.exchange()
+    if plan.ext.shape[0] == 0:
         return band
-    out = _as_tensor(op(ext if ext.is_cuda else ext.numpy()))
-    return out[len(top):len(top) + band.shape[0]]
+    out = _as_tensor(op(plan.ext if plan.ext.is_cuda else plan.ext.numpy()))
+    return out[plan.top:plan.top + plan.rows]
 
 
-def gaussian_blur_banded(eng, band, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None):
+def gaussian_blur_banded(eng, band, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None, out=None):
     """parallel_gaussian_blur (filters.rs:242-316) of a row-split image. The H pass is band-local; the
     V pass reads `r = ceil(3 sigma)` rows either side, so each rank receives r rows of *u8 input*
     from its neighbours (4 B/px instead of exchanging the 16 B/px f32 intermediate) and recomputes
     the H pass on them.  Clamp-to-edge at the true image border falls out of the extended band's own
-    edges because only ranks at the border lack a halo there.  Bit-identical to the unsplit blur."""
-    _, world = _world(group)
+    edges because only ranks at the border lack a halo there.  Bit-identical to the unsplit blur.
+
+    On the GPU engine the exchange runs on a side stream while the band's own rows go through the H pass; the halo
+    rows are filtered when they have landed, then the V pass produces the band's rows (pfe_dev_gaussian_band_h/_v).
+    `band` may be `halo_plan(...).core` itself (the producer wrote it there): then nothing is copied at all."""
+    rank, world = _world(group)
     bounds = bounds or band_bounds(h_total, world)
-    return _windowed(eng, lambda ext: eng.gaussian_blur(ext, sigma, exact=exact), band, gaussian_radius(sigma), bounds, group)
+    r = gaussian_radius(sigma)
+    band = _as_tensor(band)
+    if not (band.is_cuda and hasattr(eng, "gaussian_band_h")) or r <= 16 or band.shape[0] == 0:
+        # CPU stand-ins, empty bands, and radii small enough for the fused H+V kernel: filter the extended band whole
+        res = _windowed(eng, lambda ext: eng.gaussian_blur(ext, sigma, exact=exact), band, r, bounds, group)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    plan = halo_plan(band, r, r, bounds, group).load(band)
+    plan.exchange_async()
+    eng.gaussian_band_h(plan.ext, plan.top, plan.rows, sigma, exact=exact)  # overlaps the exchange
+    plan.wait()
+    if plan.top:
+        eng.gaussian_band_h(plan.ext, 0, plan.top, sigma, exact=exact)
+    if plan.bot:
+        eng.gaussian_band_h(plan.ext, plan.top + plan.rows, plan.bot, sigma, exact=exact)
+    return eng.gaussian_band_v(plan.ext, plan.top, plan.rows, sigma, exact=exact, out=out)
 
 
 def box_blur_banded(eng, band, h_total: int, radius: float, group=None, bounds=None):
@@ -226,47 +320,60 @@ def flatten_banded(eng, layer_bands, w: int, band_rows: int, active=None):
     return eng.flatten(layer_bands, w, band_rows, active=active)
 
 
-def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach, bounds, group, uniform=False, **warp_kw):
-    """`reach` = (up, down) halo rows this rank needs: python ints, or a 2-element device tensor. One
-    max-reduction (a single collective and a single host read) sizes the halo identically on every rank
-    (SURVEY 8e); `uniform` = every rank already holds the same numbers (mesh warps), no collective at all."""
+def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach, bounds, group, **warp_kw):
+    """`reach` = (up, down) halo rows, python ints identical on every rank. The source rows land straight in the
+    pre-allocated window; the band-form warp is stream-asynchronous (a window that turns out too small is
+    reported by `eng.check_async()`)."""
     band = _as_tensor(band)
-    rank, world = _world(group)
-    if world > 1 and not uniform:
-        t = reach if isinstance(reach, torch.Tensor) else torch.tensor(list(reach), dtype=torch.int32, device=band.device)
-        if t.device.type == "cpu" and dist.get_backend(group) == "nccl":
-            t = t.to(band.device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        up, down = (int(v) for v in t.tolist())
-    else:
-        up, down = (int(v) for v in (reach.tolist() if isinstance(reach, torch.Tensor) else reach))
-    top, bot = exchange_halo(band, up, down, bounds, group)
-    window = torch.cat([top, band, bot]) if (len(top) or len(bot)) else band
-    src_y0 = bounds[rank][0] - len(top)
+    rank, _ = _world(group)
+    up, down = int(reach[0]), int(reach[1])
+    plan = halo_plan(band, up, down, bounds, group).load(band)
+    plan.exchange()
+    window = plan.ext
+    src_y0 = bounds[rank][0] - plan.top
     out = eng.warp_band(window if window.is_cuda else window.numpy(), h_total, src_y0, w_out, h_total, y0, rows_out, **warp_kw)
     return _as_tensor(out)
 
 
-def warp_displacement_banded(eng, band, disp_band, h_total: int, group=None, bounds=None):
-    """warp_displacement_full (transform.rs:1288-1345) on a row-split canvas (source and output share
-    the split). Reach = how far (y - dy) leaves the band, taken from the band's own field: on the device in
-    one pass (pfe_dev_disp_reach), folded into the ranks' max-reduction before the host reads it."""
+def displacement_reach(eng, disp_band, h_total: int, group=None, bounds=None) -> Tuple[int, int]:
+    """(up, down): how many rows above / below ITS band any rank's warp_displacement taps reach, maximised over the
+    ranks so that every rank sizes its halo identically (one scalar max-reduction).  It is a property of
+    the FIELD: compute it once when the field changes (this call reads the result on the host) and pass it to every
+    `warp_displacement_banded(..., reach=)` that uses the field."""
     rank, world = _world(group)
     bounds = bounds or band_bounds(h_total, world)
+    if world == 1:
+        return (0, 0)
     y0, y1 = bounds[rank]
     d = _as_tensor(disp_band)
-    if world == 1:
-        reach = (0, 0)  # the band is the whole image: nothing to exchange, nothing to size
-    elif y1 > y0 and d.is_cuda and hasattr(eng, "disp_reach"):
-        mm = eng.disp_reach(d, y0, h_total)  # [min, max] of floor(clamp(y - dy, -1, h))
-        reach = torch.stack([(y0 - mm[0]).clamp(min=0), (mm[1] + 2 - y1).clamp(min=0)]).to(torch.int32)
+    if y1 > y0 and d.is_cuda and hasattr(eng, "disp_reach"):
+        mm = eng.disp_reach(d, y0, h_total)  # [min, max] of floor(clamp(y - dy, -1, h)), on the device
+        t = torch.stack([(y0 - mm[0]).clamp(min=0), (mm[1] + 2 - y1).clamp(min=0)]).to(torch.int32)
     elif y1 > y0:
         ys = torch.arange(y0, y1, dtype=torch.float32, device=d.device)[:, None]
         sy = ys - torch.nan_to_num(d[..., 1], nan=0.0, posinf=0.0, neginf=0.0)
         sy = sy.clamp(-1.0, float(h_total))
-        reach = (math.ceil(max(0.0, y0 - float(torch.floor(sy.min())))), math.ceil(max(0.0, float(torch.floor(sy.max())) + 2 - y1)))
+        t = torch.tensor([math.ceil(max(0.0, y0 - float(torch.floor(sy.min())))),
+                          math.ceil(max(0.0, float(torch.floor(sy.max())) + 2 - y1))], dtype=torch.int32, device=d.device)
     else:
-        reach = (0, 0)
+        t = torch.zeros(2, dtype=torch.int32, device=d.device)
+    if t.device.type == "cpu" and dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    up, down = (int(v) for v in t.tolist())
+    return up, down
+
+
+def warp_displacement_banded(eng, band, disp_band, h_total: int, group=None, bounds=None, reach=None):
+    """warp_displacement_full (transform.rs:1288-1345) on a row-split canvas (source and output share
+    the split). `reach` = displacement_reach(...) of the field; computed here (one collective and one host read)
+    when the caller does not pass it."""
+    rank, world = _world(group)
+    bounds = bounds or band_bounds(h_total, world)
+    y0, y1 = bounds[rank]
+    d = _as_tensor(disp_band)
+    if reach is None:
+        reach = displacement_reach(eng, d, h_total, group, bounds)
     return _warp_band(eng, band, h_total, int(d.shape[1]), y0, y1 - y0, reach, bounds, group,
                       disp_band=d if d.is_cuda else d.numpy())
 
@@ -285,5 +392,5 @@ def mesh_warp_banded(eng, band, original, deformed, cols: int, rows: int, w: int
     bounds = bounds or band_bounds(h_total, world)
     y0, y1 = bounds[rank]
     reach = mesh_reach(original, deformed)  # from the control points alone: identical on every rank
-    return _warp_band(eng, band, h_total, w, y0, y1 - y0, (reach, reach), bounds, group, uniform=True,
+    return _warp_band(eng, band, h_total, w, y0, y1 - y0, (reach, reach), bounds, group,
                       original=original, deformed=deformed, cols=cols, rows=rows)

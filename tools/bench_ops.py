@@ -135,10 +135,12 @@ def main():
     run("adjust script HSL (truncating)", lambda: eng.adjust(img, 37, (30.0, -20.0, 10.0), out=out), 8 * px)
 
     # ---- flatten: the three config-2 stacks ------------------------------------------------------------------
-    if pat.search("flatten"):
+    stacks = (("flatten 16L modes 0-15", 0, False), ("flatten 16L modes 16-24,0-6", 16, False),
+              ("flatten 16L modes 0-15 alpha {0,255}", 0, True))
+    mode_names = [f"flatten mode {m:02d} x16" for m in range(25)]
+    if any(pat.search(n) for n in [s[0] for s in stacks] + mode_names):
         layers = [torch.randint(0, 256, (H8K, W8K, 4), dtype=torch.uint8, device=dev, generator=gen) for _ in range(16)]
-        for name, off, binary in (("flatten 16L modes 0-15", 0, False), ("flatten 16L modes 16-24,0-6", 16, False),
-                                  ("flatten 16L modes 0-15 alpha {0,255}", 0, True)):
+        for name, off, binary in stacks:
             ls = layers
             if binary:
                 ls = [t.clone() for t in layers]
@@ -148,7 +150,7 @@ def main():
             run(name, lambda: eng.flatten(dl, W8K, H8K, out=out), 68 * px)
             del ls, dl
         # one mode at a time (16 layers of the same mode): which modes cost what
-        if pat.search("flatten mode"):
+        if any(pat.search(n) for n in mode_names):
             for mode in range(25):
                 dl = [make_layer(t, blend=mode, opacity=0.25 + 0.05 * i) for i, t in enumerate(layers)]
                 run(f"flatten mode {mode:02d} x16", lambda: eng.flatten(dl, W8K, H8K, out=out), 68 * px)
@@ -156,7 +158,7 @@ def main():
 
     # ---- warps on a big square canvas --------------------------------------------------------------------
     S = args.big
-    if pat.search("warp|liquify"):
+    if any(pat.search(n) for n in ("liquify push", "mesh warp 6x6 fused", "warp displacement", "mesh displacement field")):
         big = torch.randint(0, 256, (S, S, 4), dtype=torch.uint8, device=dev, generator=gen)
         bout = torch.empty_like(big)
         orig = np.zeros((49, 2), np.float32)
@@ -185,7 +187,7 @@ def main():
         del big, bout, field
 
     # ---- brush: one 2000-stamp stroke across the 8K canvas -----------------------------------------------
-    if pat.search("brush"):
+    if pat.search("brush stroke 2000 stamps size 40"):
         canvas = torch.zeros((H8K, W8K, 4), dtype=torch.uint8, device=dev)
         centres = np.stack([np.linspace(200, W8K - 200, 2000, dtype=np.float32), np.linspace(300, H8K - 300, 2000, dtype=np.float32)], 1)
         brush = eng.brush_desc(40.0, 0.6, True, (0.9, 0.2, 0.1, 1.0), flow=0.8)

@@ -1,75 +1,93 @@
-// Micro-benchmark for DESIGN.md section 9, item 1: what paces a stream of packed FMAs shaped like the Gaussian inner
-// loop - `acc[j] = fma2(in, w[j], acc[j])`, 8 accumulators per input pair - when the weight operand comes from
-//   (a) ordinary registers                (what gauss_h_kernel / gauss_v_tile_kernel do on main),
-//   (b) a __grid_constant__ table, i.e. uniform registers (what the UW = true kernels of this branch do).
+// Micro-benchmark: what paces a stream of packed FMAs shaped like the Gaussian inner loop,
+//   acc[j] = fma2(in, w[s - j], acc[j])   (N accumulator pairs per input pair, weights sliding by one per step),
+// as a function of where the weight operand comes from and how many warps share an SM sub-partition.
+//   V0  weight pair (w, w) in ordinary registers           (gauss_*_kernel<UW = false>)
+//   V1  weight pair (w, w) from a __grid_constant__ table   (uniform registers, LDCU.64; UW = true)
+//   V2  scalar weight w from the table, broadcast           (make_float2(w, w) of ONE uniform 32-bit value)
+//   V3  scalar weight in an ordinary register, broadcast
+//   V4  scalar FFMA x2 with the weight in a uniform register (the unpacked equivalent, for reference)
 // Build and run on a B200:
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o /tmp/ubench_ffma2 tools/ubench_ffma2.cu && /tmp/ubench_ffma2
-// Prints cycles per FFMA2 per SM sub-partition for 1, 2 and 4 resident warps per sub-partition (2.0 = the pipe's
-// issue rate for a 64-lane operation; anything above is operand delivery or dependency stalls).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_ffma2 tools/ubench_ffma2.cu && /tmp/ubench_ffma2
+// Prints FMA-pipe cycles per FFMA2 per SM sub-partition (2.0 = the pipe's rate for a 64-lane operation).
 #include <cstdio>
 #include <cuda_runtime.h>
 
+constexpr int N = 8;          // accumulator pairs per input pair
+constexpr int kSteps = 32;    // steps per loop iteration (fully unrolled: kSteps * N packed FMAs)
+constexpr int kIters = 512;
+
 struct Table {
-    float2 w[64];
+    float2 w2[64];
+    float w1[64];
 };
 
-constexpr int kIters = 4096;
-
-template <bool UNIFORM>
-__global__ void __launch_bounds__(512) stream_kernel(const __grid_constant__ Table T, const float2 *wreg_src, float2 *out, long long *cycles) {
-    float2 acc[8];
-    float2 wr[8];
+template <int V>
+__global__ void __launch_bounds__(1024) stream_kernel(const __grid_constant__ Table T, const float2 *wsrc, float2 *out, long long *cycles) {
+    float2 acc[N];
+    float2 wr[N];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < N; j++) {
         acc[j] = make_float2(0.f, 0.f);
-        wr[j] = wreg_src[j];
+        wr[j] = wsrc[j];
     }
-    float2 in = make_float2(1.0f + threadIdx.x, 2.0f);
+    float2 in[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) in[i] = make_float2(1.0f + threadIdx.x + i, 2.0f + i);
     __syncthreads();
     const long long t0 = clock64();
+#pragma unroll 1
     for (int it = 0; it < kIters; it++) {
 #pragma unroll
-        for (int s = 0; s < 8; s++) {  // 8 steps: the weight window slides by one per step, as in PFE_GAUSS_GROUP
+        for (int s = 0; s < kSteps; s++) {
+            const float2 x = in[s & 3];  // the input changes every step; no arithmetic on it inside the timed loop
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float2 w = UNIFORM ? T.w[(it & 7) + ((s + j) & 7)] : wr[(s + j) & 7];
-                acc[j] = __ffma2_rn(in, w, acc[j]);
+            for (int j = 0; j < N; j++) {
+                const int wi = (s - j) & 31;
+                if (V == 0) acc[j] = __ffma2_rn(x, wr[(s - j) & (N - 1)], acc[j]);
+                if (V == 1) acc[j] = __ffma2_rn(x, T.w2[wi], acc[j]);
+                if (V == 2) acc[j] = __ffma2_rn(x, make_float2(T.w1[wi], T.w1[wi]), acc[j]);
+                if (V == 3) acc[j] = __ffma2_rn(x, make_float2(wr[(s - j) & (N - 1)].x, wr[(s - j) & (N - 1)].x), acc[j]);
+                if (V == 4) { acc[j].x = __fmaf_rn(x.x, T.w1[wi], acc[j].x); acc[j].y = __fmaf_rn(x.y, T.w1[wi], acc[j].y); }
             }
-            in.x += 1.0f;  // a new input pair per step
         }
     }
     const long long t1 = clock64();
     float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 8; j++) { sum.x += acc[j].x; sum.y += acc[j].y; }
+    for (int j = 0; j < N; j++) { sum.x += acc[j].x; sum.y += acc[j].y; }
     out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+template <int V>
+void run(const char *name, const Table &T, const float2 *wsrc, float2 *out, long long *cyc) {
+    for (int warps_per_smsp = 1; warps_per_smsp <= 8; warps_per_smsp *= 2) {
+        const int threads = warps_per_smsp * 4 * 32;  // one block on one SM: warps spread over the 4 sub-partitions
+        long long c = 0;
+        for (int rep = 0; rep < 3; rep++) {
+            stream_kernel<V><<<1, threads>>>(T, wsrc, out, cyc);
+            cudaDeviceSynchronize();
+            cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
+        }
+        const double per = (double)c / ((double)kIters * kSteps * N * warps_per_smsp);
+        printf("{\"variant\": \"%s\", \"warps_per_subpartition\": %d, \"cycles_per_ffma2\": %.3f}\n", name, warps_per_smsp, per);
+    }
+}
+
 int main() {
     Table T;
-    for (int i = 0; i < 64; i++) T.w[i] = make_float2(1.0f / (i + 1), 1.0f / (i + 1));
+    for (int i = 0; i < 64; i++) { T.w2[i] = make_float2(1.0f / (i + 1), 1.0f / (i + 1)); T.w1[i] = 1.0f / (i + 1); }
     float2 *wsrc, *out;
     long long *cyc;
-    cudaMalloc(&wsrc, sizeof(T.w));
-    cudaMemcpy(wsrc, T.w, sizeof(T.w), cudaMemcpyHostToDevice);
-    cudaMalloc(&out, 512 * sizeof(float2));
+    cudaMalloc(&wsrc, sizeof(T.w2));
+    cudaMemcpy(wsrc, T.w2, sizeof(T.w2), cudaMemcpyHostToDevice);
+    cudaMalloc(&out, 1024 * sizeof(float2));
     cudaMalloc(&cyc, sizeof(long long));
-    for (int warps_per_smsp = 1; warps_per_smsp <= 4; warps_per_smsp *= 2) {
-        const int threads = warps_per_smsp * 4 * 32;  // one block on one SM: warps spread over the 4 sub-partitions
-        for (int uniform = 0; uniform < 2; uniform++) {
-            long long c = 0;
-            for (int rep = 0; rep < 3; rep++) {
-                if (uniform) stream_kernel<true><<<1, threads>>>(T, wsrc, out, cyc);
-                else stream_kernel<false><<<1, threads>>>(T, wsrc, out, cyc);
-                cudaDeviceSynchronize();
-                cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
-            }
-            const double per = (double)c / ((double)kIters * 64.0 * warps_per_smsp);
-            printf("%d warp(s) per sub-partition, weights in %s registers: %.3f cycles per FFMA2\n", warps_per_smsp,
-                   uniform ? "uniform" : "ordinary", per);
-        }
-    }
+    run<0>("V0 weight pair in registers", T, wsrc, out, cyc);
+    run<1>("V1 weight pair in uniform registers (LDCU.64)", T, wsrc, out, cyc);
+    run<2>("V2 scalar weight in a uniform register, broadcast", T, wsrc, out, cyc);
+    run<3>("V3 scalar weight in a register, broadcast", T, wsrc, out, cyc);
+    run<4>("V4 two scalar FFMA, weight in a uniform register (per pair)", T, wsrc, out, cyc);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
