@@ -42,12 +42,34 @@ def _worker(rank, world, port, q):
         for exact in (True, False):
             got = pd.gaussian_blur_banded(eng, band, h, 20.0, exact=exact, bounds=bounds)
             res[f"gauss_exact={exact}"] = torch.equal(got, eng.gaussian_blur(full, 20.0, exact=exact)[y0:y1])
+        # the producer writes straight into the plan's core rows (what bench.py's strong leg does): nothing is copied
+        plan = pd.halo_plan(band, pd.gaussian_radius(20.0), pd.gaussian_radius(20.0), bounds)
+        plan.core.copy_(band)
+        out = torch.empty_like(band)
+        for _ in range(3):  # the plan's buffers are reused call after call
+            pd.gaussian_blur_banded(eng, plan.core, h, 20.0, bounds=bounds, out=out)
+        res["gauss_plan_core"] = torch.equal(out, eng.gaussian_blur(full, 20.0)[y0:y1])
+        res["gauss_small_radius"] = torch.equal(pd.gaussian_blur_banded(eng, band, h, 3.0, exact=True, bounds=bounds),
+                                                eng.gaussian_blur(full, 3.0, exact=True)[y0:y1])
         res["box"] = torch.equal(pd.box_blur_banded(eng, band, h, 9.0, bounds=bounds), eng.box_blur(full, 9.0)[y0:y1])
         res["median"] = torch.equal(pd.median_banded(eng, band, h, 2, bounds=bounds), eng.median(full, 2)[y0:y1])
         res["sharpen"] = torch.equal(pd.sharpen_banded(eng, band, h, 1.0, 2.0, bounds=bounds), eng.sharpen(full, 1.0, 2.0)[y0:y1])
         dfull = torch.from_numpy(disp).cuda()
-        res["warp"] = torch.equal(pd.warp_displacement_banded(eng, band, dfull[y0:y1].contiguous(), h, bounds=bounds),
+        fband = dfull[y0:y1].contiguous()
+        reach = pd.displacement_reach(eng, fband, h, bounds=bounds)  # once per field
+        res["warp"] = torch.equal(pd.warp_displacement_banded(eng, band, fband, h, bounds=bounds, reach=reach),
                                   eng.warp_displacement(full, dfull)[y0:y1])
+        res["warp_reach_computed_inside"] = torch.equal(pd.warp_displacement_banded(eng, band, fband, h, bounds=bounds),
+                                                        eng.warp_displacement(full, dfull)[y0:y1])
+        eng.check_async()  # no tap fell outside the exchanged rows
+        # a halo that is too small is reported asynchronously
+        pd.warp_displacement_banded(eng, band, fband, h, bounds=bounds, reach=(0, 0))
+        try:
+            eng.check_async()
+            res["warp_short_halo_detected"] = False
+        except Exception:
+            res["warp_short_halo_detected"] = True
+        eng.check_async()  # the flag was cleared
         orig = np.array([[c / 6 * w, r / 6 * h] for r in range(7) for c in range(7)], np.float32)
         deformed = orig + np.array([[8 * np.sin(i) * np.cos(j)] * 2 for i in range(7) for j in range(7)], np.float32)
         res["mesh"] = torch.equal(pd.mesh_warp_banded(eng, band, orig, deformed, 6, 6, w, h, bounds=bounds),

@@ -1071,3 +1071,25 @@ def test_host_tier_band_pipeline(eng, oracle):
         for ex in (True, False):
             want = eng.gaussian_blur(flat_dev, sigma, exact=ex).cpu().numpy()
             exact(eng.flatten_gaussian(host_layers, w, h, sigma, active=active, exact=ex), want, f"pipelined flatten+gaussian s={sigma} exact={ex}")
+
+
+def test_warp_band_window_check_is_asynchronous(eng):
+    """pfe_dev_warp_band no longer synchronises: a source window that does not cover the warp's reach is recorded
+    in the context's sticky flag and reported (once) by pfe_ctx_check_async."""
+    import torch
+    from paintfe_b200._lib import PfeError
+
+    rng = np.random.default_rng(5)
+    w, h = 64, 96
+    src = torch.from_numpy(rng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda()
+    disp = torch.zeros((32, w, 2), dtype=torch.float32, device="cuda")
+    disp[..., 1] = 20.0  # rows 32..63 sample rows 12..43
+    ok = eng.warp_band(src[8:70].contiguous(), h, 8, w, h, 32, 32, disp_band=disp)
+    eng.check_async()
+    whole = torch.zeros((h, w, 2), dtype=torch.float32, device="cuda")
+    whole[32:64] = disp
+    assert torch.equal(ok, eng.warp_displacement(src, whole)[32:64])
+    eng.warp_band(src[30:70].contiguous(), h, 30, w, h, 32, 32, disp_band=disp)  # rows 12..29 are missing
+    with pytest.raises(PfeError):
+        eng.check_async()
+    eng.check_async()
