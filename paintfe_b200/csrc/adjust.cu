@@ -27,7 +27,8 @@ __device__ __forceinline__ uint32_t round_px(float r, float g, float b, float a)
 
 __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint8_t *lut, uint32_t v) {
     const uint32_t r8 = v & 255u, g8 = (v >> 8) & 255u, b8 = (v >> 16) & 255u, a8 = v >> 24;
-    const float r = (float)r8, g = (float)g8, b = (float)b8, a = (float)a8;
+    // u8 -> f32 as 0x4B0000xx - 2^23 (ALU + FMA pipes) instead of the quarter-rate I2F
+    const float r = pfe_u8_to_f32(r8), g = pfe_u8_to_f32(g8), b = pfe_u8_to_f32(b8), a = pfe_u8_to_f32(a8);
     switch (op) {
     case PFE_ADJ_INVERT: return round_px(255.0f - r, 255.0f - g, 255.0f - b, a);
     case PFE_ADJ_INVERT_ALPHA: return round_px(r, g, b, 255.0f - a);
@@ -48,7 +49,7 @@ __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint
         const float sat_factor = 1.0f + p[1] / 100.0f;
         const float light_offset = p[2] * 255.0f / 100.0f;
         float hh, s, l;
-        rgb_to_hsl(r / 255.0f, g / 255.0f, b / 255.0f, hh, s, l);
+        rgb_to_hsl(pfe_div255(r), pfe_div255(g), pfe_div255(b), hh, s, l);
         float t = hh + p[0] / 360.0f;
         float nh = t - truncf(t);  // f32::fract
         if (nh < 0.0f) nh = nh + 1.0f;
@@ -98,7 +99,7 @@ __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint
     }
     case PFE_ADJ_VIBRANCE: {  // vibrance_pixel, adjustments.rs:1431-1444
         float hh, sat, l;
-        rgb_to_hsl(r / 255.0f, g / 255.0f, b / 255.0f, hh, sat, l);
+        rgb_to_hsl(pfe_div255(r), pfe_div255(g), pfe_div255(b), hh, sat, l);
         const float boost = p[0] >= 0.0f ? p[0] * ((1.0f - sat) * (1.0f - sat)) : p[0] * (sat * sat);
         const float ns = pfe_clampf(sat + boost, 0.0f, 1.0f);
         float rr, gg, bb;
@@ -130,18 +131,17 @@ __device__ __forceinline__ uint32_t adjust_px(int op, const float *p, const uint
     case PFE_ADJ_S_HSL: {
         const float sat_factor = 1.0f + p[1] / 100.0f;
         const float light_offset = p[2] * 255.0f / 100.0f;
-        float fr = r / 255.0f, fg = g / 255.0f, fb = b / 255.0f;
+        float fr = pfe_div255(r), fg = pfe_div255(g), fb = pfe_div255(b);
         float cmax = fmaxf(fmaxf(fr, fg), fb), cmin = fminf(fminf(fr, fg), fb);
         float l = (cmax + cmin) / 2.0f;
         float hh = 0.0f, s = 0.0f;
-        if (!(fabsf(cmax - cmin) < 1e-10f)) {
+        if (!(fabsf(cmax - cmin) < 1e-10f)) {  // same expressions as scripting.rs:973-990, selected instead of branched
             float d = cmax - cmin;
-            s = l > 0.5f ? d / (2.0f - cmax - cmin) : d / (cmax + cmin);
-            float h6;
-            if (fabsf(cmax - fr) < 1e-10f) h6 = (fg - fb) / d + (fg < fb ? 6.0f : 0.0f);
-            else if (fabsf(cmax - fg) < 1e-10f) h6 = (fb - fr) / d + 2.0f;
-            else h6 = (fr - fg) / d + 4.0f;
-            hh = h6 / 6.0f;
+            s = pfe_fast_div(d, l > 0.5f ? 2.0f - cmax - cmin : cmax + cmin);
+            const bool is_r = fabsf(cmax - fr) < 1e-10f, is_g = fabsf(cmax - fg) < 1e-10f;
+            const float num = is_r ? fg - fb : (is_g ? fb - fr : fr - fg);
+            const float off = is_r ? (fg < fb ? 6.0f : 0.0f) : (is_g ? 2.0f : 4.0f);
+            hh = pfe_fast_div(pfe_fast_div(num, d) + off, 6.0f);
         }
         float t = hh + p[0] / 360.0f;
         float nh = fmodf(t, 1.0f);  // rem_euclid(1.0)

@@ -49,58 +49,98 @@ __host__ __device__ inline float brush_alpha(float dist, float radius, float har
     return material * coverage;
 }
 
+// One stamp on one pixel: the body of the reference's inner loop (:319-396).
+__device__ __forceinline__ uint32_t stamp_pixel(const BrushParams &B, const uint8_t *lut, uint32_t px, float fgx, float fgy,
+                                                float2 c, float draw_radius) {
+    // the stamp's own bounding box (:205-211); pixels outside it are never visited
+    if (fgx < fmaxf(floorf(c.x - draw_radius), 0.0f) || fgx > ceilf(c.x + draw_radius) ||
+        fgy < fmaxf(floorf(c.y - draw_radius), 0.0f) || fgy > ceilf(c.y + draw_radius))
+        return px;
+    float dy = fgy - c.y, dx = fgx - c.x;
+    float dist_sq = dx * dx + dy * dy;
+    if (dist_sq > B.draw_radius_sq) return px;                                // :321
+    uint32_t ga8;
+    if (B.direct) {                                                           // :325-332
+        float a = brush_alpha(sqrtf(dist_sq), B.radius, B.hardness, B.anti_aliased);
+        ga8 = (uint32_t)__float2int_rz(fminf(fmaxf(fminf(roundf(a * 255.0f), 255.0f), 0.0f), 255.0f));
+    } else {                                                                  // :334-336
+        float fi = fminf(dist_sq * B.inv_radius_sq * 255.0f, 255.0f);
+        ga8 = lut[(uint32_t)__float2int_rz(fmaxf(fi, 0.0f))];
+    }
+    if (ga8 == 0) return px;
+    float strength = (float)ga8 / 255.0f * B.src_a * B.flow;                  // :340, :347, :361
+    if (strength < 0.01f) return px;
+    if (B.is_eraser) {
+        float old_mask = (float)(px >> 24) / 255.0f;
+        if (strength > old_mask) px = pfe_as_u8(strength * 255.0f) << 24;     // :352-357
+    } else if (B.mode == 0) {
+        uint32_t a8 = pfe_as_u8(strength * 255.0f);
+        if (a8 >= (px >> 24)) px = B.rgb | (a8 << 24);                        // :366-372
+    } else {                                                                  // Dodge / Burn / Sponge :374-394
+        float hh, sat, l, nr, ng, nb;
+        const float st = strength * 0.5f;
+        rgb_to_hsl((float)(px & 255u) / 255.0f, (float)((px >> 8) & 255u) / 255.0f, (float)((px >> 16) & 255u) / 255.0f, hh, sat, l);
+        if (B.mode == 1) l = pfe_clampf(l + st, 0.0f, 1.0f);
+        else if (B.mode == 2) l = pfe_clampf(l - st, 0.0f, 1.0f);
+        else if (B.mode == 3) sat = pfe_clampf(sat - st, 0.0f, 1.0f);
+        hsl_to_rgb(hh, sat, l, 1e-6f, nr, ng, nb);
+        px = pfe_pack(pfe_as_u8(nr * 255.0f), pfe_as_u8(ng * 255.0f), pfe_as_u8(nb * 255.0f), px >> 24);
+    }
+    return px;
+}
+
+// A CTA owns a 32 x 8 pixel tile of the stroke's bounding box.  The stamp list is read 256 stamps at a time: every
+// thread tests one stamp's bounding box against the TILE, the survivors are compacted IN ORDER into shared memory
+// (warp ballots + an 8-entry prefix), and each pixel then walks just those - for a long stroke a tile meets a few dozen
+// of the thousands of stamps, and most tiles of the bounding box meet none and cost eight box tests per thread.  The
+// per-pixel sequence of stamps is unchanged, so the result is the one-thread-per-pixel-over-every-stamp result.
 __global__ void __launch_bounds__(256) brush_kernel(const __grid_constant__ BrushParams B, uint32_t *img, uint32_t w,
                                                     const float2 *centres, uint32_t n, const uint8_t *sel, int bx0,
                                                     int by0, int bw, int bh, float draw_radius) {
     __shared__ uint8_t lut[256];
+    __shared__ float2 near_c[256];
+    __shared__ uint32_t warp_count[8];
     lut[threadIdx.x] = B.lut[threadIdx.x];
-    __syncthreads();
-    const int lx = blockIdx.x * 32 + (threadIdx.x & 31), ly = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (lx >= bw || ly >= bh) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = blockIdx.x * 32 + lane, ly = blockIdx.y * 8 + warp;
     const int gx = bx0 + lx, gy = by0 + ly;
     const size_t o = (size_t)gy * w + gx;
-    if (sel && sel[o] == 0) return;                                           // :309-317
-    uint32_t px = img[o];
+    bool active = lx < bw && ly < bh;
+    if (active && sel && sel[o] == 0) active = false;                         // :309-317
+    uint32_t px = active ? img[o] : 0u;
     const uint32_t before = px;
     const float fgx = (float)gx, fgy = (float)gy;
-    for (uint32_t s = 0; s < n; s++) {
-        const float2 c = __ldg(centres + s);
-        // the stamp's own bounding box (:205-211); pixels outside it are never visited
-        if (fgx < fmaxf(floorf(c.x - draw_radius), 0.0f) || fgx > ceilf(c.x + draw_radius) ||
-            fgy < fmaxf(floorf(c.y - draw_radius), 0.0f) || fgy > ceilf(c.y + draw_radius))
-            continue;
-        float dy = fgy - c.y, dx = fgx - c.x;
-        float dist_sq = dx * dx + dy * dy;
-        if (dist_sq > B.draw_radius_sq) continue;                             // :321
-        uint32_t ga8;
-        if (B.direct) {                                                       // :325-332
-            float a = brush_alpha(sqrtf(dist_sq), B.radius, B.hardness, B.anti_aliased);
-            ga8 = (uint32_t)__float2int_rz(fminf(fmaxf(fminf(roundf(a * 255.0f), 255.0f), 0.0f), 255.0f));
-        } else {                                                              // :334-336
-            float fi = fminf(dist_sq * B.inv_radius_sq * 255.0f, 255.0f);
-            ga8 = lut[(uint32_t)__float2int_rz(fmaxf(fi, 0.0f))];
+    // tile rectangle in image coordinates (as floats: the per-stamp test below is the per-pixel test's own arithmetic)
+    const float tx0 = (float)(bx0 + (int)blockIdx.x * 32), tx1 = tx0 + 31.0f;
+    const float ty0 = (float)(by0 + (int)blockIdx.y * 8), ty1 = ty0 + 7.0f;
+    for (uint32_t base = 0; base < n; base += 256) {
+        const uint32_t s = base + threadIdx.x;
+        float2 c = make_float2(0.f, 0.f);
+        bool keep = false;
+        if (s < n) {
+            c = __ldg(centres + s);
+            // some pixel of the tile lies inside the stamp's bounding box (:205-211)
+            keep = !(tx1 < fmaxf(floorf(c.x - draw_radius), 0.0f) || tx0 > ceilf(c.x + draw_radius) ||
+                     ty1 < fmaxf(floorf(c.y - draw_radius), 0.0f) || ty0 > ceilf(c.y + draw_radius));
         }
-        if (ga8 == 0) continue;
-        float strength = (float)ga8 / 255.0f * B.src_a * B.flow;              // :340, :347, :361
-        if (strength < 0.01f) continue;
-        if (B.is_eraser) {
-            float old_mask = (float)(px >> 24) / 255.0f;
-            if (strength > old_mask) px = pfe_as_u8(strength * 255.0f) << 24; // :352-357
-        } else if (B.mode == 0) {
-            uint32_t a8 = pfe_as_u8(strength * 255.0f);
-            if (a8 >= (px >> 24)) px = B.rgb | (a8 << 24);                    // :366-372
-        } else {                                                              // Dodge / Burn / Sponge :374-394
-            float hh, sat, l, nr, ng, nb;
-            const float st = strength * 0.5f;
-            rgb_to_hsl((float)(px & 255u) / 255.0f, (float)((px >> 8) & 255u) / 255.0f, (float)((px >> 16) & 255u) / 255.0f, hh, sat, l);
-            if (B.mode == 1) l = pfe_clampf(l + st, 0.0f, 1.0f);
-            else if (B.mode == 2) l = pfe_clampf(l - st, 0.0f, 1.0f);
-            else if (B.mode == 3) sat = pfe_clampf(sat - st, 0.0f, 1.0f);
-            hsl_to_rgb(hh, sat, l, 1e-6f, nr, ng, nb);
-            px = pfe_pack(pfe_as_u8(nr * 255.0f), pfe_as_u8(ng * 255.0f), pfe_as_u8(nb * 255.0f), px >> 24);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();  // the previous chunk's list has been consumed (and, first time round, lut is complete)
+        if (lane == 0) warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t offset = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t cnt = warp_count[k];
+            offset += k < warp ? cnt : 0u;
+            total += cnt;
         }
+        if (total == 0) continue;  // CTA-uniform
+        if (keep) near_c[offset + __popc(ballot & ((1u << lane) - 1u))] = c;
+        __syncthreads();
+        if (active)
+            for (uint32_t k = 0; k < total; k++) px = stamp_pixel(B, lut, px, fgx, fgy, near_c[k], draw_radius);
     }
-    if (px != before) img[o] = px;
+    if (active && px != before) img[o] = px;
 }
 
 void fill_params(const pfe_brush_desc *b, BrushParams *P) {

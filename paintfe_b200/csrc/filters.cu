@@ -5,6 +5,7 @@
 // bit-exact by construction, motion blur sums integers in f32 (exact), vignette is strict f32.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -80,29 +81,203 @@ __global__ void __launch_bounds__(128) box_v_kernel(const uint32_t *hb, const ui
 }
 
 // ---- motion blur, blur.rs:144-210 ---------------------------------------------------------
+// `v.round() as i32` (half away from zero) for |v| < 2^22 without FRND / F2I, which run on the quarter-rate XU pipe
+// (the first version of this kernel spent 87 % of its time there): a round-toward-zero add of 0.5 to |v| cannot step
+// over an integer, and a second one against 2^23 leaves floor() of that in the low mantissa bits.
+__device__ __forceinline__ int round_half_away_i32(float v) {
+    const int n = (int)(__float_as_uint(__fadd_rz(__fadd_rz(fabsf(v), 0.5f), 8388608.0f)) & 0x007FFFFFu);
+    return v < 0.0f ? -n : n;
+}
+// SMALL: 2*steps+1 <= 257 samples, so the channel sums fit 16-bit lanes and are accumulated as packed integers (the
+// reference adds the u8 values as f32, which is exact - integer sums are the same numbers, with no I2F per sample).
+template <bool SMALL>
 __global__ void __launch_bounds__(256) motion_kernel(const uint32_t *src, const uint8_t *mask, uint32_t *dst,
                                                      int w, int h, int steps, float dx, float dy, float inv_steps) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
     const size_t o = (size_t)y * w + x;
     if (mask && mask[o] == 0) { dst[o] = src[o]; return; }
-    float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
     const float fx = (float)x, fy = (float)y;
-    for (int i = -steps; i <= steps; i++) {
-        // (x as f32 + i as f32 * dx).round() as i32, then clamp (:196-199)
-        float px = roundf(fx + (float)i * dx), py = roundf(fy + (float)i * dy);
-        int sx = pfe_clampi(__float2int_rz(px), 0, w - 1), sy = pfe_clampi(__float2int_rz(py), 0, h - 1);
-        uint32_t v = __ldg(src + (size_t)sy * w + sx);
-        sr += (float)(v & 255u); sg += (float)((v >> 8) & 255u); sb += (float)((v >> 16) & 255u); sa += (float)(v >> 24);
+    float sr, sg, sb, sa;
+    if (SMALL) {
+        uint32_t rb = 0, ga = 0;  // (r | b << 16), (g | a << 16)
+        for (int i = -steps; i <= steps; i++) {
+            // (x as f32 + i as f32 * dx).round() as i32, then clamp (:196-199)
+            const int sx = pfe_clampi(round_half_away_i32(fx + (float)i * dx), 0, w - 1);
+            const int sy = pfe_clampi(round_half_away_i32(fy + (float)i * dy), 0, h - 1);
+            const uint32_t v = __ldg(src + (size_t)sy * w + sx);
+            rb += v & 0x00FF00FFu;
+            ga += (v >> 8) & 0x00FF00FFu;
+        }
+        sr = (float)(rb & 0xFFFFu); sb = (float)(rb >> 16); sg = (float)(ga & 0xFFFFu); sa = (float)(ga >> 16);
+    } else {
+        sr = sg = sb = sa = 0.f;
+        for (int i = -steps; i <= steps; i++) {
+            float px = roundf(fx + (float)i * dx), py = roundf(fy + (float)i * dy);
+            int sx = pfe_clampi(__float2int_rz(px), 0, w - 1), sy = pfe_clampi(__float2int_rz(py), 0, h - 1);
+            uint32_t v = __ldg(src + (size_t)sy * w + sx);
+            sr += (float)(v & 255u); sg += (float)((v >> 8) & 255u); sb += (float)((v >> 16) & 255u); sa += (float)(v >> 24);
+        }
     }
     dst[o] = pfe_pack(pfe_round_u8(sr * inv_steps), pfe_round_u8(sg * inv_steps), pfe_round_u8(sb * inv_steps),
                       pfe_round_u8(sa * inv_steps));
 }
 
 // ---- median, noise.rs:357-410 --------------------------------------------------------------
-// sorted[len/2] per channel == the largest v with #(x < v) <= len/2.  Found by an 8-step bitwise
-// bisection run on all four channels at once with packed byte compares; per-channel counts live in
-// 16-bit lanes (window <= 255x255).
+// sorted[len/2] per channel over the clamp-to-edge (2r+1)^2 window.  Four kernels, all exact:
+//   r <= 2    forgetful selection in registers (median_small_kernel);
+//   r <= 32   column histograms (median_hist_kernel): cost per pixel grows with r, not with r^2;
+//   r <= 127  bitwise bisection over the window staged in shared memory (median_kernel);
+//   larger    the same bisection straight from global memory with 32-bit counts (median_global_kernel).
+
+// One compare-exchange of two pixels held as (R | B << 16, G | A << 16): afterwards a <= b in every 16-bit lane.
+// VIMNMX.U16x2 is native on sm_100; the 8-bit SIMD min / max / compares are emulated with ~6 instructions each.
+struct Px2 { uint32_t lo, hi; };
+__device__ __forceinline__ void cex(Px2 &a, Px2 &b) {
+    const uint32_t mnl = __vminu2(a.lo, b.lo), mxl = __vmaxu2(a.lo, b.lo), mnh = __vminu2(a.hi, b.hi), mxh = __vmaxu2(a.hi, b.hi);
+    a.lo = mnl; b.lo = mxl; a.hi = mnh; b.hi = mxh;
+}
+__device__ __forceinline__ Px2 widen(uint32_t v) { return Px2{v & 0x00FF00FFu, (v >> 8) & 0x00FF00FFu}; }
+
+// Forgetful selection: of any k >= M + 2 of the N = 2M + 1 window values, the smallest has at least M + 1 values above
+// it and the largest M + 1 below it, so neither is the median.  A working set of M + 2 values loses both each round and
+// gains the next window value; after M - 1 rounds three values are left and the middle one is sorted[N / 2].  The
+// compare-exchange network is data-oblivious, so all four channels run through it at once in 16-bit lanes.
+template <int R>
+__global__ void __launch_bounds__(256) median_small_kernel(const uint32_t *src, const uint8_t *mask, uint32_t *dst, int w, int h) {
+    constexpr int SIDE = 2 * R + 1, N = SIDE * SIDE, M = N / 2, K = M + 2;
+    constexpr int tw = 32 + 2 * R, th = 8 + 2 * R;
+    __shared__ uint32_t sm[th * tw];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    for (int idx = threadIdx.x; idx < tw * th; idx += blockDim.x) {
+        int ty = idx / tw, tx = idx - ty * tw;
+        sm[idx] = __ldg(src + (size_t)pfe_clampi(y0 - R + ty, 0, h - 1) * w + pfe_clampi(x0 - R + tx, 0, w - 1));
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= w || y >= h) return;
+    const size_t o = (size_t)y * w + x;
+    if (mask && mask[o] == 0) { dst[o] = src[o]; return; }
+    const uint32_t *win = sm + ly * tw + lx;
+    Px2 a[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) a[i] = widen(win[(i / SIDE) * tw + (i % SIDE)]);
+    // round with k live values a[0..k-1]: one pass bubbles the maximum up to a[k-1], one pass back bubbles the minimum
+    // down to a[0]; a[k-1] is dropped, a[0] is overwritten by the next window element: k-1 live values remain
+#pragma unroll
+    for (int k = K; k > 3; k--) {
+#pragma unroll
+        for (int i = 0; i + 1 < k; i++) cex(a[i], a[i + 1]);
+#pragma unroll
+        for (int i = k - 3; i >= 0; i--) cex(a[i], a[i + 1]);
+        constexpr int first_new = K;
+        const int e = first_new + (K - k);  // window elements K .. N-1, one per round
+        a[0] = widen(win[(e / SIDE) * tw + (e % SIDE)]);
+    }
+    cex(a[0], a[1]);
+    cex(a[1], a[2]);
+    cex(a[0], a[1]);
+    dst[o] = a[1].lo | (a[1].hi << 8);
+}
+
+// Column-histogram median (the idea of Perreault & Hebert's constant-time median, arranged for one CTA per image
+// strip).  A CTA owns a strip of 32 output columns and walks down a segment of rows; warp c handles channel c and
+// keeps, for each of the strip's 32 + 2r source columns, a histogram of that column's 2r+1 window rows: 16 coarse bins
+// (value >> 4) and 256 fine bins, 16-bit counts, two per word.  Moving down one row removes one pixel from and adds one
+// pixel to every column histogram.  A lane then sums the coarse histograms of its 2r+1 columns, finds the coarse bin
+// that holds rank len/2, sums that bin's 16 fine counters over the same columns and finds the value.  Column stride
+// 140 words: neighbouring lanes start 12 banks apart, so the quarter-warp LDS.128 of the coarse pass are conflict free.
+constexpr int kMedHistTW = 32, kMedHistStride = 140, kMedHistMaxR = 32;
+
+__global__ void __launch_bounds__(128) median_hist_kernel(const uint32_t *src, const uint8_t *mask, uint8_t *dst, int w, int h,
+                                                         int r, int seg_rows) {
+    extern __shared__ __align__(16) uint32_t hist_sm[];
+    const int nc = kMedHistTW + 2 * r;
+    const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    uint32_t *hist = hist_sm + (size_t)ch * nc * kMedHistStride;  // this warp's (= this channel's) column histograms
+    const int x0 = blockIdx.x * kMedHistTW;
+    const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+    const uint32_t shift = 8u * (uint32_t)ch;
+    const uint32_t target = (uint32_t)((2 * r + 1) * (2 * r + 1) / 2);
+
+    for (int i = lane; i < nc * kMedHistStride; i += 32) hist[i] = 0u;
+    __syncwarp();
+    // +-1 on the 16-bit lane of fine bin v and of coarse bin v >> 4.  Adding 0xFFFF to the low lane subtracts one from
+    // it and carries into the high lane, adding 0xFFFF0000 on top takes that carry back out: -1 on the low lane is
+    // += 0xFFFFFFFF... written as one add of (0xFFFF + 0xFFFF0000) = 0xFFFFFFFF, i.e. a plain 32-bit decrement, which is
+    // right as long as the low lane is >= 1 (it is: the pixel being removed was added before).
+    auto bump = [&](uint32_t *col, uint32_t v, bool add) {
+        const uint32_t lo = add ? 1u : 0xFFFFFFFFu, hi = add ? 0x00010000u : 0xFFFF0000u;
+        col[8 + (v >> 1)] += (v & 1u) ? hi : lo;
+        col[v >> 5] += ((v >> 4) & 1u) ? hi : lo;
+    };
+    auto row_pixels = [&](int yy, bool add) {
+        const uint32_t *row = src + (size_t)pfe_clampi(yy, 0, h - 1) * w;
+        for (int c = lane; c < nc; c += 32) {
+            const uint32_t v = (__ldg(row + pfe_clampi(x0 - r + c, 0, w - 1)) >> shift) & 255u;
+            bump(hist + (size_t)c * kMedHistStride, v, add);
+        }
+    };
+    for (int yy = ys - r; yy <= ys + r; yy++) row_pixels(yy, true);
+    __syncwarp();
+
+    const uint32_t *base = hist + (size_t)lane * kMedHistStride;
+    for (int y = ys; y < ye; y++) {
+        const int x = x0 + lane;
+        // ---- coarse level: 16 bins summed over the lane's 2r+1 columns (each 16-bit sum <= (2r+1)^2 <= 4225)
+        uint32_t acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0u;
+        for (int j = 0; j <= 2 * r; j++) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(base + (size_t)j * kMedHistStride);
+            const uint4 b = *reinterpret_cast<const uint4 *>(base + (size_t)j * kMedHistStride + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        uint32_t cum = 0, bin = 0, below = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const uint32_t cnt = (acc[b >> 1] >> (16 * (b & 1))) & 0xFFFFu;
+            cum += cnt;
+            const bool le = cum <= target;  // bins wholly at or below the rank
+            bin += le ? 1u : 0u;
+            below += le ? cnt : 0u;
+        }
+        // ---- fine level: the 16 counters of coarse bin `bin`, same columns
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0u;
+        const uint32_t *fbase = base + 8 + bin * 8;
+        for (int j = 0; j <= 2 * r; j++) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(fbase + (size_t)j * kMedHistStride);
+            const uint4 b = *reinterpret_cast<const uint4 *>(fbase + (size_t)j * kMedHistStride + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+        const uint32_t target2 = target - below;
+        uint32_t fcum = 0, fbin = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            fcum += (acc[b >> 1] >> (16 * (b & 1))) & 0xFFFFu;
+            fbin += fcum <= target2 ? 1u : 0u;
+        }
+        if (x < w) {
+            const size_t o = (size_t)y * w + x;
+            uint32_t v = bin * 16 + fbin;
+            if (mask && mask[o] == 0) v = (__ldg(src + o) >> shift) & 255u;
+            dst[o * 4 + ch] = (uint8_t)v;
+        }
+        __syncwarp();  // every lane has read this row's histograms
+        if (y + 1 < ye) {
+            row_pixels(y - r, false);
+            row_pixels(y + r + 1, true);
+            __syncwarp();
+        }
+    }
+}
+
+// Bitwise bisection: sorted[len/2] per channel == the largest v with #(x < v) <= len/2, found in 8 steps on all four
+// channels at once with packed byte compares; per-channel counts live in 16-bit lanes (window <= 255x255).
 __device__ __forceinline__ uint32_t median_select(const uint32_t *win, int pitch, int side, uint32_t target) {
     uint32_t cur = 0;
     const uint32_t tgt_lo = target | (target << 16);
@@ -176,20 +351,35 @@ __global__ void __launch_bounds__(256) median_global_kernel(const uint32_t *src,
 }
 
 // ---- vignette, stylize.rs:170-191 ------------------------------------------------------------
+// VEC consecutive pixels per thread (16-byte loads and stores when VEC = 4); the two divisions by image-wide constants
+// go through pfe_fast_div (dist <= a few max_dist, soft >= 0.01: nowhere near the exponent extremes).
+__device__ __forceinline__ uint32_t vignette_px(uint32_t v, int x, int y, float amount, float soft, float cx, float cy, float max_dist) {
+    float dx = (float)x - cx, dy = (float)y - cy;
+    float dist = pfe_fast_div(sqrtf(dx * dx + dy * dy), max_dist);
+    float q = fminf(pfe_fast_div(dist, soft), 1.0f);
+    float vf = pfe_clampf(1.0f - (amount * (q * q)), 0.0f, 1.0f);  // powf(2.0) == x*x exactly
+    return pfe_pack(pfe_round_u8(pfe_u8_to_f32(v & 255u) * vf), pfe_round_u8(pfe_u8_to_f32((v >> 8) & 255u) * vf),
+                    pfe_round_u8(pfe_u8_to_f32((v >> 16) & 255u) * vf), v >> 24);
+}
+template <int VEC>
 __global__ void __launch_bounds__(256) vignette_kernel(const uint32_t *src, const uint8_t *mask, uint32_t *dst, int w,
                                                        int h, float amount, float soft, float cx, float cy,
                                                        float max_dist) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * VEC, y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= w || y >= h) return;
     const size_t o = (size_t)y * w + x;
-    const uint32_t v = src[o];
-    if (mask && mask[o] == 0) { dst[o] = v; return; }
-    float dx = (float)x - cx, dy = (float)y - cy;
-    float dist = sqrtf(dx * dx + dy * dy) / max_dist;
-    float q = fminf(dist / soft, 1.0f);
-    float vf = pfe_clampf(1.0f - (amount * (q * q)), 0.0f, 1.0f);  // powf(2.0) == x*x exactly
-    dst[o] = pfe_pack(pfe_round_u8((float)(v & 255u) * vf), pfe_round_u8((float)((v >> 8) & 255u) * vf),
-                      pfe_round_u8((float)((v >> 16) & 255u) * vf), v >> 24);
+    uint32_t v[VEC];
+    if constexpr (VEC == 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(src + o);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+        v[0] = src[o];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; k++)
+        if (!(mask && mask[o + k] == 0)) v[k] = vignette_px(v[k], x + k, y, amount, soft, cx, cy, max_dist);
+    if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(dst + o) = make_uint4(v[0], v[1], v[2], v[3]);
+    else dst[o] = v[0];
 }
 
 int check(pfe_ctx *ctx, const void *src, const void *dst, uint32_t w, uint32_t h, const char *what) {
@@ -240,8 +430,13 @@ extern "C" int pfe_dev_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w,
     const int steps = (int)ceilf(distance);
     const float dx = cosf(angle), dy = sinf(angle);
     const float inv_steps = 1.0f / (float)(steps * 2 + 1);
-    PFE_KERNEL(ctx, "motion", motion_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
-        (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, steps, dx, dy, inv_steps));
+    const dim3 grid(pfe_div_up(w, 32), pfe_div_up(h, 8));
+    if (steps <= 128 && w < (1u << 21) && h < (1u << 21))
+        PFE_KERNEL(ctx, "motion", motion_kernel<true><<<grid, 256, 0, ctx->stream>>>(
+            (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, steps, dx, dy, inv_steps));
+    else
+        PFE_KERNEL(ctx, "motion", motion_kernel<false><<<grid, 256, 0, ctx->stream>>>(
+            (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, steps, dx, dy, inv_steps));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
@@ -251,14 +446,32 @@ extern "C" int pfe_dev_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint
     PFE_TRY(check(ctx, src, dst, w, h, "median: bad args"));
     if (src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "median: in-place not supported");
     const int r = radius < 1 ? 1 : (int)std::min<uint32_t>(radius, 1u << 20);   // noise.rs:364
-    if (r > 127) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "median: radius > 127");
-    const size_t smem = (size_t)(MED_BX + 2 * r) * (MED_BY + 2 * r) * 4;
-    if (smem <= 160 * 1024) {
+    if (r > 20000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "median: radius above 20000");  // (2r+1)^2 leaves 32-bit counts
+    // tuning aid: PFE_MEDIAN_KERNEL=bisect forces the bisection kernels (A/B against the oracle and for timing)
+    const char *force = getenv("PFE_MEDIAN_KERNEL");
+    const bool bisect_only = force && strcmp(force, "bisect") == 0;
+    const dim3 tiles(pfe_div_up(w, 32), pfe_div_up(h, 8));
+    if (r <= 2 && !bisect_only) {
+        if (r == 1) PFE_KERNEL(ctx, "median_small", median_small_kernel<1><<<tiles, 256, 0, ctx->stream>>>((const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h));
+        else PFE_KERNEL(ctx, "median_small", median_small_kernel<2><<<tiles, 256, 0, ctx->stream>>>((const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h));
+    } else if (r <= kMedHistMaxR && !bisect_only) {
+        const size_t smem = (size_t)4 * (kMedHistTW + 2 * r) * kMedHistStride * sizeof(uint32_t);
+        PFE_CUDA(ctx, cudaFuncSetAttribute(median_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // row segments: enough CTAs for every SM several times over, long enough that building the first window
+        // (2r+1 rows) stays a small fraction of a segment
+        const unsigned strips = pfe_div_up(w, kMedHistTW);
+        unsigned seg = std::max<unsigned>(64u, 8u * (unsigned)(2 * r + 1));
+        while (seg > 64u && (uint64_t)strips * pfe_div_up(h, seg) < (uint64_t)ctx->sm_count * 8) seg /= 2;
+        PFE_KERNEL(ctx, "median_hist", median_hist_kernel<<<dim3(strips, pfe_div_up(h, seg)), 128, smem, ctx->stream>>>(
+            (const uint32_t *)src, mask, dst, (int)w, (int)h, r, (int)seg));
+    } else if (r <= 127 && (size_t)(MED_BX + 2 * r) * (MED_BY + 2 * r) * 4 <= 160 * 1024) {
+        const size_t smem = (size_t)(MED_BX + 2 * r) * (MED_BY + 2 * r) * 4;
         if (smem > 48 * 1024) PFE_CUDA(ctx, cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PFE_KERNEL(ctx, "median", median_kernel<<<dim3(pfe_div_up(w, MED_BX), pfe_div_up(h, MED_BY)), MED_BX * MED_BY, smem, ctx->stream>>>(
+        PFE_KERNEL(ctx, "median", median_kernel<<<tiles, MED_BX * MED_BY, smem, ctx->stream>>>(
             (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, r));
     } else {
-        PFE_KERNEL(ctx, "median_global", median_global_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
+        // any radius the reference accepts (it sorts whatever window it is given, noise.rs:403): 32-bit counts
+        PFE_KERNEL(ctx, "median_global", median_global_kernel<<<tiles, 256, 0, ctx->stream>>>(
             (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, r));
     }
     PFE_LAUNCHED(ctx);
@@ -272,8 +485,12 @@ extern "C" int pfe_dev_vignette(pfe_ctx *ctx, const uint8_t *src, uint32_t w, ui
     const float cx = fw / 2.0f, cy = fh / 2.0f;
     const float max_dist = sqrtf(cx * cx + cy * cy);
     const float soft = fmaxf(softness, 0.01f);
-    PFE_KERNEL(ctx, "vignette", vignette_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
-        (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, amount, soft, cx, cy, max_dist));
+    if (w % 4 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0)
+        PFE_KERNEL(ctx, "vignette", vignette_kernel<4><<<dim3(pfe_div_up(w, 128), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
+            (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, amount, soft, cx, cy, max_dist));
+    else
+        PFE_KERNEL(ctx, "vignette", vignette_kernel<1><<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8)), 256, 0, ctx->stream>>>(
+            (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, amount, soft, cx, cy, max_dist));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }

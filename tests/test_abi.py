@@ -188,3 +188,35 @@ def test_c_caller_matches_oracle(tmp_path, oracle):
     flat = oracle.flatten([oracle.make_layer(a), oracle.make_layer(b, opacity=0.5, blend=8)], w, h)
     want = int(oracle.gaussian_blur(flat, 2.0).astype(np.uint64).sum())
     assert f"checksum {want}" in r.stdout, (r.stdout, want)
+
+
+def test_div255_two_op_sequence_is_exact(tmp_path):
+    """pfe_div255 (csrc/common.cuh): x * C1, then fma(x, C2, that) == (float)x / 255.0f for every u8 value. The
+    constants are read from the header, the arithmetic runs on the CPU with fmaf (strict f32, no contraction)."""
+    import re
+    import subprocess
+
+    src = open(os.path.join(ROOT, "paintfe_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("pfe_div255(float x)"):]
+    c1 = re.search(r"__fmul_rn\(x, ([0-9a-fx.p+-]+)f\)", body).group(1)
+    c2 = re.search(r"__fmaf_rn\(x, ([0-9a-fx.p+-]+)f, v\)", body).group(1)
+    prog = tmp_path / "d255.c"
+    prog.write_text("""
+#include <math.h>
+#include <stdio.h>
+int main(void) {
+    int bad = 0;
+    for (int x = 0; x < 256; x++) {
+        volatile float xf = (float)x;
+        volatile float v = xf * %sf;
+        float q = fmaf(xf, %sf, v);
+        volatile float ref = xf / 255.0f;
+        if (q != ref) bad++;
+    }
+    printf("%%d\\n", bad);
+    return bad != 0;
+}
+""" % (c1, c2))
+    exe = tmp_path / "d255"
+    subprocess.check_call(["gcc", "-O0", "-ffp-contract=off", "-o", str(exe), str(prog), "-lm"])
+    assert subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip() == "0"

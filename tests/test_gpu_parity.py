@@ -365,8 +365,41 @@ def test_box_motion_median_vignette_sharpen_random(eng, oracle, w, h):
 def test_median_large_radius(eng, oracle):
     rng = np.random.default_rng(9)
     img = fx.random_rgba(rng, 90, 70)
-    for r in (12, 40):
+    for r in (12, 32, 33, 40):  # 32 = last radius of the column-histogram kernel, 33 = first of the bisection kernel
         exact(eng.median(img, r), oracle.median(img, r), f"median r={r}")
+
+
+def test_median_kernels_agree(eng, oracle):
+    """Every radius class of pfe_median (forgetful selection r <= 2, column histograms r <= 32, bisection above) against
+    the oracle on images with flat areas, ramps and noise (ties are where rank selection goes wrong), at sizes that
+    are not multiples of the 32-column strips or the row segments, with a mask; then the forced bisection kernel."""
+    import os
+
+    rng = np.random.default_rng(31)
+    w, h = 203, 171
+    img = fx.random_rgba(rng, w, h)
+    img[20:90, 30:120] = (17, 200, 0, 255)                    # flat block: every window value equal
+    img[100:160, :, 0] = np.arange(w, dtype=np.uint8)[None]   # ramp
+    img[:, 150:, 3] = rng.integers(0, 3, (h, w - 150), dtype=np.uint8) * 127  # three-valued channel
+    mask = (rng.random((h, w)) < 0.5).astype(np.uint8) * 255
+    for r in (1, 2, 3, 4, 5, 9, 16):
+        exp = oracle.median(img, r)
+        exact(eng.median(img, r), exp, f"median r={r}")
+        os.environ["PFE_MEDIAN_KERNEL"] = "bisect"
+        try:
+            exact(eng.median(img, r), exp, f"median r={r} (bisection kernel)")
+        finally:
+            del os.environ["PFE_MEDIAN_KERNEL"]
+    for r in (1, 3, 6):
+        exact(eng.median(img, r, mask=mask), oracle.median(img, r, mask=mask), f"median mask r={r}")
+
+
+def test_median_radius_above_127(eng, oracle):
+    """The reference sorts any window (noise.rs:357-410); radii above the 16-bit counters' range take the global
+    kernel with 32-bit counts."""
+    rng = np.random.default_rng(3)
+    img = fx.random_rgba(rng, 37, 29)
+    exact(eng.median(img, 130), oracle.median(img, 130), "median r=130")
 
 
 def test_adjust_all_ops_random(eng, oracle):
