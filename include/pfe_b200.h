@@ -173,7 +173,8 @@ int pfe_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, fl
 int pfe_dev_motion_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float angle_deg,
                         float distance, const uint8_t *mask, uint8_t *dst);
 /* median_core (src/ops/effects/noise.rs:357-410) / GpuRenderer::median_rgba (renderer.rs:945).
- * Any radius >= 1 (radius 0 is treated as 1, noise.rs:364); integer, bit-exact. */
+ * Any radius from 1 to 20000 (radius 0 is treated as 1, noise.rs:364; PFE_ERR_UNSUPPORTED beyond); integer,
+ * bit-exact. */
 int pfe_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,
                const uint8_t *mask, uint8_t *dst);
 int pfe_dev_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, uint32_t radius,

@@ -46,6 +46,7 @@ struct GaussParams {
     float sigma;          // host side only: key of the device-resident weight table
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
+    int dbg;                  // diagnosis only (PFE_GAUSS_DBG): 1 = H pass skips its staging loads, 2 = skips its stores
     int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
     // 1 and -0 for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
@@ -150,8 +151,10 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         const int x0 = (int)(task % nseg) * SEG;
         const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
         // stage + convert: tile[p] = pixel clamp(x0 - r + p); unrolled so several loads are in flight
+        if (!(P.dbg & 1)) {
 #pragma unroll 4
-        for (int p = lane; p < tile_px; p += 32) tile[skew(p, N)] = to_f4(__ldg(row + min(max(x0 - P.radius + p, 0), rw - 1)));
+            for (int p = lane; p < tile_px; p += 32) tile[skew(p, N)] = to_f4(__ldg(row + min(max(x0 - P.radius + p, 0), rw - 1)));
+        }
         __syncwarp();
         Acc4 acc[N];
         float R[N];
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         float4 *out = reinterpret_cast<float4 *>(P.mid) + (size_t)y * P.rw;
 #pragma unroll 4
         for (int p = lane; p < SEG; p += 32)
-            if (x0 + p < rw) out[x0 + p] = tile[skew(p, N)];
+            if (x0 + p < rw && !(P.dbg & 2)) out[x0 + p] = tile[skew(p, N)];
         __syncwarp();
     }
 }
@@ -633,6 +636,7 @@ void set_steps(GaussParams &P, const std::vector<float> &k) {
     P.steps = ((N + taps - 1 + N - 1) / N) * N;  // N + 2r rounded up to a multiple of N
     P.wp_len = P.steps + N - 1;
     P.tri = (N > 1 && P.steps == N + taps - 1 && getenv("PFE_GAUSS_NO_TRI") == nullptr) ? 1 : 0;
+    P.dbg = getenv("PFE_GAUSS_DBG") ? atoi(getenv("PFE_GAUSS_DBG")) : 0;
 }
 template <int N>
 int upload_weights(pfe_ctx *ctx, GaussParams &P, const std::vector<float> &k, float sigma) {

@@ -571,6 +571,9 @@ def _copy_value(v):
     return [_copy_value(x) for x in v] if isinstance(v, list) else v
 
 
+_PROGRAMS: Dict[str, list] = {}  # source text -> parsed program (the interpreter never mutates a program)
+
+
 class Interpreter:
     """One script run over one image (the ScriptContext of scripting.rs:262)."""
 
@@ -633,7 +636,12 @@ class Interpreter:
 
     # ---------------------------------------------------------------- entry points
     def run(self, source: str):
-        program = Parser(source).program()
+        program = _PROGRAMS.get(source)  # a batch runs one script over many images: parse it once
+        if program is None:
+            program = Parser(source).program()
+            if len(_PROGRAMS) > 64:
+                _PROGRAMS.clear()
+            _PROGRAMS[source] = program
         for st in program:  # functions are visible before their definition, as in Rhai
             if st[0] == "fn":
                 self.functions[st[1]] = (st[2], st[3])

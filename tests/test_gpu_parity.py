@@ -641,6 +641,51 @@ def test_cli_flatten_pfe_and_script_batch(eng, oracle, tmp_path):
         e = oracle.adjust(e, oracle.S_HSL, (10.0, 15.0, 0.0))
         e = oracle.vignette(e, 0.5, 0.3)
         exact(np.array(Image.open(tmp_path / "out" / f"{name}.png").convert("RGBA")), e, name)
+    # the same batch one file at a time gives the same files; JPEG output drops alpha instead of failing (cli.rs:277-304)
+    rc = cli.main(["-i", str(tmp_path / "in" / "shot*.png"), "--script", str(script), "--output-dir", str(tmp_path / "out1"),
+                   "--exact", "--no-pipeline"])
+    assert rc == 0
+    for name in shots:
+        exact(np.array(Image.open(tmp_path / "out1" / f"{name}.png")), np.array(Image.open(tmp_path / "out" / f"{name}.png")), name)
+    assert cli.main(["-i", str(tmp_path / "in" / "shot*.png"), "--script", str(script), "--output-dir", str(tmp_path / "outj"), "-f", "jpg"]) == 0
+    assert Image.open(tmp_path / "outj" / "shot0.jpg").mode == "RGB"
+    # raster in, project out
+    assert cli.main(["-i", str(tmp_path / "in" / "shot1.png"), "-o", str(tmp_path / "shot1.pfe")]) == 0
+    back = pfe_io.load_pfe(str(tmp_path / "shot1.pfe"))
+    exact(back.layers[0].to_flat(back.width, back.height), shots["shot1"], "png -> pfe")
+
+
+def test_image_pipeline_keeps_order_and_contents(eng, oracle):
+    """ImagePipeline (upload / script / download on three streams, 3 images in flight): eleven images of four different
+    sizes, pageable and pinned inputs, results equal to running the script on each image alone."""
+    import torch
+
+    from paintfe_b200.pipeline import ImagePipeline
+    from paintfe_b200.script import execute_script_sync
+
+    script = "apply_blur(2.0); apply_brightness_contrast(10.0, 20.0); apply_invert();"
+    rng = np.random.default_rng(8)
+    sizes = [(64, 48), (130, 70), (33, 200), (256, 256)]
+    imgs = [fx.random_rgba(rng, *sizes[i % 4]) for i in range(11)]
+    pipe = ImagePipeline(eng, depth=3)
+    got = {}
+
+    def work(dev):
+        return execute_script_sync(eng, script, dev, exact=True)
+
+    for i, im in enumerate(imgs):
+        if pipe.full():
+            tag, out = pipe.collect()
+            got[tag] = out.copy()
+        src = im if i % 2 else torch.from_numpy(im).pin_memory()
+        pipe.submit(src, work, tag=i)
+    for tag, out in pipe.drain():
+        got[tag] = out.copy()
+    assert sorted(got) == list(range(11))
+    for i, im in enumerate(imgs):
+        e = oracle.adjust(oracle.adjust(oracle.gaussian_blur(im, 2.0), oracle.S_BRIGHTNESS_CONTRAST, (10.0, 20.0)), oracle.S_INVERT)
+        exact(got[i], e, f"pipeline image {i}")
+    assert pipe.h2d_bytes == pipe.d2h_bytes == sum(im.size for im in imgs)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -108,6 +108,12 @@ def main():
                      ("UW=1 V_WARPS=12 NV=8", {"PFE_GAUSS_V_WARPS": "12", "PFE_GAUSS_NV": "8"}),
                      ("UW=0 NV=8", {"PFE_GAUSS_UW": "0", "PFE_GAUSS_NV": "8"})):
         run(f"gaussian s20 fast [{tag}]", g20, 8 * px, env=env)
+    if torch.cuda.is_available():  # the two passes on their own (band-form entry points; the V pass reuses the H result)
+        run("gaussian s20 H pass only", lambda: eng.gaussian_band_h(img, 0, H8K, 20.0), 20 * px)
+        for tag, env in (("no staging loads", {"PFE_GAUSS_DBG": "1"}), ("no stores", {"PFE_GAUSS_DBG": "2"}), ("neither", {"PFE_GAUSS_DBG": "3"})):
+            run(f"gaussian s20 H pass only [diagnosis: {tag}]", lambda: eng.gaussian_band_h(img, 0, H8K, 20.0), 20 * px, env=env)
+        eng.gaussian_band_h(img, 0, H8K, 20.0)
+        run("gaussian s20 V pass only", lambda: eng.gaussian_band_v(img, 0, H8K, 20.0, out=out), 20 * px)
     run("gaussian s20 EXACT", lambda: eng.gaussian_blur(img, 20.0, exact=True, out=out), 8 * px)
     run("gaussian s50 fast", lambda: eng.gaussian_blur(img, 50.0, out=out), 8 * px)
     run("gaussian s4 fast (fused H+V)", lambda: eng.gaussian_blur(img, 4.0, out=out), 8 * px)
