@@ -589,6 +589,7 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
             if (cudaPointerGetAttributes(&pa, hp) != cudaSuccess || pa.type != cudaMemoryTypeHost) { cudaGetLastError(); all_pinned = false; }
         }
     }
+    int rc = PFE_OK;
     std::vector<cudaEvent_t> events;
     auto new_event = [&]() -> cudaEvent_t {
         cudaEvent_t e = nullptr;
@@ -596,7 +597,6 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
         events.push_back(e);
         return e;
     };
-    int rc = PFE_OK;
     static const bool dbg = getenv("PFE_PIPE_DEBUG") != nullptr;  // tuning aid: where the call's time goes
     cudaEvent_t t0 = nullptr, t_up = nullptr, t_cmp = nullptr, t_dn = nullptr;
     if (dbg) {
@@ -604,14 +604,23 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
         cudaEventRecord(t0, ctx->copy_stream);
     }
     uint32_t v_next = 0;  // first band whose V pass (or download) has not been issued yet
+    // Inside the band loop a CUDA error must not return: copies on copy_stream / d2h_stream may still be touching the
+    // caller's host buffers and the per-band events would leak.  Errors set rc and fall through to the common tail,
+    // which synchronises the three streams and destroys the events.
+    auto cuda_ok = [&](cudaError_t e, const char *what) -> bool {
+        if (e == cudaSuccess) return true;
+        if (rc == PFE_OK) rc = pfe_fail(ctx, PFE_ERR_CUDA, what, e);
+        return false;
+    };
     auto download_band = [&](uint32_t k) -> int {
         const uint32_t y0 = band_y0[k], rows = band_rows[k];
         cudaEvent_t e = new_event();
         if (!e) return pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate");
-        PFE_CUDA(ctx, cudaEventRecord(e, ctx->stream));
-        PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
-        PFE_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)y0 * w * 4, out + (size_t)y0 * w * 4, (size_t)rows * w * 4,
-                                      cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        if (!cuda_ok(cudaEventRecord(e, ctx->stream), "cudaEventRecord") ||
+            !cuda_ok(cudaStreamWaitEvent(ctx->d2h_stream, e, 0), "cudaStreamWaitEvent") ||
+            !cuda_ok(cudaMemcpyAsync(dst + (size_t)y0 * w * 4, out + (size_t)y0 * w * 4, (size_t)rows * w * 4,
+                                     cudaMemcpyDeviceToHost, ctx->d2h_stream), "cudaMemcpyAsync (download)"))
+            return rc;
         return PFE_OK;
     };
     for (uint32_t b = 0; b < nbands && rc == PFE_OK; b++) {
@@ -645,12 +654,14 @@ static int flatten_pipeline(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t
             }
         }
         if (!batched)
-            for (size_t c = 0; c < cp_dst.size(); c++)
-                PFE_CUDA(ctx, cudaMemcpyAsync(cp_dst[c], cp_src[c], cp_len[c], cudaMemcpyHostToDevice, ctx->copy_stream));
+            for (size_t c = 0; c < cp_dst.size() && rc == PFE_OK; c++)
+                cuda_ok(cudaMemcpyAsync(cp_dst[c], cp_src[c], cp_len[c], cudaMemcpyHostToDevice, ctx->copy_stream), "cudaMemcpyAsync (upload)");
+        if (rc != PFE_OK) break;
         cudaEvent_t up = new_event();
         if (!up) { rc = pfe_fail(ctx, PFE_ERR_CUDA, "cudaEventCreate"); break; }
-        PFE_CUDA(ctx, cudaEventRecord(up, ctx->copy_stream));
-        PFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+        if (!cuda_ok(cudaEventRecord(up, ctx->copy_stream), "cudaEventRecord") ||
+            !cuda_ok(cudaStreamWaitEvent(ctx->stream, up, 0), "cudaStreamWaitEvent"))
+            break;
         rc = pfe_dev_flatten(ctx, bl.data(), n, w, rows, active_dev ? active_dev + (size_t)(y0 / PFE_CHUNK_SIZE) * chunks_x : nullptr,
                              flat + off4);
         if (rc != PFE_OK) break;
