@@ -102,6 +102,26 @@ __device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float w, 
     else if (P.tri && g == P.steps - N) { PFE_GAUSS_GROUP_C(LOAD, j >= s) }                     \
     else { PFE_GAUSS_GROUP_C(LOAD, true) }
 
+// The same with the FIRST input of each group carried across the loop in `pre_in`: the group loads the next group's
+// first input (LOAD_NEXT) before its own FMAs, so the address arithmetic and shared-memory latency of that load hide
+// under 128 FFMA2 instead of stalling the first FFMA2 of every group (10 % of all stall samples in the r02 ncu source
+// view of the H pass).  NEXT_OK (warp-uniform) says whether a next group exists whose input may be read already.
+#define PFE_GAUSS_GROUP_PC(LOAD, LOAD_NEXT, NEXT_OK, COND)                                      \
+    {                                                                                           \
+        const float4 first_in = pre_in;                                                         \
+        if (NEXT_OK) pre_in = LOAD_NEXT;                                                        \
+        _Pragma("unroll") for (int s = 0; s < N; s++) {                                         \
+            R[(s + N - 1) % N] = wsm[g + s + N - 1];                                            \
+            const float4 in = s == 0 ? first_in : LOAD(s);                                      \
+            _Pragma("unroll") for (int j = 0; j < N; j++)                                       \
+                if (COND) tap<EXACT>(acc[j], in, R[(s - j - 1 + 2 * N) % N], P.one, P.nzero);   \
+        }                                                                                       \
+    }
+#define PFE_GAUSS_GROUP_P(LOAD, LOAD_NEXT, NEXT_OK)                                             \
+    if (P.tri && g == 0) PFE_GAUSS_GROUP_PC(LOAD, LOAD_NEXT, NEXT_OK, j <= s)                   \
+    else if (P.tri && g == P.steps - N) PFE_GAUSS_GROUP_PC(LOAD, LOAD_NEXT, NEXT_OK, j >= s)    \
+    else PFE_GAUSS_GROUP_PC(LOAD, LOAD_NEXT, NEXT_OK, true)
+
 __host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
 // u8 -> f32 uses PRMT + FADD against 2^23 (ALU/FMA pipes) instead of the quarter-rate I2F:
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     // round trips per task (measured at 8K sigma 20: 0.60 ms with the loads in line, 0.53 ms without any loads at all).
     // Tiles wider than 32 * PRE pixels (large sigma) keep the in-line staging.
     constexpr int PRE = 12;
-    const bool use_pre = tile_px <= 32 * PRE && !(P.dbg & 1);
+    const bool use_pre = tile_px <= 32 * PRE && !(P.dbg & (1 | 4));  // dbg 4: in-line staging (A/B)
     const uint64_t stride = (uint64_t)gridDim.x * WARPS;
     uint32_t pre[PRE];
     auto fetch = [&](uint64_t t) {
@@ -192,10 +212,12 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         for (int m = 0; m < N - 1; m++) R[m] = wsm[m];
         // input i of this lane sits at skew(lane*N + i) = lane*(N+1) + i + i/N
         const float4 *tl = tile + lane * (N + 1);
+        float4 pre_in = tl[0];
         for (int g = 0; g < P.steps; g += N) {
             const float4 *tg = tl + g + g / N;  // within a group i/N is constant: step s is tg[s]
 #define H_LOAD(s) tg[s]
-            PFE_GAUSS_GROUP(H_LOAD)
+            // the next group's first input sits one skew slot further: tl[(g + N) + (g + N) / N] = tg[N + 1]
+            PFE_GAUSS_GROUP_P(H_LOAD, tg[N + 1], g + N < P.steps)
 #undef H_LOAD
         }
         __syncwarp();
@@ -390,10 +412,12 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
             const int c = q / chunk_groups;
             mbar_wait(full0 + 8u * (uint32_t)c, parity);
             const int q_stop = min(q_end, (c + 1) * chunk_groups);
+            float4 pre_in = col[(size_t)g * 32];  // this chunk has landed: its first group's first row
             for (; q < q_stop; q++, g += N) {
                 const float4 *cg = col + (size_t)g * 32;
 #define VT_LOAD(s) cg[(s) * 32]
-                PFE_GAUSS_GROUP(VT_LOAD)
+                // the next group's first row may be read ahead only while it lies in the chunk just waited for
+                PFE_GAUSS_GROUP_P(VT_LOAD, cg[N * 32], q + 1 < q_stop)
 #undef VT_LOAD
             }
             __syncwarp();  // every lane has read the chunk's rows

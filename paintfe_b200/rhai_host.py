@@ -395,8 +395,26 @@ def to_text(v) -> str:
     return str(v)
 
 
-def _wrap_i64(v):
-    return v  # Rhai raises on i64 overflow; scripts on 8-bit channels never get there
+_I64_MIN, _I64_MAX = -(1 << 63), (1 << 63) - 1
+
+
+def _checked_i64(op, a, b, r, line=None):
+    """Rhai's default (checked) integer arithmetic: a result outside i64 is an error, not a bigger integer.
+    Whole-image evaluation works on int64 arrays, where an overflow would wrap silently: operands large enough to get
+    there send the closure to the per-pixel path, which checks every operation."""
+    if _is_vec(r):
+        big = 1 << (31 if op in ("*", "**") else 62)
+        for v in (a, b):
+            if (_is_vec(v) and v.size and int(np.abs(v).max()) >= big) or (not _is_vec(v) and abs(int(v)) >= big):
+                raise _NotVectorisable()
+        if op == "**":
+            with np.errstate(over="ignore"):
+                if float(np.max(np.power(np.abs(np.asarray(a, np.float64)), np.asarray(b, np.float64)), initial=0.0)) >= 2.0 ** 62:
+                    raise _NotVectorisable()
+        return r
+    if not _I64_MIN <= r <= _I64_MAX:
+        raise ScriptError("Arithmetic overflow" if op != "**" else "Number raised to power overflows", line)
+    return r
 
 
 def _trunc_div(a, b):
@@ -441,11 +459,11 @@ def _binary(op, a, b, line=None):
         raise ScriptError(f"Function not found: {op} ({_type_name(a)}, {_type_name(b)})", line)
     ints = _is_int(a) and _is_int(b)
     if op == "+":
-        return a + b
+        return _checked_i64(op, a, b, a + b, line) if ints else a + b
     if op == "-":
-        return a - b
+        return _checked_i64(op, a, b, a - b, line) if ints else a - b
     if op == "*":
-        return a * b
+        return _checked_i64(op, a, b, a * b, line) if ints else a * b
     if op == "/":
         if ints:
             return _trunc_div(a, b)
@@ -464,10 +482,12 @@ def _binary(op, a, b, line=None):
             if _is_vec(a) or _is_vec(b):
                 if (np.asarray(b) < 0).any():
                     raise _NotVectorisable()
-                return np.power(a, b)
+                return _checked_i64(op, a, b, np.power(a, b), line)
             if b < 0:
                 raise ScriptError("Integer raised to a negative power", line)
-            return a ** b
+            if abs(a) > 1 and b > 64:
+                raise ScriptError("Number raised to power overflows", line)
+            return _checked_i64(op, a, b, a ** b, line)
         if _is_vec(a) or _is_vec(b):
             return np.power(np.asarray(a, np.float64), b)
         try:
@@ -590,6 +610,8 @@ class Interpreter:
         self.functions: Dict[str, tuple] = {}
         self.scopes: List[Dict[str, Any]] = [{}]
         self.vector_mode = False
+        self._outer_scopes = frozenset()  # ids of the scope dicts a whole-image closure evaluation must not write to
+        self._outer_lists = frozenset()   # ids of the arrays reachable from them
         self.ops = 0
         self.bulk_evaluations = {"whole_image": 0, "per_pixel": 0}  # how closures of the bulk calls were evaluated
         self._host: Optional[np.ndarray] = None  # host copy of a device image while pixel access is in use
@@ -693,9 +715,13 @@ class Interpreter:
             val = self.eval(rhs)
             if target[0] == "var":
                 sc = self.lookup(target[1], line)
+                if self.vector_mode and id(sc) in self._outer_scopes:
+                    raise _NotVectorisable()  # a captured variable is shared and mutated PER PIXEL in Rhai (counters, sums)
                 sc[target[1]] = _copy_value(val if op == "=" else _binary(op[:-1], sc[target[1]], val, line))
             else:
                 arr, idx = self.eval(target[1]), self.eval(target[2])
+                if self.vector_mode and isinstance(arr, list) and id(arr) in self._outer_lists:
+                    raise _NotVectorisable()  # e.g. hist[bin] += 1 on a captured array
                 if not isinstance(arr, list) or not _is_int(idx) or _is_vec(idx):
                     if self.vector_mode:
                         raise _NotVectorisable()
@@ -872,6 +898,8 @@ class Interpreter:
             raise ScriptError(f"Property {name} not found on {_type_name(obj)}", line)
         args = [self.eval(a) for a in args_e]
         if isinstance(obj, list):
+            if self.vector_mode and name in ("push", "pop", "clear") and id(obj) in self._outer_lists:
+                raise _NotVectorisable()  # a captured array grows / shrinks once per pixel in Rhai
             if name == "len":
                 return len(obj)
             if name == "push":
@@ -1102,7 +1130,21 @@ class Interpreter:
         src = self.host_pixels()
         region = src[y0:y1, x0:x1].astype(np.int64)
         out = None
-        saved_ops, saved_console = self.ops, len(self.console)
+        saved_ops, saved_console, saved_rng = self.ops, len(self.console), self.rng_state
+        # Only a PURE closure may be evaluated once over whole-image arrays: writes to anything outside its own call
+        # frame (captured variables, arrays reachable from them) abort the attempt before they happen, so the
+        # per-pixel evaluation below starts from untouched state.
+        outer = list(fn.scopes)
+        self._outer_scopes = frozenset(id(sc) for sc in outer)
+        lists, stack = set(), [v for sc in outer for v in sc.values()]
+        while stack:
+            v = stack.pop()
+            if isinstance(v, list) and id(v) not in lists:
+                lists.add(id(v))
+                stack.extend(v)
+            elif isinstance(v, Closure):
+                stack.extend(x for sc in v.scopes for x in sc.values() if isinstance(x, list))
+        self._outer_lists = frozenset(lists)
         try:
             self.vector_mode = True
             ys, xs = np.mgrid[y0:y1, x0:x1].astype(np.int64)
@@ -1112,9 +1154,10 @@ class Interpreter:
         except (_NotVectorisable, ScriptError, ValueError, TypeError, IndexError):
             out = None  # evaluate per pixel instead; a genuine script error is raised again there
             del self.console[saved_console:]
-            self.ops = saved_ops
+            self.ops, self.rng_state = saved_ops, saved_rng
         finally:
             self.vector_mode = False
+            self._outer_scopes = self._outer_lists = frozenset()
         self.bulk_evaluations["whole_image" if out is not None else "per_pixel"] += 1
         if out is None:
             out = self._bulk_scalar(fn, region, x0, y0, with_xy)

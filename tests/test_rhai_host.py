@@ -349,3 +349,53 @@ def test_reference_readme_script(run, oracle):
     exp[..., 0] = np.clip(exp[..., 0] + 15, 0, 255)
     exp[..., 2] = np.clip(exp[..., 2] - 8, 0, 255)
     assert (out == exp.astype(np.uint8)).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# closures that write outside their own frame: Rhai shares captured variables and runs the closure once per pixel, so
+# counters, running sums, histograms and captured arrays must see every pixel - the whole-image evaluation has to
+# decline them (and leave no trace of its attempt behind)
+# ---------------------------------------------------------------------------------------------------------------
+def _host_only(src, img):
+    from paintfe_b200.rhai_host import Interpreter
+
+    it = Interpreter(None, img.copy())
+    out = it.run(src)
+    return it, out
+
+
+def test_impure_closures_are_evaluated_per_pixel():
+    img = (np.arange(20 * 4, dtype=np.uint8).reshape(4, 5, 4) * 3).astype(np.uint8)
+    it, _ = _host_only("let count = 0; for_each_pixel(|x,y,r,g,b,a| { count += 1; [r,g,b,a] }); print(count);", img)
+    assert it.console == ["20"] and it.bulk_evaluations == {"whole_image": 0, "per_pixel": 1}
+    it, _ = _host_only("let t = 0; for_each_pixel(|x,y,r,g,b,a| { t = t + r; [r,g,b,a] }); print(t);", img)
+    assert it.console == [str(int(img[..., 0].astype(int).sum()))]
+    it, _ = _host_only("let hist = [0, 0]; map_channels(|r,g,b,a| { if r > 100 { hist[1] += 1 } else { hist[0] += 1 }; [r,g,b,a] }); print(hist);", img)
+    hi = int((img[..., 0] > 100).sum())
+    assert it.console == [f"[{20 - hi}, {hi}]"]
+    # mutation BEFORE the construct that forces the per-pixel path: nothing of the abandoned attempt may survive
+    it, _ = _host_only("let acc = []; let count = 0; for_each_pixel(|x,y,r,g,b,a| { count += 1; let v = rand_int(0, 10); acc.push(v); [r,g,b,a] });"
+                       " print(count); print(acc.len());", img)
+    assert it.console == ["20", "20"]
+    # the random sequence starts where it would have without the attempt
+    a, _ = _host_only("let s = 0; for_each_pixel(|x,y,r,g,b,a| { s += rand_int(0, 1000); [r,g,b,a] }); print(s);", img)
+    b, _ = _host_only("let s = 0; for x in 0..20 { s += rand_int(0, 1000); } print(s);", img)
+    assert a.console == b.console
+    # a pure closure still takes the whole-image path, and gives the per-pixel result
+    it, out = _host_only("for_each_pixel(|x,y,r,g,b,a| { let k = 255 - r; [k, g, b, a] });", img)
+    assert it.bulk_evaluations == {"whole_image": 1, "per_pixel": 0} and np.array_equal(out[..., 0], 255 - img[..., 0])
+
+
+def test_integer_arithmetic_is_checked_like_rhai():
+    from paintfe_b200.rhai_host import ScriptError
+
+    img = np.zeros((2, 2, 4), np.uint8)
+    for src in ("let x = 9223372036854775807; x += 1;", "let x = 3037000500; let y = x * x;", "let z = 2 ** 70;",
+                "let m = -9223372036854775807 - 2;"):
+        with pytest.raises(ScriptError):
+            _host_only(src, img)
+    it, _ = _host_only("print(2 ** 62); print(9223372036854775807 - 1);", img)
+    assert it.console == ["4611686018427387904", "9223372036854775806"]
+    # products that would wrap in int64 arrays leave the whole-image path instead of wrapping
+    it, out = _host_only("for_each_pixel(|x,y,r,g,b,a| { let k = ((r + 7) * 3000000000) / 3000000000; [k, g, b, a] });", img)
+    assert np.all(out[..., 0] == 7)

@@ -110,7 +110,8 @@ def main():
         run(f"gaussian s20 fast [{tag}]", g20, 8 * px, env=env)
     if torch.cuda.is_available():  # the two passes on their own (band-form entry points; the V pass reuses the H result)
         run("gaussian s20 H pass only", lambda: eng.gaussian_band_h(img, 0, H8K, 20.0), 20 * px)
-        for tag, env in (("no staging loads", {"PFE_GAUSS_DBG": "1"}), ("no stores", {"PFE_GAUSS_DBG": "2"}), ("neither", {"PFE_GAUSS_DBG": "3"})):
+        for tag, env in (("no staging loads", {"PFE_GAUSS_DBG": "1"}), ("no stores", {"PFE_GAUSS_DBG": "2"}), ("neither", {"PFE_GAUSS_DBG": "3"}),
+                         ("in-line staging instead of the register prefetch", {"PFE_GAUSS_DBG": "4"})):
             run(f"gaussian s20 H pass only [diagnosis: {tag}]", lambda: eng.gaussian_band_h(img, 0, H8K, 20.0), 20 * px, env=env)
         eng.gaussian_band_h(img, 0, H8K, 20.0)
         run("gaussian s20 V pass only", lambda: eng.gaussian_band_v(img, 0, H8K, 20.0, out=out), 20 * px)
