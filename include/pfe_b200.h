@@ -134,7 +134,14 @@ int pfe_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers, uint32_t 
                       uint32_t h, uint8_t *dst);
 int pfe_dev_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers_with_dev_tables,
                           uint32_t n_layers, uint32_t w, uint32_t h, uint8_t *dst_dev);
-/* A TiledImage resident on the device: chunk pool + pointer table + occupancy bytes.
+/* A TiledImage resident on the device: pointer table + occupancy bytes over chunks that live in the context's
+ * reference-counted chunk pool, so that images cloned from one another share unchanged chunks the way
+ * `Vec<Option<Arc<RgbaImage>>>` does (copy on write: Arc::make_mut, tiled_image.rs:330, ensure_chunk_mut :868).
+ * An image belongs to the context that created it.
+ * clone      a second image sharing every chunk of the first (an undo snapshot): no pixel is copied.
+ * make_mut   ensure_chunk_mut for a list of chunk indices: each becomes populated (fresh chunks are transparent) and
+ *            private to this image (a shared chunk is copied first), so device code may write it through the table.
+ * chunk_ids  pool slot per chunk, -1 = none: two images share a chunk exactly when the ids agree.
  * upload     TiledImage -> device; only populated chunks cross PCIe.
  * from_flat  TiledImage::from_rgba_image (tiled_image.rs:50-104) on the device: a chunk is populated iff
  *            some pixel in it has alpha != 0.
@@ -144,6 +151,9 @@ int pfe_dev_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers_with_d
 typedef struct pfe_tiled pfe_tiled;
 int pfe_tiled_create(pfe_ctx *ctx, uint32_t w, uint32_t h, pfe_tiled **out);
 int pfe_tiled_destroy(pfe_ctx *ctx, pfe_tiled *t);
+int pfe_tiled_clone(pfe_ctx *ctx, const pfe_tiled *src, pfe_tiled **out);
+int pfe_tiled_make_mut(pfe_ctx *ctx, pfe_tiled *t, const uint32_t *chunk_indices, uint32_t n);
+int pfe_tiled_chunk_ids(pfe_ctx *ctx, const pfe_tiled *t, int32_t *ids_out);
 int pfe_tiled_upload(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *const *host_chunk_table);
 int pfe_tiled_from_flat(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *flat_dev);
 int pfe_tiled_to_flat(pfe_ctx *ctx, const pfe_tiled *t, uint8_t *flat_dev);
@@ -450,6 +460,15 @@ int pfe_dev_mesh_warp(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t
                       const float *original_points, const float *deformed_points, uint32_t cols,
                       uint32_t rows, uint32_t w, uint32_t h, uint32_t y0, uint32_t rows_out,
                       uint8_t *dst_band);
+/* warp_displacement_region (src/ops/transform.rs:1206-1285; the liquify tool's incremental preview): dst = prev
+ * everywhere, except inside dirty_rect = {x0, y0, x1, y1} (half-open, clamped like the reference: x0.max(0),
+ * (x1 as u32).min(w) - so a negative x1 means "to the right edge"), where it is the displacement warp of src.
+ * prev and dst are w*h*4 bytes and may be the same buffer; an inverted rect changes nothing. */
+int pfe_warp_displacement_region(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h, const float *disp,
+                                 const uint8_t *prev, const int32_t dirty_rect[4], uint32_t w, uint32_t h, uint8_t *dst);
+int pfe_dev_warp_displacement_region(pfe_ctx *ctx, const uint8_t *src, uint32_t src_w, uint32_t src_h, const float *disp,
+                                     const uint8_t *prev, const int32_t dirty_rect[4], uint32_t w, uint32_t h,
+                                     uint8_t *dst);
 /* Row-band form of both warps for a canvas split across GPUs: produce output rows
  * [y0, y0+rows_out) of the w x h result from a WINDOW of source rows [src_y0, src_y0+src_nrows) of
  * the src_w x src_h source (own band + halo). disp_band != NULL: displacement warp with the band's

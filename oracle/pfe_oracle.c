@@ -971,6 +971,22 @@ void pfo_warp_displacement(const uint8_t *src, uint32_t sw, uint32_t sh, const f
         }
 }
 
+/* warp_displacement_region :1206-1285: prev everywhere, the warp inside dirty_rect = (x0, y0, x1, y1).  The rect is
+ * clamped the way the reference does it: x0.max(0), (x1 as u32).min(out_w) - a negative x1 wraps to a huge u32 and
+ * clamps to the full width.  An inverted rect (the reference would panic on the row length) is treated as empty. */
+void pfo_warp_displacement_region(const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp, const uint8_t *prev,
+                                  const int rect[4], uint32_t w, uint32_t h, uint8_t *dst) {
+    uint32_t dx0 = rect[0] > 0 ? (uint32_t)rect[0] : 0u, dy0 = rect[1] > 0 ? (uint32_t)rect[1] : 0u;
+    uint32_t dx1 = (uint32_t)rect[2] < w ? (uint32_t)rect[2] : w, dy1 = (uint32_t)rect[3] < h ? (uint32_t)rect[3] : h;
+    memcpy(dst, prev, (size_t)w * h * 4);
+    if (dx1 <= dx0 || dy1 <= dy0) return;
+    uint8_t *full = (uint8_t *)malloc((size_t)w * h * 4);
+    pfo_warp_displacement(src, sw, sh, disp, w, h, full);  /* per-pixel formula is the full warp's (:1288-1345) */
+    for (uint32_t y = dy0; y < dy1; y++)
+        memcpy(dst + ((size_t)y * w + dx0) * 4, full + ((size_t)y * w + dx0) * 4, (size_t)(dx1 - dx0) * 4);
+    free(full);
+}
+
 /* warp_mesh_catmull_rom :1743-1761 */
 void pfo_mesh_warp(const uint8_t *src, uint32_t sw, uint32_t sh, const float *orig, const float *def,
                    int cols, int rows, uint32_t w, uint32_t h, uint8_t *dst) {

@@ -254,6 +254,17 @@ def warp_displacement(src, disp):
     return dst
 
 
+def warp_displacement_region(src, disp, prev, rect):
+    src, disp, prev = _u8(src), _f32(disp), _u8(prev)
+    sh, sw = src.shape[:2]
+    h, w = disp.shape[:2]
+    dst = np.empty((h, w, 4), np.uint8)
+    r = (C.c_int * 4)(*[int(v) for v in rect])
+    lib().pfo_warp_displacement_region(_p(src), C.c_uint32(sw), C.c_uint32(sh), _p(disp), _p(prev), r, C.c_uint32(w),
+                                       C.c_uint32(h), _p(dst))
+    return dst
+
+
 def mesh_warp(src, orig, deformed, cols, rows, w, h):
     src = _u8(src)
     sh, sw = src.shape[:2]

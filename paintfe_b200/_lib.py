@@ -73,6 +73,9 @@ SIGNATURES = {
     "pfe_dev_flatten_tiles": (C.c_int, [_ctx, C.POINTER(TileLayerDesc), _u32, _u32, _u32, _vp]),
     "pfe_tiled_create": (C.c_int, [_ctx, _u32, _u32, C.POINTER(_vp)]),
     "pfe_tiled_destroy": (C.c_int, [_ctx, _vp]),
+    "pfe_tiled_clone": (C.c_int, [_ctx, _vp, C.POINTER(_vp)]),
+    "pfe_tiled_make_mut": (C.c_int, [_ctx, _vp, _vp, _u32]),
+    "pfe_tiled_chunk_ids": (C.c_int, [_ctx, _vp, _vp]),
     "pfe_tiled_upload": (C.c_int, [_ctx, _vp, _vp]),
     "pfe_tiled_from_flat": (C.c_int, [_ctx, _vp, _vp]),
     "pfe_tiled_to_flat": (C.c_int, [_ctx, _vp, _vp]),
@@ -152,6 +155,8 @@ SIGNATURES = {
     "pfe_dev_resize": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, C.c_int, _vp]),
     "pfe_warp_displacement": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _u32, _u32, _vp]),
     "pfe_dev_warp_displacement": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _u32, _u32, _vp]),
+    "pfe_warp_displacement_region": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _vp]),
+    "pfe_dev_warp_displacement_region": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _vp]),
     "pfe_mesh_displacement": (C.c_int, [_ctx, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_mesh_displacement": (C.c_int, [_ctx, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_mesh_warp": (C.c_int, [_ctx, _vp, _u32, _u32, _vp, _vp, _u32, _u32, _u32, _u32, _vp]),

@@ -156,6 +156,7 @@ int pfe_ctx_destroy(pfe_ctx *c) {
     if (c->dev_small) cudaFree(c->dev_small);
     if (c->async_err) cudaFree(c->async_err);
     if (c->gauss_mem) cudaFree(c->gauss_mem);
+    for (uint8_t *slab : c->chunks.slabs) cudaFree(slab);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (int i = 0; i < 2; i++) {
         if (c->stage[i]) cudaFreeHost(c->stage[i]);
@@ -442,6 +443,24 @@ int pfe_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_
     PFE_CUDA(ctx, cudaMemcpyAsync(a, src, sb, cudaMemcpyHostToDevice, ctx->stream));
     PFE_CUDA(ctx, cudaMemcpyAsync(f, disp, fb, cudaMemcpyHostToDevice, ctx->stream));
     PFE_TRY(pfe_dev_warp_displacement(ctx, (uint8_t *)a, sw, sh, (float *)f, w, h, (uint8_t *)b));
+    PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, db, cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+
+int pfe_warp_displacement_region(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp,
+                                 const uint8_t *prev, const int32_t rect[4], uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!ctx || !src || !disp || !prev || !rect || !dst || !sw || !sh || !w || !h) return PFE_ERR_INVALID_ARG;
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t sb = (size_t)sw * sh * 4, db = (size_t)w * h * 4, fb = (size_t)w * h * 8;
+    void *a, *b, *f;
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, sb, &a));
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, db, &b));
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, fb, &f));
+    PFE_CUDA(ctx, cudaMemcpyAsync(a, src, sb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_CUDA(ctx, cudaMemcpyAsync(b, prev, db, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_CUDA(ctx, cudaMemcpyAsync(f, disp, fb, cudaMemcpyHostToDevice, ctx->stream));
+    PFE_TRY(pfe_dev_warp_displacement_region(ctx, (uint8_t *)a, sw, sh, (float *)f, (uint8_t *)b, rect, w, h, (uint8_t *)b));
     PFE_CUDA(ctx, cudaMemcpyAsync(dst, b, db, cudaMemcpyDeviceToHost, ctx->stream));
     PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PFE_OK;

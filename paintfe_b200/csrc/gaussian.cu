@@ -46,6 +46,7 @@ struct GaussParams {
     float sigma;          // host side only: key of the device-resident weight table
     int steps;            // T: padded step count, multiple of N
     int wp_len;           // steps + N - 1
+    const uint32_t *bb;       // selection blur: device {min_x, min_y, max_x, max_y} of the mask, or null (see bb_skip)
     int dbg;                  // diagnosis only (PFE_GAUSS_DBG): 1 = H pass skips its staging loads, 2 = skips its stores
     int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
@@ -124,6 +125,19 @@ __device__ __forceinline__ void tap(Acc4 &acc, const float4 &in, const float w, 
 
 __host__ __device__ __forceinline__ int skew(int p, int n) { return p + p / n; }
 
+// blur_with_selection (filters.rs:141-207) crops to the mask's bounding box grown by ceil(3 sigma), blurs the crop and
+// copies back where the mask is set.  A selected pixel is at least the radius away from every crop edge that is not an
+// image edge, so its taps (and the taps of the H values its V pass reads) never meet the crop's clamp: blurring in the
+// full image's geometry gives it the very same value.  The kernels therefore keep the whole-image geometry and only
+// SKIP work that no selected pixel can see - decided on the device from the bounding box the mask_bbox kernel left
+// there, so nothing is read back and the call stays asynchronous.  True when the pixel rectangle [x0, x1] x [y0, y1]
+// (inclusive) lies outside the box grown by (gx, gy); an empty selection (min > max) skips everything.
+__device__ __forceinline__ bool bb_skip(const uint32_t *bb, int x0, int x1, int y0, int y1, int gx, int gy) {
+    const int bx0 = (int)__ldg(bb), by0 = (int)__ldg(bb + 1), bx1 = (int)__ldg(bb + 2), by1 = (int)__ldg(bb + 3);
+    if ((uint32_t)bx0 > (uint32_t)bx1 || (uint32_t)by0 > (uint32_t)by1) return true;
+    return x1 < bx0 - gx || x0 > bx1 + gx || y1 < by0 - gy || y0 > by1 + gy;
+}
+
 // u8 -> f32 uses PRMT + FADD against 2^23 (ALU/FMA pipes) instead of the quarter-rate I2F:
 // 0x4B0000xx is 2^23 + xx as a float, so one PRMT per channel and an exact subtract.
 __device__ __forceinline__ float4 to_f4(uint32_t v) {
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     // round trips per task (measured at 8K sigma 20: 0.60 ms with the loads in line, 0.53 ms without any loads at all).
     // Tiles wider than 32 * PRE pixels (large sigma) keep the in-line staging.
     constexpr int PRE = 12;
-    const bool use_pre = tile_px <= 32 * PRE && !(P.dbg & (1 | 4));  // dbg 4: in-line staging (A/B)
+    const bool use_pre = tile_px <= 32 * PRE && !(P.dbg & (1 | 4)) && !P.bb;  // dbg 4: in-line staging (A/B)
     const uint64_t stride = (uint64_t)gridDim.x * WARPS;
     uint32_t pre[PRE];
     auto fetch = [&](uint64_t t) {
@@ -191,6 +205,8 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         const uint32_t y = (uint32_t)(task / nseg);
         const int x0 = (int)(task % nseg) * SEG;
         const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
+        // selection blur: H values are read by the V pass of selected pixels in the same columns, up to radius rows away
+        if (P.bb && bb_skip(P.bb, x0, x0 + SEG - 1, (int)y, (int)y, 0, P.radius)) continue;
         // stage + convert: tile[p] = pixel clamp(x0 - r + p)
         if (use_pre) {
 #pragma unroll
@@ -277,6 +293,7 @@ __global__ void __launch_bounds__(128) gauss_v_kernel(const __grid_constant__ Ga
     const float4 *mid = reinterpret_cast<const float4 *>(P.mid) + x;
     const int y_end = (int)(P.v_y0 + P.v_rows);
     for (int y0 = (int)P.v_y0 + blockIdx.y * N; y0 < y_end; y0 += gridDim.y * N) {
+        if (P.bb && bb_skip(P.bb, x, x, y0, y0 + N - 1, 0, 0)) continue;
         Acc4 acc[N];
         float R[N];
 #pragma unroll
@@ -366,10 +383,11 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
 
     if (warp == WARPS) {
         // ===== producer warp =====
-        uint32_t it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        uint32_t it = 0;  // tiles actually processed: both roles skip the same tiles, so their phase counters agree
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
             const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
+            if (P.bb && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
             const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
             for (int c = 0; c < nchunks; c++) {
                 const int r0 = c * chunk_rows, nrows = min(chunk_rows, rows - r0);
@@ -386,6 +404,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
                                  : "memory");
                 }
             }
+            it++;
         }
         return;
     }
@@ -393,9 +412,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     // ===== consumer warps =====
     const int row_first = warp * N;  // first ring row this warp reads
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
-        const uint32_t parity = it & 1u;
+        if (P.bb && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
+        const uint32_t parity = it++ & 1u;
         Acc4 acc[N];
         float R[N];
 #pragma unroll
@@ -998,29 +1018,31 @@ extern "C" int pfe_dev_gaussian_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t 
         if (src == dst) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "gaussian: in-place not supported without a mask");
         return gauss_common(ctx, src, dst, w, w, w, h, sigma, flags, nullptr, 0.0f, nullptr, 0);
     }
-    // blur_with_selection, filters.rs:141-207
+    // blur_with_selection, filters.rs:141-207.  The bounding box stays on the device (see bb_skip): no read-back, no
+    // stream synchronisation - the call is asynchronous like every other pfe_dev_* entry point.
     void *bbd;
     uint32_t init[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u};
     PFE_TRY(pfe_small_upload(ctx, init, sizeof(init), &bbd));
     PFE_KERNEL(ctx, "mask_bbox", bbox_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(mask, w, h, (uint32_t *)bbd));
     PFE_LAUNCHED(ctx);
-    uint32_t bb[4];
-    PFE_CUDA(ctx, cudaMemcpyAsync(bb, bbd, sizeof(bb), cudaMemcpyDeviceToHost, ctx->stream));
-    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const size_t n = (size_t)w * h;
-    if (bb[0] > bb[2] || bb[1] > bb[3]) {  // nothing selected: clone
-        if (dst != src) PFE_CUDA(ctx, cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        return PFE_OK;
-    }
-    float padf = ceilf(sigma * 3.0f);
-    uint32_t pad = padf > 0.0f ? (padf > 4.0e9f ? 0xFFFFFFFFu : (uint32_t)padf) : 0u;
-    uint32_t cx = bb[0] > pad ? bb[0] - pad : 0, cy = bb[1] > pad ? bb[1] - pad : 0;
-    uint64_t cx2 = std::min<uint64_t>((uint64_t)bb[2] + 1 + pad, w), cy2 = std::min<uint64_t>((uint64_t)bb[3] + 1 + pad, h);
-    void *tmp;
+    int radius;
+    std::vector<float> k = build_kernel(sigma, &radius);
+    if (radius > 4000) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "gaussian: sigma too large");
+    void *tmp, *mid;
     PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, n * 4, &tmp));
-    PFE_TRY(pfe_gauss_region(ctx, src, (uint8_t *)tmp, w, cx, cy, (uint32_t)(cx2 - cx), (uint32_t)(cy2 - cy), sigma, flags));
-    // pixels outside the crop are never selected (the crop contains the bbox), so reading the
-    // uninitialised part of tmp is masked out by mask == 0.
+    PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_F32, n * 16, &mid));
+    GaussParams P;
+    memset(&P, 0, sizeof(P));
+    P.one = 1.0f; P.nzero = -0.0f;
+    P.src = src; P.mid = (float *)mid; P.dst = (uint8_t *)tmp;
+    P.src_pitch = w; P.dst_pitch = w; P.rw = w; P.rh = h; P.radius = radius; P.sigma = sigma;
+    P.v_y0 = 0; P.v_rows = h;
+    P.bb = (const uint32_t *)bbd;
+    if (flags & PFE_GAUSS_EXACT) { PFE_TRY(dispatch_h<true>(ctx, P, k)); PFE_TRY(dispatch_v<true>(ctx, P, k)); }
+    else { PFE_TRY(dispatch_h<false>(ctx, P, k)); PFE_TRY(dispatch_v<false>(ctx, P, k)); }
+    // pixels the kernels skipped are never selected (they lie outside the mask's bounding box), so the stale parts of
+    // tmp are masked out by mask == 0
     PFE_KERNEL(ctx, "select", select_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const uint32_t *)src, (const uint32_t *)tmp, mask,
                                                               (uint32_t *)dst, n));
     PFE_LAUNCHED(ctx);

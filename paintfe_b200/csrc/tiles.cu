@@ -15,9 +15,15 @@
 
 #include "blend.cuh"
 
+// A TiledImage on the device.  Chunks live in the context's pool (pfe_ctx::chunks) and are reference counted on the
+// host: `slot[c]` is the pool slot of chunk c or -1; a clone shares every slot, and whoever writes a shared chunk first
+// gets a private copy (Arc::make_mut, tiled_image.rs:330, :868).  `table` is what the kernels walk: the slot's address
+// where the chunk is populated, null where it is not (a slot can be assigned but unpopulated after from_flat, whose
+// alpha scan runs on the device).
 struct pfe_tiled {
+    pfe_ctx *owner = nullptr;
     uint32_t w = 0, h = 0, chunks_x = 0, chunks_y = 0;
-    uint8_t *pool = nullptr;          // n_chunks slots of 16 KiB (every chunk has a slot; the table says which are live)
+    std::vector<int32_t> slot;        // host: pool slot per chunk, -1 = none
     const uint8_t **table = nullptr;  // device array: chunk pointer or null
     uint8_t *occupancy = nullptr;     // device bytes, 1 = populated
 };
@@ -132,10 +138,11 @@ __global__ void __launch_bounds__(256, 3) flatten_tiles_kernel(const __grid_cons
 
 // TiledImage::from_rgba_image on the device (tiled_image.rs:50-104): one CTA per chunk copies the chunk
 // into its pool slot (zero padded past the canvas edge) and records whether any pixel has alpha != 0.
+// On entry table[chunk] is the slot assigned to the chunk; on exit it is that slot or null.
 __global__ void __launch_bounds__(256) tiles_from_flat_kernel(const uint32_t *flat, uint32_t w, uint32_t h, uint32_t chunks_x,
-                                                              uint8_t *pool, const uint8_t **table, uint8_t *occupancy) {
+                                                              const uint8_t **table, uint8_t *occupancy) {
     const uint32_t chunk = blockIdx.x, cy = chunk / chunks_x, cx = chunk - cy * chunks_x;
-    uint32_t *slot = reinterpret_cast<uint32_t *>(pool + (size_t)chunk * kChunkBytes);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(table[chunk]));
     bool any = false;
     for (uint32_t i = threadIdx.x; i < PFE_CHUNK_SIZE * PFE_CHUNK_SIZE; i += blockDim.x) {
         const uint32_t ly = i / PFE_CHUNK_SIZE, lx = i % PFE_CHUNK_SIZE;
@@ -148,6 +155,21 @@ __global__ void __launch_bounds__(256) tiles_from_flat_kernel(const uint32_t *fl
     if (threadIdx.x == 0) {
         occupancy[chunk] = has ? 1 : 0;
         table[chunk] = has ? reinterpret_cast<const uint8_t *>(slot) : nullptr;
+    }
+}
+// consecutive staged chunks -> their pool slots; copy of one slot to another (make_mut of a shared chunk)
+__global__ void __launch_bounds__(256) scatter_chunks_kernel(const uint4 *src, uint8_t *const *dst, uint32_t n) {
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        uint4 *d = reinterpret_cast<uint4 *>(dst[c]);
+        const uint4 *s = src + (size_t)c * (kChunkBytes / 16);
+        for (uint32_t i = threadIdx.x; i < kChunkBytes / 16; i += blockDim.x) d[i] = s[i];
+    }
+}
+__global__ void __launch_bounds__(256) copy_chunks_kernel(const uint8_t *const *src, uint8_t *const *dst, uint32_t n) {
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        uint4 *d = reinterpret_cast<uint4 *>(dst[c]);
+        const uint4 *s = reinterpret_cast<const uint4 *>(src[c]);  // null = a fresh chunk: zeros
+        for (uint32_t i = threadIdx.x; i < kChunkBytes / 16; i += blockDim.x) d[i] = s ? s[i] : make_uint4(0, 0, 0, 0);
     }
 }
 // TiledImage::to_rgba_image (tiled_image.rs:271-293): absent chunks are transparent
@@ -318,6 +340,70 @@ extern "C" int pfe_flatten_tiles(pfe_ctx *ctx, const pfe_tile_layer_desc *layers
 }
 
 // ---- device-resident TiledImage -----------------------------------------------------------------
+namespace {
+uint8_t *slot_ptr(pfe_ctx *ctx, int32_t id) {
+    return ctx->chunks.slabs[(uint32_t)id / pfe_ctx::ChunkPool::kPerSlab] + (size_t)((uint32_t)id % pfe_ctx::ChunkPool::kPerSlab) * kChunkBytes;
+}
+int slot_alloc(pfe_ctx *ctx, int32_t *out) {
+    auto &cp = ctx->chunks;
+    if (cp.free_list.empty()) {
+        uint8_t *slab = nullptr;
+        cudaError_t e = cudaMalloc(&slab, (size_t)pfe_ctx::ChunkPool::kPerSlab * kChunkBytes);
+        if (e != cudaSuccess) { cudaGetLastError(); return pfe_fail(ctx, PFE_ERR_OOM, "tiled: chunk pool", e); }
+        const uint32_t base = (uint32_t)cp.refs.size();
+        cp.slabs.push_back(slab);
+        cp.refs.resize(base + pfe_ctx::ChunkPool::kPerSlab, 0);
+        for (uint32_t i = pfe_ctx::ChunkPool::kPerSlab; i-- > 0;) cp.free_list.push_back(base + i);
+    }
+    *out = (int32_t)cp.free_list.back();
+    cp.free_list.pop_back();
+    cp.refs[*out] = 1;
+    return PFE_OK;
+}
+void slot_release(pfe_ctx *ctx, int32_t id) {
+    if (id < 0) return;
+    if (--ctx->chunks.refs[id] == 0) ctx->chunks.free_list.push_back((uint32_t)id);  // reuse is ordered by the stream
+}
+int check_tiled(pfe_ctx *ctx, const pfe_tiled *t) {
+    if (!ctx || !t) return PFE_ERR_INVALID_ARG;
+    if (t->owner != ctx) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "tiled: image belongs to another context");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return PFE_OK;
+}
+// Give every chunk in `which` a slot nobody else holds.  keep = the chunk's pixels survive (shared chunks are copied,
+// absent ones start as zeros); otherwise the caller overwrites the whole chunk.  Returns the chunks' slot addresses.
+int make_private(pfe_ctx *ctx, pfe_tiled *t, const std::vector<uint32_t> &which, bool keep, std::vector<uint64_t> *addrs) {
+    std::vector<uint64_t> copy_src, copy_dst;
+    addrs->assign(which.size(), 0);
+    for (size_t k = 0; k < which.size(); k++) {
+        const uint32_t c = which[k];
+        const int32_t old = t->slot[c];
+        if (old >= 0 && ctx->chunks.refs[old] == 1) { (*addrs)[k] = (uint64_t)(uintptr_t)slot_ptr(ctx, old); continue; }
+        int32_t fresh;
+        PFE_TRY(slot_alloc(ctx, &fresh));
+        if (keep) {
+            copy_src.push_back(old >= 0 ? (uint64_t)(uintptr_t)slot_ptr(ctx, old) : 0);
+            copy_dst.push_back((uint64_t)(uintptr_t)slot_ptr(ctx, fresh));
+        }
+        slot_release(ctx, old);
+        t->slot[c] = fresh;
+        (*addrs)[k] = (uint64_t)(uintptr_t)slot_ptr(ctx, fresh);
+    }
+    if (!copy_dst.empty()) {
+        const size_t n = copy_dst.size();
+        void *lists;
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_C, n * 16, &lists));
+        PFE_CUDA(ctx, cudaMemcpyAsync(lists, copy_src.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_CUDA(ctx, cudaMemcpyAsync((char *)lists + n * 8, copy_dst.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_KERNEL(ctx, "tiled_copy_chunks", copy_chunks_kernel<<<(unsigned)std::min<size_t>(n, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+            (const uint8_t *const *)lists, (uint8_t *const *)((char *)lists + n * 8), (uint32_t)n));
+        PFE_LAUNCHED(ctx);
+        PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // copy_src / copy_dst are host vectors
+    }
+    return PFE_OK;
+}
+}  // namespace
+
 extern "C" int pfe_tiled_create(pfe_ctx *ctx, uint32_t w, uint32_t h, pfe_tiled **out) {
     if (!ctx || !out) return PFE_ERR_INVALID_ARG;
     *out = nullptr;
@@ -325,12 +411,13 @@ extern "C" int pfe_tiled_create(pfe_ctx *ctx, uint32_t w, uint32_t h, pfe_tiled 
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
     pfe_tiled *t = new (std::nothrow) pfe_tiled();
     if (!t) return PFE_ERR_OOM;
+    t->owner = ctx;
     t->w = w; t->h = h;
     t->chunks_x = pfe_div_up(w, PFE_CHUNK_SIZE);
     t->chunks_y = pfe_div_up(h, PFE_CHUNK_SIZE);
     const size_t nch = (size_t)t->chunks_x * t->chunks_y;
-    cudaError_t e = cudaMalloc(&t->pool, nch * kChunkBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&t->table, nch * sizeof(void *));
+    t->slot.assign(nch, -1);
+    cudaError_t e = cudaMalloc(&t->table, nch * sizeof(void *));
     if (e == cudaSuccess) e = cudaMalloc(&t->occupancy, nch);
     if (e == cudaSuccess) e = cudaMemsetAsync(t->table, 0, nch * sizeof(void *), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(t->occupancy, 0, nch, ctx->stream);
@@ -346,65 +433,135 @@ extern "C" int pfe_tiled_destroy(pfe_ctx *ctx, pfe_tiled *t) {
     if (!ctx || !t) return PFE_ERR_INVALID_ARG;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (t->pool) cudaFree(t->pool);
+    if (t->owner == ctx)
+        for (int32_t id : t->slot) slot_release(ctx, id);
     if (t->table) cudaFree((void *)t->table);
     if (t->occupancy) cudaFree(t->occupancy);
     delete t;
     return PFE_OK;
 }
+// A second image that shares every chunk of `src` (the snapshot an undo step keeps): no pixel is copied.
+extern "C" int pfe_tiled_clone(pfe_ctx *ctx, const pfe_tiled *src, pfe_tiled **out) {
+    if (!out) return PFE_ERR_INVALID_ARG;
+    *out = nullptr;
+    PFE_TRY(check_tiled(ctx, src));
+    pfe_tiled *t = nullptr;
+    PFE_TRY(pfe_tiled_create(ctx, src->w, src->h, &t));
+    t->slot = src->slot;
+    for (int32_t id : t->slot)
+        if (id >= 0) ctx->chunks.refs[id]++;
+    const size_t nch = t->slot.size();
+    cudaError_t e = cudaMemcpyAsync(t->table, src->table, nch * sizeof(void *), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->occupancy, src->occupancy, nch, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { pfe_tiled_destroy(ctx, t); return pfe_fail(ctx, PFE_ERR_CUDA, "tiled_clone", e); }
+    *out = t;
+    return PFE_OK;
+}
+// TiledImage::ensure_chunk_mut (tiled_image.rs:868) for a list of chunks: afterwards each is populated (a fresh chunk
+// starts transparent) and held by this image alone, so device code may write it through pfe_tiled_table.
+extern "C" int pfe_tiled_make_mut(pfe_ctx *ctx, pfe_tiled *t, const uint32_t *chunk_indices, uint32_t n) {
+    PFE_TRY(check_tiled(ctx, t));
+    if (n && !chunk_indices) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "tiled_make_mut: null list");
+    std::vector<uint32_t> which(chunk_indices, chunk_indices + n);
+    for (uint32_t c : which)
+        if (c >= t->slot.size()) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "tiled_make_mut: chunk index out of range");
+    // a slot that is assigned but unpopulated (from_flat found no alpha) holds stale pixels: treat it as absent
+    std::vector<uint8_t> occ(t->slot.size());
+    PFE_CUDA(ctx, cudaMemcpyAsync(occ.data(), t->occupancy, occ.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t c : which)
+        if (!occ[c] && t->slot[c] >= 0) { slot_release(ctx, t->slot[c]); t->slot[c] = -1; }
+    std::vector<uint64_t> addrs;
+    PFE_TRY(make_private(ctx, t, which, true, &addrs));
+    const uint8_t one = 1;
+    for (size_t k = 0; k < which.size(); k++) {  // n is small (the chunks under one edit)
+        PFE_CUDA(ctx, cudaMemcpyAsync((void *)(t->table + which[k]), &addrs[k], 8, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_CUDA(ctx, cudaMemcpyAsync(t->occupancy + which[k], &one, 1, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PFE_OK;
+}
+// Pool slot of every chunk (-1 = none): two images share a chunk exactly when their ids agree.  For tests and for a
+// caller that wants to know what a snapshot costs.
+extern "C" int pfe_tiled_chunk_ids(pfe_ctx *ctx, const pfe_tiled *t, int32_t *ids_out) {
+    PFE_TRY(check_tiled(ctx, t));
+    if (!ids_out) return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "tiled_chunk_ids: null output");
+    memcpy(ids_out, t->slot.data(), t->slot.size() * sizeof(int32_t));
+    return PFE_OK;
+}
 extern "C" int pfe_tiled_upload(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *const *host_chunk_table) {
-    if (!ctx || !t || !host_chunk_table) return PFE_ERR_INVALID_ARG;
-    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t nch = (size_t)t->chunks_x * t->chunks_y;
-    // populated chunks go to their own slots; runs of consecutive populated chunks share one staged copy
+    PFE_TRY(check_tiled(ctx, t));
+    if (!host_chunk_table) return PFE_ERR_INVALID_ARG;
+    const size_t nch = t->slot.size();
+    // populated chunks get private slots (their old content is replaced), the others give theirs back
+    std::vector<uint32_t> which;
+    std::vector<const uint8_t *> src;
+    for (size_t c = 0; c < nch; c++) {
+        if (host_chunk_table[c]) { which.push_back((uint32_t)c); src.push_back(host_chunk_table[c]); }
+        else { slot_release(ctx, t->slot[c]); t->slot[c] = -1; }
+    }
+    std::vector<uint64_t> addrs;
+    PFE_TRY(make_private(ctx, t, which, false, &addrs));
     std::vector<uint64_t> table(nch, 0);
     std::vector<uint8_t> occ(nch, 0);
-    std::vector<const uint8_t *> run;
-    size_t run_start = 0;
-    auto flush = [&]() -> int {
-        if (run.empty()) return PFE_OK;
-        int s = upload_chunks(ctx, run, t->pool + run_start * kChunkBytes);
-        run.clear();
-        return s;
-    };
-    for (size_t c = 0; c < nch; c++) {
-        if (!host_chunk_table[c]) { PFE_TRY(flush()); continue; }
-        if (run.empty()) run_start = c;
-        run.push_back(host_chunk_table[c]);
-        table[c] = (uint64_t)(uintptr_t)(t->pool + c * kChunkBytes);
-        occ[c] = 1;
+    for (size_t k = 0; k < which.size(); k++) { table[which[k]] = addrs[k]; occ[which[k]] = 1; }
+    if (!src.empty()) {
+        // staged uploads land consecutively in scratch; one kernel moves them to their slots
+        void *stage_dev;
+        PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_A, src.size() * (kChunkBytes + 8), &stage_dev));
+        uint8_t *lists = (uint8_t *)stage_dev + src.size() * kChunkBytes;
+        PFE_TRY(upload_chunks(ctx, src, (uint8_t *)stage_dev));
+        PFE_CUDA(ctx, cudaMemcpyAsync(lists, addrs.data(), addrs.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_KERNEL(ctx, "tiled_scatter", scatter_chunks_kernel<<<(unsigned)std::min<size_t>(src.size(), (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+            (const uint4 *)stage_dev, (uint8_t *const *)lists, (uint32_t)src.size()));
+        PFE_LAUNCHED(ctx);
     }
-    PFE_TRY(flush());
     PFE_CUDA(ctx, cudaMemcpyAsync(t->table, table.data(), nch * 8, cudaMemcpyHostToDevice, ctx->stream));
     PFE_CUDA(ctx, cudaMemcpyAsync(t->occupancy, occ.data(), nch, cudaMemcpyHostToDevice, ctx->stream));
     PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PFE_OK;
 }
 extern "C" int pfe_tiled_from_flat(pfe_ctx *ctx, pfe_tiled *t, const uint8_t *flat_dev) {
-    if (!ctx || !t || !flat_dev) return PFE_ERR_INVALID_ARG;
-    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFE_TRY(check_tiled(ctx, t));
+    if (!flat_dev) return PFE_ERR_INVALID_ARG;
+    // which chunks end up populated is decided on the device (the alpha scan): every chunk gets a private slot to be
+    // written into; the kernel nulls the table entries of the chunks that turn out transparent
+    const size_t nch = t->slot.size();
+    std::vector<uint32_t> all(nch);
+    for (size_t c = 0; c < nch; c++) all[c] = (uint32_t)c;
+    std::vector<uint64_t> addrs;
+    PFE_TRY(make_private(ctx, t, all, false, &addrs));
+    if (nch * 8 <= PFE_SMALL_BYTES / 2) {  // through the context's pinned ring: the call stays asynchronous
+        void *stage;
+        PFE_TRY(pfe_small_upload(ctx, addrs.data(), nch * 8, &stage));
+        PFE_CUDA(ctx, cudaMemcpyAsync(t->table, stage, nch * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        PFE_CUDA(ctx, cudaMemcpyAsync(t->table, addrs.data(), nch * 8, cudaMemcpyHostToDevice, ctx->stream));
+        PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `addrs` is a host vector
+    }
     PFE_KERNEL(ctx, "tiles_from_flat", tiles_from_flat_kernel<<<t->chunks_x * t->chunks_y, 256, 0, ctx->stream>>>(
-        (const uint32_t *)flat_dev, t->w, t->h, t->chunks_x, t->pool, t->table, t->occupancy));
+        (const uint32_t *)flat_dev, t->w, t->h, t->chunks_x, t->table, t->occupancy));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
 extern "C" int pfe_tiled_to_flat(pfe_ctx *ctx, const pfe_tiled *t, uint8_t *flat_dev) {
-    if (!ctx || !t || !flat_dev) return PFE_ERR_INVALID_ARG;
-    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFE_TRY(check_tiled(ctx, t));
+    if (!flat_dev) return PFE_ERR_INVALID_ARG;
     PFE_KERNEL(ctx, "tiles_to_flat", tiles_to_flat_kernel<<<t->chunks_x * t->chunks_y, 256, 0, ctx->stream>>>(
         t->table, t->w, t->h, t->chunks_x, (uint32_t *)flat_dev));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }
 extern "C" int pfe_tiled_download(pfe_ctx *ctx, const pfe_tiled *t, uint8_t *occupancy, uint8_t *tiles) {
-    if (!ctx || !t || !occupancy) return PFE_ERR_INVALID_ARG;
-    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t nch = (size_t)t->chunks_x * t->chunks_y;
+    PFE_TRY(check_tiled(ctx, t));
+    if (!occupancy) return PFE_ERR_INVALID_ARG;
+    const size_t nch = t->slot.size();
     PFE_CUDA(ctx, cudaMemcpyAsync(occupancy, t->occupancy, nch, cudaMemcpyDeviceToHost, ctx->stream));
     PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (tiles)
         for (size_t c = 0; c < nch; c++)
-            if (occupancy[c]) PFE_CUDA(ctx, cudaMemcpyAsync(tiles + c * kChunkBytes, t->pool + c * kChunkBytes, kChunkBytes, cudaMemcpyDeviceToHost, ctx->stream));
+            if (occupancy[c] && t->slot[c] >= 0)
+                PFE_CUDA(ctx, cudaMemcpyAsync(tiles + c * kChunkBytes, slot_ptr(ctx, t->slot[c]), kChunkBytes, cudaMemcpyDeviceToHost, ctx->stream));
     PFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PFE_OK;
 }

@@ -137,6 +137,15 @@ __global__ void __launch_bounds__(256) warp_kernel(const uint32_t *__restrict__ 
         if (ya + r < h) dst[(size_t)(ya + r) * w + x] = o[r];
 }
 
+// warp_displacement_region: the same sample, only for the pixels of the dirty rectangle
+__global__ void __launch_bounds__(256) warp_region_kernel(const uint32_t *__restrict__ src, int sw, int sh, const float2 *__restrict__ disp,
+                                                          uint32_t *__restrict__ dst, int w, int rx0, int ry0, int rx1, int ry1) {
+    const int x = rx0 + blockIdx.x * 32 + (threadIdx.x & 31), y = ry0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= rx1 || y >= ry1) return;
+    const float2 d = __ldg(disp + (size_t)y * w + x);
+    dst[(size_t)y * w + x] = warp_sample(src, sw, sh, x, y, d.x, d.y);
+}
+
 __global__ void __launch_bounds__(256) mesh_disp_kernel(const __grid_constant__ MeshParams M, float2 *out, uint32_t w,
                                                         uint32_t h) {
     __shared__ float sdef[PFE_MESH_MAX_POINTS * 2], sorig[PFE_MESH_MAX_POINTS * 2];
@@ -286,6 +295,23 @@ extern "C" int pfe_dev_warp_displacement(pfe_ctx *ctx, const uint8_t *src, uint3
     PFE_CUDA(ctx, cudaSetDevice(ctx->device));
     PFE_KERNEL(ctx, "warp", warp_kernel<<<dim3(pfe_div_up(w, 32), pfe_div_up(h, 8 * kWarpRows)), 256, 0, ctx->stream>>>(
         (const uint32_t *)src, (int)sw, (int)sh, (const float2 *)disp, (uint32_t *)dst, (int)w, (int)h));
+    PFE_LAUNCHED(ctx);
+    return PFE_OK;
+}
+
+extern "C" int pfe_dev_warp_displacement_region(pfe_ctx *ctx, const uint8_t *src, uint32_t sw, uint32_t sh, const float *disp,
+                                                const uint8_t *prev, const int32_t rect[4], uint32_t w, uint32_t h, uint8_t *dst) {
+    if (!ctx) return PFE_ERR_INVALID_ARG;
+    if (!src || !disp || !prev || !rect || !dst || !sw || !sh || !w || !h || src == dst)
+        return pfe_fail(ctx, PFE_ERR_INVALID_ARG, "warp_region: bad args");
+    PFE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (dst != prev) PFE_CUDA(ctx, cudaMemcpyAsync(dst, prev, (size_t)w * h * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // transform.rs:1214-1218
+    const uint32_t x0 = rect[0] > 0 ? (uint32_t)rect[0] : 0u, y0 = rect[1] > 0 ? (uint32_t)rect[1] : 0u;
+    const uint32_t x1 = std::min((uint32_t)rect[2], w), y1 = std::min((uint32_t)rect[3], h);
+    if (x1 <= x0 || y1 <= y0) return PFE_OK;
+    PFE_KERNEL(ctx, "warp_region", warp_region_kernel<<<dim3(pfe_div_up(x1 - x0, 32), pfe_div_up(y1 - y0, 8)), 256, 0, ctx->stream>>>(
+        (const uint32_t *)src, (int)sw, (int)sh, (const float2 *)disp, (uint32_t *)dst, (int)w, (int)x0, (int)y0, (int)x1, (int)y1));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }

@@ -320,6 +320,25 @@ def flatten_banded(eng, layer_bands, w: int, band_rows: int, active=None):
     return eng.flatten(layer_bands, w, band_rows, active=active)
 
 
+def adjust_banded(eng, band, h_total: int, op: int, params=(), luts=None, mask_band=None, occupancy=None, group=None, bounds=None):
+    """apply_pixel_transform (adjustments.rs:21-42) on this rank's band: per pixel, so band-local - no collective.
+    `occupancy` is the WHOLE canvas' chunk bitmap (ceil(h/64) x ceil(w/64), tiled_image.rs:905-933: unpopulated chunks
+    are left alone); bands are 64-row aligned, so the band's chunk rows are a contiguous slice of it and a chunk never
+    straddles two ranks."""
+    rank, world = _world(group)
+    bounds = bounds or band_bounds(h_total, world)
+    y0, y1 = bounds[rank]
+    if y1 <= y0:
+        return band
+    occ = None
+    if occupancy is not None:
+        if y0 % CHUNK:
+            raise ValueError("adjust_banded: bands must start on a chunk row when an occupancy bitmap is given")
+        occ = occupancy[y0 // CHUNK:(y1 + CHUNK - 1) // CHUNK]
+        occ = occ.contiguous() if isinstance(occ, torch.Tensor) else np.ascontiguousarray(occ)
+    return eng.adjust(band, op, params, luts=luts, mask=mask_band, occupancy=occ)
+
+
 def _warp_band(eng, band, h_total, w_out, y0, rows_out, reach, bounds, group, **warp_kw):
     """`reach` = (up, down) halo rows, python ints identical on every rank. The source rows land straight in the
     pre-allocated window; the band-form warp is stream-asynchronous (a window that turns out too small is

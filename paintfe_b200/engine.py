@@ -51,12 +51,33 @@ def make_layer(rgba=None, opacity=1.0, blend=0, visible=True, mask=None, kind=0,
 class DeviceTiled:
     """A TiledImage resident on the device (`pfe_tiled`): chunk pool, pointer table, occupancy."""
 
-    def __init__(self, eng, w, h):
+    def __init__(self, eng, w, h, _handle=None):
         self.eng, self.w, self.h = eng, int(w), int(h)
-        hnd = C.c_void_p()
-        eng._ck(eng.lib.pfe_tiled_create(eng.h, self.w, self.h, C.byref(hnd)))
+        hnd = _handle
+        if hnd is None:
+            hnd = C.c_void_p()
+            eng._ck(eng.lib.pfe_tiled_create(eng.h, self.w, self.h, C.byref(hnd)))
         self.hnd = hnd
         self.n_chunks = ((self.w + 63) // 64) * ((self.h + 63) // 64)
+
+    def clone(self):
+        """A snapshot sharing every chunk (copy on write): pfe_tiled_clone."""
+        self.eng.use_torch_stream()
+        hnd = C.c_void_p()
+        self.eng._ck(self.eng.lib.pfe_tiled_clone(self.eng.h, self.hnd, C.byref(hnd)))
+        return DeviceTiled(self.eng, self.w, self.h, _handle=hnd)
+
+    def make_mut(self, chunk_indices):
+        """ensure_chunk_mut for the listed chunks: populated, and private to this image afterwards."""
+        idx = np.ascontiguousarray(np.asarray(chunk_indices, np.uint32).reshape(-1))
+        self.eng.use_torch_stream()
+        self.eng._ck(self.eng.lib.pfe_tiled_make_mut(self.eng.h, self.hnd, _ptr(idx), len(idx)))
+        return self
+
+    def chunk_ids(self):
+        ids = np.empty(self.n_chunks, np.int32)
+        self.eng._ck(self.eng.lib.pfe_tiled_chunk_ids(self.eng.h, self.hnd, _ptr(ids)))
+        return ids
 
     @property
     def table(self):
@@ -529,6 +550,19 @@ class Engine:
         dst = out if out is not None else self._out_like(src, (h, w, 4))
         fn = self.lib.pfe_dev_warp_displacement if self._dev(src, disp, dst) else self.lib.pfe_warp_displacement
         self._ck(fn(self.h, _ptr(src), sw, sh, _ptr(disp), w, h, _ptr(dst)))
+        return dst
+
+    def warp_displacement_region(self, src, disp, prev, dirty_rect, out=None):
+        """warp_displacement_region (transform.rs:1206-1285): `prev` outside dirty_rect = (x0, y0, x1, y1), the warp inside."""
+        src, prev = self._prep(src), self._prep(prev)
+        sh, sw = self._hw(src)
+        if not _is_tensor(disp):
+            disp = np.ascontiguousarray(disp, dtype=np.float32)
+        h, w = int(disp.shape[0]), int(disp.shape[1])
+        rect = (C.c_int32 * 4)(*[int(v) for v in dirty_rect])
+        dst = out if out is not None else self._out_like(prev)
+        fn = self.lib.pfe_dev_warp_displacement_region if self._dev(src, disp, prev, dst) else self.lib.pfe_warp_displacement_region
+        self._ck(fn(self.h, _ptr(src), sw, sh, _ptr(disp), _ptr(prev), rect, w, h, _ptr(dst)))
         return dst
 
     @staticmethod

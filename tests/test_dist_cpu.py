@@ -29,6 +29,10 @@ class OracleEngine:
     def bokeh_blur(self, img, r, mask=None, out=None): return self.o.bokeh_blur(img, r, mask=mask)
     def reduce_noise(self, img, s, r, mask=None, out=None): return self.o.reduce_noise(img, s, r, mask=mask)
     def motion_blur(self, img, a, d, mask=None, out=None): return self.o.motion_blur(img, a, d, mask=mask)
+    def adjust(self, img, op, params=(), luts=None, mask=None, occupancy=None, out=None):
+        return self.o.adjust(np.asarray(img), op, params, luts=luts, mask=None if mask is None else np.asarray(mask),
+                             occupancy=None if occupancy is None else np.asarray(occupancy))
+
     def flatten(self, layers, w, h, active=None, out=None):
         return self.o.flatten([self.o.make_layer(**{k: (np.asarray(v) if k in ("rgba", "mask") and v is not None else v)
                                                     for k, v in L.items()}) for L in layers], w, h, active=active)
@@ -106,6 +110,17 @@ def _worker(rank, world, port, case, q):
             layers = [dict(rgba=torch.from_numpy(im[y0:y1].copy()), **m) for im, m in zip(imgs, meta)]
             out = torch.from_numpy(pd.flatten_banded(eng, layers, w, y1 - y0))
             exp = eng.o.flatten([eng.o.make_layer(im, **m) for im, m in zip(imgs, meta)], w, h)
+        elif case == "adjust":  # per-pixel adjustment with an occupancy bitmap whose populated chunks cross the band edges
+            cyn, cxn = (h + 63) // 64, (w + 63) // 64
+            occ = (rng.random((cyn, cxn)) < 0.6).astype(np.uint8)
+            for r in range(1, world):  # chunk rows either side of every band edge: one populated, one not, per column
+                e = bounds[r][0] // 64
+                if 0 < e < cyn:
+                    occ[e - 1], occ[e] = np.arange(cxn) % 2, (np.arange(cxn) + 1) % 2
+            mask = (rng.random((h, w)) < 0.8).astype(np.uint8) * 255
+            out = pd.adjust_banded(eng, band, h, 5, (30.0, -20.0, 10.0), mask_band=torch.from_numpy(mask[y0:y1].copy()),
+                                   occupancy=occ, bounds=bounds)
+            exp = eng.o.adjust(img, 5, (30.0, -20.0, 10.0), mask=mask, occupancy=occ)
         elif case == "warp":
             disp = rng.normal(0, 9, (h, w, 2)).astype(np.float32)
             out = pd.warp_displacement_banded(eng, band, torch.from_numpy(disp[y0:y1].copy()), h, bounds=bounds)
@@ -142,13 +157,17 @@ def _run(case, world):
         assert ok, f"{case}: rank {rank} band differs from the whole-image result"
 
 
-@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "effects", "flatten", "warp", "mesh"])
+@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "effects", "flatten", "adjust", "warp", "mesh"])
 def test_band_split_equals_whole_world2(case):
     _run(case, 2)
 
 
 def test_band_split_halo_spans_several_ranks_world3():
     _run("thin", 3)
+
+
+def test_banded_adjust_world3():
+    _run("adjust", 3)
 
 
 def test_band_bounds_and_sharding():

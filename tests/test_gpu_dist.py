@@ -70,6 +70,13 @@ def _worker(rank, world, port, q):
         except Exception:
             res["warp_short_halo_detected"] = True
         eng.check_async()  # the flag was cleared
+        # per-pixel adjustment with an occupancy bitmap whose populated chunks differ either side of the band edge (row e3)
+        cyn, cxn = (h + 63) // 64, (w + 63) // 64
+        occ = (rng.random((cyn, cxn)) < 0.6).astype(np.uint8)
+        e = bounds[1][0] // 64
+        occ[e - 1], occ[e] = np.arange(cxn) % 2, (np.arange(cxn) + 1) % 2
+        got = pd.adjust_banded(eng, band, h, 5, (30.0, -20.0, 10.0), occupancy=torch.from_numpy(occ).cuda(), bounds=bounds)
+        res["adjust_occupancy"] = torch.equal(got, eng.adjust(full, 5, (30.0, -20.0, 10.0), occupancy=occ)[y0:y1])
         orig = np.array([[c / 6 * w, r / 6 * h] for r in range(7) for c in range(7)], np.float32)
         deformed = orig + np.array([[8 * np.sin(i) * np.cos(j)] * 2 for i in range(7) for j in range(7)], np.float32)
         res["mesh"] = torch.equal(pd.mesh_warp_banded(eng, band, orig, deformed, 6, 6, w, h, bounds=bounds),

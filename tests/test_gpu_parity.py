@@ -939,6 +939,47 @@ def test_device_tiled_roundtrip(eng, oracle):
         t.close(); t2.close()
 
 
+def test_device_tiled_copy_on_write(eng, oracle):
+    """Snapshots of a device TiledImage share chunks until one side writes (Arc::make_mut, tiled_image.rs:330, :868)."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    w, h = 300, 200  # 5 x 4 chunks
+    img = fx.random_rgba(rng, w, h)
+    img[:64, :128] = 0  # chunks 0 and 1 unpopulated
+    a = eng.tiled(w, h).from_flat(torch.from_numpy(img).cuda())
+    occ_a, tiles_a = a.download()
+    assert list(np.flatnonzero(occ_a == 0)) == [0, 1]
+    snap = a.clone()
+    assert np.array_equal(a.chunk_ids(), snap.chunk_ids())  # nothing copied: every chunk shared
+    exact(snap.to_flat().cpu().numpy(), oracle.tiled_roundtrip(img)[0], "clone reads like the original")
+    # write chunk 7 (populated, shared) and chunk 0 (absent) of the original through make_mut
+    a.make_mut([7, 0])
+    ids_a, ids_s = a.chunk_ids(), snap.chunk_ids()
+    assert ids_a[7] != ids_s[7] and ids_a[0] >= 0
+    same = [k for k in range(a.n_chunks) if k not in (0, 7) and occ_a[k]]
+    assert all(ids_a[k] == ids_s[k] for k in same)
+    occ2, tiles2 = a.download()
+    assert occ2[0] == 1 and not tiles2[0].any()                 # a fresh chunk is transparent
+    assert np.array_equal(tiles2[7], tiles_a[7])                 # the private copy carries the pixels over
+    exact(snap.to_flat().cpu().numpy(), oracle.tiled_roundtrip(img)[0], "the snapshot is untouched")
+    # replacing the original's content leaves the snapshot alone, and the flatten reads each through its own table
+    img2 = fx.random_rgba(rng, w, h)
+    a.from_flat(torch.from_numpy(img2).cuda())
+    assert not set(a.chunk_ids()[a.chunk_ids() >= 0]) & set(snap.chunk_ids()[snap.chunk_ids() >= 0])
+    exact(snap.to_flat().cpu().numpy(), oracle.tiled_roundtrip(img)[0], "snapshot after the original was overwritten")
+    exact(a.to_flat().cpu().numpy(), oracle.tiled_roundtrip(img2)[0], "original after from_flat")
+    got = eng.flatten_tiles([dict(tiles=snap, opacity=1.0, blend=0), dict(tiles=a, opacity=0.6, blend=8)], w, h)
+    exp = oracle.flatten([oracle.make_layer(oracle.tiled_roundtrip(img)[0]), oracle.make_layer(oracle.tiled_roundtrip(img2)[0], opacity=0.6, blend=8)], w, h)
+    exact(got.cpu().numpy(), exp, "flatten of a snapshot under its successor")
+    # dropping the snapshot returns its chunks to the pool: a new image reuses them
+    freed = set(snap.chunk_ids()[snap.chunk_ids() >= 0])
+    snap.close()
+    b = eng.tiled(w, h).from_flat(torch.from_numpy(img).cuda())
+    assert set(b.chunk_ids()[b.chunk_ids() >= 0]) & freed
+    a.close(); b.close()
+
+
 def test_gaussian_ring_pipeline_full_8k(eng, monkeypatch):
     """The V pass's producer/consumer ring (one CTA walks ~56 tiles back to back at 8K) against the
     direct-from-global V kernel on EVERY pixel of an 8K image, repeatedly: a chunk refilled while a slow
@@ -1171,3 +1212,24 @@ def test_warp_band_window_check_is_asynchronous(eng):
     with pytest.raises(PfeError):
         eng.check_async()
     eng.check_async()
+
+
+def test_warp_displacement_region(eng, oracle):
+    """warp_displacement_region (transform.rs:1206-1285): prev outside the dirty rect, the warp inside; the reference's
+    rect clamping (negative x1 = to the edge), an inverted rect, in place on prev; host tier == device tier."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    w, h = 150, 97
+    src, prev = fx.random_rgba(rng, w, h), fx.random_rgba(rng, w, h)
+    disp = rng.normal(0, 6, (h, w, 2)).astype(np.float32)
+    for rect in ((10, 20, 90, 70), (-5, -5, 400, 400), (30, 10, -1, 50), (80, 40, 20, 60), (0, 0, 0, 0), (149, 96, 150, 97)):
+        exp = oracle.warp_displacement_region(src, disp, prev, rect)
+        exact(eng.warp_displacement_region(src, disp, prev, rect), exp, f"region {rect} host tier")
+        d = eng.warp_displacement_region(torch.from_numpy(src).cuda(), torch.from_numpy(disp).cuda(), torch.from_numpy(prev).cuda(), rect)
+        exact(d.cpu().numpy(), exp, f"region {rect} device tier")
+    p = torch.from_numpy(prev).cuda()
+    eng.warp_displacement_region(torch.from_numpy(src).cuda(), torch.from_numpy(disp).cuda(), p, (10, 20, 90, 70), out=p)
+    exact(p.cpu().numpy(), oracle.warp_displacement_region(src, disp, prev, (10, 20, 90, 70)), "region in place")
+    # inside a full-canvas rect it is the full warp
+    exact(eng.warp_displacement_region(src, disp, prev, (0, 0, w, h)), oracle.warp_displacement(src, disp), "full rect == full warp")
