@@ -129,7 +129,7 @@ def run_one(eng, inp: str, outp: str, script: Optional[str], verbose: bool, flat
         else:
             img = eng.tiles_to_flat(tables[ai], w, h)
     else:
-        img = np.ascontiguousarray(np.asarray(Image.open(inp).convert("RGBA")))
+        img = np.array(Image.open(inp).convert("RGBA"))  # a writable copy (PIL hands out read-only views)
         if script:
             # one upload, the whole script on the device (every apply_* is a pfe_dev_* call on the resident image),
             # one download - not a PCIe round trip per effect call
@@ -169,7 +169,7 @@ def run_batch_pipelined(eng, jobs, script: str, verbose: bool, exact: bool, fmt:
     pipe = ImagePipeline(eng, depth)
 
     def decode(path):
-        return np.ascontiguousarray(np.asarray(Image.open(path).convert("RGBA")))
+        return np.array(Image.open(path).convert("RGBA"))
 
     def work(dev):
         it = Interpreter(eng, dev, exact=exact)
