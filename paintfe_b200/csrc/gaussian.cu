@@ -159,7 +159,11 @@ struct WeightTable {
     float wk[kWeightTableLen];
 };
 
-template <int N, bool EXACT, int WARPS, bool UW>
+// BB: the selection-blur variant that skips work outside the mask's bounding box (see bb_skip).  A separate
+// instantiation, because the test inside the task loop changed ptxas' allocation of the ordinary kernel from 71 to
+// 96 registers (5 instead of 7 resident CTAs, 0.57 -> 0.69 ms at 8K); kernels without a BB instantiation simply
+// blur everything, which gives the same selected pixels.
+template <int N, bool EXACT, int WARPS, bool UW, bool BB = false>
 __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ WeightTable W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *wshared = reinterpret_cast<float *>(smem_raw);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     // round trips per task (measured at 8K sigma 20: 0.60 ms with the loads in line, 0.53 ms without any loads at all).
     // Tiles wider than 32 * PRE pixels (large sigma) keep the in-line staging.
     constexpr int PRE = 12;
-    const bool use_pre = tile_px <= 32 * PRE && !(P.dbg & (1 | 4)) && !P.bb;  // dbg 4: in-line staging (A/B)
+    const bool use_pre = !BB && tile_px <= 32 * PRE && !(P.dbg & (1 | 4));  // dbg 4: in-line staging (A/B)
     const uint64_t stride = (uint64_t)gridDim.x * WARPS;
     uint32_t pre[PRE];
     auto fetch = [&](uint64_t t) {
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         const int x0 = (int)(task % nseg) * SEG;
         const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
         // selection blur: H values are read by the V pass of selected pixels in the same columns, up to radius rows away
-        if (P.bb && bb_skip(P.bb, x0, x0 + SEG - 1, (int)y, (int)y, 0, P.radius)) continue;
+        if (BB && bb_skip(P.bb, x0, x0 + SEG - 1, (int)y, (int)y, 0, P.radius)) continue;
         // stage + convert: tile[p] = pixel clamp(x0 - r + p)
         if (use_pre) {
 #pragma unroll
@@ -339,7 +343,7 @@ constexpr int kChunks = 8;
 // Blur outputs are non-negative (weights and inputs are >= 0): the clamp-free rounding applies directly.
 __device__ __forceinline__ uint32_t round_u8_nonneg(float x) { return pfe_round_u8_nonneg(x); }
 
-template <int N, bool EXACT, int WARPS, bool UW>
+template <int N, bool EXACT, int WARPS, bool UW, bool BB = false>
 __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __grid_constant__ GaussParams P, const __grid_constant__ WeightTable W) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TH = WARPS * N;
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
             const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
-            if (P.bb && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
+            if (BB && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
             const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
             for (int c = 0; c < nchunks; c++) {
                 const int r0 = c * chunk_rows, nrows = min(chunk_rows, rows - r0);
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
-        if (P.bb && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
+        if (BB && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
         const uint32_t parity = it++ & 1u;
         Acc4 acc[N];
         float R[N];
@@ -765,7 +769,17 @@ int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
     // Exactly one resident wave of grid-stride CTAs: the task loop strides by the grid, so a CTA that does not fit
     // next to the others would run its share alone after they finish (the r01 grid of 8 per SM did exactly that
     // where 7 fit: 30 % warps-active average and a second wave at 1/7 occupancy).
-    if (warps == 4) {
+    bool done = false;
+    if constexpr (UW && N >= 4) {
+        if (warps == 4 && P.bb) {  // selection blur
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4, UW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned blocks = pfe_persistent_grid(ctx, gauss_h_kernel<N, EXACT, 4, UW, true>, 128, smem, (ntask + 3) / 4);
+            PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4, UW, true><<<blocks, 128, smem, ctx->stream>>>(P, W));
+            done = true;
+        }
+    }
+    if (done) {
+    } else if (warps == 4) {
         PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_h_kernel<N, EXACT, 4, UW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = pfe_persistent_grid(ctx, gauss_h_kernel<N, EXACT, 4, UW>, 128, smem, (ntask + 3) / 4);
         PFE_KERNEL(ctx, "gauss_h", gauss_h_kernel<N, EXACT, 4, UW><<<blocks, 128, smem, ctx->stream>>>(P, W));
@@ -815,7 +829,19 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
         return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra;
     };
     const int vw = v_tile_warps<N>(P);
-    if (vw == 12) {
+    bool done = false;
+    if constexpr (UW && N >= 4) {
+        if (vw == 12 && P.bb) {  // selection blur
+            const size_t smem = tile_smem(12);
+            const unsigned tiles12 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 12 * N);
+            PFE_CUDA(ctx, cudaFuncSetAttribute(gauss_v_tile_kernel<N, EXACT, 12, UW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned blocks = pfe_persistent_grid(ctx, gauss_v_tile_kernel<N, EXACT, 12, UW, true>, 416, smem, tiles12);
+            PFE_KERNEL(ctx, "gauss_v", gauss_v_tile_kernel<N, EXACT, 12, UW, true><<<blocks, 416, smem, ctx->stream>>>(P, W));
+            done = true;
+        }
+    }
+    if (done) {
+    } else if (vw == 12) {
         // 12 consumer warps: a taller tile (less halo per output row) and, with N = 8, two CTAs per SM
         const size_t smem = tile_smem(12);
         const unsigned tiles12 = pfe_div_up(P.rw, 32) * pfe_div_up(P.v_rows, 12 * N);

@@ -220,3 +220,30 @@ int main(void) {
     exe = tmp_path / "d255"
     subprocess.check_call(["gcc", "-O0", "-ffp-contract=off", "-o", str(exe), str(prog), "-lm"])
     assert subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip() == "0"
+
+
+def test_headline_kernel_register_budgets():
+    """Occupancy of the three headline kernels hangs on their register counts (7 resident CTAs of the H pass need
+    <= 72, two 13-warp CTAs of the V pass <= 72, three CTAs of the flatten <= 80), and an innocent-looking edit can move
+    them: adding the selection-blur test to the H pass's task loop once took it from 71 to 96 registers and the 8K pass
+    from 0.57 to 0.69 ms.  Read from the built objects (no compile)."""
+    import shutil
+
+    build = os.path.join(ROOT, "paintfe_b200", "build")
+    if not shutil.which("cuobjdump") or not os.path.exists(os.path.join(build, "gaussian.o")):
+        pytest.skip("needs cuobjdump and the in-tree build")
+    from paintfe_b200 import build as B
+    B.build()
+
+    def regs(obj, needle):
+        out = subprocess.run(["cuobjdump", "-res-usage", os.path.join(build, obj)], capture_output=True, text=True).stdout
+        lines = out.splitlines()
+        for i, line in enumerate(lines):
+            if "Function" in line and needle in line:
+                m = re.search(r"REG:(\d+)", lines[i + 1])
+                return int(m.group(1))
+        raise AssertionError(f"{needle} not found in {obj}")
+
+    assert regs("gaussian.o", "gauss_h_kernelILi8ELb0ELi4ELb1ELb0E") <= 72
+    assert regs("gaussian.o", "gauss_v_tile_kernelILi8ELb0ELi12ELb1ELb0E") <= 72
+    assert regs("flatten.o", "flatten_kernelILi4ELi256ELi3E") <= 80
