@@ -349,20 +349,20 @@ def run_b200(args):
         rows = y1 - y0
         radius = pd.gaussian_radius(SIGMA)
         band_layers = [make_layer(t[y0:y1], **m) for t, m in zip(layers, meta)]
-        plan = pd.halo_plan(flat[y0:y1], radius, radius, bounds)
-        out_band = torch.empty((rows, w, 4), dtype=torch.uint8, device=dev)
-
-        def strong_step():
-            eng.flatten(band_layers, w, rows, out=plan.core)  # band-local, written where the blur wants it
-            pd.gaussian_blur_banded(eng, plan.core, h, SIGMA, bounds=bounds, out=out_band)
+        # edge rows first, exchange on the side stream, interior flatten + H pass under it (paintfe_b200/dist.py)
+        pipe = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds)
+        plan, out_band = pipe.plan, pipe.out
+        strong_step = pipe.step
 
         strong_ms = timed(strong_step, args.steps, warm=warmup)
         ok = torch.tensor([1.0 if torch.equal(out_band, whole[y0:y1]) else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         exch_ms = timed(plan.exchange, max(args.steps, 10), warm=3)
         # the same band-local kernels without any exchange (halo rows left as they are): what the exchange costs on top
+        whole_band = eng.prepare_layers(band_layers, w, rows)
+
         def no_exchange_step():
-            eng.flatten(band_layers, w, rows, out=plan.core)
+            eng.flatten_prepared(whole_band, plan.core)
             eng.gaussian_band_h(plan.ext, 0, plan.ext.shape[0], SIGMA)
             eng.gaussian_band_v(plan.ext, plan.top, rows, SIGMA, out=out_band)
 
@@ -373,9 +373,9 @@ def run_b200(args):
                   "halo_bytes": int(halo), "exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
                   "parity": bool(ok.item() == 1.0), "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
                   "speedup_vs_one_gpu_step": ms_step / strong_ms,
-                  "note": "exchange on a side stream under the band's own H pass; halo rows recompute the H pass; "
+                  "note": "edge rows flattened first, exchange on a side stream under the interior flatten and the band's own H pass; halo rows recompute the H pass; "
                           "exchange_ms = the exchange alone, back to back; ms_per_step_no_exchange = same kernels, no transfer"}
-        del whole, plan, out_band, band_layers
+        del whole, plan, out_band, band_layers, pipe, whole_band, strong_step
 
     # ---- BASELINE config 4: 16384^2 mesh warp + liquify warp on one canvas in row bands ----------------
     config4 = None

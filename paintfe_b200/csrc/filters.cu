@@ -21,8 +21,12 @@ __device__ __forceinline__ void add4(uint4 &s, uint32_t v) {
 __device__ __forceinline__ void sub4(uint4 &s, uint32_t v) {
     s.x -= v & 255u; s.y -= (v >> 8) & 255u; s.z -= (v >> 16) & 255u; s.w -= v >> 24;
 }
-__device__ __forceinline__ uint32_t box_out(const uint4 &s, uint32_t d) {  // (sum + d/2) / d, blur.rs:269
-    uint32_t h = d / 2;
+// (sum + d/2) / d, blur.rs:269.  The divisor is the same for every pixel, so the quotient is one IMAD.HI against
+// magic = floor(2^32 / d) + 1: exact for every numerator below 256 d as long as 256 d^2 <= 2^32, i.e. d <= 4096
+// (checked exhaustively on the host for the divisors the tests use); magic == 0 selects the plain division.
+__device__ __forceinline__ uint32_t box_out(const uint4 &s, uint32_t d, uint32_t magic) {
+    const uint32_t h = d / 2;
+    if (magic) return pfe_pack(__umulhi(s.x + h, magic), __umulhi(s.y + h, magic), __umulhi(s.z + h, magic), __umulhi(s.w + h, magic));
     return pfe_pack((s.x + h) / d, (s.y + h) / d, (s.z + h) / d, (s.w + h) / d);
 }
 
@@ -31,7 +35,7 @@ __device__ __forceinline__ uint32_t box_out(const uint4 &s, uint32_t d) {  // (s
 // sum along its run (sums are windows over clamped indices, identical to the reference's
 // incremental add/remove at blur.rs:272-278).
 constexpr int BOX_COLS = 128;
-__global__ void __launch_bounds__(128) box_h_kernel(const uint32_t *src, uint32_t *dst, int w, int h, int r) {
+__global__ void __launch_bounds__(128) box_h_kernel(const uint32_t *src, uint32_t *dst, int w, int h, int r, uint32_t magic) {
     extern __shared__ uint32_t sm[];
     const int tw = BOX_COLS + 2 * r;       // tile width
     const int pitch = tw | 1;              // odd pitch: lanes (rows) hit distinct banks
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(128) box_h_kernel(const uint32_t *src, uint32_
     uint4 s = make_uint4(0, 0, 0, 0);
     for (int k = 0; k < (int)d; k++) add4(s, row[k]);
     for (int c = 0; c < 32; c++) {
-        tout[lane * (BOX_COLS + 1) + warp * 32 + c] = box_out(s, d);
+        tout[lane * (BOX_COLS + 1) + warp * 32 + c] = box_out(s, d, magic);
         sub4(s, row[c]);
         add4(s, row[c + (int)d]);  // within the padded tile (+1 column slack below)
     }
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(128) box_h_kernel(const uint32_t *src, uint32_
 // ---- box blur V pass: lanes along x (coalesced), each thread slides down a band of rows.
 constexpr int BOX_BAND = 128;
 __global__ void __launch_bounds__(128) box_v_kernel(const uint32_t *hb, const uint32_t *src, const uint8_t *mask,
-                                                    uint32_t *dst, int w, int h, int r) {
+                                                    uint32_t *dst, int w, int h, int r, uint32_t magic) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
     const int y0 = blockIdx.y * BOX_BAND, y1 = min(y0 + BOX_BAND, h);
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(128) box_v_kernel(const uint32_t *hb, const ui
     for (int k = -r; k <= r; k++) add4(s, __ldg(hb + (size_t)pfe_clampi(y0 + k, 0, h - 1) * w + x));
     for (int y = y0; y < y1; y++) {
         size_t o = (size_t)y * w + x;
-        dst[o] = (mask && mask[o] == 0) ? src[o] : box_out(s, d);            // blur.rs:298-306
+        dst[o] = (mask && mask[o] == 0) ? src[o] : box_out(s, d, magic);            // blur.rs:298-306
         sub4(s, __ldg(hb + (size_t)pfe_clampi(y - r, 0, h - 1) * w + x));
         add4(s, __ldg(hb + (size_t)pfe_clampi(y + r + 1, 0, h - 1) * w + x));
     }
@@ -407,14 +411,16 @@ extern "C" int pfe_dev_box_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, ui
     const int r = (int)c;
     const size_t smem = ((size_t)32 * ((BOX_COLS + 2 * r) | 1) + 32 * (BOX_COLS + 1) + 64) * 4;
     if (smem > 220 * 1024) return pfe_fail(ctx, PFE_ERR_UNSUPPORTED, "box_blur: radius too large for the H tile");
+    const uint32_t dwin = 2u * (uint32_t)r + 1u;
+    const uint32_t magic = dwin <= 4096u ? (uint32_t)((1ull << 32) / dwin) + 1u : 0u;
     void *hb;
     PFE_TRY(pfe_scratch(ctx, PFE_SCRATCH_B, (size_t)w * h * 4, &hb));
     if (smem > 48 * 1024) PFE_CUDA(ctx, cudaFuncSetAttribute(box_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PFE_KERNEL(ctx, "box_h", box_h_kernel<<<dim3(pfe_div_up(w, BOX_COLS), pfe_div_up(h, 32)), 128, smem, ctx->stream>>>(
-        (const uint32_t *)src, (uint32_t *)hb, (int)w, (int)h, r));
+        (const uint32_t *)src, (uint32_t *)hb, (int)w, (int)h, r, magic));
     PFE_LAUNCHED(ctx);
     PFE_KERNEL(ctx, "box_v", box_v_kernel<<<dim3(pfe_div_up(w, 128), pfe_div_up(h, BOX_BAND)), 128, 0, ctx->stream>>>(
-        (const uint32_t *)hb, (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, r));
+        (const uint32_t *)hb, (const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h, r, magic));
     PFE_LAUNCHED(ctx);
     return PFE_OK;
 }

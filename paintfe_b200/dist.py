@@ -255,6 +255,60 @@ def gaussian_blur_banded(eng, band, h_total: int, sigma: float, exact: bool = Fa
     return eng.gaussian_band_v(plan.ext, plan.top, plan.rows, sigma, exact=exact, out=out)
 
 
+class BandedFlattenBlur:
+    """composite() + parallel_gaussian_blur of ONE canvas on this rank's row band, scheduled so that the halo exchange
+    hides: the band's edge rows (the ones the neighbours need) are flattened first, the exchange starts on the side
+    stream, and the interior flatten and the band's own H pass run under it; the halo rows are H-filtered when they
+    have landed, then the V pass writes the band.  `layers` are this rank's band rows of every layer (device tensors
+    in `rgba`, plus opacity / blend / ...).  Descriptors and buffers are set up once; `step()` only enqueues."""
+
+    def __init__(self, eng, layers, w: int, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None):
+        rank, world = _world(group)
+        self.eng, self.sigma, self.exact = eng, float(sigma), bool(exact)
+        self.bounds = bounds or band_bounds(h_total, world)
+        y0, y1 = self.bounds[rank]
+        self.rows, self.w, self.h_total = y1 - y0, int(w), int(h_total)
+        r = gaussian_radius(sigma)
+        first = next(L["rgba"] for L in layers if L.get("rgba") is not None)
+        self.plan = halo_plan(first, r, r, self.bounds, group)
+        self.out = torch.empty((self.rows, w, 4), dtype=torch.uint8, device=first.device)
+        e = min(r, self.rows)
+        # row ranges of the band: [0, e) and [rows - e, rows) feed the neighbours; the interior is everything else
+        if self.rows > 2 * e and world > 1:
+            self.parts = [(0, e), (self.rows - e, self.rows), (e, self.rows - e)]
+            self.exchange_after = 2
+        else:
+            self.parts = [(0, self.rows)]
+            self.exchange_after = 1
+
+        def sub(a, b):
+            ls = [dict(L, rgba=L["rgba"][a:b], mask=(None if L.get("mask") is None else L["mask"][a:b])) if L.get("rgba") is not None else L
+                  for L in layers]
+            return eng.prepare_layers(ls, w, b - a)
+
+        self.prepared = [sub(a, b) for a, b in self.parts]
+        self.fused = r <= 16  # small radii: the fused H+V kernel on the extended band (see gaussian_blur_banded)
+
+    def step(self):
+        eng, plan = self.eng, self.plan
+        for k, ((a, b), prep) in enumerate(zip(self.parts, self.prepared)):
+            eng.flatten_prepared(prep, plan.core[a:b])
+            if k + 1 == self.exchange_after:
+                plan.exchange_async()
+        if self.fused:
+            plan.wait()
+            res = eng.gaussian_blur(plan.ext, self.sigma, exact=self.exact)
+            self.out.copy_(res[plan.top:plan.top + plan.rows])
+            return self.out
+        eng.gaussian_band_h(plan.ext, plan.top, plan.rows, self.sigma, exact=self.exact)
+        plan.wait()
+        if plan.top:
+            eng.gaussian_band_h(plan.ext, 0, plan.top, self.sigma, exact=self.exact)
+        if plan.bot:
+            eng.gaussian_band_h(plan.ext, plan.top + plan.rows, plan.bot, self.sigma, exact=self.exact)
+        return eng.gaussian_band_v(plan.ext, plan.top, plan.rows, self.sigma, exact=self.exact, out=self.out)
+
+
 def box_blur_banded(eng, band, h_total: int, radius: float, group=None, bounds=None):
     """box_blur_core (effects/blur.rs:233-318); halo = ceil(radius)."""
     _, world = _world(group)

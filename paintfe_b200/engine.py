@@ -245,6 +245,20 @@ class Engine:
             self._ck(self.lib.pfe_flatten(self.h, arr, len(layers), w, h, _ptr(active), _ptr(dst)))
         return dst
 
+    def prepare_layers(self, layers: Sequence[Layer], w: int, h: int):
+        """Marshal a layer list once (the pfe_layer_desc array) for repeated `flatten_prepared` calls: a caller that
+        flattens the same device-resident stack every step then pays no per-call Python marshalling."""
+        arr, keep, dev = self._layer_array(layers, h, w)
+        if not dev and any(Ly.get("rgba") is not None for Ly in layers):
+            raise ValueError("prepare_layers is for device-resident layers")
+        return (arr, keep, len(layers), int(w), int(h))
+
+    def flatten_prepared(self, prepared, out, active=None):
+        arr, _keep, n, w, h = prepared
+        self.use_torch_stream()
+        self._ck(self.lib.pfe_dev_flatten(self.h, arr, n, w, h, _ptr(active), _ptr(out)))
+        return out
+
     def flatten_gaussian(self, layers, w, h, sigma, active=None, exact=False, out=None):
         """Host tier only: composite() then parallel_gaussian_blur without leaving the device."""
         arr, keep, dev = self._layer_array(layers, h, w)

@@ -49,6 +49,19 @@ def _worker(rank, world, port, q):
         for _ in range(3):  # the plan's buffers are reused call after call
             pd.gaussian_blur_banded(eng, plan.core, h, 20.0, bounds=bounds, out=out)
         res["gauss_plan_core"] = torch.equal(out, eng.gaussian_blur(full, 20.0)[y0:y1])
+        # flatten + blur of one canvas with the edge-rows-first schedule (bench.py's strong leg)
+        from paintfe_b200.engine import make_layer
+        lrng = np.random.default_rng(5)
+        limgs = [torch.from_numpy(lrng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda() for _ in range(5)]
+        lmeta = [dict(blend=(7 * i) % 25, opacity=0.3 + 0.15 * i) for i in range(5)]
+        want = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 20.0)[y0:y1]
+        fb = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 20.0, bounds=bounds)
+        for _ in range(3):
+            got = fb.step()
+        res["flatten_blur_edge_first"] = torch.equal(got, want) and len(fb.parts) == 3
+        fb2 = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 4.0, exact=True, bounds=bounds)
+        want2 = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 4.0, exact=True)[y0:y1]
+        res["flatten_blur_small_radius"] = torch.equal(fb2.step(), want2)
         res["gauss_small_radius"] = torch.equal(pd.gaussian_blur_banded(eng, band, h, 3.0, exact=True, bounds=bounds),
                                                 eng.gaussian_blur(full, 3.0, exact=True)[y0:y1])
         res["box"] = torch.equal(pd.box_blur_banded(eng, band, h, 9.0, bounds=bounds), eng.box_blur(full, 9.0)[y0:y1])
