@@ -129,15 +129,18 @@ class HaloPlan:
                     self.recvs.append((peer, ov[0] - ext_y0, ov[1] - ext_y0))
         self.halo_bytes = sum((b - a) for _, a, b in self.recvs) * int(np.prod(row_shape)) * self.ext.element_size()
         self._side = self._ready = self._done = None
+        self._op_list = None
         if self.ext.is_cuda:
             self._side = torch.cuda.Stream(device=device)
             self._ready = torch.cuda.Event()
             self._done = torch.cuda.Event()
 
     def _ops(self):
-        ops = [dist.P2POp(dist.isend, self.ext[a:b], peer, self.group) for peer, a, b in self.sends]
-        ops += [dist.P2POp(dist.irecv, self.ext[a:b], peer, self.group) for peer, a, b in self.recvs]
-        return ops
+        if self._op_list is None:  # the buffers never move: build the descriptors once
+            ops = [dist.P2POp(dist.isend, self.ext[a:b], peer, self.group) for peer, a, b in self.sends]
+            ops += [dist.P2POp(dist.irecv, self.ext[a:b], peer, self.group) for peer, a, b in self.recvs]
+            self._op_list = ops
+        return self._op_list
 
     def exchange(self):
         """Fill the halo rows; on return (CPU) / in stream order (CUDA) `ext` is complete."""
