@@ -12,10 +12,13 @@ resident in HBM.  Rank 0 prints ONE JSON line.  What the line carries:
   e2e                   the same step through the host-pointer C ABI call pfe_flatten_gaussian from pinned host
                         buffers (H2D + D2H inside the timed region), plus `bare_copy_ms`: the same bytes copied
                         with nothing else running, so the record itself shows how much of e2e is the PCIe fabric.
-  strong (N > 1)        ONE 8K canvas split into N row bands: flatten is band-local, the Gaussian exchanges
-                        ceil(3 sigma) rows of u8 input with the neighbours over NCCL (paintfe_b200.dist) on a side
-                        stream while the band's own rows go through the H pass.  Every rank checks its band against
-                        the single-GPU result of the whole canvas (parity) outside the timed region.
+  strong (N > 1)        ONE 8K canvas split into N row bands: flatten is band-local, the Gaussian needs ceil(3 sigma)
+                        rows of u8 input from each neighbour.  The flatten kernel of the band's edge rows stores them a
+                        second time, straight into the neighbour's halo rows over NVLink peer memory, and flags them
+                        (pfe_dev_flatten_peer; paintfe_b200.dist.PeerHalo); the interior flatten and the band's own H
+                        pass run while they travel.  The same schedule over NCCL isend/irecv is timed beside it.  Every
+                        rank checks its band against the single-GPU result of the whole canvas (parity) outside the
+                        timed region.
   config4               BASELINE config 4: 16384^2 mesh warp 6x6 + liquify warp, one canvas in N row bands with a
                         halo exchange sized by the warp's reach, parity-checked the same way.
   kernels / roofline    per-kernel CUDA-event times from inside the timed region; `extra` times the EXACT-mode
@@ -335,7 +338,7 @@ def run_b200(args):
     value = world * px / (ms_step * 1e-3) / 1e6
     e2e_value = world * px / (e2e_ms / e2e_steps * 1e-3) / 1e6
 
-    # ---- strong scaling: ONE 8K canvas in row bands, NCCL halo exchange for the Gaussian ----------------
+    # ---- strong scaling: ONE 8K canvas in row bands, halo rows over peer memory (or NCCL) for the Gaussian ----
     strong = None
     if world > 1:
         del host_layers, hl_np
@@ -349,14 +352,26 @@ def run_b200(args):
         rows = y1 - y0
         radius = pd.gaussian_radius(SIGMA)
         band_layers = [make_layer(t[y0:y1], **m) for t, m in zip(layers, meta)]
-        # edge rows first, exchange on the side stream, interior flatten + H pass under it (paintfe_b200/dist.py)
+        # edge rows first - the flatten kernel stores them straight into the neighbours' halo rows over NVLink peer
+        # memory and flags them - then the interior flatten + the band's own H pass while they travel (dist.py)
         pipe = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds)
         plan, out_band = pipe.plan, pipe.out
         strong_step = pipe.step
 
+        def parity_of(result):
+            okt = torch.tensor([1.0 if torch.equal(result, whole[y0:y1]) else 0.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            return bool(okt.item() == 1.0)
+
         strong_ms = timed(strong_step, args.steps, warm=warmup)
-        ok = torch.tensor([1.0 if torch.equal(out_band, whole[y0:y1]) else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        ok = parity_of(out_band)
+        eng.check_async()  # a flag wait that timed out would be reported here
+        nccl_ms = nccl_ok = None
+        if pipe.transport == "peer":  # the same schedule with batched NCCL isend/irecv on a side stream, for comparison
+            pipe_n = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="nccl")
+            nccl_ms = timed(pipe_n.step, args.steps, warm=warmup)
+            nccl_ok = parity_of(pipe_n.out)
+            del pipe_n
         exch_ms = timed(plan.exchange, max(args.steps, 10), warm=3)
         # the same band-local kernels without any exchange (halo rows left as they are): what the exchange costs on top
         whole_band = eng.prepare_layers(band_layers, w, rows)
@@ -368,13 +383,19 @@ def run_b200(args):
 
         noex_ms = timed(no_exchange_step, args.steps, warm=2)
         halo = max_over_ranks(float(plan.halo_bytes))[0]
-        strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20 with an NCCL halo exchange of %d u8 rows per side" % (world, radius),
+        how = ("the edge flatten stores its rows into the neighbours' halo over NVLink peer memory (pfe_dev_flatten_peer) and flags them"
+               if pipe.transport == "peer" else "an NCCL halo exchange on a side stream")
+        strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20, %d u8 halo rows per side: %s" % (world, radius, how),
+                  "transport": pipe.transport, "peer_unavailable": getattr(pipe, "peer_error", None),
                   "ms_per_step": strong_ms, "mpx_s": px / strong_ms / 1e3, "band_rows": [b - a for a, b in bounds],
-                  "halo_bytes": int(halo), "exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
-                  "parity": bool(ok.item() == 1.0), "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
+                  "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok,
+                  "nccl_exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
+                  "parity": ok, "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
                   "speedup_vs_one_gpu_step": ms_step / strong_ms,
-                  "note": "edge rows flattened first, exchange on a side stream under the interior flatten and the band's own H pass; halo rows recompute the H pass; "
-                          "exchange_ms = the exchange alone, back to back; ms_per_step_no_exchange = same kernels, no transfer"}
+                  "note": "edge rows flattened first, interior flatten and the band's own H pass while they travel; halo rows recompute the H pass; "
+                          "ms_per_step_nccl = same schedule over NCCL isend/irecv; nccl_exchange_ms = that exchange alone, back to back; "
+                          "ms_per_step_no_exchange = same kernels, no transfer"}
+        pipe.close()
         del whole, plan, out_band, band_layers, pipe, whole_band, strong_step
 
     # ---- BASELINE config 4: 16384^2 mesh warp + liquify warp on one canvas in row bands ----------------

@@ -57,7 +57,7 @@ int pfe_ctx_use_own_stream(pfe_ctx *ctx);
 int pfe_ctx_sync(pfe_ctx *ctx);
 /* Stream-asynchronous device-tier calls that can only detect a caller error on the device (today:
  * pfe_dev_warp_band, whose source-row window may turn out not to cover the warp's reach) record it in a
- * sticky flag instead of synchronising.  This call synchronises the context's stream, returns
+ * sticky flag instead of synchronising (so does pfe_dev_peer_wait for a timeout).  This call synchronises the context's stream, returns
  * PFE_ERR_INVALID_ARG (message in pfe_last_error) if any such error was recorded since the last call, PFE_OK
  * otherwise, and clears the flag. */
 int pfe_ctx_check_async(pfe_ctx *ctx);
@@ -495,6 +495,30 @@ int pfe_dev_gaussian_band_h(pfe_ctx *ctx, const uint8_t *ext, uint32_t w, uint32
                             uint32_t rows, float sigma, uint32_t flags);
 int pfe_dev_gaussian_band_v(pfe_ctx *ctx, uint32_t w, uint32_t ext_rows, uint32_t y0, uint32_t rows, float sigma,
                             uint8_t *dst_rows, uint32_t flags);
+/* Halo rows over peer memory (one process per GPU on one NVSwitch node).  Instead of flattening a
+ * band's edge rows and then sending them, the flatten kernel itself stores them a second time, straight into the
+ * neighbour GPU's extended band, and the last CTA to finish releases a flag in the neighbour's memory: the transfer
+ * is the kernel's own NVLink stores, tile by tile, and there is no send/receive at all.
+ *   pfe_peer_alloc   cudaMalloc (zero-filled) + a 64-byte handle another PROCESS of this node can open;
+ *   pfe_peer_open    map a neighbour's allocation here (also enables peer access between the two devices);
+ *   pfe_peer_close / pfe_peer_free   unmap / release - close every mapping before its owner frees;
+ *   pfe_dev_flatten_peer  pfe_dev_flatten that also writes every result at the same offset from peer_dst and
+ *                    then, if peer_flag != NULL, stores flag_value to *peer_flag with release semantics at system
+ *                    scope (whoever sees the flag sees the rows).  peer_dst / peer_flag need not be remote;
+ *   pfe_dev_peer_wait  stream-ordered wait until every flags[0..n) (in THIS device's memory, n <= 32) has reached
+ *                    value (wrap-around compare: flags are step counters that only grow).  If that takes longer than
+ *                    timeout_ms the wait gives up and sets the sticky error pfe_ctx_check_async reports.
+ * A buffer a neighbour writes into must not be reused for the next step before the neighbour can know it was read:
+ * callers alternate between two buffers, so that the flag of step k+1 orders the reads of step k before the writes
+ * of step k+2 (paintfe_b200/dist.py PeerHalo). */
+int pfe_peer_alloc(pfe_ctx *ctx, size_t bytes, void **dptr, uint8_t handle[64]);
+int pfe_peer_open(pfe_ctx *ctx, const uint8_t handle[64], void **dptr);
+int pfe_peer_close(pfe_ctx *ctx, void *dptr);
+int pfe_peer_free(pfe_ctx *ctx, void *dptr);
+int pfe_dev_flatten_peer(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n_layers, uint32_t w, uint32_t h,
+                         const uint8_t *active_chunks, uint8_t *dst, uint8_t *peer_dst, uint32_t *peer_flag,
+                         uint32_t flag_value);
+int pfe_dev_peer_wait(pfe_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t value, uint32_t timeout_ms);
 /* Reach of a band's displacement field, for sizing the halo of pfe_dev_warp_band: minmax_dev[0..1] (DEVICE
  * memory, int32) = min / max over the band's rows [y0, y0+rows) of floor(clamp(y - dy, -1, h_total)), with
  * non-finite dy counted as 0. Asynchronous: the result stays on the device so that it can go straight into

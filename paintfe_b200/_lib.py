@@ -164,6 +164,12 @@ SIGNATURES = {
     "pfe_dev_warp_band": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
     "pfe_dev_gaussian_band_h": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _f32, _u32]),
     "pfe_dev_gaussian_band_v": (C.c_int, [_ctx, _u32, _u32, _u32, _u32, _f32, _vp, _u32]),
+    "pfe_peer_alloc": (C.c_int, [_ctx, C.c_size_t, C.POINTER(_vp), _vp]),
+    "pfe_peer_open": (C.c_int, [_ctx, _vp, C.POINTER(_vp)]),
+    "pfe_peer_close": (C.c_int, [_ctx, _vp]),
+    "pfe_peer_free": (C.c_int, [_ctx, _vp]),
+    "pfe_dev_flatten_peer": (C.c_int, [_ctx, C.POINTER(LayerDesc), _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32]),
+    "pfe_dev_peer_wait": (C.c_int, [_ctx, _vp, _u32, _u32, _u32]),
     "pfe_dev_disp_reach": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "pfe_dev_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),

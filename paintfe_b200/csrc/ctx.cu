@@ -204,7 +204,65 @@ int pfe_ctx_check_async(pfe_ctx *c) {
     PFE_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!flag) return PFE_OK;
     PFE_CUDA(c, cudaMemsetAsync(c->async_err, 0, sizeof(int), c->stream));
+    if (flag & PFE_ASYNC_PEER_TIMEOUT)
+        return pfe_fail(c, PFE_ERR_INVALID_ARG, "peer_wait: a neighbour's halo rows did not arrive before the timeout");
     return pfe_fail(c, PFE_ERR_INVALID_ARG, "warp_band: the source row window does not cover the warp's reach");
+}
+
+// -- device memory shared between the processes of one node (one process per GPU) ------------------------------
+// The halo rows of a canvas split across GPUs travel as the producing kernel's own stores into the neighbour's
+// buffer (pfe_dev_flatten_peer).  That needs the neighbour's allocation mapped here: CUDA IPC, which also enables
+// peer access between the two devices (NVLink on an NVSwitch box).
+int pfe_peer_alloc(pfe_ctx *c, size_t bytes, void **dptr, uint8_t handle[64]) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    if (!dptr || !handle || !bytes) return pfe_fail(c, PFE_ERR_INVALID_ARG, "peer_alloc: bad args");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return pfe_fail(c, PFE_ERR_OOM, "peer_alloc: cudaMalloc", e); }
+    cudaIpcMemHandle_t hd;
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        return pfe_fail(c, PFE_ERR_CUDA, "peer_alloc: cudaIpcGetMemHandle", e);
+    }
+    memcpy(handle, &hd, 64);
+    *dptr = p;
+    return PFE_OK;
+}
+
+int pfe_peer_open(pfe_ctx *c, const uint8_t handle[64], void **dptr) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    if (!dptr || !handle) return pfe_fail(c, PFE_ERR_INVALID_ARG, "peer_open: bad args");
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return pfe_fail(c, PFE_ERR_CUDA, "peer_open: cudaIpcOpenMemHandle", e); }
+    *dptr = p;
+    return PFE_OK;
+}
+
+int pfe_peer_close(pfe_ctx *c, void *dptr) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    if (!dptr) return PFE_OK;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaIpcCloseMemHandle(dptr));
+    return PFE_OK;
+}
+
+int pfe_peer_free(pfe_ctx *c, void *dptr) {
+    if (!c) return PFE_ERR_INVALID_ARG;
+    if (!dptr) return PFE_OK;
+    PFE_CUDA(c, cudaSetDevice(c->device));
+    PFE_CUDA(c, cudaDeviceSynchronize());
+    PFE_CUDA(c, cudaFree(dptr));
+    return PFE_OK;
 }
 
 const char *pfe_last_error(const pfe_ctx *c) { return c ? c->err.c_str() : "null context"; }

@@ -104,7 +104,7 @@ __device__ __forceinline__ uint32_t warp_sample(const uint32_t *src, int sw, int
     for (int k = 0; k < 4; k++) {
         int px = x0 + (k & 1), py = y0 + (k >> 1);
         if (px < 0 || py < 0 || px >= sw || py >= sh) q[k] = 0u;
-        else if (py < sy0 || py - sy0 >= snr) { q[k] = 0u; if (missing) *missing = 1; }
+        else if (py < sy0 || py - sy0 >= snr) { q[k] = 0u; if (missing) atomicOr(missing, PFE_ASYNC_WARP_WINDOW); }
         else q[k] = __ldg(src + (size_t)(py - sy0) * sw + px);
     }
     uint32_t o[4];

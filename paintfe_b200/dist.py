@@ -258,14 +258,124 @@ def gaussian_blur_banded(eng, band, h_total: int, sigma: float, exact: bool = Fa
     return eng.gaussian_band_v(plan.ext, plan.top, plan.rows, sigma, exact=exact, out=out)
 
 
-class BandedFlattenBlur:
-    """composite() + parallel_gaussian_blur of ONE canvas on this rank's row band, scheduled so that the halo exchange
-    hides: the band's edge rows (the ones the neighbours need) are flattened first, the exchange starts on the side
-    stream, and the interior flatten and the band's own H pass run under it; the halo rows are H-filtered when they
-    have landed, then the V pass writes the band.  `layers` are this rank's band rows of every layer (device tensors
-    in `rgba`, plus opacity / blend / ...).  Descriptors and buffers are set up once; `step()` only enqueues."""
+class PeerUnavailable(RuntimeError):
+    """The neighbours' memory cannot be mapped here (no CUDA IPC between the ranks, or bands thinner than the halo)."""
 
-    def __init__(self, eng, layers, w: int, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None):
+
+class _RawDeviceMemory:
+    def __init__(self, addr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 3, "strides": None}
+
+
+def _device_view(addr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_RawDeviceMemory(addr, nbytes), device=device)
+
+
+class PeerHalo:
+    """A HaloPlan's extended band, twice, in device memory the two row neighbours have mapped (CUDA IPC -> NVLink peer
+    access), plus one u32 flag per buffer and side.  Nothing is sent or received: the neighbour's flatten kernel stores
+    its edge rows straight into this rank's halo rows and releases the flag (pfe_dev_flatten_peer), and this rank's
+    stream waits for the flag right before its first kernel that reads a halo row (pfe_dev_peer_wait).
+
+    Two buffers, used alternately, replace an acknowledgement: a neighbour writes buffer p again at step k+2, after it
+    has seen this rank's flag of step k+1, which this rank's stream released after its reads of step k.
+
+        block:  [ flags u32[2 buffers][2 sides] | pad to 4 KB ][ ext buffer 0 ][ ext buffer 1 ]
+        side 0 = written by the upper neighbour (top halo), side 1 = by the lower neighbour (bottom halo)
+    """
+    HEADER = 4096
+
+    def __init__(self, eng, plan: HaloPlan, halo: int, group=None):
+        self.eng, self.plan, self.group = eng, plan, group
+        self.rank, self.world = plan.rank, plan.world
+        self.addr = self.up = self.down = None
+        if not plan.ext.is_cuda or self.world < 2:
+            raise PeerUnavailable("peer halos need CUDA and more than one rank")
+        if min(b - a for a, b in plan.bounds) < halo:  # same answer on every rank: decided before anything is allocated
+            raise PeerUnavailable("a band is thinner than the halo: rows would come from beyond the adjacent neighbour")
+        shape = tuple(plan.ext.shape)
+        self.row_bytes = int(np.prod(shape[1:])) * plan.ext.element_size()
+        ext_bytes = shape[0] * self.row_bytes
+        self.stride = (ext_bytes + 4095) // 4096 * 4096
+        err = None
+        try:
+            self.addr, handle = eng.peer_alloc(self.HEADER + 2 * self.stride)
+        except Exception as e:  # noqa: BLE001 - whatever it is, every rank must learn of it
+            err, handle = str(e), None
+        infos = self._gather((handle, plan.top, plan.rows, plan.bot, self.stride))
+        if err is None and all(i[0] is not None for i in infos):
+            try:
+                if self.rank > 0:
+                    self.up = eng.peer_open(infos[self.rank - 1][0])
+                if self.rank + 1 < self.world:
+                    self.down = eng.peer_open(infos[self.rank + 1][0])
+            except Exception as e:  # noqa: BLE001
+                err = str(e)
+        elif err is None:
+            err = "a neighbour could not allocate"
+        errs = self._gather(err)
+        if any(errs):
+            self._release()
+            raise PeerUnavailable("; ".join(sorted({e for e in errs if e})))
+        dev = plan.ext.device
+        self.ext = [_device_view(self.addr + self.HEADER + p * self.stride, ext_bytes, dev).view(plan.ext.dtype).view(shape) for p in (0, 1)]
+        self.core = [e[plan.top:plan.top + plan.rows] for e in self.ext]
+        self.flags = _device_view(self.addr, 16, dev).view(torch.int32)
+        # where this rank's edge rows go, per buffer: (ext address in the neighbour, flag address in the neighbour)
+        self.put_up = self.put_down = None
+        self.rows_up = self.rows_down = 0
+        if self.up is not None:
+            _, top_u, rows_u, bot_u, stride_u = infos[self.rank - 1]
+            self.rows_up = bot_u  # my first bot_u rows are the upper neighbour's bottom halo
+            self.put_up = [(self.up + self.HEADER + p * stride_u + (top_u + rows_u) * self.row_bytes, self.up + 4 * (p * 2 + 1)) for p in (0, 1)]
+        if self.down is not None:
+            _, top_d, _rows_d, _bot_d, stride_d = infos[self.rank + 1]
+            self.rows_down = top_d  # my last top_d rows are the lower neighbour's top halo
+            self.put_down = [(self.down + self.HEADER + p * stride_d, self.down + 4 * (p * 2 + 0)) for p in (0, 1)]
+        self.halo_bytes = (plan.top + plan.bot) * self.row_bytes
+
+    def _gather(self, obj):
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def wait_args(self, p: int) -> Tuple[int, int]:
+        """(address of the first flag, count) this rank waits on for buffer p."""
+        first = 0 if self.up is not None else 1
+        n = (self.up is not None) + (self.down is not None)
+        return self.addr + 4 * (p * 2 + first), n
+
+    def _release(self):
+        for a in (self.up, self.down):
+            if a is not None:
+                self.eng.peer_close(a)
+        self.up = self.down = None
+
+    def close(self):
+        """Collective: unmap the neighbours, then (once every rank has) free this rank's block."""
+        if self.addr is None:
+            return
+        torch.cuda.synchronize()
+        self.ext = self.core = self.flags = None
+        self._release()
+        dist.barrier(group=self.group)
+        self.eng.peer_free(self.addr)
+        self.addr = None
+
+
+class BandedFlattenBlur:
+    """composite() + parallel_gaussian_blur of ONE canvas on this rank's row band, scheduled so that the halo transfer
+    hides: the band's edge rows (the ones the neighbours need) are flattened first, the interior flatten and the band's
+    own H pass run while they travel; the halo rows are H-filtered when they have landed, then the V pass writes the
+    band.  `layers` are this rank's band rows of every layer (device tensors in `rgba`, plus opacity / blend / ...).
+    Descriptors and buffers are set up once; `step()` only enqueues.
+
+    transport "peer": the edge flatten stores its rows straight into the neighbours' halo rows over NVLink peer memory
+    and flags them (PeerHalo) - one stream, no send/receive.  "nccl": batched isend/irecv on a side stream (HaloPlan).
+    "auto" takes "peer" when every rank can map its neighbours, else "nccl" (the decision is collective)."""
+
+    def __init__(self, eng, layers, w: int, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None,
+                 transport: str = "auto", timeout_ms: int = 2000):
         rank, world = _world(group)
         self.eng, self.sigma, self.exact = eng, float(sigma), bool(exact)
         self.bounds = bounds or band_bounds(h_total, world)
@@ -275,13 +385,36 @@ class BandedFlattenBlur:
         first = next(L["rgba"] for L in layers if L.get("rgba") is not None)
         self.plan = halo_plan(first, r, r, self.bounds, group)
         self.out = torch.empty((self.rows, w, 4), dtype=torch.uint8, device=first.device)
+        self.fused = r <= 16  # small radii: the fused H+V kernel on the extended band (see gaussian_blur_banded)
+        self.peer, self.k, self.timeout_ms = None, 0, int(timeout_ms)
+        if transport not in ("auto", "peer", "nccl"):
+            raise ValueError("transport must be auto, peer or nccl")
+        if transport != "nccl" and world > 1 and not self.fused and hasattr(eng, "flatten_prepared_peer"):
+            try:
+                self.peer = PeerHalo(eng, self.plan, r, group)
+            except PeerUnavailable as e:
+                self.peer_error = str(e)
+                if transport == "peer":
+                    raise
+        elif transport == "peer":
+            raise PeerUnavailable("peer transport needs the GPU engine, more than one rank and a two-pass radius")
+        self.transport = "peer" if self.peer is not None else "nccl"
         e = min(r, self.rows)
         # row ranges of the band: [0, e) and [rows - e, rows) feed the neighbours; the interior is everything else
-        if self.rows > 2 * e and world > 1:
-            self.parts = [(0, e), (self.rows - e, self.rows), (e, self.rows - e)]
+        if self.peer is not None:
+            pr = self.peer
+            cut_a, cut_b = pr.rows_up, self.rows - pr.rows_down
+            if cut_a > cut_b:  # edges overlap (a band barely taller than the halo): the overlap is flattened twice
+                self.parts = [(0, pr.rows_up, "up"), (self.rows - pr.rows_down, self.rows, "down")]
+            else:
+                self.parts = [(0, cut_a, "up"), (cut_b, self.rows, "down"), (cut_a, cut_b, None)]
+            self.parts = [p for p in self.parts if p[1] > p[0]]
+            self.exchange_after = None
+        elif self.rows > 2 * e and world > 1:
+            self.parts = [(0, e, None), (self.rows - e, self.rows, None), (e, self.rows - e, None)]
             self.exchange_after = 2
         else:
-            self.parts = [(0, self.rows)]
+            self.parts = [(0, self.rows, None)]
             self.exchange_after = 1
 
         def sub(a, b):
@@ -289,12 +422,37 @@ class BandedFlattenBlur:
                   for L in layers]
             return eng.prepare_layers(ls, w, b - a)
 
-        self.prepared = [sub(a, b) for a, b in self.parts]
-        self.fused = r <= 16  # small radii: the fused H+V kernel on the extended band (see gaussian_blur_banded)
+        self.prepared = [sub(a, b) for a, b, _ in self.parts]
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+
+    def _step_peer(self):
+        eng, plan, pr = self.eng, self.plan, self.peer
+        self.k += 1
+        p, value = self.k & 1, self.k
+        ext, core = pr.ext[p], pr.core[p]
+        for (a, b, to), prep in zip(self.parts, self.prepared):
+            put = pr.put_up if to == "up" else pr.put_down if to == "down" else None
+            if put is None:
+                eng.flatten_prepared(prep, core[a:b])
+            else:
+                eng.flatten_prepared_peer(prep, core[a:b], put[p][0], put[p][1], value)
+        eng.gaussian_band_h(ext, plan.top, plan.rows, self.sigma, exact=self.exact)  # the halo rows travel meanwhile
+        eng.peer_wait(*pr.wait_args(p), value, self.timeout_ms)
+        if plan.top:
+            eng.gaussian_band_h(ext, 0, plan.top, self.sigma, exact=self.exact)
+        if plan.bot:
+            eng.gaussian_band_h(ext, plan.top + plan.rows, plan.bot, self.sigma, exact=self.exact)
+        return eng.gaussian_band_v(ext, plan.top, plan.rows, self.sigma, exact=self.exact, out=self.out)
 
     def step(self):
+        if self.peer is not None:
+            return self._step_peer()
         eng, plan = self.eng, self.plan
-        for k, ((a, b), prep) in enumerate(zip(self.parts, self.prepared)):
+        for k, ((a, b, _), prep) in enumerate(zip(self.parts, self.prepared)):
             eng.flatten_prepared(prep, plan.core[a:b])
             if k + 1 == self.exchange_after:
                 plan.exchange_async()

@@ -259,6 +259,39 @@ class Engine:
         self._ck(self.lib.pfe_dev_flatten(self.h, arr, n, w, h, _ptr(active), _ptr(out)))
         return out
 
+    def flatten_prepared_peer(self, prepared, out, peer_dst: int, peer_flag: int = 0, flag_value: int = 0, active=None):
+        """pfe_dev_flatten_peer: flatten into `out` and, with the same stores, into the raw device address `peer_dst`
+        (normally a neighbour GPU's halo rows, see `peer_open`); then release `flag_value` at address `peer_flag`."""
+        arr, _keep, n, w, h = prepared
+        self.use_torch_stream()
+        self._ck(self.lib.pfe_dev_flatten_peer(self.h, arr, n, w, h, _ptr(active), _ptr(out), C.c_void_p(peer_dst),
+                                               C.c_void_p(peer_flag) if peer_flag else None, flag_value & 0xFFFFFFFF))
+        return out
+
+    def peer_wait(self, flags_addr: int, n: int, value: int, timeout_ms: int = 2000):
+        """Stream-ordered wait until the `n` u32 flags at device address `flags_addr` have all reached `value`."""
+        self.use_torch_stream()
+        self._ck(self.lib.pfe_dev_peer_wait(self.h, C.c_void_p(flags_addr), n, value & 0xFFFFFFFF, timeout_ms))
+
+    def peer_alloc(self, nbytes: int):
+        """(device address, 64-byte handle) of zero-filled device memory other processes of this node can map."""
+        p = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        self._ck(self.lib.pfe_peer_alloc(self.h, nbytes, C.byref(p), handle))
+        return int(p.value), bytes(handle)
+
+    def peer_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._ck(self.lib.pfe_peer_open(self.h, buf, C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, addr: int):
+        self._ck(self.lib.pfe_peer_close(self.h, C.c_void_p(addr)))
+
+    def peer_free(self, addr: int):
+        self._ck(self.lib.pfe_peer_free(self.h, C.c_void_p(addr)))
+
     def flatten_gaussian(self, layers, w, h, sigma, active=None, exact=False, out=None):
         """Host tier only: composite() then parallel_gaussian_blur without leaving the device."""
         arr, keep, dev = self._layer_array(layers, h, w)

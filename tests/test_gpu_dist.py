@@ -59,6 +59,17 @@ def _worker(rank, world, port, q):
         for _ in range(3):
             got = fb.step()
         res["flatten_blur_edge_first"] = torch.equal(got, want) and len(fb.parts) == 3
+        res["flatten_blur_default_transport_is_peer"] = fb.transport == "peer"
+        fbn = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 20.0, bounds=bounds, transport="nccl")
+        for _ in range(3):
+            got = fbn.step()
+        res["flatten_blur_nccl_transport"] = torch.equal(got, want) and fbn.transport == "nccl"
+        for t in limgs:  # new pixels every step: a stale halo row would show
+            t.add_(3)
+        want = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 20.0)[y0:y1]
+        res["flatten_blur_peer_new_pixels"] = torch.equal(fb.step(), want)
+        eng.check_async()  # no wait timed out
+        fb.close()
         fb2 = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 4.0, exact=True, bounds=bounds)
         want2 = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 4.0, exact=True)[y0:y1]
         res["flatten_blur_small_radius"] = torch.equal(fb2.step(), want2)
@@ -98,6 +109,78 @@ def _worker(rank, world, port, q):
         eng.close()
     finally:
         dist.destroy_process_group()
+
+
+def _peer_worker(rank, world, port, q):
+    """Ranks of ONE node that share GPU 0: the rendezvous is gloo, the halo rows travel through CUDA-IPC mapped memory
+    exactly as they do between two GPUs (the mapping is then local instead of NVLink)."""
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0")
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from paintfe_b200 import dist as pd
+        from paintfe_b200.engine import Engine, make_layer
+
+        eng = Engine(0)
+        w, h = 520, 700
+        bounds = pd.band_bounds(h, world)
+        y0, y1 = bounds[rank]
+        lrng = np.random.default_rng(5)
+        limgs = [torch.from_numpy(lrng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda() for _ in range(5)]
+        lmeta = [dict(blend=(7 * i) % 25, opacity=0.3 + 0.15 * i) for i in range(5)]
+        res = {}
+        fb = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 20.0, bounds=bounds,
+                                  transport="peer", timeout_ms=20000)
+        res["transport"] = fb.transport == "peer"
+        ok = True
+        for step in range(5):  # new pixels every step, both buffers used more than once
+            for t in limgs:
+                t.add_(1 + step)
+            want = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 20.0)[y0:y1]
+            ok = ok and torch.equal(fb.step(), want)
+        res["five_steps_bit_equal"] = ok
+        eng.check_async()
+        res["flags"] = [int(v) for v in fb.peer.flags.cpu()]
+        dist.barrier()
+        # a neighbour that never produces its rows: the wait gives up and says so instead of hanging the GPU
+        if rank == 0:
+            eng.peer_wait(fb.peer.wait_args(0)[0], 1, 1000, timeout_ms=50)
+            try:
+                eng.check_async()
+                res["timeout_reported"] = False
+            except Exception as e:
+                res["timeout_reported"] = "did not arrive" in str(e)
+            eng.check_async()
+        fb.close()
+        q.put((rank, res))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_halo_three_ranks_on_one_gpu():
+    import torch.multiprocessing as mp
+
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in results:
+        flags = res.pop("flags")
+        assert all(res.values()), (rank, res)
+        # side 0 = from the upper neighbour, side 1 = from the lower; steps 4 and 5 were the last into buffers 0 and 1
+        want = [4 if rank > 0 else 0, 4 if rank < world - 1 else 0, 5 if rank > 0 else 0, 5 if rank < world - 1 else 0]
+        assert flags == want, (rank, flags)
 
 
 def test_row_bands_over_nccl_match_single_gpu():

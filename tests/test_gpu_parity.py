@@ -1233,3 +1233,37 @@ def test_warp_displacement_region(eng, oracle):
     exact(p.cpu().numpy(), oracle.warp_displacement_region(src, disp, prev, (10, 20, 90, 70)), "region in place")
     # inside a full-canvas rect it is the full warp
     exact(eng.warp_displacement_region(src, disp, prev, (0, 0, w, h)), oracle.warp_displacement(src, disp), "full rect == full warp")
+
+
+def test_flatten_peer_stores_twice_and_flags(eng):
+    """pfe_dev_flatten_peer with a local "peer": both destinations hold the flatten, the flag carries the value, a
+    wait on it passes and a wait on a value nobody will write times out into the sticky error."""
+    import torch
+    from paintfe_b200.engine import make_layer
+
+    rng = np.random.default_rng(31)
+    for (w, h, n) in ((256, 40, 6), (13, 9, 3), (64, 16, 40)):  # one launch; scalar tail (odd width); chained launches
+        imgs = [torch.from_numpy(rng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda() for _ in range(n)]
+        layers = [make_layer(t, blend=(5 * i) % 25, opacity=0.2 + 0.02 * i) for i, t in enumerate(imgs)]
+        want = eng.flatten(layers, w, h)
+        prep = eng.prepare_layers(layers, w, h)
+        out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        far = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+        eng.flatten_prepared_peer(prep, out, far.data_ptr(), flags.data_ptr() + 4, 7)
+        eng.peer_wait(flags.data_ptr() + 4, 1, 7, timeout_ms=1000)
+        assert torch.equal(out, want) and torch.equal(far, want)
+        assert flags.tolist() == [0, 7, 0, 0]
+        eng.check_async()
+    # without a flag: stores only
+    far.zero_()
+    eng.flatten_prepared_peer(prep, out, far.data_ptr())
+    assert torch.equal(far, want)
+    # counters wrap: 0xFFFFFFFE has "reached" 0xFFFFFFFD but not 2
+    flags[0] = -2
+    eng.peer_wait(flags.data_ptr(), 1, 0xFFFFFFFD, timeout_ms=1000)
+    eng.check_async()
+    eng.peer_wait(flags.data_ptr(), 1, 2, timeout_ms=20)
+    with pytest.raises(Exception, match="did not arrive"):
+        eng.check_async()
+    eng.check_async()
