@@ -387,6 +387,7 @@ class BandedFlattenBlur:
         self.out = torch.empty((self.rows, w, 4), dtype=torch.uint8, device=first.device)
         self.fused = r <= 16  # small radii: the fused H+V kernel on the extended band (see gaussian_blur_banded)
         self.peer, self.k, self.timeout_ms = None, 0, int(timeout_ms)
+        self._side = self._ev = None
         if transport not in ("auto", "peer", "nccl"):
             raise ValueError("transport must be auto, peer or nccl")
         if transport != "nccl" and world > 1 and not self.fused and hasattr(eng, "flatten_prepared_peer"):
@@ -409,13 +410,10 @@ class BandedFlattenBlur:
             else:
                 self.parts = [(0, cut_a, "up"), (cut_b, self.rows, "down"), (cut_a, cut_b, None)]
             self.parts = [p for p in self.parts if p[1] > p[0]]
-            self.exchange_after = None
         elif self.rows > 2 * e and world > 1:
-            self.parts = [(0, e, None), (self.rows - e, self.rows, None), (e, self.rows - e, None)]
-            self.exchange_after = 2
+            self.parts = [(0, e, "up"), (self.rows - e, self.rows, "down"), (e, self.rows - e, None)]
         else:
             self.parts = [(0, self.rows, None)]
-            self.exchange_after = 1
 
         def sub(a, b):
             ls = [dict(L, rgba=L["rgba"][a:b], mask=(None if L.get("mask") is None else L["mask"][a:b])) if L.get("rgba") is not None else L
@@ -429,44 +427,73 @@ class BandedFlattenBlur:
             self.peer.close()
             self.peer = None
 
-    def _step_peer(self):
+    def _step_two_streams(self):
+        """Two streams so that the small launches never leave the GPU idling behind their last wave (a 60-row edge
+        flatten is 450 CTAs for 444 resident slots: alone on a stream it costs two waves):
+
+            side (high priority)  flatten edge rows -> neighbours | wait for the neighbours' rows | H pass of the halo rows
+            main                  flatten interior rows           | H pass of the band's rows     | V pass
+
+        The edge CTAs are scheduled first and the interior CTAs fill the slots they leave; main joins side twice
+        (band flattened; halo rows filtered).  Peer transport: the edge flatten's own stores carry the rows and the
+        wait is a flag wait.  NCCL transport: a batched isend/irecv after the edge flatten."""
         eng, plan, pr = self.eng, self.plan, self.peer
-        self.k += 1
-        p, value = self.k & 1, self.k
-        ext, core = pr.ext[p], pr.core[p]
+        if pr is not None:
+            self.k += 1
+            p, value = self.k & 1, self.k
+            ext, core = pr.ext[p], pr.core[p]
+        else:
+            ext, core = plan.ext, plan.core
+        main = torch.cuda.current_stream(ext.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=ext.device, priority=-1)
+            self._ev = [torch.cuda.Event() for _ in range(3)]
+        side, (ev_prev, ev_flat, ev_halo) = self._side, self._ev
+        ev_prev.record(main)  # the previous step's passes have read these rows and the H scratch
+        with torch.cuda.stream(side):
+            side.wait_event(ev_prev)
+            for (a, b, to), prep in zip(self.parts, self.prepared):
+                if to is None:
+                    continue
+                put = None if pr is None else pr.put_up if to == "up" else pr.put_down
+                if put is None:
+                    eng.flatten_prepared(prep, core[a:b])
+                else:
+                    eng.flatten_prepared_peer(prep, core[a:b], put[p][0], put[p][1], value)
+            ev_flat.record(side)
+            if pr is None:
+                plan.exchange_async()
         for (a, b, to), prep in zip(self.parts, self.prepared):
-            put = pr.put_up if to == "up" else pr.put_down if to == "down" else None
-            if put is None:
+            if to is None:
                 eng.flatten_prepared(prep, core[a:b])
+        main.wait_event(ev_flat)
+        with torch.cuda.stream(side):
+            if pr is None:
+                plan.wait()
             else:
-                eng.flatten_prepared_peer(prep, core[a:b], put[p][0], put[p][1], value)
-        eng.gaussian_band_h(ext, plan.top, plan.rows, self.sigma, exact=self.exact)  # the halo rows travel meanwhile
-        eng.peer_wait(*pr.wait_args(p), value, self.timeout_ms)
-        if plan.top:
-            eng.gaussian_band_h(ext, 0, plan.top, self.sigma, exact=self.exact)
-        if plan.bot:
-            eng.gaussian_band_h(ext, plan.top + plan.rows, plan.bot, self.sigma, exact=self.exact)
+                eng.peer_wait(*pr.wait_args(p), value, self.timeout_ms)
+            if plan.top:
+                eng.gaussian_band_h(ext, 0, plan.top, self.sigma, exact=self.exact)
+            if plan.bot:
+                eng.gaussian_band_h(ext, plan.top + plan.rows, plan.bot, self.sigma, exact=self.exact)
+            ev_halo.record(side)
+        eng.gaussian_band_h(ext, plan.top, plan.rows, self.sigma, exact=self.exact)
+        main.wait_event(ev_halo)
         return eng.gaussian_band_v(ext, plan.top, plan.rows, self.sigma, exact=self.exact, out=self.out)
 
     def step(self):
-        if self.peer is not None:
-            return self._step_peer()
         eng, plan = self.eng, self.plan
-        for k, ((a, b, _), prep) in enumerate(zip(self.parts, self.prepared)):
+        if plan.ext.is_cuda and not self.fused and len(self.parts) > 1:
+            return self._step_two_streams()
+        for (a, b, _), prep in zip(self.parts, self.prepared):
             eng.flatten_prepared(prep, plan.core[a:b])
-            if k + 1 == self.exchange_after:
-                plan.exchange_async()
-        if self.fused:
-            plan.wait()
-            res = eng.gaussian_blur(plan.ext, self.sigma, exact=self.exact)
+        plan.exchange_async()
+        plan.wait()
+        if self.fused or not hasattr(eng, "gaussian_band_h"):
+            res = _as_tensor(eng.gaussian_blur(plan.ext if plan.ext.is_cuda else plan.ext.numpy(), self.sigma, exact=self.exact))
             self.out.copy_(res[plan.top:plan.top + plan.rows])
             return self.out
-        eng.gaussian_band_h(plan.ext, plan.top, plan.rows, self.sigma, exact=self.exact)
-        plan.wait()
-        if plan.top:
-            eng.gaussian_band_h(plan.ext, 0, plan.top, self.sigma, exact=self.exact)
-        if plan.bot:
-            eng.gaussian_band_h(plan.ext, plan.top + plan.rows, plan.bot, self.sigma, exact=self.exact)
+        eng.gaussian_band_h(plan.ext, 0, plan.ext.shape[0], self.sigma, exact=self.exact)
         return eng.gaussian_band_v(plan.ext, plan.top, plan.rows, self.sigma, exact=self.exact, out=self.out)
 
 
