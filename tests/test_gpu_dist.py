@@ -126,7 +126,7 @@ def _peer_worker(rank, world, port, q):
 
         eng = Engine(0)
         w, h = 520, 700
-        bounds = pd.band_bounds(h, world)
+        bounds = pd.band_bounds(h, world, align=4)  # dense layers: bands need not sit on chunk rows (236 / 232 / 232)
         y0, y1 = bounds[rank]
         lrng = np.random.default_rng(5)
         limgs = [torch.from_numpy(lrng.integers(0, 256, (h, w, 4), dtype=np.uint8)).cuda() for _ in range(5)]
