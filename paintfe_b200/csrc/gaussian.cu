@@ -49,6 +49,7 @@ struct GaussParams {
     const uint32_t *bb;       // selection blur: device {min_x, min_y, max_x, max_y} of the mask, or null (see bb_skip)
     int dbg;                  // diagnosis only (PFE_GAUSS_DBG): 1 = H pass skips its staging loads, 2 = skips its stores
     int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
+    int vchunk;               // V tile kernel: N-row groups per ring chunk (launch_v)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
     // 1 and -0 for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
     // stage can see their values (see tap<true> below and blend.cuh).
@@ -338,7 +339,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-constexpr int kChunks = 8;
+constexpr int kChunks = 32;     // barrier pairs laid out; a tile uses ceil(groups / chunk_groups) of them
+constexpr int kDefaultChunks = 3;  // measured at sigma 20, 8K (12 warps, 27 groups per tile): 9 groups per chunk 0.572 ms, 4: 0.578, 2: 0.599, 14: 0.597
 
 // Blur outputs are non-negative (weights and inputs are >= 0): the clamp-free rounding applies directly.
 __device__ __forceinline__ uint32_t round_u8_nonneg(float x) { return pfe_round_u8_nonneg(x); }
@@ -348,10 +350,10 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int TH = WARPS * N;
     const int rows = TH + P.steps - N;  // a multiple of N
-    const int ring_rows = ((rows + kChunks - 1) / kChunks) * kChunks;  // region size the host laid out (>= rows)
+    const int ring_rows = rows;  // region size the host laid out
     // Chunks hold a whole number of N-row groups: a consumer's group then never straddles two chunks, so it waits once
     // per chunk, runs that chunk's groups in a tight loop and hands the chunk back - no per-group bookkeeping.
-    const int chunk_groups = (rows / N + kChunks - 1) / kChunks;
+    const int chunk_groups = P.vchunk;
     const int chunk_rows = chunk_groups * N;
     const int nchunks = (rows + chunk_rows - 1) / chunk_rows;  // <= kChunks
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);                       // ring_rows x 32 float4
@@ -432,20 +434,25 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         // mis-read its parity)
         int q = warp, g = 0;  // ring group about to be read; step offset of that group in this warp's filter
         const int q_end = warp + P.steps / N;
-        while (q < q_end) {
-            const int c = q / chunk_groups;
-            mbar_wait(full0 + 8u * (uint32_t)c, parity);
-            const int q_stop = min(q_end, (c + 1) * chunk_groups);
-            float4 pre_in = col[(size_t)g * 32];  // this chunk has landed: its first group's first row
-            for (; q < q_stop; q++, g += N) {
-                const float4 *cg = col + (size_t)g * 32;
+        int c = q / chunk_groups;
+        int q_stop = min(q_end, (c + 1) * chunk_groups);  // first group beyond chunk c
+        mbar_wait(full0 + 8u * (uint32_t)c, parity);
+        float4 pre_in = col[0];  // the first chunk has landed: its first group's first row
+        for (; q < q_end; q++, g += N) {
+            const bool chunk_ends = q + 1 == q_stop, more = q + 1 < q_end;
+            // The next chunk is waited for BEFORE this chunk's last group, so that group can read the next group's
+            // first row ahead like every other one: the FMA stream does not break at a chunk boundary.
+            if (chunk_ends && more) mbar_wait(full0 + 8u * (uint32_t)(c + 1), parity);
+            const float4 *cg = col + (size_t)g * 32;
 #define VT_LOAD(s) cg[(s) * 32]
-                // the next group's first row may be read ahead only while it lies in the chunk just waited for
-                PFE_GAUSS_GROUP_P(VT_LOAD, cg[N * 32], q + 1 < q_stop)
+            PFE_GAUSS_GROUP_P(VT_LOAD, cg[N * 32], more)
 #undef VT_LOAD
+            if (chunk_ends) {
+                __syncwarp();  // every lane has read the chunk's rows
+                if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)c);
+                c++;
+                q_stop = min(q_end, (c + 1) * chunk_groups);
             }
-            __syncwarp();  // every lane has read the chunk's rows
-            if (lane == 0) mbar_arrive(empty0 + 8u * (uint32_t)c);
         }
         const int x = x0 + lane, yw = y0 + row_first;
         if (x < rw) {
@@ -811,7 +818,7 @@ int v_tile_warps(const GaussParams &P) {
     const size_t extra = (size_t)((P.wp_len + 1) & ~1) * 8 + 16 * kChunks + 64;
     auto fits = [&](int warps) {
         const int rows = warps * N + P.steps - N;
-        return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra <= 225 * 1024;
+        return (size_t)rows * 512 + extra <= 225 * 1024;
     };
     const char *force = getenv("PFE_GAUSS_V_WARPS");
     const int want = force ? atoi(force) : 12;
@@ -821,14 +828,26 @@ int v_tile_warps(const GaussParams &P) {
 
 // V pass: tile variant when its shared-memory footprint fits, else the direct variant
 template <int N, bool EXACT, bool UW>
-int launch_v(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
-    const int wp_pad = (P.wp_len + 1) & ~1;
+int launch_v(pfe_ctx *ctx, const GaussParams &P0, const WeightTable &W) {
+    const int wp_pad = (P0.wp_len + 1) & ~1;
     const size_t extra = (size_t)wp_pad * 8 + 16 * kChunks + 64;
     auto tile_smem = [&](int warps) {
-        const int rows = warps * N + P.steps - N;
-        return (size_t)((rows + kChunks - 1) / kChunks) * kChunks * 512 + extra;
+        const int rows = warps * N + P0.steps - N;
+        return (size_t)rows * 512 + extra;
     };
-    const int vw = v_tile_warps<N>(P);
+    const int vw = v_tile_warps<N>(P0);
+    // Ring chunk size in N-row groups.  A chunk is refilled for the next tile once its last reader has released it, and
+    // the rows in the middle of the tile are read by every warp: the last of them at the very end of its tile, the first
+    // right at the start of the next.  Coarse chunks leave that refill little slack, fine chunks cost a wait, a warp
+    // barrier and an arrive each; measured, a tile in kDefaultChunks chunks is the best trade (PFE_GAUSS_VCHUNK overrides).
+    GaussParams P = P0;
+    {
+        const int groups = (std::max(vw, 1) * N + P.steps - N) / N;
+        const int forced = getenv("PFE_GAUSS_VCHUNK") ? atoi(getenv("PFE_GAUSS_VCHUNK")) : 0;
+        int cg = forced > 0 ? forced : (groups + kDefaultChunks - 1) / kDefaultChunks;
+        if ((groups + cg - 1) / cg > kChunks) cg = (groups + kChunks - 1) / kChunks;
+        P.vchunk = cg;
+    }
     bool done = false;
     if constexpr (UW && N >= 4) {
         if (vw == 12 && P.bb) {  // selection blur
