@@ -365,7 +365,11 @@ def run_b200(args):
 
         strong_ms = timed(strong_step, args.steps, warm=warmup)
         ok = parity_of(out_band)
-        eng.check_async()  # a flag wait that timed out would be reported here
+        async_error = None
+        try:
+            eng.check_async()  # a flag wait that timed out is reported here
+        except Exception as e:  # noqa: BLE001 - the line must still be printed, with the failure in it
+            async_error, ok = str(e), False
         nccl_ms = nccl_ok = None
         if pipe.transport == "peer":  # the same schedule with batched NCCL isend/irecv on a side stream, for comparison
             pipe_n = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="nccl")
@@ -386,7 +390,7 @@ def run_b200(args):
         how = ("the edge flatten stores its rows into the neighbours' halo over NVLink peer memory (pfe_dev_flatten_peer) and flags them"
                if pipe.transport == "peer" else "an NCCL halo exchange on a side stream")
         strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20, %d u8 halo rows per side: %s" % (world, radius, how),
-                  "transport": pipe.transport, "peer_unavailable": getattr(pipe, "peer_error", None),
+                  "transport": pipe.transport, "peer_unavailable": getattr(pipe, "peer_error", None), "async_error": async_error,
                   "ms_per_step": strong_ms, "mpx_s": px / strong_ms / 1e3, "band_rows": [b - a for a, b in bounds],
                   "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok,
                   "nccl_exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,

@@ -397,6 +397,10 @@ class BandedFlattenBlur:
                 self.peer_error = str(e)
                 if transport == "peer":
                     raise
+            except Exception as e:  # noqa: BLE001 - "auto" must end up with a working transport
+                if transport == "peer":
+                    raise
+                self.peer_error = "%s: %s" % (type(e).__name__, e)
         elif transport == "peer":
             raise PeerUnavailable("peer transport needs the GPU engine, more than one rank and a two-pass radius")
         self.transport = "peer" if self.peer is not None else "nccl"
