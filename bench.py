@@ -370,7 +370,17 @@ def run_b200(args):
             eng.check_async()  # a flag wait that timed out is reported here
         except Exception as e:  # noqa: BLE001 - the line must still be printed, with the failure in it
             async_error, ok = str(e), False
-        nccl_ms = nccl_ok = None
+        nccl_ms = nccl_ok = copy_ms = copy_ok = None
+        if pipe.transport == "peer":  # the rows by a device-to-device copy behind a plain flatten instead of the kernel's own stores
+            try:
+                pipe_c = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="peer", peer_put="copy")
+                copy_ms = timed(pipe_c.step, args.steps, warm=warmup)
+                copy_ok = parity_of(pipe_c.out)
+                eng.check_async()
+                pipe_c.close()
+                del pipe_c
+            except Exception as e:  # noqa: BLE001
+                copy_ok, async_error = False, async_error or str(e)
         if pipe.transport == "peer":  # the same schedule with batched NCCL isend/irecv on a side stream, for comparison
             pipe_n = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="nccl")
             nccl_ms = timed(pipe_n.step, args.steps, warm=warmup)
@@ -392,12 +402,12 @@ def run_b200(args):
         strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20, %d u8 halo rows per side: %s" % (world, radius, how),
                   "transport": pipe.transport, "peer_unavailable": getattr(pipe, "peer_error", None), "async_error": async_error,
                   "ms_per_step": strong_ms, "mpx_s": px / strong_ms / 1e3, "band_rows": [b - a for a, b in bounds],
-                  "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok,
+                  "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok, "ms_per_step_peer_copy": copy_ms, "parity_peer_copy": copy_ok,
                   "nccl_exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
                   "parity": ok, "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
                   "speedup_vs_one_gpu_step": ms_step / strong_ms,
                   "note": "edge rows flattened first, interior flatten and the band's own H pass while they travel; halo rows recompute the H pass; "
-                          "ms_per_step_nccl = same schedule over NCCL isend/irecv; nccl_exchange_ms = that exchange alone, back to back; "
+                          "ms_per_step_nccl = same schedule over NCCL isend/irecv; ms_per_step_peer_copy = peer memory filled by a device-to-device copy behind a plain flatten; nccl_exchange_ms = that exchange alone, back to back; "
                           "ms_per_step_no_exchange = same kernels, no transfer"}
         pipe.close()
         del whole, plan, out_band, band_layers, pipe, whole_band, strong_step

@@ -505,6 +505,9 @@ int pfe_dev_gaussian_band_v(pfe_ctx *ctx, uint32_t w, uint32_t ext_rows, uint32_
  *   pfe_dev_flatten_peer  pfe_dev_flatten that also writes every result at the same offset from peer_dst and
  *                    then, if peer_flag != NULL, stores flag_value to *peer_flag with release semantics at system
  *                    scope (whoever sees the flag sees the rows).  peer_dst / peer_flag need not be remote;
+ *   pfe_dev_peer_signal  the hand-over alone, for rows that were put into the neighbour's buffer by other means (a
+ *                    device-to-device copy to the mapped address): everything enqueued on the context's stream before
+ *                    it is visible to whoever sees the flag;
  *   pfe_dev_peer_wait  stream-ordered wait until every flags[0..n) (in THIS device's memory, n <= 32) has reached
  *                    value (wrap-around compare: flags are step counters that only grow).  If that takes longer than
  *                    timeout_ms the wait gives up and sets the sticky error pfe_ctx_check_async reports.
@@ -518,6 +521,7 @@ int pfe_peer_free(pfe_ctx *ctx, void *dptr);
 int pfe_dev_flatten_peer(pfe_ctx *ctx, const pfe_layer_desc *layers, uint32_t n_layers, uint32_t w, uint32_t h,
                          const uint8_t *active_chunks, uint8_t *dst, uint8_t *peer_dst, uint32_t *peer_flag,
                          uint32_t flag_value);
+int pfe_dev_peer_signal(pfe_ctx *ctx, uint32_t *peer_flag, uint32_t flag_value);
 int pfe_dev_peer_wait(pfe_ctx *ctx, const uint32_t *flags, uint32_t n, uint32_t value, uint32_t timeout_ms);
 /* Reach of a band's displacement field, for sizing the halo of pfe_dev_warp_band: minmax_dev[0..1] (DEVICE
  * memory, int32) = min / max over the band's rows [y0, y0+rows) of floor(clamp(y - dy, -1, h_total)), with

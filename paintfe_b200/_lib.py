@@ -169,6 +169,7 @@ SIGNATURES = {
     "pfe_peer_close": (C.c_int, [_ctx, _vp]),
     "pfe_peer_free": (C.c_int, [_ctx, _vp]),
     "pfe_dev_flatten_peer": (C.c_int, [_ctx, C.POINTER(LayerDesc), _u32, _u32, _u32, _vp, _vp, _vp, _vp, _u32]),
+    "pfe_dev_peer_signal": (C.c_int, [_ctx, _vp, _u32]),
     "pfe_dev_peer_wait": (C.c_int, [_ctx, _vp, _u32, _u32, _u32]),
     "pfe_dev_disp_reach": (C.c_int, [_ctx, _vp, _u32, _u32, _u32, _u32, _vp]),
     "pfe_liquify": (C.c_int, [_ctx, _vp, _u32, _u32, C.c_int, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),

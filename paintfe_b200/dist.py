@@ -18,6 +18,7 @@ GPU; the CPU tests pass a stand-in built on the oracle) and never computes pixel
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -375,7 +376,7 @@ class BandedFlattenBlur:
     "auto" takes "peer" when every rank can map its neighbours, else "nccl" (the decision is collective)."""
 
     def __init__(self, eng, layers, w: int, h_total: int, sigma: float, exact: bool = False, group=None, bounds=None,
-                 transport: str = "auto", timeout_ms: int = 2000):
+                 transport: str = "auto", timeout_ms: int = 2000, peer_put: Optional[str] = None):
         rank, world = _world(group)
         self.eng, self.sigma, self.exact = eng, float(sigma), bool(exact)
         self.bounds = bounds or band_bounds(h_total, world)
@@ -404,6 +405,12 @@ class BandedFlattenBlur:
         elif transport == "peer":
             raise PeerUnavailable("peer transport needs the GPU engine, more than one rank and a two-pass radius")
         self.transport = "peer" if self.peer is not None else "nccl"
+        # how the edge rows get into the neighbour's buffer: "store" = the flatten kernel's own second store
+        # (pfe_dev_flatten_peer), "copy" = a device-to-device copy behind a plain flatten (PFE_PEER_PUT overrides)
+        self.peer_put = peer_put or os.environ.get("PFE_PEER_PUT", "store")
+        if self.peer_put not in ("store", "copy"):
+            raise ValueError("peer_put must be store or copy")
+        self._put_views = {}
         e = min(r, self.rows)
         # row ranges of the band: [0, e) and [rows - e, rows) feed the neighbours; the interior is everything else
         if self.peer is not None:
@@ -427,6 +434,7 @@ class BandedFlattenBlur:
         self.prepared = [sub(a, b) for a, b, _ in self.parts]
 
     def close(self):
+        self._put_views = {}
         if self.peer is not None:
             self.peer.close()
             self.peer = None
@@ -462,8 +470,18 @@ class BandedFlattenBlur:
                 put = None if pr is None else pr.put_up if to == "up" else pr.put_down
                 if put is None:
                     eng.flatten_prepared(prep, core[a:b])
-                else:
+                elif self.peer_put == "store":
                     eng.flatten_prepared_peer(prep, core[a:b], put[p][0], put[p][1], value)
+                else:  # "copy": plain flatten, then a device-to-device copy into the neighbour's rows and the flag
+                    eng.flatten_prepared(prep, core[a:b])
+                    key = (to, p)
+                    if key not in self._put_views:
+                        rows_here = core[a:b]
+                        self._put_views[key] = (_device_view(put[p][0], rows_here.numel() * rows_here.element_size(), rows_here.device),
+                                                rows_here.reshape(-1).view(torch.uint8))
+                    far, near = self._put_views[key]
+                    far.copy_(near)
+                    eng.peer_signal(put[p][1], value)
             ev_flat.record(side)
             if pr is None:
                 plan.exchange_async()

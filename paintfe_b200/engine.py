@@ -268,6 +268,11 @@ class Engine:
                                                C.c_void_p(peer_flag) if peer_flag else None, flag_value & 0xFFFFFFFF))
         return out
 
+    def peer_signal(self, flag_addr: int, value: int):
+        """Release `value` at device address `flag_addr` (system scope) after everything enqueued on the stream so far."""
+        self.use_torch_stream()
+        self._ck(self.lib.pfe_dev_peer_signal(self.h, C.c_void_p(flag_addr), value & 0xFFFFFFFF))
+
     def peer_wait(self, flags_addr: int, n: int, value: int, timeout_ms: int = 2000):
         """Stream-ordered wait until the `n` u32 flags at device address `flags_addr` have all reached `value`."""
         self.use_torch_stream()

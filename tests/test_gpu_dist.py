@@ -145,6 +145,17 @@ def _peer_worker(rank, world, port, q):
         eng.check_async()
         res["flags"] = [int(v) for v in fb.peer.flags.cpu()]
         dist.barrier()
+        fc = pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 20.0, bounds=bounds,
+                                  transport="peer", timeout_ms=20000, peer_put="copy")
+        okc = True
+        for step in range(3):
+            for t in limgs:
+                t.add_(7)
+            want = eng.gaussian_blur(eng.flatten([make_layer(t, **m) for t, m in zip(limgs, lmeta)], w, h), 20.0)[y0:y1]
+            okc = okc and torch.equal(fc.step(), want)
+        res["copy_put_bit_equal"] = okc
+        eng.check_async()
+        fc.close()
         # a neighbour that never produces its rows: the wait gives up and says so instead of hanging the GPU
         if rank == 0:
             eng.peer_wait(fb.peer.wait_args(0)[0], 1, 1000, timeout_ms=50)
