@@ -13,10 +13,11 @@ resident in HBM.  Rank 0 prints ONE JSON line.  What the line carries:
                         buffers (H2D + D2H inside the timed region), plus `bare_copy_ms`: the same bytes copied
                         with nothing else running, so the record itself shows how much of e2e is the PCIe fabric.
   strong (N > 1)        ONE 8K canvas split into N row bands: flatten is band-local, the Gaussian needs ceil(3 sigma)
-                        rows of u8 input from each neighbour.  The flatten kernel of the band's edge rows stores them a
-                        second time, straight into the neighbour's halo rows over NVLink peer memory, and flags them
-                        (pfe_dev_flatten_peer; paintfe_b200.dist.PeerHalo); the interior flatten and the band's own H
-                        pass run while they travel.  The same schedule over NCCL isend/irecv is timed beside it.  Every
+                        rows of u8 input from each neighbour.  The band's edge rows are flattened first and go straight
+                        into the neighbour's halo rows over NVLink peer memory, followed by a flag (paintfe_b200.dist
+                        PeerHalo: a device-to-device copy, or the flatten kernel's own second store -
+                        pfe_dev_flatten_peer - both timed); the interior flatten and the band's own H pass run while
+                        they travel.  The same schedule over NCCL isend/irecv is timed beside it.  Every
                         rank checks its band against the single-GPU result of the whole canvas (parity) outside the
                         timed region.
   config4               BASELINE config 4: 16384^2 mesh warp 6x6 + liquify warp, one canvas in N row bands with a
@@ -371,9 +372,10 @@ def run_b200(args):
         except Exception as e:  # noqa: BLE001 - the line must still be printed, with the failure in it
             async_error, ok = str(e), False
         nccl_ms = nccl_ok = copy_ms = copy_ok = None
-        if pipe.transport == "peer":  # the rows by a device-to-device copy behind a plain flatten instead of the kernel's own stores
+        other_put = "store" if pipe.peer_put == "copy" else "copy"
+        if pipe.transport == "peer":  # the other way of getting the rows into the neighbour's buffer (dist.py: peer_put)
             try:
-                pipe_c = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="peer", peer_put="copy")
+                pipe_c = pd.BandedFlattenBlur(eng, band_layers, w, h, SIGMA, bounds=bounds, transport="peer", peer_put=other_put)
                 copy_ms = timed(pipe_c.step, args.steps, warm=warmup)
                 copy_ok = parity_of(pipe_c.out)
                 eng.check_async()
@@ -397,17 +399,18 @@ def run_b200(args):
 
         noex_ms = timed(no_exchange_step, args.steps, warm=2)
         halo = max_over_ranks(float(plan.halo_bytes))[0]
-        how = ("the edge flatten stores its rows into the neighbours' halo over NVLink peer memory (pfe_dev_flatten_peer) and flags them"
+        how = ("the edge rows go into the neighbours' halo rows over NVLink peer memory (%s) followed by a flag" %
+               ("device-to-device copy behind the edge flatten" if pipe.peer_put == "copy" else "the flatten kernel's own stores, pfe_dev_flatten_peer")
                if pipe.transport == "peer" else "an NCCL halo exchange on a side stream")
         strong = {"workload": "ONE 8K 16-layer canvas in %d row bands: flatten (band-local) + Gaussian sigma=20, %d u8 halo rows per side: %s" % (world, radius, how),
                   "transport": pipe.transport, "peer_unavailable": getattr(pipe, "peer_error", None), "async_error": async_error,
                   "ms_per_step": strong_ms, "mpx_s": px / strong_ms / 1e3, "band_rows": [b - a for a, b in bounds],
-                  "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok, "ms_per_step_peer_copy": copy_ms, "parity_peer_copy": copy_ok,
+                  "halo_bytes": int(halo), "ms_per_step_nccl": nccl_ms, "parity_nccl": nccl_ok, "peer_put": pipe.peer_put, "ms_per_step_peer_" + other_put: copy_ms, "parity_peer_" + other_put: copy_ok,
                   "nccl_exchange_ms": exch_ms, "ms_per_step_no_exchange": noex_ms,
                   "parity": ok, "parity_against": "single-GPU flatten + Gaussian of the whole canvas, bit for bit",
                   "speedup_vs_one_gpu_step": ms_step / strong_ms,
                   "note": "edge rows flattened first, interior flatten and the band's own H pass while they travel; halo rows recompute the H pass; "
-                          "ms_per_step_nccl = same schedule over NCCL isend/irecv; ms_per_step_peer_copy = peer memory filled by a device-to-device copy behind a plain flatten; nccl_exchange_ms = that exchange alone, back to back; "
+                          "ms_per_step_nccl = same schedule over NCCL isend/irecv; ms_per_step_peer_store / _copy = the other way of filling the neighbour's rows (the flatten kernel's own stores / a device-to-device copy); nccl_exchange_ms = that exchange alone, back to back; "
                           "ms_per_step_no_exchange = same kernels, no transfer"}
         pipe.close()
         del whole, plan, out_band, band_layers, pipe, whole_band, strong_step
