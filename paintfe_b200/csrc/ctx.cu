@@ -138,7 +138,7 @@ int pfe_ctx_create(int device, pfe_ctx **out) {
               cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) == cudaSuccess &&
               cudaMallocHost(&c->pinned, PFE_SMALL_BYTES) == cudaSuccess &&
               cudaMalloc(&c->dev_small, PFE_SMALL_BYTES) == cudaSuccess &&
-              cudaMalloc((void **)&c->async_err, 64) == cudaSuccess && cudaMemset(c->async_err, 0, 64) == cudaSuccess;
+              cudaMalloc((void **)&c->async_err, PFE_ASYNC_BLOCK_BYTES) == cudaSuccess && cudaMemset(c->async_err, 0, PFE_ASYNC_BLOCK_BYTES) == cudaSuccess;
     if (!ok) { pfe_ctx_destroy(c); return PFE_ERR_CUDA; }
     c->pinned_bytes = PFE_SMALL_BYTES;
     c->stream = c->own_stream;

@@ -50,6 +50,7 @@ struct GaussParams {
     int dbg;                  // diagnosis only (PFE_GAUSS_DBG): 1 = H pass skips its staging loads, 2 = skips its stores
     int tri;                  // steps == N + taps - 1: triangular first / last groups (see PFE_GAUSS_GROUP)
     int vchunk;               // V tile kernel: N-row groups per ring chunk (launch_v)
+    uint32_t *queue;          // persistent passes: {next task, finished grabbers} of this launch (pfe_queue_slot)
     int seg_rows, nseg, lag;  // fused kernel: rows per strip segment, segments per strip, V lag in batches
     // 1 and -0 for the EXACT path's packed arithmetic. They travel as parameters so that no compiler
     // stage can see their values (see tap<true> below and blend.cuh).
@@ -185,13 +186,16 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
     const uint64_t ntask = (uint64_t)nseg * P.rh;
     const int rw = (int)P.rw;
 
+    // Tasks come from a queue, not from a fixed stride: the warp scheduler favours the older warps of an SM
+    // sub-partition, so with equal shares they finished one after the other and the partition ran its last seventh on a
+    // single warp (r02 ncu: 4.6 of 7 warps resident on average, FMA pipe 80 % active).  Every warp now holds one task
+    // in hand (`next`) and takes another whenever it starts one, so all seven stay busy until the queue is empty.
     // The NEXT task's source pixels travel in registers while this one is filtered (PRE words per lane), so the global
     // load latency of the staging step hides under ~4000 cycles of FMAs instead of stalling the warp three dependent
     // round trips per task (measured at 8K sigma 20: 0.60 ms with the loads in line, 0.53 ms without any loads at all).
     // Tiles wider than 32 * PRE pixels (large sigma) keep the in-line staging.
     constexpr int PRE = 12;
     const bool use_pre = !BB && tile_px <= 32 * PRE && !(P.dbg & (1 | 4));  // dbg 4: in-line staging (A/B)
-    const uint64_t stride = (uint64_t)gridDim.x * WARPS;
     uint32_t pre[PRE];
     auto fetch = [&](uint64_t t) {
         const uint32_t fy = (uint32_t)(t / nseg);
@@ -203,12 +207,20 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
             pre[i] = p < tile_px ? __ldg(frow + min(max(fx0 + p, 0), rw - 1)) : 0u;
         }
     };
-    const uint64_t first = (uint64_t)blockIdx.x * WARPS + warp;
-    if (use_pre && first < ntask) fetch(first);
+    auto grab = [&]() -> uint64_t {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(P.queue, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    uint64_t task = grab();
+    if (use_pre && task < ntask) fetch(task);
 
-    for (uint64_t task = first; task < ntask; task += stride) {
-        const uint32_t y = (uint32_t)(task / nseg);
-        const int x0 = (int)(task % nseg) * SEG;
+    while (task < ntask) {
+        const uint64_t next = grab();
+        const uint64_t cur = task;
+        task = next;
+        const uint32_t y = (uint32_t)(cur / nseg);
+        const int x0 = (int)(cur % nseg) * SEG;
         const uint32_t *row = reinterpret_cast<const uint32_t *>(P.src) + (size_t)y * P.src_pitch;
         // selection blur: H values are read by the V pass of selected pixels in the same columns, up to radius rows away
         if (BB && bb_skip(P.bb, x0, x0 + SEG - 1, (int)y, (int)y, 0, P.radius)) continue;
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
                 const int p = lane + 32 * i;
                 if (p < tile_px) tile[skew(p, N)] = to_f4(pre[i]);
             }
-            if (task + stride < ntask) fetch(task + stride);
+            if (next < ntask) fetch(next);
         } else if (!(P.dbg & 1)) {
 #pragma unroll 4
             for (int p = lane; p < tile_px; p += 32) tile[skew(p, N)] = to_f4(__ldg(row + min(max(x0 - P.radius + p, 0), rw - 1)));
@@ -252,6 +264,12 @@ __global__ void __launch_bounds__(WARPS * 32) gauss_h_kernel(const __grid_consta
         for (int p = lane; p < SEG; p += 32)
             if (x0 + p < rw && !(P.dbg & 2)) out[x0 + p] = tile[skew(p, N)];
         __syncwarp();
+    }
+    // every warp makes exactly one grab past the end; the last one to have done so leaves the queue zeroed for the
+    // launch that gets this slot next
+    if (lane == 0 && atomicAdd(P.queue + 1, 1u) == gridDim.x * WARPS - 1) {
+        P.queue[0] = 0u;
+        P.queue[1] = 0u;
     }
 }
 
@@ -387,20 +405,42 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
     const int tx = (rw + 31) / 32, ty = ((int)P.v_rows + TH - 1) / TH;
     const int ntiles = tx * ty;
 
+    // Tiles come from a queue (P.queue), not from a fixed stride: with equal shares the CTAs - and the warps the
+    // scheduler favours inside them - ran out of work one after the other (r02 ncu: 20 of 26 warps resident on average).
+    // The producer warp takes the next tile and publishes its index in tile_id[lap parity] before it arms the tile's
+    // first chunk; a consumer reads it once the first chunk it waits for has landed.  Slot reuse is safe for the reason
+    // the ring is: the producer reaches tile L only after every chunk of tile L-2 was handed back, so every consumer has
+    // long read tile L-2's index.  When the queue is empty the producer sends a null tile (-1) through the same
+    // barriers, so that consumers parked on `full` wake up and leave.
+    volatile int *tile_id = reinterpret_cast<volatile int *>(bars + 2 * kChunks);
     if (warp == WARPS) {
         // ===== producer warp =====
-        uint32_t it = 0;  // tiles actually processed: both roles skip the same tiles, so their phase counters agree
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            // column-major tile order: consecutive CTAs walk down a strip, so halo rows are L2-hot
-            const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
-            if (BB && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
+        for (uint32_t it = 0;; it++) {
+            int t;
+            for (;;) {
+                uint32_t q = 0;
+                if (lane == 0) q = atomicAdd(P.queue, 1u);
+                q = __shfl_sync(0xffffffffu, q, 0);
+                t = q < (uint32_t)ntiles ? (int)q : -1;
+                if (!BB || t < 0) break;
+                // column-major tile order: consecutive tiles walk down a strip, so halo rows are L2-hot
+                const int bx0 = (t / ty) * 32, by0 = (int)P.v_y0 + (t % ty) * TH;
+                if (!bb_skip(P.bb, bx0, bx0 + 31, by0, by0 + TH - 1, 0, 0)) break;
+            }
+            const int x0 = (max(t, 0) / ty) * 32, y0 = (int)P.v_y0 + (max(t, 0) % ty) * TH;
             const uint32_t row_bytes = (uint32_t)min(32, rw - x0) * 16u;
             for (int c = 0; c < nchunks; c++) {
                 const int r0 = c * chunk_rows, nrows = min(chunk_rows, rows - r0);
                 if (it > 0) mbar_wait(empty0 + 8u * c, (it - 1) & 1u);  // its readers are done with the previous tile's chunk c
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
+                if (lane == 0) {
+                    if (c == 0) tile_id[it & 1u] = t;
+                    if (t >= 0)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8u * c), "r"(row_bytes * (uint32_t)nrows) : "memory");
+                    else
+                        mbar_arrive(full0 + 8u * c);
+                }
                 __syncwarp();
+                if (t < 0) continue;
                 for (int rr = r0 + lane; rr < r0 + nrows; rr += 32) {
                     const int sy = min(max(y0 - P.radius + rr, 0), rh - 1);
                     const float4 *src = reinterpret_cast<const float4 *>(P.mid) + (size_t)sy * rw + x0;
@@ -410,18 +450,24 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
                                  : "memory");
                 }
             }
-            it++;
+            if (t < 0) break;
+        }
+        // one grab past the end per CTA; the last CTA to make it leaves the queue zeroed for the slot's next launch
+        if (lane == 0 && atomicAdd(P.queue + 1, 1u) == gridDim.x - 1) {
+            P.queue[0] = 0u;
+            P.queue[1] = 0u;
         }
         return;
     }
 
     // ===== consumer warps =====
     const int row_first = warp * N;  // first ring row this warp reads
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (uint32_t it = 0;; it++) {
+        const uint32_t parity = it & 1u;
+        mbar_wait(full0 + 8u * (uint32_t)(warp / chunk_groups), parity);  // the first chunk this warp reads
+        const int t = tile_id[parity];
+        if (t < 0) break;
         const int x0 = (t / ty) * 32, y0 = (int)P.v_y0 + (t % ty) * TH;
-        if (BB && bb_skip(P.bb, x0, x0 + 31, y0, y0 + TH - 1, 0, 0)) continue;
-        const uint32_t parity = it++ & 1u;
         Acc4 acc[N];
         float R[N];
 #pragma unroll
@@ -436,8 +482,7 @@ __global__ void __launch_bounds__((WARPS + 1) * 32) gauss_v_tile_kernel(const __
         const int q_end = warp + P.steps / N;
         int c = q / chunk_groups;
         int q_stop = min(q_end, (c + 1) * chunk_groups);  // first group beyond chunk c
-        mbar_wait(full0 + 8u * (uint32_t)c, parity);
-        float4 pre_in = col[0];  // the first chunk has landed: its first group's first row
+        float4 pre_in = col[0];  // the first chunk has landed (waited for above): its first group's first row
         for (; q < q_end; q++, g += N) {
             const bool chunk_ends = q + 1 == q_stop, more = q + 1 < q_end;
             // The next chunk is waited for BEFORE this chunk's last group, so that group can read the next group's
@@ -765,7 +810,9 @@ static void fill_weight_table(WeightTable &W, const std::vector<float> &k) {
 }
 
 template <int N, bool EXACT, bool UW>
-int launch_h(pfe_ctx *ctx, const GaussParams &P, const WeightTable &W) {
+int launch_h(pfe_ctx *ctx, const GaussParams &P0, const WeightTable &W) {
+    GaussParams P = P0;
+    P.queue = pfe_queue_slot(ctx);
     const int wp_pad = UW ? 0 : (P.wp_len + 3) & ~3;  // float entries, keeps the tiles 16-byte aligned
     const int tile_len = skew(31 * N + P.steps, N) + 1;
     int warps = 4;
@@ -830,6 +877,7 @@ int v_tile_warps(const GaussParams &P) {
 template <int N, bool EXACT, bool UW>
 int launch_v(pfe_ctx *ctx, const GaussParams &P0, const WeightTable &W) {
     const int wp_pad = (P0.wp_len + 1) & ~1;
+    uint32_t *const queue = pfe_queue_slot(ctx);
     const size_t extra = (size_t)wp_pad * 8 + 16 * kChunks + 64;
     auto tile_smem = [&](int warps) {
         const int rows = warps * N + P0.steps - N;
@@ -847,6 +895,7 @@ int launch_v(pfe_ctx *ctx, const GaussParams &P0, const WeightTable &W) {
         int cg = forced > 0 ? forced : (groups + kDefaultChunks - 1) / kDefaultChunks;
         if ((groups + cg - 1) / cg > kChunks) cg = (groups + kChunks - 1) / kChunks;
         P.vchunk = cg;
+        P.queue = queue;
     }
     bool done = false;
     if constexpr (UW && N >= 4) {
