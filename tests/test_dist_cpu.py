@@ -37,6 +37,14 @@ class OracleEngine:
         return self.o.flatten([self.o.make_layer(**{k: (np.asarray(v) if k in ("rgba", "mask") and v is not None else v)
                                                     for k, v in L.items()}) for L in layers], w, h, active=active)
 
+    def prepare_layers(self, layers, w, h):
+        return (list(layers), int(w), int(h))
+
+    def flatten_prepared(self, prepared, out, active=None):
+        layers, w, h = prepared
+        out.copy_(torch.from_numpy(self.flatten(layers, w, h, active=active)))
+        return out
+
     def warp_band(self, src_rows, src_h, src_y0, w, h, y0, rows_out, disp_band=None, original=None, deformed=None,
                   cols=0, rows=0, out=None):
         src_rows = np.asarray(src_rows)
@@ -110,6 +118,19 @@ def _worker(rank, world, port, case, q):
             layers = [dict(rgba=torch.from_numpy(im[y0:y1].copy()), **m) for im, m in zip(imgs, meta)]
             out = torch.from_numpy(pd.flatten_banded(eng, layers, w, y1 - y0))
             exp = eng.o.flatten([eng.o.make_layer(im, **m) for im, m in zip(imgs, meta)], w, h)
+        elif case in ("flatten_blur", "flatten_blur_small"):  # BandedFlattenBlur on the CPU stand-in: NCCL-shaped plan over gloo, sequential step
+            sigma = 7.0 if case == "flatten_blur" else 2.0
+            imgs = [fx.random_rgba(rng, w, h) for _ in range(4)]
+            meta = [dict(blend=(5 * i) % 25, opacity=0.4 + 0.15 * i) for i in range(4)]
+            layers = [dict(rgba=torch.from_numpy(im[y0:y1].copy()), **m) for im, m in zip(imgs, meta)]
+            fb = pd.BandedFlattenBlur(eng, layers, w, h, sigma, exact=True, bounds=bounds)
+            assert fb.transport == "nccl" and fb.peer is None  # peer memory needs CUDA: "auto" settles on the collective plan
+            assert sum(b - a for a, b, _ in fb.parts) == y1 - y0
+            for _ in range(2):  # buffers are reused step after step
+                out = fb.step().clone()
+            exp = eng.gaussian_blur(eng.o.flatten([eng.o.make_layer(im, **m) for im, m in zip(imgs, meta)], w, h), sigma)
+            with pytest.raises(pd.PeerUnavailable):
+                pd.BandedFlattenBlur(eng, layers, w, h, sigma, exact=True, bounds=bounds, transport="peer")
         elif case == "adjust":  # per-pixel adjustment with an occupancy bitmap whose populated chunks cross the band edges
             cyn, cxn = (h + 63) // 64, (w + 63) // 64
             occ = (rng.random((cyn, cxn)) < 0.6).astype(np.uint8)
@@ -157,7 +178,7 @@ def _run(case, world):
         assert ok, f"{case}: rank {rank} band differs from the whole-image result"
 
 
-@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "effects", "flatten", "adjust", "warp", "mesh"])
+@pytest.mark.parametrize("case", ["gaussian", "box", "median", "sharpen", "effects", "flatten", "flatten_blur", "flatten_blur_small", "adjust", "warp", "mesh"])
 def test_band_split_equals_whole_world2(case):
     _run(case, 2)
 
