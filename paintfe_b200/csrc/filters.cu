@@ -399,6 +399,99 @@ int copy_through(pfe_ctx *ctx, const uint8_t *src, uint8_t *dst, uint32_t w, uin
     return PFE_OK;
 }
 
+// The same algorithm with 8-bit column counters (a column holds at most 2r+1 <= 65 pixels of a value): a column is
+// 16 coarse + 256 fine bytes = 68 words, half the shared memory of the 16-bit layout, so twice the CTAs fit an SM - the
+// kernel is bound by shared-memory latency, not by issue.  Window sums need 16 bits: a lane adds up to K = 255 / (2r+1)
+// columns byte-wise in a 32-bit word (no carry can cross a byte), then widens the four bytes into two 16-bit pairs.
+constexpr int kMedHist8Stride = 68;  // words; 17 x 16 bytes: eight consecutive lanes hit eight different bank groups
+__global__ void __launch_bounds__(128) median_hist8_kernel(const uint32_t *src, const uint8_t *mask, uint8_t *dst, int w, int h,
+                                                          int r, int seg_rows) {
+    extern __shared__ __align__(16) uint32_t hist_sm[];
+    const int nc = kMedHistTW + 2 * r;
+    const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    uint32_t *hist = hist_sm + (size_t)ch * nc * kMedHist8Stride;  // this warp's (= this channel's) column histograms
+    const int x0 = blockIdx.x * kMedHistTW;
+    const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+    const uint32_t shift = 8u * (uint32_t)ch;
+    const int side = 2 * r + 1, K = 255 / side;
+    const uint32_t target = (uint32_t)(side * side / 2);
+
+    for (int i = lane; i < nc * kMedHist8Stride; i += 32) hist[i] = 0u;
+    __syncwarp();
+    // +-1 on the byte of fine bin v and of coarse bin v >> 4: a byte being decremented is >= 1, so no borrow leaves it
+    auto bump = [&](uint32_t *col, uint32_t v, bool add) {
+        const uint32_t f = 1u << (8u * (v & 3u)), c = 1u << (8u * ((v >> 4) & 3u));
+        col[4 + (v >> 2)] += add ? f : 0u - f;
+        col[v >> 6] += add ? c : 0u - c;
+    };
+    auto row_pixels = [&](int yy, bool add) {
+        const uint32_t *row = src + (size_t)pfe_clampi(yy, 0, h - 1) * w;
+        for (int c = lane; c < nc; c += 32) {
+            const uint32_t v = (__ldg(row + pfe_clampi(x0 - r + c, 0, w - 1)) >> shift) & 255u;
+            bump(hist + (size_t)c * kMedHist8Stride, v, add);
+        }
+    };
+    for (int yy = ys - r; yy <= ys + r; yy++) row_pixels(yy, true);
+    __syncwarp();
+
+    const uint32_t *base = hist + (size_t)lane * kMedHist8Stride;
+    // 16 byte counters at `p` of each of the lane's 2r+1 columns -> s[2k] = bins 4k (low half) and 4k+2, s[2k+1] = bins 4k+1 and 4k+3
+    auto window16 = [&](const uint32_t *p, uint32_t (&s)[8]) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = 0u;
+        for (int j0 = 0; j0 < side; j0 += K) {
+            uint32_t a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+            const int j1 = min(j0 + K, side);
+#pragma unroll 4
+            for (int j = j0; j < j1; j++) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(p + (size_t)j * kMedHist8Stride);
+                a0 += q.x; a1 += q.y; a2 += q.z; a3 += q.w;
+            }
+            s[0] += a0 & 0x00FF00FFu; s[1] += (a0 >> 8) & 0x00FF00FFu;
+            s[2] += a1 & 0x00FF00FFu; s[3] += (a1 >> 8) & 0x00FF00FFu;
+            s[4] += a2 & 0x00FF00FFu; s[5] += (a2 >> 8) & 0x00FF00FFu;
+            s[6] += a3 & 0x00FF00FFu; s[7] += (a3 >> 8) & 0x00FF00FFu;
+        }
+    };
+    auto count = [](const uint32_t (&s)[8], int b) -> uint32_t {  // bin b of the 16
+        return (s[2 * (b >> 2) + (b & 1)] >> (16 * ((b >> 1) & 1))) & 0xFFFFu;
+    };
+    for (int y = ys; y < ye; y++) {
+        const int x = x0 + lane;
+        uint32_t s[8];
+        window16(base, s);  // coarse level
+        uint32_t cum = 0, bin = 0, below = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            const uint32_t cnt = count(s, b);
+            cum += cnt;
+            const bool le = cum <= target;  // bins wholly at or below the rank
+            bin += le ? 1u : 0u;
+            below += le ? cnt : 0u;
+        }
+        window16(base + 4 + bin * 4, s);  // fine level: the 16 counters of coarse bin `bin`
+        const uint32_t target2 = target - below;
+        uint32_t fcum = 0, fbin = 0;
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+            fcum += count(s, b);
+            fbin += fcum <= target2 ? 1u : 0u;
+        }
+        if (x < w) {
+            const size_t o = (size_t)y * w + x;
+            uint32_t v = bin * 16 + fbin;
+            if (mask && mask[o] == 0) v = (__ldg(src + o) >> shift) & 255u;
+            dst[o * 4 + ch] = (uint8_t)v;
+        }
+        __syncwarp();  // every lane has read this row's histograms
+        if (y + 1 < ye) {
+            row_pixels(y - r, false);
+            row_pixels(y + r + 1, true);
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int pfe_dev_box_blur(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint32_t h, float radius,
@@ -461,15 +554,20 @@ extern "C" int pfe_dev_median(pfe_ctx *ctx, const uint8_t *src, uint32_t w, uint
         if (r == 1) PFE_KERNEL(ctx, "median_small", median_small_kernel<1><<<tiles, 256, 0, ctx->stream>>>((const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h));
         else PFE_KERNEL(ctx, "median_small", median_small_kernel<2><<<tiles, 256, 0, ctx->stream>>>((const uint32_t *)src, mask, (uint32_t *)dst, (int)w, (int)h));
     } else if (r <= kMedHistMaxR && !bisect_only) {
-        const size_t smem = (size_t)4 * (kMedHistTW + 2 * r) * kMedHistStride * sizeof(uint32_t);
-        PFE_CUDA(ctx, cudaFuncSetAttribute(median_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool wide = force && strcmp(force, "hist16") == 0;  // the 16-bit counter layout (A/B)
+        const size_t smem = (size_t)4 * (kMedHistTW + 2 * r) * (wide ? kMedHistStride : kMedHist8Stride) * sizeof(uint32_t);
+        PFE_CUDA(ctx, cudaFuncSetAttribute(wide ? median_hist_kernel : median_hist8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // row segments: enough CTAs for every SM several times over, long enough that building the first window
         // (2r+1 rows) stays a small fraction of a segment
         const unsigned strips = pfe_div_up(w, kMedHistTW);
         unsigned seg = std::max<unsigned>(64u, 8u * (unsigned)(2 * r + 1));
         while (seg > 64u && (uint64_t)strips * pfe_div_up(h, seg) < (uint64_t)ctx->sm_count * 8) seg /= 2;
-        PFE_KERNEL(ctx, "median_hist", median_hist_kernel<<<dim3(strips, pfe_div_up(h, seg)), 128, smem, ctx->stream>>>(
-            (const uint32_t *)src, mask, dst, (int)w, (int)h, r, (int)seg));
+        if (wide)
+            PFE_KERNEL(ctx, "median_hist", median_hist_kernel<<<dim3(strips, pfe_div_up(h, seg)), 128, smem, ctx->stream>>>(
+                (const uint32_t *)src, mask, dst, (int)w, (int)h, r, (int)seg));
+        else
+            PFE_KERNEL(ctx, "median_hist", median_hist8_kernel<<<dim3(strips, pfe_div_up(h, seg)), 128, smem, ctx->stream>>>(
+                (const uint32_t *)src, mask, dst, (int)w, (int)h, r, (int)seg));
     } else if (r <= 127 && (size_t)(MED_BX + 2 * r) * (MED_BY + 2 * r) * 4 <= 160 * 1024) {
         const size_t smem = (size_t)(MED_BX + 2 * r) * (MED_BY + 2 * r) * 4;
         if (smem > 48 * 1024) PFE_CUDA(ctx, cudaFuncSetAttribute(median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

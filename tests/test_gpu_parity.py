@@ -365,7 +365,7 @@ def test_box_motion_median_vignette_sharpen_random(eng, oracle, w, h):
 def test_median_large_radius(eng, oracle):
     rng = np.random.default_rng(9)
     img = fx.random_rgba(rng, 90, 70)
-    for r in (12, 32, 33, 40):  # 32 = last radius of the column-histogram kernel, 33 = first of the bisection kernel
+    for r in (12, 21, 32, 33, 40):  # 32 = last radius of the column-histogram kernel (65 pixels per column), 33 = first of the bisection kernel
         exact(eng.median(img, r), oracle.median(img, r), f"median r={r}")
 
 
@@ -385,11 +385,12 @@ def test_median_kernels_agree(eng, oracle):
     for r in (1, 2, 3, 4, 5, 9, 16):
         exp = oracle.median(img, r)
         exact(eng.median(img, r), exp, f"median r={r}")
-        os.environ["PFE_MEDIAN_KERNEL"] = "bisect"
-        try:
-            exact(eng.median(img, r), exp, f"median r={r} (bisection kernel)")
-        finally:
-            del os.environ["PFE_MEDIAN_KERNEL"]
+        for forced in ("bisect", "hist16"):  # hist16: the column-histogram kernel with 16-bit counters (8-bit is the default)
+            os.environ["PFE_MEDIAN_KERNEL"] = forced
+            try:
+                exact(eng.median(img, r), exp, f"median r={r} ({forced} kernel)")
+            finally:
+                del os.environ["PFE_MEDIAN_KERNEL"]
     for r in (1, 3, 6):
         exact(eng.median(img, r, mask=mask), oracle.median(img, r, mask=mask), f"median mask r={r}")
 

@@ -129,6 +129,9 @@ def main():
     run("median r2", lambda: eng.median(img, 2, out=out), 8 * px)
     run("median r7", lambda: eng.median(img, 7, out=out), 8 * px)
     run("median r20", lambda: eng.median(img, 20, out=out), 8 * px)
+    for rr in (7, 20):
+        run(f"median r{rr} [16-bit column counters]", lambda: eng.median(img, rr, out=out), 8 * px, env={"PFE_MEDIAN_KERNEL": "hist16"})
+    run("median r32", lambda: eng.median(img, 32, out=out), 8 * px)
     run("vignette", lambda: eng.vignette(img, 0.8, 0.5, out=out), 8 * px)
 
     # ---- per-pixel adjustments ---------------------------------------------------------------------------

@@ -1,13 +1,15 @@
 #!/bin/bash
-# Round 2, GPU call M (1 GPU): flatten after the mode changes: parity, timing, ncu source-level capture.
+# Round 2, GPU call M (1 GPU): median with 8-bit column counters: parity, timing against the 16-bit layout
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "blend or flatten or stack or tile or golden or headline or 8k" > gpurun_out/m_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/m_pytest.log
-timeout 300 python tools/bench_ops.py --only "flatten" > gpurun_out/m_flatten.jsonl 2> gpurun_out/m.err
-timeout 600 ncu --set full --clock-control none --import-source on --nvtx --nvtx-include "measure/" -o gpurun_out/m_flatten \
-    python tools/bench_ops.py --once --only "flatten 16L modes 0-15$" > gpurun_out/m_ncu.out 2>&1
-tail -4 gpurun_out/m_pytest.log; python - <<'PY'
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -k "median" > gpurun_out/m_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc" >> gpurun_out/m_pytest.log
+tail -5 gpurun_out/m_pytest.log
+timeout 600 python tools/bench_ops.py --only "median" > gpurun_out/m_ops.jsonl 2> gpurun_out/m.err
+tail -3 gpurun_out/m.err
+python - <<PY
 import json
-for l in open('gpurun_out/m_flatten.jsonl'):
-    d = json.loads(l); print(f"{d['op']:45s} {d['ms']:.4f}")
+for l in open('gpurun_out/m_ops.jsonl'):
+    try: d=json.loads(l)
+    except Exception: continue
+    if 'ms' in d: print('  ', d['op'], round(d['ms'],4))
 PY
