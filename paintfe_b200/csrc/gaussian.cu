@@ -152,10 +152,10 @@ __device__ __forceinline__ float4 to_f4(uint32_t v) {
 // A warp owns one row segment of 32*N pixels. The u8 pixels are converted to f32 once while being
 // staged into a skewed shared-memory tile (one pad float4 every N, so lane stride N+1 keeps
 // LDS.128 conflict free); results return through the same tile for fully coalesced stores.
-// EXPERIMENT (branch next/gauss-uniform-weights): the padded weight table as a kernel parameter.  With UW = true the
-// per-step weight is an `LDCU.64` into a uniform register pair and every tap becomes `FFMA2 acc, in.reuse, UR, acc`:
-// one fresh 64-bit register operand per instruction instead of two, no weight LDS, N fewer live register pairs.
-// Same table, same arithmetic, same results.  Not yet timed on a GPU.
+// UW: the padded weight table travels in the kernel parameters.  The per-step weight is then an `LDCU` into a uniform
+// register and every tap `FFMA2 acc, in, UR.F32, acc` (one scalar weight broadcast to both lanes - the operand form that
+// issues at the pipe's own rate, tools/ubench_ffma2.cu): no weight LDS, no per-thread weight registers.  Same table, same
+// arithmetic, same results; measured 1.47 -> 1.25 ms at sigma 20, 8K (profiles/r02_gauss_steps.txt).
 constexpr int kWeightTableLen = 800;  // floats: 3.2 KB of the 4 KB parameter space; wp_len <= 800 covers sigma <= ~128
 struct WeightTable {
     float wk[kWeightTableLen];
