@@ -1,10 +1,15 @@
 #!/bin/bash
-# Round 2, GPU call F (1 GPU): new median / HSL / vignette / motion / brush kernels: parity suite, op timings;
-# Gaussian inner-loop micro-benchmark (per-step LDS / LDCU variants).
+# Round 2, GPU call F (1 GPU): flatten with a per-warp loop bound and lane*4 kept in a register: parity, timing
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/f_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/f_pytest.log
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/ubench_ffma2 tools/ubench_ffma2.cu && timeout 120 /tmp/ubench_ffma2 > gpurun_out/f_ubench_ffma2.jsonl 2>&1
-timeout 600 python tools/bench_ops.py --only "median|adjust|vignette|motion|brush|box" > gpurun_out/f_ops.jsonl 2> gpurun_out/f_ops.err
-PFE_MEDIAN_KERNEL=bisect timeout 300 python tools/bench_ops.py --only "median r2|median r7" > gpurun_out/f_ops_bisect.jsonl 2>> gpurun_out/f_ops.err
-tail -5 gpurun_out/f_pytest.log; grep -E "V[5-8]" gpurun_out/f_ubench_ffma2.jsonl; cut -c1-110 gpurun_out/f_ops.jsonl gpurun_out/f_ops_bisect.jsonl
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py -x -q -k "flatten or blend or stack or tile or peer or smoke" > gpurun_out/f_pytest.log 2>&1; rc=$?; echo "pytest rc=$rc" >> gpurun_out/f_pytest.log
+tail -4 gpurun_out/f_pytest.log
+timeout 600 python tools/bench_ops.py --only "flatten" > gpurun_out/f_ops.jsonl 2> gpurun_out/f.err
+tail -3 gpurun_out/f.err
+python - <<PY
+import json
+for l in open('gpurun_out/f_ops.jsonl'):
+    try: d=json.loads(l)
+    except Exception: continue
+    if 'ms' in d: print('  ', d['op'], round(d['ms'],4))
+PY
