@@ -1268,3 +1268,24 @@ def test_flatten_peer_stores_twice_and_flags(eng):
     with pytest.raises(Exception, match="did not arrive"):
         eng.check_async()
     eng.check_async()
+
+
+def test_flatten_plain_instantiation_matches_general(eng, oracle):
+    """A stack of raster layers without masks takes the PLAIN instantiation of the flatten kernel (kind and mask tests
+    compiled out); PFE_FLATTEN_NO_PLAIN forces the general one. Both must equal the oracle."""
+    import os
+
+    rng = np.random.default_rng(77)
+    w, h = 332, 75
+    imgs = [fx.random_rgba(rng, w, h) for _ in range(25)]
+    imgs[3][:, : w // 2] = 0  # a half-transparent layer: the warp-level skip fires
+    layers = [dict(rgba=im, blend=i, opacity=[1.0, 0.6, 0.25][i % 3]) for i, im in enumerate(imgs)]
+    exp = oracle.flatten([oracle.make_layer(**L) for L in layers], w, h)
+    from paintfe_b200.engine import make_layer
+    got = eng.flatten([make_layer(**L) for L in layers], w, h)
+    exact(got, exp, "flatten PLAIN")
+    os.environ["PFE_FLATTEN_NO_PLAIN"] = "1"
+    try:
+        exact(eng.flatten([make_layer(**L) for L in layers], w, h), exp, "flatten general")
+    finally:
+        del os.environ["PFE_FLATTEN_NO_PLAIN"]
