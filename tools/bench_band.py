@@ -52,7 +52,29 @@ def main():
             eng.gaussian_band_v(ext, top, rows, SIGMA, out=out)
 
         c = timed(chain)
-        rec = {"world": world, "band_rows": rows, "ext_rows": ext.shape[0], "flatten_ms": f, "h_ms": h, "v_ms": v, "sum_ms": f + h + v, "chained_ms": c}
+        # the same work as two half-bands on two streams (each flatten -> H), joined before the V pass: the halves fill
+        # each other's partial waves and one half's H pass runs under the other's flatten
+        h1 = (rows // 2) // 4 * 4
+        prep_a = eng.prepare_layers([make_layer(t[:h1], **m) for t, m in zip(layers, meta)], W, h1)
+        prep_b = eng.prepare_layers([make_layer(t[h1:rows], **m) for t, m in zip(layers, meta)], W, rows - h1)
+        side = torch.cuda.Stream(device=dev, priority=-1)
+        ev0, ev1 = torch.cuda.Event(), torch.cuda.Event()
+
+        def split2():
+            main = torch.cuda.current_stream(dev)
+            ev0.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev0)
+                eng.flatten_prepared(prep_a, ext[top:top + h1])
+                eng.gaussian_band_h(ext, 0, top + h1, SIGMA)
+                ev1.record(side)
+            eng.flatten_prepared(prep_b, ext[top + h1:top + rows])
+            eng.gaussian_band_h(ext, top + h1, ext.shape[0] - top - h1, SIGMA)
+            main.wait_event(ev1)
+            eng.gaussian_band_v(ext, top, rows, SIGMA, out=out)
+
+        c2 = timed(split2)
+        rec = {"world": world, "band_rows": rows, "ext_rows": ext.shape[0], "flatten_ms": f, "h_ms": h, "v_ms": v, "sum_ms": f + h + v, "chained_ms": c, "split2_ms": c2}
         if full is None:
             full = rec
         else:
