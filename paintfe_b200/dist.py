@@ -407,8 +407,8 @@ class BandedFlattenBlur:
         self.transport = "peer" if self.peer is not None else "nccl"
         # how the edge rows get into the neighbour's buffer: "copy" = a device-to-device copy to the mapped address behind
         # a plain flatten (a copy engine moves them while the SMs flatten the interior), "store" = the flatten kernel's
-        # own second store (pfe_dev_flatten_peer).  Measured on 8 B200s, 8K canvas: copy 0.402 ms, store 0.409 ms, NCCL
-        # 0.436 ms per step (profiles/r02_bench_n8.json).  PFE_PEER_PUT overrides the default.
+        # own second store (pfe_dev_flatten_peer).  Measured on 8 B200s, 8K canvas: copy 0.398 ms, store 0.404 ms, NCCL
+        # 0.460 ms per step (profiles/r02_bench_n8.json).  PFE_PEER_PUT overrides the default.
         self.peer_put = peer_put or os.environ.get("PFE_PEER_PUT", "copy")
         if self.peer_put not in ("store", "copy"):
             raise ValueError("peer_put must be store or copy")
