@@ -949,8 +949,13 @@ int run_v(pfe_ctx *ctx, GaussParams P, const std::vector<float> &k) {
 // overhead (input load, weight fetch, ring bookkeeping: worth about 6 FFMA2 slots per step with the weights in
 // uniform registers, half that relative to the doubled arithmetic of the EXACT path).  Measured at sigma 20 on
 // 8K (profiles/r02_ops_a.jsonl): N = 8 for both passes (128 steps for 121 taps; N = 16 pads to 144).
-static int pick_n(int taps, double per_step_overhead, const char *pass_knob) {
-    auto cost = [&](int n) { int steps = ((n + taps - 1 + n - 1) / n) * n; return (double)steps * (4.0 * n + per_step_overhead) / n; };
+// n16_penalty: the N = 16 V tile kernel runs one 9-warp CTA per SM at 128 registers; measured on 8K (fast path) N = 8 is
+// 6 % faster at sigma 35 (211 taps) and equal at sigma 50 where this model gave N = 16 a 1-5 % edge.
+static int pick_n(int taps, double per_step_overhead, const char *pass_knob, double n16_penalty = 1.0) {
+    auto cost = [&](int n) {
+        int steps = ((n + taps - 1 + n - 1) / n) * n;
+        return (double)steps * (4.0 * n + per_step_overhead) / n * (n == 16 ? n16_penalty : 1.0);
+    };
     int best = 1;
     if (taps >= 3) {
         best = 4;
@@ -979,7 +984,7 @@ int dispatch_h(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) 
 template <bool EXACT>
 int dispatch_v(pfe_ctx *ctx, const GaussParams &P, const std::vector<float> &k) {
     const int taps = (int)k.size();
-    switch (pick_n(taps, EXACT ? 3.0 : 6.0, "PFE_GAUSS_NV")) {
+    switch (pick_n(taps, EXACT ? 3.0 : 6.0, "PFE_GAUSS_NV", EXACT ? 1.0 : 1.07)) {
         case 16: return run_v<16, EXACT>(ctx, P, k);
         case 8: return run_v<8, EXACT>(ctx, P, k);
         case 4: return run_v<4, EXACT>(ctx, P, k);
