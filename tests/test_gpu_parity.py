@@ -989,7 +989,7 @@ def test_gaussian_ring_pipeline_full_8k(eng, monkeypatch):
 
     g = torch.Generator(device="cuda").manual_seed(1)
     img = torch.randint(0, 256, (4320, 7680, 4), dtype=torch.uint8, device="cuda", generator=g)
-    for sigma in (20.0, 5.0, 50.0):
+    for sigma in (20.0, 5.0, 35.0, 50.0):
         monkeypatch.setenv("PFE_GAUSS_V_DIRECT", "1")
         ref = eng.gaussian_blur(img, sigma).clone()
         monkeypatch.delenv("PFE_GAUSS_V_DIRECT")
