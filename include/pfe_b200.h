@@ -495,7 +495,9 @@ int pfe_dev_gaussian_band_h(pfe_ctx *ctx, const uint8_t *ext, uint32_t w, uint32
                             uint32_t rows, float sigma, uint32_t flags);
 int pfe_dev_gaussian_band_v(pfe_ctx *ctx, uint32_t w, uint32_t ext_rows, uint32_t y0, uint32_t rows, float sigma,
                             uint8_t *dst_rows, uint32_t flags);
-/* Halo rows over peer memory (one process per GPU on one NVSwitch node).  Instead of flattening a
+/* Halo rows over peer memory (one process per GPU on one NVSwitch node).  No counterpart in the reference,
+ * which is single-device (src/gpu/context.rs:123 refuses large sizes, src/cli.rs:159 is a serial loop): these entry
+ * points exist so that ONE canvas can be split across GPUs below the ABI.  Instead of flattening a
  * band's edge rows and then sending them, the flatten kernel itself stores them a second time, straight into the
  * neighbour GPU's extended band, and the last CTA to finish releases a flag in the neighbour's memory: the transfer
  * is the kernel's own NVLink stores, tile by tile, and there is no send/receive at all.
