@@ -105,6 +105,50 @@ br = pfo.make_brush(12.0, 0.8, True, (1, 0, 0, 1))
 pfo.brush_line(a, br, 10.0, 10.0, 150.0, 120.0)
 eng.brush_stamps(b, eng.brush_desc(12.0, 0.8, True, (1, 0, 0, 1)), eng.brush_line_centres(w, h, 10.0, 10.0, 150.0, 120.0))
 check("brush", b, a)
+# ---- round 2 kernels --------------------------------------------------------------------------------------------
+import torch
+
+for r in (5, 20):  # column histograms with 8-bit counters
+    check(f"median hist r={r}", eng.median(img, r), pfo.median(img, r))
+os.environ["PFE_MEDIAN_KERNEL"] = "hist16"
+check("median hist16 r=5", eng.median(img, 5), pfo.median(img, 5))
+del os.environ["PFE_MEDIAN_KERNEL"]
+dimg = torch.from_numpy(img).cuda()
+# band-form Gaussian (work queues in both passes): rows [40, 110) of the image from an extended band with 60-row halos
+for exact in (True, False):
+    want = pfo.gaussian_blur(img, 20.0)
+    ext = dimg[0:150].contiguous()  # the whole image as "extended band": top halo 40 rows, band 70 rows, bottom halo 40 rows
+    eng.gaussian_band_h(ext, 40, 70, 20.0, exact=exact)
+    eng.gaussian_band_h(ext, 0, 40, 20.0, exact=exact)
+    eng.gaussian_band_h(ext, 110, 40, 20.0, exact=exact)
+    got = eng.gaussian_band_v(ext, 40, 70, 20.0, exact=exact)
+    check(f"gaussian band exact={exact}", got.cpu().numpy(), want[40:110], 0 if exact else 1)
+check("gaussian masked s=20", eng.gaussian_blur(img, 20.0, mask=mask, exact=True), pfo.gaussian_blur(img, 20.0, mask=mask))
+# the flatten that also stores into a (here local) peer buffer and releases a flag, then the flag wait
+dl = [make_layer(torch.from_numpy(im).cuda(), **m) for im, m in zip(layers, meta)]
+prep = eng.prepare_layers(dl, w, h)
+near = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+far = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+flags = torch.zeros(4, dtype=torch.int32, device="cuda")
+eng.flatten_prepared_peer(prep, near, far.data_ptr(), flags.data_ptr() + 8, 3)
+eng.peer_wait(flags.data_ptr() + 8, 1, 3, timeout_ms=5000)
+want = pfo.flatten([pfo.make_layer(im, **m) for im, m in zip(layers, meta)], w, h)
+check("flatten_peer near", near.cpu().numpy(), want)
+check("flatten_peer far", far.cpu().numpy(), want)
+eng.peer_signal(flags.data_ptr(), 9)
+eng.peer_wait(flags.data_ptr(), 1, 9, timeout_ms=5000)
+eng.check_async()
+check("peer flags", flags.cpu().numpy(), np.array([9, 0, 3, 0], np.int32))
+# region warp and a long binned stroke
+rect = (20, 30, 150, 120)
+check("warp region", eng.warp_displacement_region(img, disp, img, rect), pfo.warp_displacement_region(img, disp, img, rect))
+a, b = img.copy(), img.copy()
+pts = [(float(10 + (i * 7) % 180), float(10 + (i * 13) % 130)) for i in range(600)]
+brd = pfo.make_brush(9.0, 0.7, True, (0, 1, 0, 1))
+for x, y in pts:
+    pfo.brush_stamp(a, brd, x, y)
+eng.brush_stamps(b, eng.brush_desc(9.0, 0.7, True, (0, 1, 0, 1)), np.array(pts, np.float32))
+check("brush 600 stamps", b, a)
 eng.close()
 print("SANITIZE_SMOKE", "OK" if ok else "MISMATCH")
 sys.exit(0 if ok else 1)
