@@ -315,8 +315,12 @@ class PeerHalo:
         elif err is None:
             err = "a neighbour could not allocate"
         errs = self._gather(err)
-        if any(errs):
+        if any(errs):  # every rank takes this path together: unmap, wait for the others to have unmapped, free
             self._release()
+            dist.barrier(group=self.group)
+            if self.addr is not None:
+                eng.peer_free(self.addr)
+                self.addr = None
             raise PeerUnavailable("; ".join(sorted({e for e in errs if e})))
         dev = plan.ext.device
         self.ext = [_device_view(self.addr + self.HEADER + p * self.stride, ext_bytes, dev).view(plan.ext.dtype).view(shape) for p in (0, 1)]
