@@ -156,6 +156,18 @@ def _peer_worker(rank, world, port, q):
         res["store_put_bit_equal"] = okc and fb.peer_put == "copy"
         eng.check_async()
         fc.close()
+        # one rank cannot map its neighbour: every rank learns of it, releases what it had and reports PeerUnavailable
+        real_open = eng.peer_open
+        if rank == 1:
+            def broken(handle):
+                raise RuntimeError("boom: no mapping on this rank")
+            eng.peer_open = broken
+        try:
+            pd.BandedFlattenBlur(eng, [make_layer(t[y0:y1], **m) for t, m in zip(limgs, lmeta)], w, h, 20.0, bounds=bounds, transport="peer")
+            res["setup_failure_is_collective"] = False
+        except pd.PeerUnavailable as e:
+            res["setup_failure_is_collective"] = "boom" in str(e)
+        eng.peer_open = real_open
         # a neighbour that never produces its rows: the wait gives up and says so instead of hanging the GPU
         if rank == 0:
             eng.peer_wait(fb.peer.wait_args(0)[0], 1, 1000, timeout_ms=50)
