@@ -22,6 +22,9 @@ resident in HBM.  Rank 0 prints ONE JSON line.  What the line carries:
                         timed region.
   config4               BASELINE config 4: 16384^2 mesh warp 6x6 + liquify warp, one canvas in N row bands with a
                         halo exchange sized by the warp's reach, parity-checked the same way.
+  config5               BASELINE config 5 (the CLI batch): 64 4K images per rank through blur + HSL + vignette from pinned
+                        host buffers and back, on the three-stream pipeline of paintfe_b200/pipeline.py, beside the bare
+                        copy of the same bytes.
   kernels / roofline    per-kernel CUDA-event times from inside the timed region; `extra` times the EXACT-mode
                         Gaussian (what INTEGRATION.md's drop-in wrapper binds) and the other two config-2 stacks.
 
@@ -421,6 +424,12 @@ def run_b200(args):
         del layers, dl, dl2, flat, out
         torch.cuda.empty_cache()
         config4 = run_config4(eng, pd, dev, rank, world, timed, max(3, args.steps // 4))
+    config5 = None
+    if not args.no_config5:
+        try:
+            config5 = run_config5(eng, dev, world)
+        except Exception as e:  # noqa: BLE001 - an extra leg must not cost the headline line
+            config5 = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -493,7 +502,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline, "roofline_whole_step": whole_step, "roofline_compute": compute, "kernels": per_kernel,
             "kernel_spans_share_of_step": span_share, "extra": extra,
-            "strong": strong, "config4": config4,
+            "strong": strong, "config4": config4, "config5": config5,
             "cpu_baseline": cpu,
         }
         if _real_stdout is not None:
@@ -504,6 +513,70 @@ def run_b200(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_config5(eng, dev, world, images=64):
+    """BASELINE config 5 (the CLI batch): 4K images through `apply_blur(4); apply_hsl(10,15,0); apply_vignette(.5,.3)` from
+    PINNED HOST buffers and back, through the three-stream pipeline the CLI uses (paintfe_b200/pipeline.py): every rank
+    runs `images` of them (independent images, no collective).  Codec excluded.  Reported beside the same uploads and
+    downloads with no compute at all."""
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    from paintfe_b200.pipeline import ImagePipeline
+    from paintfe_b200.script import execute_script_sync
+
+    script = "apply_blur(4.0); apply_hsl(10.0, 15.0, 0.0); apply_vignette(0.5, 0.3);"
+    w, h = 3840, 2160
+    pool = [torch.randint(0, 256, (h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(4)]  # distinct inputs, reused in turn
+    pipe = ImagePipeline(eng, depth=3)
+    touched = [0]
+
+    def work(d):
+        return execute_script_sync(eng, script, d)
+
+    def run_e2e():
+        for k in range(images):
+            if pipe.full():
+                touched[0] += int(pipe.collect()[1][0, 0, 0])  # the result is on the host
+            pipe.submit(pool[k % len(pool)], work, tag=k)
+        for _, out in pipe.drain():
+            touched[0] += int(out[0, 0, 0])
+
+    dev_a, dev_b = torch.empty((h, w, 4), dtype=torch.uint8, device=dev), torch.empty((h, w, 4), dtype=torch.uint8, device=dev)
+    host_out = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def bare():
+        for k in range(images):
+            with torch.cuda.stream(s_up):
+                dev_a.copy_(pool[k % len(pool)], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                host_out.copy_(dev_b, non_blocking=True)
+
+    def wall(fn):
+        fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt[0])
+
+    ms, ms_bare = wall(run_e2e), wall(bare)
+    n = images * world
+    return {"workload": "%d x 4K images per rank from pinned host buffers, script: %s" % (images, script), "n_gpus": world,
+            "ms_total": ms, "images_s": n / ms * 1e3, "mpx_s": n * w * h / ms / 1e3,
+            "h2d_bytes_per_image": w * h * 4, "d2h_bytes_per_image": w * h * 4,
+            "bare_copy_images_s": n / ms_bare * 1e3, "frac_of_bare_copy": ms_bare / ms,
+            "note": "ImagePipeline: upload of image k+1, script of image k, download of image k-1 on three streams; wall clock around the "
+                    "whole batch, max over ranks; bare copy = the same uploads and downloads, both directions at once, no compute"}
 
 
 def run_config4(eng, pd, dev, rank, world, timed, steps, S=16384):
@@ -570,6 +643,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
