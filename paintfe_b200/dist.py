@@ -272,6 +272,26 @@ def _device_view(addr: int, nbytes: int, device) -> torch.Tensor:
     return torch.as_tensor(_RawDeviceMemory(addr, nbytes), device=device)
 
 
+def peer_targets(infos, rank: int, up_base: Optional[int], down_base: Optional[int], row_bytes: int, header: int = 4096):
+    """Where a rank's edge rows go (pure address arithmetic, tested on the CPU).  infos[r] = (handle, top, rows, bot, stride)
+    of rank r's block [flags | pad to `header`][ext buffer 0][ext buffer 1], ext = [top halo | band | bottom halo] rows;
+    up_base / down_base = where the neighbours' blocks are mapped here (None at the image edges).  Returns
+    (rows_up, put_up, rows_down, put_down): my first rows_up rows are the upper neighbour's bottom halo, my last rows_down
+    rows the lower neighbour's top halo; put_x[p] = (address of those halo rows in buffer p, address of the flag to release):
+    flag u32[p * 2 + side], side 0 = written by the upper neighbour of the flag's owner, side 1 = by the lower."""
+    rows_up = rows_down = 0
+    put_up = put_down = None
+    if up_base is not None:
+        _, top_u, rows_u, bot_u, stride_u = infos[rank - 1]
+        rows_up = bot_u
+        put_up = [(up_base + header + p * stride_u + (top_u + rows_u) * row_bytes, up_base + 4 * (p * 2 + 1)) for p in (0, 1)]
+    if down_base is not None:
+        _, top_d, _rows_d, _bot_d, stride_d = infos[rank + 1]
+        rows_down = top_d
+        put_down = [(down_base + header + p * stride_d, down_base + 4 * (p * 2 + 0)) for p in (0, 1)]
+    return rows_up, put_up, rows_down, put_down
+
+
 class PeerHalo:
     """A HaloPlan's extended band, twice, in device memory the two row neighbours have mapped (CUDA IPC -> NVLink peer
     access), plus one u32 flag per buffer and side.  Nothing is sent or received: the neighbour's flatten kernel stores
@@ -326,17 +346,7 @@ class PeerHalo:
         self.ext = [_device_view(self.addr + self.HEADER + p * self.stride, ext_bytes, dev).view(plan.ext.dtype).view(shape) for p in (0, 1)]
         self.core = [e[plan.top:plan.top + plan.rows] for e in self.ext]
         self.flags = _device_view(self.addr, 16, dev).view(torch.int32)
-        # where this rank's edge rows go, per buffer: (ext address in the neighbour, flag address in the neighbour)
-        self.put_up = self.put_down = None
-        self.rows_up = self.rows_down = 0
-        if self.up is not None:
-            _, top_u, rows_u, bot_u, stride_u = infos[self.rank - 1]
-            self.rows_up = bot_u  # my first bot_u rows are the upper neighbour's bottom halo
-            self.put_up = [(self.up + self.HEADER + p * stride_u + (top_u + rows_u) * self.row_bytes, self.up + 4 * (p * 2 + 1)) for p in (0, 1)]
-        if self.down is not None:
-            _, top_d, _rows_d, _bot_d, stride_d = infos[self.rank + 1]
-            self.rows_down = top_d  # my last top_d rows are the lower neighbour's top halo
-            self.put_down = [(self.down + self.HEADER + p * stride_d, self.down + 4 * (p * 2 + 0)) for p in (0, 1)]
+        self.rows_up, self.put_up, self.rows_down, self.put_down = peer_targets(infos, self.rank, self.up, self.down, self.row_bytes)
         self.halo_bytes = (plan.top + plan.bot) * self.row_bytes
 
     def _gather(self, obj):

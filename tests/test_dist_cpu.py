@@ -222,3 +222,25 @@ def test_script_parser_and_cli_helpers(tmp_path):
     assert cli.build_output_path("x/y/shot.jpg", None, "out", "png") == os.path.join("out", "shot.png")
     assert cli.build_output_path("shot.jpg", "r.png", None, "png") == "r.png"
     assert cli.build_output_path("shot.jpg", None, None, "png") is None
+
+
+def test_peer_targets_address_arithmetic():
+    """Where a rank's edge rows land in its neighbours' blocks (paintfe_b200.dist.peer_targets): three ranks, 60-row halos."""
+    from paintfe_b200 import dist as pd
+
+    row_bytes, header = 520 * 4, 4096
+    infos = [(b"a", 0, 236, 60, 4096 * 155), (b"b", 60, 232, 60, 4096 * 180), (b"c", 60, 232, 0, 4096 * 150)]
+    up, down = 1 << 30, 2 << 30
+    # rank 1, in the middle: both neighbours
+    rows_up, put_up, rows_down, put_down = pd.peer_targets(infos, 1, up, down, row_bytes, header)
+    assert (rows_up, rows_down) == (60, 60)
+    for p in (0, 1):
+        # my first 60 rows -> rank 0's BOTTOM halo (after its 0 top rows and 236 band rows), flagged as "from below" (side 1)
+        assert put_up[p] == (up + header + p * infos[0][4] + (0 + 236) * row_bytes, up + 4 * (2 * p + 1))
+        # my last 60 rows -> rank 2's TOP halo (row 0 of its extended band), flagged as "from above" (side 0)
+        assert put_down[p] == (down + header + p * infos[2][4], down + 4 * (2 * p))
+        assert put_up[p][0] % 16 == 0 and put_down[p][0] % 16 == 0  # the flatten kernel's 16-byte stores
+    # the image edges have one neighbour
+    assert pd.peer_targets(infos, 0, None, down, row_bytes, header)[:2] == (0, None)
+    r = pd.peer_targets(infos, 2, up, None, row_bytes, header)
+    assert r[2:] == (0, None) and r[0] == 60 and r[1][0][0] == up + header + (60 + 232) * row_bytes
